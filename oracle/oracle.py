@@ -1,0 +1,342 @@
+"""TEST INFRASTRUCTURE ONLY -- Python front-end of the CPU parity oracle.
+
+Restates the reference's hot path (ciclope 2.0.3) on the CPU:
+
+* ``remove_unconnected``  <- src/ciclope/utils/preprocess.py:119-143
+* ``vol2ugrid``           <- src/ciclope/core/voxelFE.py:15-283
+* ``mesh2voxelfe``        <- src/ciclope/core/voxelFE.py:474-772
+* ``matpropdictionary``   <- src/ciclope/core/voxelFE.py:774-819
+
+The voxel / node / text loops are in ``ciclope_oracle.c`` (sequential C, built by
+``oracle/build_oracle.py``); the header, PROPERTY cards and template copy are Python string
+work here.  Parity status: PINNED against golden vectors produced by the unmodified
+reference (tests/golden/, tests/test_oracle_golden.py).
+
+Nothing under ``ciclope_b200/`` may import this module: it is the checker, not the product.
+"""
+import collections
+import ctypes
+import os
+from datetime import datetime
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+_i64 = ctypes.c_int64
+_p_u8 = ctypes.POINTER(ctypes.c_uint8)
+_p_i64 = ctypes.POINTER(ctypes.c_int64)
+_p_f64 = ctypes.POINTER(ctypes.c_double)
+
+
+class _Sets6(ctypes.Structure):
+    _fields_ = [("ids", _p_i64 * 6), ("n", _i64 * 6)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            from . import build_oracle
+            build_oracle.build()
+        L = ctypes.CDLL(_LIB_PATH)
+        L.orc_remove_unconnected.restype = _i64
+        L.orc_remove_unconnected.argtypes = [_p_u8, _i64, _i64, _i64, _p_u8]
+        L.orc_count_components.restype = _i64
+        L.orc_count_components.argtypes = [_p_u8, _i64, _i64, _i64]
+        L.orc_count_cells.restype = _i64
+        L.orc_count_cells.argtypes = [_p_u8, _i64, _i64, _i64, ctypes.c_int]
+        L.orc_fill_cells.restype = None
+        L.orc_fill_cells.argtypes = [_p_u8, _i64, _i64, _i64, ctypes.c_int, _p_i64, _p_u8]
+        L.orc_boundary_sets.restype = ctypes.c_int
+        L.orc_boundary_sets.argtypes = [_p_u8, _i64, _i64, _i64, ctypes.c_int, ctypes.c_int, _i64, _i64,
+                                        ctypes.POINTER(_Sets6), ctypes.POINTER(_Sets6)]
+        L.orc_free_sets.restype = None
+        L.orc_free_sets.argtypes = [ctypes.POINTER(_Sets6)]
+        L.orc_refnode.restype = None
+        L.orc_refnode.argtypes = [_p_i64, _i64, _i64, _i64, _p_f64, _p_f64, _p_f64, _p_f64]
+        L.orc_deck_body.restype = ctypes.c_int
+        L.orc_deck_body.argtypes = [_p_f64, _i64, _p_i64, _i64, _p_u8, ctypes.c_char_p,
+                                    ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_p_i64), _p_i64,
+                                    ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_p_i64), _p_i64,
+                                    ctypes.POINTER(ctypes.c_void_p), _p_i64]
+        L.orc_free.restype = None
+        L.orc_free.argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.bool_:
+        a = a.view(np.uint8)
+    if a.dtype != np.uint8:
+        raise TypeError("oracle handles bool / uint8 volumes, got %s" % a.dtype)
+    return a
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+# ----------------------------------------------------------------------------- CCL
+
+def remove_unconnected(bwimage):
+    """preprocess.py:119-143 -- largest 6-connected component, ties -> first in raster order."""
+    bw = np.asarray(bwimage)
+    if bw.ndim != 3:
+        raise ValueError("oracle remove_unconnected expects a 3-D volume")
+    u = _u8(bw)
+    out = np.empty(u.shape, dtype=np.uint8)
+    Z, Y, X = u.shape
+    kept = lib().orc_remove_unconnected(_ptr(u, _p_u8), Z, Y, X, _ptr(out, _p_u8))
+    if kept < 0:
+        # occurrences[1:].argmax() on an empty array (preprocess.py:141)
+        raise ValueError("attempt to get argmax of an empty sequence")
+    return out.view(np.bool_)
+
+
+def count_components(bwimage):
+    u = _u8(np.asarray(bwimage))
+    Z, Y, X = u.shape
+    return int(lib().orc_count_components(_ptr(u, _p_u8), Z, Y, X))
+
+
+# ----------------------------------------------------------------------------- vol2ugrid
+
+CellBlock = collections.namedtuple("CellBlock", ["type", "data"])
+
+NODE_SET_NAMES = ["NODES_X0", "NODES_X1", "NODES_Y0", "NODES_Y1", "NODES_Z0", "NODES_Z1"]
+CELL_SET_NAMES = ["CELLS_X0", "CELLS_X1", "CELLS_Y0", "CELLS_Y1", "CELLS_Z0", "CELLS_Z1"]
+
+
+class OracleMesh:
+    """The meshio-5.0.0 surface the reference and its tests touch (voxelFE.py:271-274)."""
+
+    def __init__(self, points, cells, cell_data, point_sets, cell_sets):
+        self.points = points
+        self.cells = [CellBlock("hexahedron", cells)]
+        self.cell_data = cell_data
+        self.point_sets = point_sets
+        self.cell_sets = cell_sets
+
+    @property
+    def cells_dict(self):
+        return {"hexahedron": self.cells[0].data}
+
+
+def gv_threshold(GVmin):
+    """Integer t with (GV > GVmin) <=> (GV > t) for GV in 0..255 (voxelFE.py:141)."""
+    import math
+    if GVmin < 0:
+        return -1
+    return int(min(math.floor(GVmin), 255))
+
+
+def coordinate_tables(voxelsize, shape):
+    """Per-axis coordinate values exactly as voxelFE.py:70-73, 202 computes them, converted to
+    the dtype np.asarray(nodes) would pick (meshio.Mesh -> np.asarray(points))."""
+    Z, Y, X = shape
+    if not isinstance(voxelsize, (list, np.ndarray)):
+        voxelsize = [voxelsize, voxelsize, voxelsize]
+    if len(voxelsize) == 1:
+        voxelsize = [voxelsize[0]] * 3
+    xs = [voxelsize[0] * c for c in range(X + 1)]
+    ys = [voxelsize[1] * r for r in range(Y + 1)]
+    zs = [voxelsize[2] * s for s in range(Z + 1)]
+    dtype = np.asarray([[xs[0], ys[0], zs[0]], [xs[-1], ys[-1], zs[-1]]]).dtype
+    return (np.asarray(xs).astype(dtype), np.asarray(ys).astype(dtype), np.asarray(zs).astype(dtype))
+
+
+def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_level_lock_num=1,
+              locking_strategy="plane", refnodes=False, verbose=False):
+    voldata = np.asarray(voldata)
+    if locking_strategy not in ("plane", "exact"):
+        raise ValueError("locking_strategy must be 'plane' or 'exact'")
+    u = _u8(voldata)
+    Z, Y, X = u.shape
+    thr = gv_threshold(GVmin)
+    L = lib()
+    n_el = int(L.orc_count_cells(_ptr(u, _p_u8), Z, Y, X, thr))
+    cells = np.empty((n_el, 8), dtype=np.int64)
+    gv = np.empty(n_el, dtype=np.uint8)
+    L.orc_fill_cells(_ptr(u, _p_u8), Z, Y, X, thr, _ptr(cells, _p_i64), _ptr(gv, _p_u8))
+    if voldata.dtype == np.bool_:
+        gv = gv.view(np.bool_)
+
+    xs, ys, zs = coordinate_tables(voxelsize, (Z, Y, X))
+    points = np.empty((Z + 1, Y + 1, X + 1, 3), dtype=xs.dtype)
+    points[..., 0] = xs[None, None, :]
+    points[..., 1] = ys[None, :, None]
+    points[..., 2] = zs[:, None, None]
+    points = points.reshape(-1, 3)
+
+    ns, cs = _Sets6(), _Sets6()
+    L.orc_boundary_sets(_ptr(u, _p_u8), Z, Y, X, thr, 0 if locking_strategy == "plane" else 1,
+                        int(plane_lock_num), int(node_level_lock_num), ctypes.byref(ns), ctypes.byref(cs))
+    point_sets, cell_sets = {}, {}
+    node_arrays = []
+    for q in range(6):
+        a = np.ctypeslib.as_array(ns.ids[q], shape=(ns.n[q],)).copy() if ns.n[q] else np.empty(0, np.int64)
+        node_arrays.append(a)
+        point_sets[NODE_SET_NAMES[q]] = a.tolist()
+        b = np.ctypeslib.as_array(cs.ids[q], shape=(cs.n[q],)).copy() if cs.n[q] else np.empty(0, np.int64)
+        cell_sets[CELL_SET_NAMES[q]] = b.tolist()
+    L.orc_free_sets(ctypes.byref(ns))
+    L.orc_free_sets(ctypes.byref(cs))
+    point_sets["NODES_X0Y0Z0"] = point_sets["NODES_Z0"][0:2]
+    point_sets["NODES_X0Y0Z1"] = point_sets["NODES_Z1"][0:2]
+
+    mesh = OracleMesh(points, cells, {"GV": [gv]}, point_sets, cell_sets)
+    if not refnodes:
+        return mesh
+    # voxelFE.py:202-223, 254-268: sequential float64 sums of the Python coordinate values
+    x64 = np.asarray(xs, dtype=np.float64)
+    y64 = np.asarray(ys, dtype=np.float64)
+    z64 = np.asarray(zs, dtype=np.float64)
+    rn = {}
+    for q, key in enumerate(["X0", "X1", "Y0", "Y1", "Z0", "Z1"]):
+        out = np.zeros(3)
+        a = node_arrays[q]
+        L.orc_refnode(_ptr(a, _p_i64), len(a), Y, X, _ptr(x64, _p_f64), _ptr(y64, _p_f64), _ptr(z64, _p_f64),
+                      _ptr(out, _p_f64))
+        rn[key] = out
+    return mesh, rn
+
+
+# ----------------------------------------------------------------------------- mesh2voxelfe
+
+def _resolve_matprop(matprop, existing_GV, GVmax):
+    """voxelFE.py:579-610 -- returns {file index: (lo, hi)}; mutates matprop like the reference."""
+    prop_GV = {}
+    if matprop is None:
+        return prop_GV
+    if "range" not in matprop and len(matprop["file"]) > 1:
+        raise IOError('Incorrect material property definition: GV ranges required when using multiple property files.')
+    elif "range" not in matprop and len(matprop["file"]) == 1:
+        matprop["range"] = [[1, GVmax]]
+    ranges = []
+    for n, GVrange in enumerate(matprop["range"]):
+        lo, hi = int(GVrange[0]), int(GVrange[1])
+        if lo < 0:
+            raise IOError('property GV range below min representable integer')
+        if hi > GVmax:
+            raise IOError('property GV range exceeds max representable integer')
+        prop_GV[n] = (lo, hi)
+        ranges.append(set(range(lo, hi + 1)))
+    for i in range(len(ranges) - 1):
+        if not ranges[i].isdisjoint(ranges[i + 1]):
+            raise IOError('GV ranges assigned to different material properties cannot overlap')
+    return prop_GV
+
+
+def _property_section(matprop, prop_GV, existing_GV):
+    """voxelFE.py:691-746."""
+    out = ['** User material property definition:\n',
+           '** internal variables are: "SetName", "MatName", "GV"\n']
+    for n, fname in enumerate(matprop["file"]):
+        with open(fname, 'r') as f:
+            lines = f.readlines()
+        for GV in existing_GV:  # noqa: N806 -- 'GV' is the name the cards' expressions use
+            if not (prop_GV[n][0] <= GV <= prop_GV[n][1]):
+                continue
+            setname = 'SET' + str(GV)
+            for line in lines:
+                line = line.replace('\n', '')
+                if line.startswith('**'):
+                    out.append(line + '\n')
+                    continue
+                if 'SetName' in line:
+                    line = line.replace('SetName', setname)
+                if 'MatName' in line:
+                    line = line.replace('MatName', 'MAT' + setname)
+                if 'GV' in line:
+                    pieces = line.split(',')
+                    env = {"GV": GV, "np": np}
+                    out.append(','.join('{}'.format(eval(p, env)) if 'GV' in p else p for p in pieces) + '\n')
+                else:
+                    out.append(line + '\n')
+    return ''.join(out)
+
+
+def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'ELSET'], eltype='C3D8',
+                 matpropbits=8, refnode=None, verbose=False):
+    keys = list(mesh.cell_data)
+    cell_GV = mesh.cell_data.get(keys[0])
+    if type(cell_GV) is list:
+        cell_GV = cell_GV[0]
+    cell_GV = np.asarray(cell_GV)
+    if cell_GV.size == 0:
+        raise ValueError("min() iterable argument is empty")  # voxelFE.py:564
+    GVmax = 2 ** matpropbits - 1
+    binary_model = bool(cell_GV.min() == 0) and bool(cell_GV.max() == 1) and \
+        issubclass(cell_GV.dtype.type, np.integer)
+    existing_GV = np.unique(cell_GV)
+    if max(existing_GV) > GVmax:
+        GVmax = max(existing_GV)
+    if binary_model:
+        prop_GV = {0: (1, 1)}
+    else:
+        prop_GV = _resolve_matprop(matprop, existing_GV, GVmax)
+
+    L = lib()
+    points = np.ascontiguousarray(mesh.points, dtype=np.float64)
+    cells = np.ascontiguousarray(mesh.cells_dict["hexahedron"], dtype=np.int64)
+    gv8 = np.ascontiguousarray(cell_GV).astype(np.uint8)
+
+    def pack(sets):
+        names = list(sets)
+        arrs = [np.asarray(sets[k], dtype=np.int64) for k in names]
+        c_names = (ctypes.c_char_p * max(len(names), 1))(*[k.encode() for k in names])
+        c_ids = (_p_i64 * max(len(names), 1))(*[_ptr(a, _p_i64) for a in arrs])
+        c_n = np.asarray([len(a) for a in arrs] + [0], dtype=np.int64)
+        return len(names), c_names, c_ids, c_n, arrs
+
+    nn, nnames, nids, ncnt, _keep1 = pack(mesh.point_sets)
+    en, enames, eids, ecnt, _keep2 = pack(mesh.cell_sets)
+    if 'NSET' not in keywords:
+        nn = -1
+    if 'ELSET' not in keywords:
+        en = -1
+    out_p = ctypes.c_void_p()
+    out_n = _i64()
+    L.orc_deck_body(_ptr(points, _p_f64), len(points), _ptr(cells, _p_i64), len(cells), _ptr(gv8, _p_u8),
+                    eltype.encode(), nn, nnames, nids, _ptr(ncnt, _p_i64), en, enames, eids, _ptr(ecnt, _p_i64),
+                    ctypes.byref(out_p), ctypes.byref(out_n))
+    body = ctypes.string_at(out_p.value, out_n.value)
+    L.orc_free(out_p)
+
+    with open(fileout, 'wb') as INP:
+        INP.write(b'** ---------------------------------------------------------\n')
+        INP.write('** Abaqus .INP file written by Voxel_FEM script on {}\n'.format(datetime.now()).encode())
+        INP.write(b'** ---------------------------------------------------------\n')
+        INP.write(body)
+        if 'PROPERTY' in keywords:
+            INP.write(_property_section(matprop, prop_GV, existing_GV).encode())
+        with open(templatefile, 'r') as template:
+            for line in template.readlines():
+                if refnode is not None:
+                    line = line.replace('refnodeX', str(round(refnode[0], 4)))
+                    line = line.replace('refnodeY', str(round(refnode[1], 4)))
+                    line = line.replace('refnodeZ', str(round(refnode[2], 4)))
+                INP.write(line.encode())
+
+
+def matpropdictionary(proplist):
+    """voxelFE.py:774-819."""
+    if proplist is None or len(proplist) == 0:
+        return None
+    if len(proplist) == 1:
+        if not os.path.isfile(proplist[0]):
+            raise IOError('Property file {0} doesnt exist.', format(proplist[0]))
+        return {"file": [proplist[0]]}
+    if len(proplist) % 3 != 0:
+        raise IOError('Mapping dictionary error (probably due to incorrect use of --mapping flag): each material '
+                      'property file must be followed by MIN and MAX of the corresponding GV range.')
+    matprop = {'file': [], 'range': []}
+    for i in range(len(proplist) // 3):
+        matprop['file'].append(proplist[3 * i])
+        matprop['range'].append([int(proplist[3 * i + 1]), int(proplist[3 * i + 2])])
+    return matprop
