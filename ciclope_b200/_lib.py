@@ -1,0 +1,107 @@
+"""ctypes binding of libciclope_b200.so (include/ciclope_b200.h).
+
+There is NO CPU fallback: if the CUDA library is missing or no CUDA device is present the
+public functions raise.  torch is used for device memory, streams and torch.distributed only.
+"""
+import ctypes
+import os
+
+import torch  # noqa: F401  (loads libcudart before our library; provides device memory)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libciclope_b200.so")
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_vp = ctypes.c_void_p
+c_sz = ctypes.c_size_t
+
+
+class CfeSetDesc(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                ("s0", c_i64), ("s1", c_i64), ("r0", c_i64), ("r1", c_i64), ("c0", c_i64), ("c1", c_i64),
+                ("vs0", c_i64), ("vs1", c_i64), ("vr0", c_i64), ("vr1", c_i64), ("vc0", c_i64), ("vc1", c_i64),
+                ("n_cand", c_i64), ("tile_base", c_i64)]
+
+
+class CfeItemSeg(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                ("item0", c_i64), ("lit_off", c_i64), ("lit_len", c_i64), ("id0", c_i64), ("rank0", c_i64)]
+
+
+_SIGNATURES = {
+    "cfe_version": (c_int, []),
+    "cfe_last_error": (ctypes.c_char_p, []),
+    "cfe_pack_bits": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
+    "cfe_scan_workspace_bytes": (c_sz, [c_i64]),
+    "cfe_scan_elements": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_scan_run_starts": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_scan_nodes": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_fill_list": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "cfe_scan_u32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_ccl_max_runs": (c_sz, [c_i64, c_i64]),
+    "cfe_ccl_largest": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_sets_count": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_sets_fill": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                              c_vp]),
+    "cfe_refnode_sums": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_fill_cells": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "cfe_gather_gv": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "cfe_fill_points": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "cfe_emit_nodes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "cfe_emit_elements": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_emit_items": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_put_literal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_gv_histogram": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    "cfe_partition_tiles": (c_i64, [c_i64]),
+    "cfe_partition_hist": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "cfe_partition_scatter": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+}
+
+EXPORTED_SYMBOLS = sorted(_SIGNATURES)
+
+_lib = None
+
+
+class CfeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library (no compute).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CfeError("%s not found: build it with `python -m ciclope_b200.build` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise CfeError("ciclope_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return load()
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise CfeError with cfe_last_error() on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise CfeError("%s failed (%d): %s" % (name, rc, lib.cfe_last_error().decode()))
+
+
+def ptr(t):
+    """Device (or pinned host) pointer of a torch tensor, or NULL for None."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

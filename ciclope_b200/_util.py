@@ -1,0 +1,52 @@
+"""Host-side helpers shared by the facade modules (device volumes, scratch buffers)."""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def as_device_volume(vol, allow_2d=False):
+    """Return (uint8 CUDA tensor [Z,Y,X] contiguous, is_bool, came_from_numpy).
+
+    Accepts numpy arrays and torch tensors (CPU or CUDA) of dtype bool or uint8.  Other dtypes
+    raise TypeError: the CUDA path computes on 8-bit grey values and there is no CPU fallback."""
+    _lib.require_cuda()
+    from_numpy = False
+    if isinstance(vol, np.ndarray):
+        from_numpy = True
+        if vol.dtype not in (np.bool_, np.uint8):
+            raise TypeError("ciclope_b200 handles bool / uint8 volumes, got %s" % vol.dtype)
+        a = np.ascontiguousarray(vol)
+        is_bool = a.dtype == np.bool_
+        t = torch.from_numpy(a.view(np.uint8))
+    elif isinstance(vol, torch.Tensor):
+        if vol.dtype not in (torch.bool, torch.uint8):
+            raise TypeError("ciclope_b200 handles bool / uint8 volumes, got %s" % vol.dtype)
+        is_bool = vol.dtype == torch.bool
+        t = vol.contiguous()
+        if is_bool:
+            t = t.view(torch.uint8)
+    else:
+        raise TypeError("volume must be a numpy.ndarray or torch.Tensor, got %s" % type(vol).__name__)
+    if t.dim() == 2 and allow_2d:
+        t = t.unsqueeze(0)
+    if t.dim() != 3:
+        raise ValueError("volume must be 3-D [slices, rows, cols], got %d-D" % t.dim())
+    if not t.is_cuda:
+        t = t.cuda(non_blocking=True)
+    return t, is_bool, from_numpy
+
+
+def empty_u32(n, device):
+    return torch.empty(max(int(n), 1), dtype=torch.int32, device=device)
+
+
+def scan_workspace(n_items, device):
+    nbytes = _lib.load().cfe_scan_workspace_bytes(int(n_items))
+    return torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=device)
+
+
+def check_slab_size(Z, Y, X):
+    if (Z + 1) * (Y + 1) * (X + 1) >= 2 ** 32:
+        raise ValueError("a single-GPU slab must hold fewer than 2^32 grid nodes; shard the volume as "
+                         "z-slabs over more GPUs")

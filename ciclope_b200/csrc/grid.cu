@@ -1,0 +1,546 @@
+// ciclope_b200 -- voxel-grid kernels (sm_100a): bit packing, element / node / run numbering
+// by decoupled look-back scans over 32-voxel words, list filling, boundary sets.
+//
+// Replaces the Python loops of ciclope/core/voxelFE.py:135-192 (cell loop) and :195-251 (node
+// loop) and np.unique(cells) (:628).  Layout in HBM (one z-slab per GPU):
+//   vol    uint8 [Zl][Y][X]                      the caller's volume, read once per pass
+//   bits   u32   [Zl*Y][W], W = ceil(X/32)       bit b of word w <-> column 32w+b, 1 = element
+//   pref   u32   [Zl*Y*W]                        exclusive count of elements before each word
+//   nbits  u32   [NL*(Y+1)][WN], WN=ceil((X+1)/32)  1 = grid node touched by >= 1 element
+//   npref  u32   [NL*(Y+1)*WN]                   exclusive count of used nodes before each word
+#include "common.cuh"
+#include "ciclope_b200.h"
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+// ------------------------------------------------------------------------------------------
+// K0: pack (v > thr) into bit rows
+
+__device__ __forceinline__ u32 cmp_nibble(u32 x, u32 thr4, bool all)
+{
+    u32 m = all ? 0xffffffffu : __vcmpgtu4(x, thr4);
+    return ((m & 0x08040201u) * 0x01010101u) >> 24;
+}
+
+// FLAT: X % 32 == 0 and vol 16-byte aligned -> the volume is a flat array of 16-byte chunks.
+template <bool FLAT>
+__global__ void __launch_bounds__(256) k_pack_bits(const uint8_t* __restrict__ vol, i64 rows, int X, int W,
+                                                   int thr, u32* __restrict__ bits)
+{
+    const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const i64 nchunks = rows * 2 * (i64)W;
+    const bool all = thr < 0;
+    const u32 thr4 = (u32)(thr < 0 ? 0 : thr) * 0x01010101u;
+    u32 m16 = 0;
+    if (g < nchunks) {
+        if (FLAT) {
+            uint4 v = __ldg(reinterpret_cast<const uint4*>(vol) + g);
+            m16 = cmp_nibble(v.x, thr4, all) | (cmp_nibble(v.y, thr4, all) << 4) |
+                  (cmp_nibble(v.z, thr4, all) << 8) | (cmp_nibble(v.w, thr4, all) << 12);
+        } else {
+            const i64 row = g / (2 * W);
+            const int c0 = (int)(g - row * 2 * W) * 16;
+            const uint8_t* p = vol + row * (i64)X + c0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (c0 + k < X) m16 |= (u32)((int)p[k] > thr) << k;
+        }
+    }
+    const u32 other = __shfl_xor_sync(CFE_FULL_MASK, m16, 1);
+    if (g < nchunks && !(threadIdx.x & 1)) bits[g >> 1] = m16 | (other << 16);
+}
+
+extern "C" int cfe_pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t* bits,
+                             cudaStream_t stream)
+{
+    if (rows <= 0 || X <= 0) return 0;
+    const int W = (int)((X + 31) / 32);
+    const i64 nchunks = rows * 2 * (i64)W;
+    const i64 blocks = (nchunks + 255) / 256;
+    if (blocks > 0x7fffffffLL) { cfe_set_error("cfe_pack_bits: volume too large"); return -1; }
+    const bool flat = (X % 32 == 0) && ((reinterpret_cast<uintptr_t>(vol) & 15u) == 0);
+    if (flat)
+        k_pack_bits<true><<<(unsigned)blocks, 256, 0, stream>>>(vol, rows, (int)X, W, thr, bits);
+    else
+        k_pack_bits<false><<<(unsigned)blocks, 256, 0, stream>>>(vol, rows, (int)X, W, thr, bits);
+    CFE_CHECK_LAUNCH("k_pack_bits");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Word functors for the scan kernel.
+
+struct NodeGeom {
+    int Zl, Y, W, WN;        // local voxel slices, rows, words per voxel row / node row
+    int n_layers;            // node layers owned by this slab (Zl, or Zl+1 on the last slab)
+    const u32* bits;         // [Zl*Y][W]
+    const u32* halo_below;   // [Y][W] element bits of the voxel plane below local slice 0, or null
+};
+
+// 1 bit per grid node of node row (layer s, row r), word w: node used <=> any of the <= 8
+// adjacent voxels is an element (np.unique(cells), voxelFE.py:628).
+__device__ __forceinline__ u32 node_used_word(const NodeGeom& g, int s, int r, int w)
+{
+    u32 u = 0, up = 0;
+#pragma unroll
+    for (int ds = 0; ds < 2; ++ds) {
+        const int vs = s - ds;
+        const u32* plane;
+        if (vs >= 0 && vs < g.Zl) plane = g.bits + (size_t)vs * g.Y * g.W;
+        else if (vs == -1 && g.halo_below) plane = g.halo_below;
+        else continue;
+#pragma unroll
+        for (int dr = 0; dr < 2; ++dr) {
+            const int vr = r - dr;
+            if (vr < 0 || vr >= g.Y) continue;
+            const u32* row = plane + (size_t)vr * g.W;
+            if (w < g.W) u |= __ldg(row + w);
+            if (w > 0) up |= __ldg(row + w - 1);
+        }
+    }
+    return u | (u << 1) | (up >> 31);
+}
+
+// MODE 0: popc(bits[i])                       element numbering        (voxelFE.py:142)
+// MODE 1: popc(run starts of bits[i])         x-run numbering for CCL
+// MODE 2: popc(node_used_word) + store word   used-node numbering      (voxelFE.py:628)
+template <int MODE>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_words(const u32* __restrict__ bits, i64 n_words, int W, NodeGeom geom, u32* __restrict__ nbits,
+             u32* __restrict__ pref, u64* __restrict__ total, u64* __restrict__ ws)
+{
+    __shared__ u32 s_scan[33];
+    __shared__ u64 s_excl;
+    const u32 tile = scan_next_tile(ws);
+    const i64 i0 = (i64)tile * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+    u32 cnt[SCAN_ITEMS];
+    u32 sum = 0;
+    if (MODE == 2) {
+        // decompose the first word index once, then step
+        const i64 words_per_layer = (i64)(geom.Y + 1) * geom.WN;
+        int s = (int)(i0 / words_per_layer);
+        i64 rem = i0 - (i64)s * words_per_layer;
+        int r = (int)(rem / geom.WN);
+        int w = (int)(rem - (i64)r * geom.WN);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            u32 word = 0;
+            if (i0 + k < n_words) {
+                word = node_used_word(geom, s, r, w);
+                nbits[i0 + k] = word;
+            }
+            cnt[k] = __popc(word);
+            sum += cnt[k];
+            if (++w == geom.WN) { w = 0; if (++r == geom.Y + 1) { r = 0; ++s; } }
+        }
+    } else {
+        u32 prev = 0;
+        if (MODE == 1 && i0 > 0 && i0 < n_words && (i0 % W) != 0) prev = __ldg(bits + i0 - 1);
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            u32 word = (i0 + k < n_words) ? __ldg(bits + i0 + k) : 0u;
+            if (MODE == 1) {
+                const u32 carry = ((i0 + k) % W != 0) ? (prev >> 31) : 0u;
+                const u32 starts = word & ~((word << 1) | carry);
+                prev = word;
+                cnt[k] = __popc(starts);
+            } else {
+                cnt[k] = __popc(word);
+            }
+            sum += cnt[k];
+        }
+    }
+    u32 block_total;
+    u32 excl = block_exclusive_scan<u32>(sum, s_scan, block_total);
+    if (threadIdx.x < 32) {
+        u64 e = scan_lookback(ws, tile, (u64)block_total);
+        if (threadIdx.x == 0) {
+            s_excl = e;
+            if ((i64)(tile + 1) * SCAN_TILE >= n_words) *total = e + block_total;  // last tile
+        }
+    }
+    __syncthreads();
+    u32 run = (u32)s_excl + excl;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (i0 + k < n_words) pref[i0 + k] = run;
+        run += cnt[k];
+    }
+}
+
+extern "C" size_t cfe_scan_workspace_bytes(int64_t n_items)
+{
+    // one status word per SCAN_TILE items (+ counter); callers may use the same workspace for
+    // any tile size >= 256 items.
+    return (size_t)((n_items + 255) / 256 + 2) * sizeof(u64);
+}
+
+static int launch_scan(int mode, const u32* bits, i64 n_words, int W, const NodeGeom& geom, u32* nbits,
+                       u32* pref, u64* total, void* ws, cudaStream_t stream)
+{
+    if (n_words >= (1LL << 32) * 32 / 32) {
+        // prefixes are u32: a slab holds < 2^32 voxels / nodes
+    }
+    const i64 tiles = (n_words + SCAN_TILE - 1) / SCAN_TILE;
+    CFE_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(tiles + 2) * sizeof(u64), stream));
+    if (tiles == 0) {
+        CFE_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(u64), stream));
+        return 0;
+    }
+    if (tiles > 0x7fffffffLL) { cfe_set_error("scan: too many tiles"); return -1; }
+    u64* w = reinterpret_cast<u64*>(ws);
+    switch (mode) {
+    case 0: k_scan_words<0><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w); break;
+    case 1: k_scan_words<1><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w); break;
+    default: k_scan_words<2><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w); break;
+    }
+    CFE_CHECK_LAUNCH("k_scan_words");
+    return 0;
+}
+
+extern "C" int cfe_scan_elements(const uint32_t* bits, int64_t n_words, uint32_t* pref, uint64_t* total,
+                                 void* ws, cudaStream_t stream)
+{
+    NodeGeom g = {};
+    return launch_scan(0, bits, n_words, 1, g, nullptr, pref, reinterpret_cast<u64*>(total), ws, stream);
+}
+
+extern "C" int cfe_scan_run_starts(const uint32_t* bits, int64_t rows, int64_t X, uint32_t* pref,
+                                   uint64_t* total, void* ws, cudaStream_t stream)
+{
+    NodeGeom g = {};
+    const int W = (int)((X + 31) / 32);
+    return launch_scan(1, bits, rows * W, W, g, nullptr, pref, reinterpret_cast<u64*>(total), ws, stream);
+}
+
+extern "C" int cfe_scan_nodes(const uint32_t* bits, const uint32_t* halo_below, int64_t Zl, int64_t Y,
+                              int64_t X, int64_t n_layers, uint32_t* nbits, uint32_t* npref,
+                              uint64_t* total, void* ws, cudaStream_t stream)
+{
+    NodeGeom g;
+    g.Zl = (int)Zl; g.Y = (int)Y; g.W = (int)((X + 31) / 32); g.WN = (int)((X + 1 + 31) / 32);
+    g.n_layers = (int)n_layers; g.bits = bits; g.halo_below = halo_below;
+    const i64 n_words = n_layers * (Y + 1) * (i64)g.WN;
+    return launch_scan(2, bits, n_words, g.WN, g, nbits, npref, reinterpret_cast<u64*>(total), ws, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// K9: expand set bits into an index list: list[pref[i] + k] = row*rowlen + 32*w + b
+// (elements: rowlen = X, words per row W; nodes: rowlen = X+1, words per row WN).
+
+__global__ void __launch_bounds__(256)
+k_fill_list(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 n_words, int wpr, int rowlen,
+            u32* __restrict__ list)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    u32 word = __ldg(bits + i);
+    if (!word) return;
+    const i64 row = i / wpr;
+    const int w = (int)(i - row * wpr);
+    const u32 base = (u32)(row * rowlen + (i64)w * 32);
+    u32 o = __ldg(pref + i);
+    while (word) {
+        const int b = __ffs((int)word) - 1;
+        word &= word - 1;
+        list[o++] = base + (u32)b;
+    }
+}
+
+extern "C" int cfe_fill_list(const uint32_t* bits, const uint32_t* pref, int64_t n_words,
+                             int64_t words_per_row, int64_t row_len, uint32_t* list, cudaStream_t stream)
+{
+    if (n_words <= 0) return 0;
+    const i64 blocks = (n_words + 255) / 256;
+    k_fill_list<<<(unsigned)blocks, 256, 0, stream>>>(bits, pref, n_words, (int)words_per_row, (int)row_len, list);
+    CFE_CHECK_LAUNCH("k_fill_list");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: boundary sets (voxelFE.py:163-192, 205-251).  Every set is "candidates in a box of the
+// node / voxel grid, kept when a predicate holds", enumerated in raster order (ascending id).
+// Two passes over the candidates (count per 256-candidate tile -> flat scan -> fill).
+
+struct SetGeom {
+    int Zl, Y, X, W;
+    i64 z0;                  // global slice index of local slice 0
+    i64 eid_offset;          // elements in the slabs below (global element id = offset + local + 1)
+    const u32* bits;
+    const u32* pref;         // element prefix per word (kind 2)
+    const u32* halo_below;   // [Y][W] or null
+};
+
+__device__ __forceinline__ bool voxel_bit(const SetGeom& g, int s, int r, int c)
+{
+    // s is a LOCAL slice index; -1 addresses the halo plane
+    if (r < 0 || r >= g.Y || c < 0 || c >= g.X) return false;
+    const u32* plane;
+    if (s >= 0 && s < g.Zl) plane = g.bits + (size_t)s * g.Y * g.W;
+    else if (s == -1 && g.halo_below) plane = g.halo_below;
+    else return false;
+    return (__ldg(plane + (size_t)r * g.W + (c >> 5)) >> (c & 31)) & 1u;
+}
+
+__device__ __forceinline__ bool set_candidate(const CfeSetDesc& d, const SetGeom& g, i64 k, i64& id)
+{
+    // candidate k of the box -> (s, r, c) in GLOBAL coordinates
+    const i64 nr = d.r1 - d.r0, nc = d.c1 - d.c0;
+    const i64 s = d.s0 + k / (nr * nc);
+    const i64 rem = k % (nr * nc);
+    const int r = (int)(d.r0 + rem / nc);
+    const int c = (int)(d.c0 + rem % nc);
+    const int sl = (int)(s - g.z0);
+    if (d.kind == 2) {
+        if (!voxel_bit(g, sl, r, c)) return false;
+        const size_t wi = ((size_t)sl * g.Y + r) * g.W + (c >> 5);
+        const u32 word = __ldg(g.bits + wi);
+        id = g.eid_offset + (i64)__ldg(g.pref + wi) + __popc(word & mask_lt(c & 31)) + 1;
+        return true;
+    }
+    bool hit = false;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const i64 vs = s - (t >> 2);
+        const int vr = r - ((t >> 1) & 1), vc = c - (t & 1);
+        if (vs < d.vs0 || vs >= d.vs1 || vr < d.vr0 || vr >= d.vr1 || vc < d.vc0 || vc >= d.vc1) continue;
+        hit |= voxel_bit(g, (int)(vs - g.z0), vr, vc);
+    }
+    id = ((i64)(g.X + 1) * (g.Y + 1)) * s + (i64)(g.X + 1) * r + c;
+    return hit;
+}
+
+__device__ __forceinline__ int find_set(const CfeSetDesc* descs, int n_sets, i64 tile)
+{
+    int q = 0;
+    while (q + 1 < n_sets && tile >= descs[q + 1].tile_base) ++q;
+    return q;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_sets(const CfeSetDesc* __restrict__ descs, int n_sets, SetGeom g, u32* __restrict__ tile_count,
+       const u64* __restrict__ tile_off, i64* __restrict__ ids)
+{
+    __shared__ u32 s_scan[33];
+    const i64 tile = blockIdx.x;
+    const int q = find_set(descs, n_sets, tile);
+    const CfeSetDesc d = descs[q];
+    const i64 k = (tile - d.tile_base) * 256 + threadIdx.x;
+    i64 id = 0;
+    bool keep = false;
+    if (k < d.n_cand) keep = set_candidate(d, g, k, id);
+    if (!FILL) {
+        const int n = __syncthreads_count(keep);
+        if (threadIdx.x == 0) tile_count[tile] = (u32)n;
+    } else {
+        u32 tot;
+        const u32 e = block_exclusive_scan<u32>(keep ? 1u : 0u, s_scan, tot);
+        if (keep) ids[tile_off[tile] + e] = id;
+    }
+}
+
+// generic exclusive scan u32 -> u64 (small arrays: tile counts, per-bin histograms)
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_u32(const u32* __restrict__ in, i64 n, u64* __restrict__ out, u64* __restrict__ total, u64* __restrict__ ws)
+{
+    __shared__ u64 s_scan[33];
+    __shared__ u64 s_excl;
+    const u32 tile = scan_next_tile(ws);
+    const i64 i0 = (i64)tile * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+    u32 v[SCAN_ITEMS];
+    u64 sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+        sum += v[k];
+    }
+    u64 block_total;
+    u64 excl = block_exclusive_scan<u64>(sum, s_scan, block_total);
+    if (threadIdx.x < 32) {
+        u64 e = scan_lookback(ws, tile, block_total);
+        if (threadIdx.x == 0) {
+            s_excl = e;
+            if ((i64)(tile + 1) * SCAN_TILE >= n) *total = e + block_total;
+        }
+    }
+    __syncthreads();
+    u64 run = s_excl + excl;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (i0 + k < n) out[i0 + k] = run;
+        run += v[k];
+    }
+}
+
+extern "C" int cfe_scan_u32(const uint32_t* in, int64_t n, uint64_t* out, uint64_t* total, void* ws,
+                            cudaStream_t stream)
+{
+    const i64 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    CFE_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(tiles + 2) * sizeof(u64), stream));
+    if (tiles == 0) {
+        CFE_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(u64), stream));
+        return 0;
+    }
+    k_scan_u32<<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(in, n, reinterpret_cast<u64*>(out),
+                                                             reinterpret_cast<u64*>(total),
+                                                             reinterpret_cast<u64*>(ws));
+    CFE_CHECK_LAUNCH("k_scan_u32");
+    return 0;
+}
+
+extern "C" int cfe_sets_count(const CfeSetDesc* descs_dev, int n_sets, int64_t n_tiles, int64_t Zl,
+                              int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, const uint32_t* bits,
+                              const uint32_t* pref, const uint32_t* halo_below, uint32_t* tile_count,
+                              cudaStream_t stream)
+{
+    if (n_tiles <= 0) return 0;
+    SetGeom g;
+    g.Zl = (int)Zl; g.Y = (int)Y; g.X = (int)X; g.W = (int)((X + 31) / 32);
+    g.z0 = z0; g.eid_offset = eid_offset; g.bits = bits; g.pref = pref; g.halo_below = halo_below;
+    k_sets<false><<<(unsigned)n_tiles, 256, 0, stream>>>(descs_dev, n_sets, g, tile_count, nullptr, nullptr);
+    CFE_CHECK_LAUNCH("k_sets<count>");
+    return 0;
+}
+
+extern "C" int cfe_sets_fill(const CfeSetDesc* descs_dev, int n_sets, int64_t n_tiles, int64_t Zl,
+                             int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, const uint32_t* bits,
+                             const uint32_t* pref, const uint32_t* halo_below, const uint64_t* tile_off,
+                             int64_t* ids, cudaStream_t stream)
+{
+    if (n_tiles <= 0) return 0;
+    SetGeom g;
+    g.Zl = (int)Zl; g.Y = (int)Y; g.X = (int)X; g.W = (int)((X + 31) / 32);
+    g.z0 = z0; g.eid_offset = eid_offset; g.bits = bits; g.pref = pref; g.halo_below = halo_below;
+    k_sets<true><<<(unsigned)n_tiles, 256, 0, stream>>>(descs_dev, n_sets, g, nullptr,
+                                                        reinterpret_cast<const u64*>(tile_off),
+                                                        reinterpret_cast<i64*>(ids));
+    CFE_CHECK_LAUNCH("k_sets<fill>");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Materialisers for the lazy Mesh (meshio surface): cells (n_el,8) int64, GV, points.
+
+__global__ void __launch_bounds__(256)
+k_fill_cells(const u32* __restrict__ elem_vox, i64 n_el, int Y, int X, i64 z0, FastDiv dYX, FastDiv dX,
+             i64* __restrict__ cells)
+{
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;  // one (element, node) pair per thread
+    const i64 e = t >> 3;
+    if (e >= n_el) return;
+    const int j = (int)(t & 7);
+    const u32 v = __ldg(elem_vox + e);
+    const u32 s = fd_div(v, dYX);
+    const u32 rem = v - s * (u32)(Y * X);
+    const u32 r = fd_div(rem, dX);
+    const u32 c = rem - r * (u32)X;
+    const i64 RN = X + 1, SN = (i64)(X + 1) * (Y + 1);
+    const i64 base = SN * ((i64)s + z0) + RN * r + c;
+    // C3D8 order (voxelFE.py:145-154): b, b+1, b+RN+1, b+RN, b+SN, b+SN+1, b+SN+RN+1, b+SN+RN
+    const i64 off = ((j >> 2) ? SN : 0) + (((j & 3) == 1 || (j & 3) == 2) ? 1 : 0) + (((j & 3) >= 2) ? RN : 0);
+    cells[t] = base + off;
+}
+
+extern "C" int cfe_fill_cells(const uint32_t* elem_vox, int64_t n_el, int64_t Y, int64_t X, int64_t z0,
+                              int64_t* cells, cudaStream_t stream)
+{
+    if (n_el <= 0) return 0;
+    const i64 threads = n_el * 8;
+    k_fill_cells<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
+        elem_vox, n_el, (int)Y, (int)X, z0, make_fastdiv((u32)(Y * X)), make_fastdiv((u32)X),
+        reinterpret_cast<i64*>(cells));
+    CFE_CHECK_LAUNCH("k_fill_cells");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_u8(const uint8_t* __restrict__ vol, const u32* __restrict__ idx, i64 n, uint8_t* __restrict__ out)
+{
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = __ldg(vol + __ldg(idx + t));
+}
+
+extern "C" int cfe_gather_gv(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, uint8_t* gv,
+                             cudaStream_t stream)
+{
+    if (n_el <= 0) return 0;
+    k_gather_u8<<<(unsigned)((n_el + 255) / 256), 256, 0, stream>>>(vol, elem_vox, n_el, gv);
+    CFE_CHECK_LAUNCH("k_gather_u8");
+    return 0;
+}
+
+// points[(s,r,c)] = (xs[c], ys[r], zs[s]) copied as raw ELEM-byte values (float64/int64: 8,
+// float32: 4) from the host-computed per-axis tables (voxelFE.py:202).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fill_points(const T* __restrict__ xs, const T* __restrict__ ys, const T* __restrict__ zs, i64 n_nodes,
+              int RN, i64 SN, T* __restrict__ out)
+{
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_nodes) return;
+    const i64 s = t / SN;
+    const i64 rem = t - s * SN;
+    const int r = (int)(rem / RN);
+    const int c = (int)(rem - (i64)r * RN);
+    out[3 * t + 0] = xs[c];
+    out[3 * t + 1] = ys[r];
+    out[3 * t + 2] = zs[s];
+}
+
+extern "C" int cfe_fill_points(const void* xs, const void* ys, const void* zs, int elem_bytes,
+                               int64_t n_layers, int64_t Y, int64_t X, void* out, cudaStream_t stream)
+{
+    const i64 n = n_layers * (Y + 1) * (X + 1);
+    if (n <= 0) return 0;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (elem_bytes == 8)
+        k_fill_points<u64><<<blocks, 256, 0, stream>>>((const u64*)xs, (const u64*)ys, (const u64*)zs, n,
+                                                       (int)(X + 1), (X + 1) * (Y + 1), (u64*)out);
+    else if (elem_bytes == 4)
+        k_fill_points<u32><<<blocks, 256, 0, stream>>>((const u32*)xs, (const u32*)ys, (const u32*)zs, n,
+                                                       (int)(X + 1), (X + 1) * (Y + 1), (u32*)out);
+    else { cfe_set_error("cfe_fill_points: elem_bytes must be 4 or 8"); return -1; }
+    CFE_CHECK_LAUNCH("k_fill_points");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Reference-node barycentre sums (voxelFE.py:208-223): float64 accumulation in ascending node
+// order, one thread per set so that the summation ORDER (hence every rounding) is the
+// reference's.  acc[q][0..2] is read-modify-written so z-slabs can be chained.
+
+__global__ void k_refnode_sums(const i64* __restrict__ ids, const i64* __restrict__ first,
+                               const i64* __restrict__ count, int n_sets, i64 SN, i64 RN,
+                               const double* __restrict__ xs, const double* __restrict__ ys,
+                               const double* __restrict__ zs, double* __restrict__ acc)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_sets) return;
+    double a0 = acc[3 * q], a1 = acc[3 * q + 1], a2 = acc[3 * q + 2];
+    const i64* p = ids + first[q];
+    const i64 n = count[q];
+    for (i64 i = 0; i < n; ++i) {
+        const i64 id = p[i];
+        const i64 s = id / SN, rem = id - s * SN;
+        const i64 r = rem / RN, c = rem - r * RN;
+        a0 = __dadd_rn(a0, xs[c]);
+        a1 = __dadd_rn(a1, ys[r]);
+        a2 = __dadd_rn(a2, zs[s]);
+    }
+    acc[3 * q] = a0; acc[3 * q + 1] = a1; acc[3 * q + 2] = a2;
+}
+
+extern "C" int cfe_refnode_sums(const int64_t* ids, const int64_t* first, const int64_t* count, int n_sets,
+                                int64_t Y, int64_t X, const double* xs, const double* ys, const double* zs,
+                                double* acc, cudaStream_t stream)
+{
+    if (n_sets <= 0) return 0;
+    k_refnode_sums<<<1, 32, 0, stream>>>(reinterpret_cast<const i64*>(ids), reinterpret_cast<const i64*>(first),
+                                         reinterpret_cast<const i64*>(count), n_sets, (X + 1) * (Y + 1), X + 1,
+                                         xs, ys, zs, acc);
+    CFE_CHECK_LAUNCH("k_refnode_sums");
+    return 0;
+}

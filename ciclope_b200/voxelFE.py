@@ -1,0 +1,696 @@
+"""B200-native drop-in for the voxel-FE hot path of ``ciclope.core.voxelFE``:
+
+* ``vol2ugrid``          (reference: src/ciclope/core/voxelFE.py:15-283)
+* ``mesh2voxelfe``       (reference: src/ciclope/core/voxelFE.py:474-772)
+* ``matpropdictionary``  (reference: src/ciclope/core/voxelFE.py:774-819)
+
+Signatures, defaults, argument meaning and error behaviour are the reference's.  All voxel,
+node and text loops run as hand-written sm_100a CUDA kernels behind the C ABI of
+``include/ciclope_b200.h``; the mesh object is *lazy* (device-resident numbering, host arrays
+only when an attribute is read) because ``points``/``cells`` of a 1024^3 volume do not fit a
+host.  Host Python keeps only what is O(#grey values): the deck header, the PROPERTY cards
+(the reference evaluates them with ``eval`` on NumPy scalars, voxelFE.py:729-736, so the same
+interpreter arithmetic must produce the digits) and the template copy.
+
+There is no CPU fallback: without the CUDA library or a CUDA device every function raises.
+"""
+import collections
+import ctypes
+import logging
+import math
+import os
+from datetime import datetime
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CfeItemSeg, CfeSetDesc
+from ._util import as_device_volume, check_slab_size, empty_u32, scan_workspace
+
+CellBlock = collections.namedtuple("CellBlock", ["type", "data"])  # meshio 5.0.0 CellBlock
+
+NODE_SET_NAMES = ["NODES_X0", "NODES_X1", "NODES_Y0", "NODES_Y1", "NODES_Z0", "NODES_Z1"]
+CELL_SET_NAMES = ["CELLS_X0", "CELLS_X1", "CELLS_Y0", "CELLS_Y1", "CELLS_Z0", "CELLS_Z1"]
+_ELEM_HDR_SLOT = 64
+
+
+# --------------------------------------------------------------------------------------------
+# host helpers
+
+def _gv_threshold(GVmin):
+    """Integer t such that (GV > GVmin) <=> (GV > t) for 8-bit GV (voxelFE.py:140-141)."""
+    if GVmin < 0:
+        return -1
+    return int(min(math.floor(GVmin), 255))
+
+
+def _coordinate_tables(voxelsize, Z, Y, X):
+    """Per-axis coordinate values computed by the reference's own expressions
+    (voxelFE.py:70-73, 202) and converted to the dtype ``np.asarray(nodes)`` gives."""
+    if not isinstance(voxelsize, (list, np.ndarray)):
+        voxelsize = [voxelsize, voxelsize, voxelsize]
+    if len(voxelsize) == 1:
+        voxelsize = [voxelsize[0]] * 3
+    xs = [voxelsize[0] * c for c in range(X + 1)]
+    ys = [voxelsize[1] * r for r in range(Y + 1)]
+    zs = [voxelsize[2] * s for s in range(Z + 1)]
+    dtype = np.asarray([[xs[0], ys[0], zs[0]], [xs[-1], ys[-1], zs[-1]]]).dtype
+    if dtype.kind not in "fiu" or dtype.itemsize not in (4, 8):
+        raise TypeError("unsupported voxelsize type (points dtype %s)" % dtype)
+    return tuple(np.asarray(v).astype(dtype) for v in (xs, ys, zs))
+
+
+def _field_table(values):
+    """16-byte slots with the '{:12.6f}' field of each value (voxelFE.py:630)."""
+    fields = [format(v, "12.6f") for v in values.tolist()]
+    if any(len(f) != 12 for f in fields):
+        raise NotImplementedError("node coordinates wider than the 12-character field (|coord| >= 1e5) are not "
+                                  "supported by the CUDA deck writer yet")
+    return b"".join(f.encode("ascii") + b"\0\0\0\0" for f in fields)
+
+
+def _int_lock(v, name):
+    if isinstance(v, (bool, np.bool_)) or int(v) != v:
+        raise TypeError("%s must be an integer" % name)
+    return int(v)
+
+
+def _clip_box(lo, hi, n):
+    lo, hi = max(lo, 0), min(hi, n)
+    return (lo, hi) if hi > lo else (0, 0)
+
+
+def _boundary_boxes(strategy, p, k, Z, Y, X):
+    """Voxel boxes of the six locked strips ("plane", voxelFE.py:163-187) or node boxes of the
+    six locked levels ("exact", voxelFE.py:228-245), order X0, X1, Y0, Y1, Z0, Z1.
+    Each box is ((s0, s1), (r0, r1), (c0, c1)), half-open."""
+    full = ((0, Z), (0, Y), (0, X))
+    boxes = []
+    if strategy == "plane":
+        for axis, n in ((2, X), (1, Y), (0, Z)):
+            for lo, hi in ((0, p), (n - p, n)):          # idx < p ; idx >= n - p
+                b = list(full)
+                b[axis] = _clip_box(lo, hi, n)
+                boxes.append(tuple(b))
+    else:
+        fulln = ((0, Z + 1), (0, Y + 1), (0, X + 1))
+        for axis, n in ((2, X), (1, Y), (0, Z)):
+            for lo, hi in ((0, k), (n - k + 1, n + 1)):  # idx < k ; idx > n - k
+                b = list(fulln)
+                b[axis] = _clip_box(lo, hi, n + 1)
+                boxes.append(tuple(b))
+    return boxes
+
+
+def _box_count(b):
+    return max(b[0][1] - b[0][0], 0) * max(b[1][1] - b[1][0], 0) * max(b[2][1] - b[2][0], 0)
+
+
+# --------------------------------------------------------------------------------------------
+# lazy mesh
+
+class VoxelMesh:
+    """Device-resident hexahedral voxel mesh with the meshio-5.0.0 surface the reference and its
+    tests touch (voxelFE.py:271-274): ``points``, ``cells[0].type/.data/[0]/[1]``, ``cells_dict``,
+    ``cell_data["GV"][0]``, ``point_sets``, ``cell_sets``.  Host arrays are materialised by CUDA
+    kernels the first time an attribute is read."""
+
+    def __init__(self):
+        self._points = None
+        self._cells = None
+        self._cell_data = None
+        self._point_sets = None
+        self._cell_sets = None
+
+    # -- sizes ------------------------------------------------------------------------------
+    @property
+    def n_points(self):
+        return (self.Z + 1) * (self.Y + 1) * (self.X + 1)
+
+    @property
+    def n_cells(self):
+        return self.n_el
+
+    # -- materialisers ----------------------------------------------------------------------
+    @property
+    def points(self):
+        if self._points is None:
+            dev = self.vol.device
+            dt = self.xs.dtype
+            tdt = {4: torch.int32, 8: torch.int64}[dt.itemsize]
+            with torch.cuda.device(dev):
+                tabs = [torch.from_numpy(np.ascontiguousarray(a).view({4: np.int32, 8: np.int64}[dt.itemsize])).to(dev)
+                        for a in (self.xs, self.ys, self.zs)]
+                out = torch.empty((self.n_points, 3), dtype=tdt, device=dev)
+                _lib.call("cfe_fill_points", tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(),
+                          dt.itemsize, self.Z + 1, self.Y, self.X, out.data_ptr(), _lib.stream())
+                self._points = out.cpu().numpy().view(dt)
+        return self._points
+
+    @points.setter
+    def points(self, value):
+        self._points = value
+
+    @property
+    def cells(self):
+        if self._cells is None:
+            dev = self.vol.device
+            with torch.cuda.device(dev):
+                out = torch.empty((self.n_el, 8), dtype=torch.int64, device=dev)
+                _lib.call("cfe_fill_cells", self.elem_vox.data_ptr(), self.n_el, self.Y, self.X, 0,
+                          out.data_ptr(), _lib.stream())
+                self._cells = [CellBlock("hexahedron", out.cpu().numpy())]
+        return self._cells
+
+    @property
+    def cells_dict(self):
+        return {"hexahedron": self.cells[0].data}
+
+    def _gv_array(self):
+        dev = self.vol.device
+        with torch.cuda.device(dev):
+            out = torch.empty(max(self.n_el, 1), dtype=torch.uint8, device=dev)
+            _lib.call("cfe_gather_gv", self.vol.data_ptr(), self.elem_vox.data_ptr(), self.n_el,
+                      out.data_ptr(), _lib.stream())
+            a = out[: self.n_el].cpu().numpy()
+        return a.view(np.bool_) if self.is_bool else a
+
+    @property
+    def cell_data(self):
+        if self._cell_data is None:
+            self._gv_host = self._gv_array()
+            self._cell_data = {"GV": [self._gv_host]}
+        return self._cell_data
+
+    @cell_data.setter
+    def cell_data(self, value):
+        self._cell_data = value
+
+    def _set_lists(self, first, count):
+        ids = self.set_ids
+        out = []
+        for f, c in zip(first, count):
+            out.append(ids[f:f + c].cpu().numpy().tolist() if c else [])
+        return out
+
+    @property
+    def point_sets(self):
+        if self._point_sets is None:
+            lists = self._set_lists(self.set_first[:6], self.set_count[:6])
+            d = dict(zip(NODE_SET_NAMES, lists))
+            d["NODES_X0Y0Z0"] = d["NODES_Z0"][0:2]   # voxelFE.py:250-251
+            d["NODES_X0Y0Z1"] = d["NODES_Z1"][0:2]
+            self._point_sets = d
+            self._point_sets_snapshot = dict(d)
+        return self._point_sets
+
+    @property
+    def cell_sets(self):
+        if self._cell_sets is None:
+            lists = self._set_lists(self.set_first[6:], self.set_count[6:])
+            self._cell_sets = dict(zip(CELL_SET_NAMES, lists))
+            self._cell_sets_snapshot = dict(self._cell_sets)
+        return self._cell_sets
+
+    def _check_unmodified(self):
+        """mesh2voxelfe emits from device state; refuse meshes whose host views were edited."""
+        if self._point_sets is not None and (list(self._point_sets) != list(self._point_sets_snapshot) or any(
+                self._point_sets[k] is not self._point_sets_snapshot[k] for k in self._point_sets)):
+            raise NotImplementedError("point_sets were modified on the host; the CUDA deck writer emits the sets "
+                                      "computed by vol2ugrid")
+        if self._cell_sets is not None and (list(self._cell_sets) != list(self._cell_sets_snapshot) or any(
+                self._cell_sets[k] is not self._cell_sets_snapshot[k] for k in self._cell_sets)):
+            raise NotImplementedError("cell_sets were modified on the host; the CUDA deck writer emits the sets "
+                                      "computed by vol2ugrid")
+
+    def __repr__(self):
+        return "<ciclope_b200 voxel mesh>\n  Number of points: {}\n  Number of cells:\n    hexahedron: {}\n" \
+               "  Point sets: {}\n  Cell sets: {}\n  Cell data: GV".format(
+                   self.n_points, self.n_el, ", ".join(NODE_SET_NAMES + ["NODES_X0Y0Z0", "NODES_X0Y0Z1"]),
+                   ", ".join(CELL_SET_NAMES))
+
+
+# --------------------------------------------------------------------------------------------
+# vol2ugrid
+
+def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_level_lock_num=1,
+              locking_strategy="plane", refnodes=False, verbose=False):
+    """Generate unstructured grid mesh from 3D volume data (drop-in for voxelFE.py:15-283).
+
+    Parameters are the reference's.  ``voldata`` may be a NumPy array or a (CUDA) torch tensor
+    of dtype bool or uint8.  Returns a :class:`VoxelMesh` (and the reference-node dictionary
+    when ``refnodes`` is True).
+    """
+    if verbose:
+        logging.basicConfig(level=logging.INFO)
+    if locking_strategy not in ("plane", "exact"):
+        raise ValueError("locking_strategy must be 'plane' or 'exact'")
+    if isinstance(voxelsize, tuple):
+        raise TypeError("voxelsize must be a list, a numpy array or a scalar (the reference mis-handles tuples)")
+    p = _int_lock(plane_lock_num, "plane_lock_num")
+    k = _int_lock(node_level_lock_num, "node_level_lock_num")
+    vol, is_bool, _ = as_device_volume(voldata)
+    Z, Y, X = (int(v) for v in vol.shape)
+    check_slab_size(Z, Y, X)
+    thr = _gv_threshold(GVmin)
+    dev = vol.device
+
+    m = VoxelMesh()
+    m.vol, m.is_bool, m.thr = vol, is_bool, thr
+    m.Z, m.Y, m.X = Z, Y, X
+    m.strategy, m.plane_lock_num, m.node_level_lock_num = locking_strategy, p, k
+    m.xs, m.ys, m.zs = _coordinate_tables(voxelsize, Z, Y, X)
+
+    logging.info('Calculating cell array')
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        W, WN = (X + 31) // 32, (X + 32) // 32
+        rows, nrows = Z * Y, (Z + 1) * (Y + 1)
+        bits = empty_u32(rows * W, dev)
+        epref = empty_u32(rows * W, dev)
+        nbits = empty_u32(nrows * WN, dev)
+        npref = empty_u32(nrows * WN, dev)
+        ws = scan_workspace(max(rows * W, nrows * WN), dev)
+
+        # boundary-set descriptors: node sets X0..Z1 then cell sets X0..Z1
+        boxes = _boundary_boxes(locking_strategy, p, k, Z, Y, X)
+        descs = (CfeSetDesc * 12)()
+        tile_base = 0
+        for q in range(12):
+            d = descs[q]
+            b = boxes[q % 6]
+            if locking_strategy == "plane":
+                if q < 6:      # nodes of the locked voxel strip: both node layers of every voxel
+                    d.kind = 0
+                    cand = tuple((lo, hi + 1) if hi > lo else (0, 0) for lo, hi in b)
+                    vbox = b
+                else:
+                    d.kind = 2
+                    cand = b
+                    vbox = b
+            else:
+                if q < 6:      # existing nodes on the locked node levels
+                    d.kind = 1
+                    cand = b
+                    vbox = ((0, Z), (0, Y), (0, X))
+                else:          # voxelFE.py: the cell sets stay empty under "exact"
+                    d.kind = 2
+                    cand = ((0, 0), (0, 0), (0, 0))
+                    vbox = cand
+            (d.s0, d.s1), (d.r0, d.r1), (d.c0, d.c1) = cand
+            (d.vs0, d.vs1), (d.vr0, d.vr1), (d.vc0, d.vc1) = vbox
+            d.n_cand = _box_count(cand)
+            d.tile_base = tile_base
+            tile_base += (d.n_cand + 255) // 256
+        n_tiles = tile_base
+        descs_host = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
+        descs_dev = descs_host.to(dev, non_blocking=False)
+        tile_count = empty_u32(n_tiles, dev)
+        tile_off = torch.empty(max(n_tiles, 1) + 1, dtype=torch.int64, device=dev)
+        stats = torch.zeros(4, dtype=torch.int64, device=dev)   # n_el, n_nd, n_set_ids
+        bases = torch.tensor([descs[q].tile_base for q in range(12)], dtype=torch.int64, device=dev)
+
+        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
+        _lib.call("cfe_scan_elements", bits.data_ptr(), rows * W, epref.data_ptr(), stats.data_ptr(),
+                  ws.data_ptr(), s)
+        _lib.call("cfe_scan_nodes", bits.data_ptr(), None, Z, Y, X, Z + 1, nbits.data_ptr(), npref.data_ptr(),
+                  stats.data_ptr() + 8, ws.data_ptr(), s)
+        logging.info('Detecting node coordinates and boundary nodes')
+        _lib.call("cfe_sets_count", descs_dev.data_ptr(), 12, n_tiles, Z, Y, X, 0, 0, bits.data_ptr(),
+                  epref.data_ptr(), None, tile_count.data_ptr(), s)
+        _lib.call("cfe_scan_u32", tile_count.data_ptr(), n_tiles, tile_off.data_ptr(), stats.data_ptr() + 16,
+                  ws.data_ptr(), s)
+        # one device->host read: counts + first id of every set
+        tile_off[n_tiles] = stats[2]
+        host = torch.cat([stats, tile_off[bases.clamp(max=n_tiles)]]).cpu().tolist()
+        n_el, n_nd, n_ids = host[0], host[1], host[2]
+        first = host[4:16]
+        count = [(first[q + 1] if q < 11 else n_ids) - first[q] for q in range(12)]
+
+        elem_vox = empty_u32(n_el, dev)
+        node_list = empty_u32(n_nd, dev)
+        set_ids = torch.empty(max(n_ids, 1), dtype=torch.int64, device=dev)
+        _lib.call("cfe_fill_list", bits.data_ptr(), epref.data_ptr(), rows * W, W, X, elem_vox.data_ptr(), s)
+        _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
+                  node_list.data_ptr(), s)
+        _lib.call("cfe_sets_fill", descs_dev.data_ptr(), 12, n_tiles, Z, Y, X, 0, 0, bits.data_ptr(),
+                  epref.data_ptr(), None, tile_off.data_ptr(), set_ids.data_ptr(), s)
+
+    m.bits, m.epref = bits, epref
+    m.n_el, m.n_nd = int(n_el), int(n_nd)
+    m.elem_vox, m.node_list = elem_vox, node_list
+    m.set_ids, m.set_first, m.set_count = set_ids, [int(v) for v in first], [int(v) for v in count]
+
+    logging.info('Generated the following mesh with {0} nodes and {1} elements:'.format(m.n_points, m.n_el))
+    logging.info(m)
+    if refnodes:
+        return m, _refnodes(m)
+    return m
+
+
+def _refnodes(m):
+    """Barycentres of the six boundary node sets (voxelFE.py:254-268), float64 sums accumulated on
+    the GPU in the reference's (ascending node) order."""
+    dev = m.vol.device
+    with torch.cuda.device(dev):
+        tabs = [torch.from_numpy(np.asarray(a, dtype=np.float64)).to(dev) for a in (m.xs, m.ys, m.zs)]
+        first = torch.tensor(m.set_first[:6], dtype=torch.int64, device=dev)
+        count = torch.tensor(m.set_count[:6], dtype=torch.int64, device=dev)
+        acc = torch.zeros((6, 3), dtype=torch.float64, device=dev)
+        _lib.call("cfe_refnode_sums", m.set_ids.data_ptr(), first.data_ptr(), count.data_ptr(), 6, m.Y, m.X,
+                  tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(), acc.data_ptr(), _lib.stream())
+        sums = acc.cpu().numpy()
+    out = {}
+    for q, key in enumerate(["X0", "X1", "Y0", "Y1", "Z0", "Z1"]):
+        v = sums[q].copy()
+        v /= m.set_count[q] if m.set_count[q] else 1
+        out[key] = v
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# mesh2voxelfe
+
+def _resolve_matprop(matprop, GVmax):
+    """Range checks of voxelFE.py:579-610 (mutates ``matprop`` like the reference does)."""
+    prop_GV = {}
+    if matprop is None:
+        logging.warning('matprop not given: material property mapping disabled.')
+        return prop_GV
+    if "range" not in matprop and len(matprop["file"]) > 1:
+        raise IOError('Incorrect material property definition: GV ranges required when using multiple '
+                      'property files.')
+    elif "range" not in matprop and len(matprop["file"]) == 1:
+        matprop["range"] = [[1, GVmax]]
+    spans = []
+    for n, GVrange in enumerate(matprop["range"]):
+        lo, hi = int(GVrange[0]), int(GVrange[1])
+        if lo < 0:
+            raise IOError('property GV range below min representable integer')
+        if hi > GVmax:
+            raise IOError('property GV range exceeds max representable integer')
+        prop_GV[n] = (lo, hi)
+        spans.append((lo, hi))
+    for i in range(len(spans) - 1):
+        if max(spans[i][0], spans[i + 1][0]) <= min(spans[i][1], spans[i + 1][1]):
+            raise IOError('GV ranges assigned to different material properties cannot overlap')
+    return prop_GV
+
+
+def _property_cards(matprop, prop_GV, existing_GV):
+    """PROPERTY section (voxelFE.py:691-746): O(#GV) lines of host string work."""
+    parts = ['** User material property definition:\n',
+             '** internal variables are: "SetName", "MatName", "GV"\n']
+    for n, fname in enumerate(matprop["file"]):
+        with open(fname, 'r') as f:
+            card = f.readlines()
+        for GV in existing_GV:  # noqa: N806 -- the cards' expressions name this variable
+            if not (prop_GV[n][0] <= GV <= prop_GV[n][1]):
+                continue
+            setname = 'SET' + str(GV)
+            scope = {"GV": GV, "np": np}
+            for line in card:
+                line = line.replace('\n', '')
+                if line.startswith('**'):
+                    parts.append(line + '\n')
+                    continue
+                line = line.replace('SetName', setname).replace('MatName', 'MAT' + setname)
+                if 'GV' in line:
+                    fields = [str(eval(f, scope)) if 'GV' in f else f for f in line.split(',')]
+                    parts.append(','.join(fields) + '\n')
+                else:
+                    parts.append(line + '\n')
+    return ''.join(parts)
+
+
+def _template_text(templatefile, refnode):
+    """Analysis template copy with refnodeX/Y/Z substitution (voxelFE.py:748-768)."""
+    with open(templatefile, 'r') as f:
+        lines = f.readlines()
+    if refnode is not None:
+        subs = [('refnodeX', str(round(refnode[0], 4))), ('refnodeY', str(round(refnode[1], 4))),
+                ('refnodeZ', str(round(refnode[2], 4)))]
+        out = []
+        for line in lines:
+            for key, val in subs:
+                line = line.replace(key, val)
+            out.append(line)
+        lines = out
+    return ''.join(lines)
+
+
+class _Blob:
+    """Host byte blob with 16-byte aligned pieces, shipped to the device in one copy."""
+
+    def __init__(self):
+        self.parts = []
+        self.size = 0
+
+    def add(self, data):
+        off = self.size
+        self.parts.append(data)
+        padn = (-len(data)) % 16
+        if padn:
+            self.parts.append(b"\0" * padn)
+        self.size += len(data) + padn
+        return off
+
+    def to_device(self, dev):
+        host = torch.frombuffer(bytearray(b"".join(self.parts) or b"\0"), dtype=torch.uint8)
+        return host.to(dev)
+
+
+def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'], eltype='C3D8', matpropbits=8,
+                   refnode=None):
+    """Build the whole .INP deck in HBM.  Returns a uint8 CUDA tensor holding exactly the bytes
+    the reference's mesh2voxelfe would write (voxelFE.py:612-768)."""
+    if not isinstance(mesh, VoxelMesh):
+        raise NotImplementedError("the CUDA deck writer consumes meshes produced by ciclope_b200.vol2ugrid; "
+                                  "generic meshio meshes are not supported (no CPU fallback)")
+    mesh._check_unmodified()
+    m = mesh
+    lib = _lib.require_cuda()
+    dev = m.vol.device
+    Z, Y, X = m.Z, m.Y, m.X
+
+    # ---- prologue (voxelFE.py:540-610)
+    gv_dtype = np.bool_ if m.is_bool else np.uint8
+    if m._cell_data is not None:
+        keys = list(m._cell_data)
+        cell_GV = m._cell_data.get(keys[0])
+        if type(cell_GV) is list:
+            cell_GV = cell_GV[0]
+        cell_GV = np.asarray(cell_GV)
+        if cell_GV is not m._gv_host:
+            # e.g. the notebooks' cell_data['GV'] = cell_data['GV'][0].astype('uint8')
+            if cell_GV.shape != m._gv_host.shape or not np.array_equal(cell_GV, m._gv_host):
+                raise NotImplementedError("cell_data was modified on the host; the CUDA deck writer emits the "
+                                          "grey values of the volume given to vol2ugrid")
+            if cell_GV.dtype not in (np.bool_, np.uint8):
+                raise NotImplementedError("cell_data dtype %s is not supported by the CUDA deck writer"
+                                          % cell_GV.dtype)
+            gv_dtype = cell_GV.dtype.type
+    if m.n_el == 0:
+        raise ValueError("min() iterable argument is empty")   # voxelFE.py:564
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        if m.is_bool:
+            hist = np.zeros(256, dtype=np.int64)
+            hist[1] = m.n_el
+        else:
+            hist_dev = torch.empty(256, dtype=torch.int64, device=dev)
+            _lib.call("cfe_gv_histogram", m.vol.data_ptr(), Z * Y * X, m.thr, hist_dev.data_ptr(), s)
+            hist = hist_dev.cpu().numpy()
+    gvs = np.flatnonzero(hist)
+    existing_GV = gvs.astype(gv_dtype)                        # np.unique(cell_GV), voxelFE.py:570
+    GVmax = 2 ** matpropbits - 1
+    binary_model = bool(gvs.min() == 0) and bool(gvs.max() == 1) and issubclass(gv_dtype, np.integer)
+    if binary_model:
+        logging.warning('cell_data is binary. Material property mapping disabled.')
+    if max(existing_GV) > GVmax:
+        GVmax = max(existing_GV)
+    prop_GV = {0: (1, 1)} if binary_model else _resolve_matprop(matprop, GVmax)
+
+    # ---- host text
+    head = ('** ---------------------------------------------------------\n'
+            '** Abaqus .INP file written by Voxel_FEM script on {}\n'
+            '** ---------------------------------------------------------\n'
+            '** Node coordinates from input model\n'
+            '*NODE\n').format(datetime.now()).encode()
+    elem_comment = b'** Elements and Element sets from input model\n'
+    tail = ''
+    if 'PROPERTY' in keywords:
+        tail += _property_cards(matprop, prop_GV, existing_GV)
+    tail += _template_text(templatefile, refnode)
+    tail = tail.encode()
+
+    hdr_text = bytearray(256 * _ELEM_HDR_SLOT)
+    hdr_len = np.zeros(256, dtype=np.uint8)
+    for g in gvs.tolist():
+        h = '*ELEMENT, TYPE={0}, ELSET={1}\n'.format(eltype, 'SET' + str(int(g))).encode()
+        if len(h) > _ELEM_HDR_SLOT:
+            raise ValueError("eltype too long for the element block header slot")
+        hdr_text[g * _ELEM_HDR_SLOT: g * _ELEM_HDR_SLOT + len(h)] = h
+        hdr_len[g] = len(h)
+    first = np.zeros(256, dtype=np.int64)
+    first[1:] = np.cumsum(hist)[:-1]
+    first[hist == 0] = -1        # never matches an emission index
+
+    blob = _Blob()
+    o_head = blob.add(head)
+    o_cmt = blob.add(elem_comment)
+    o_tail = blob.add(tail)
+    o_hdr = blob.add(bytes(hdr_text))
+    o_hlen = blob.add(hdr_len.tobytes())
+    o_first = blob.add(first.tobytes())
+    o_xt = blob.add(_field_table(m.xs))
+    o_yt = blob.add(_field_table(m.ys))
+    o_zt = blob.add(_field_table(m.zs))
+
+    # NSET / ELSET item stream (voxelFE.py:650-688)
+    lits = bytearray()
+    segs = []
+    n_items = 0
+
+    def literal(text):
+        nonlocal n_items
+        t = text.encode()
+        segs.append((0, n_items, len(lits), len(t), 0, 0))
+        lits.extend(t)
+        n_items += 1
+
+    def idlist(first_id, cnt):
+        nonlocal n_items
+        if cnt:
+            segs.append((1, n_items, 0, 0, first_id, 0))
+            n_items += cnt
+
+    n_set_ids = 0
+    if 'NSET' in keywords:
+        literal('** Additional nset from voxel model. New generated nsets are:\n')
+        literal('** {}, \n'.format(NODE_SET_NAMES[0]))
+        corner = {"NODES_X0Y0Z0": (m.set_first[4], min(2, m.set_count[4])),
+                  "NODES_X0Y0Z1": (m.set_first[5], min(2, m.set_count[5]))}
+        for q, name in enumerate(NODE_SET_NAMES + ["NODES_X0Y0Z0", "NODES_X0Y0Z1"]):
+            literal('*NSET, NSET={0}\n'.format(name))
+            f, c = (m.set_first[q], m.set_count[q]) if q < 6 else corner[name]
+            idlist(f, c)
+            n_set_ids += c
+            literal('\n')
+    if 'ELSET' in keywords:
+        literal('** Additional elset from voxel model. New generated elsets are:\n')
+        literal('** {}, \n'.format(CELL_SET_NAMES[0]))
+        for q, name in enumerate(CELL_SET_NAMES):
+            literal('*ELSET, ELSET={}\n'.format(name))
+            idlist(m.set_first[6 + q], m.set_count[6 + q])
+            n_set_ids += m.set_count[6 + q]
+            literal('\n')
+    seg_arr = (CfeItemSeg * max(len(segs), 1))()
+    for i, (kind, item0, lo, ll, id0, rank0) in enumerate(segs):
+        sg = seg_arr[i]
+        sg.kind, sg.item0, sg.lit_off, sg.lit_len, sg.id0, sg.rank0 = kind, item0, lo, ll, id0, rank0
+    o_lits = blob.add(bytes(lits))
+    o_segs = blob.add(bytes(seg_arr))
+
+    # ---- capacity and layout
+    max_node_id = (Z + 1) * (Y + 1) * (X + 1) - 1
+    if max_node_id >= 10 ** 10:
+        raise NotImplementedError("node ids wider than the 10-character field are not supported")
+    max_line = len(str(m.n_el)) + 8 * len(str(max_node_id)) + 9
+    off_nodes = len(head)
+    off_cmt = off_nodes + 53 * m.n_nd
+    off_elem = off_cmt + len(elem_comment)
+    cap = (off_elem + m.n_el * max_line + int(hdr_len.astype(np.int64).sum())
+           + n_set_ids * (len(str(max(max_node_id, m.n_el))) + 1) + len(lits) + len(tail) + 64)
+
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        dblob = blob.to_device(dev)
+        base = dblob.data_ptr()
+        out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        totals = torch.zeros(2, dtype=torch.int64, device=dev)   # element bytes, set bytes
+        ws = scan_workspace(max(m.n_el, n_items, 1), dev)
+        _lib.call("cfe_put_literal", base + o_head, len(head), out.data_ptr(), None, None, s)
+        _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, base + o_xt, base + o_yt, base + o_zt,
+                  Y, X, 0, out.data_ptr() + off_nodes, s)
+        _lib.call("cfe_put_literal", base + o_cmt, len(elem_comment), out.data_ptr() + off_cmt, None, None, s)
+        perm = None
+        single_gv = int(gvs[0])
+        if len(gvs) > 1:
+            n_ptiles = lib.cfe_partition_tiles(m.n_el)
+            mat = empty_u32(256 * n_ptiles, dev)
+            mat_off = torch.empty(256 * n_ptiles, dtype=torch.int64, device=dev)
+            perm = torch.empty((m.n_el, 2), dtype=torch.int32, device=dev)
+            _lib.call("cfe_partition_hist", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, mat.data_ptr(), s)
+            ws_p = scan_workspace(256 * n_ptiles, dev)
+            scratch_total = torch.empty(1, dtype=torch.int64, device=dev)
+            _lib.call("cfe_scan_u32", mat.data_ptr(), 256 * n_ptiles, mat_off.data_ptr(), scratch_total.data_ptr(),
+                      ws_p.data_ptr(), s)
+            _lib.call("cfe_partition_scatter", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el,
+                      mat_off.data_ptr(), perm.data_ptr(), s)
+            single_gv = -1
+        _lib.call("cfe_emit_elements", m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(),
+                  base + o_first, base + o_hdr, base + o_hlen, single_gv, Y, X, 0, 0,
+                  out.data_ptr() + off_elem, totals.data_ptr(), None, ws.data_ptr(), s)
+        _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base + o_lits,
+                  out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, ws.data_ptr(), s)
+        _lib.call("cfe_put_literal", base + o_tail, len(tail), out.data_ptr() + off_elem, totals.data_ptr(),
+                  totals.data_ptr() + 8, s)
+        t = totals.cpu().tolist()
+    length = off_elem + t[0] + t[1] + len(tail)
+    if length > cap:
+        raise _lib.CfeError("internal error: deck length %d exceeds the reserved capacity %d" % (length, cap))
+    mesh._last_keepalive = (dblob,)
+    return out[:length]
+
+
+def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'ELSET'], eltype='C3D8',
+                 matpropbits=8, refnode=None, verbose=False):
+    """Generate ABAQUS voxel Finite Element (FE) input file from 3D Unstructured Grid mesh data
+    (drop-in for voxelFE.py:474-772).  Parameters are the reference's.
+
+    ``fileout`` is the path of the .INP file.  Additively it may be a pinned/CPU uint8
+    ``torch.Tensor`` that receives the deck bytes (the number of bytes is returned), which is
+    what the end-to-end benchmark uses as its host buffer.
+    """
+    if verbose:
+        logging.basicConfig(level=logging.INFO)
+    logging.info('Start writing INP file')
+    deck = deck_to_device(mesh, templatefile, matprop=matprop, keywords=keywords, eltype=eltype,
+                          matpropbits=matpropbits, refnode=refnode)
+    n = deck.numel()
+    if isinstance(fileout, torch.Tensor):
+        if fileout.dtype != torch.uint8 or fileout.numel() < n:
+            raise ValueError("fileout tensor must be uint8 with at least %d elements" % n)
+        fileout[:n].copy_(deck, non_blocking=True)
+        torch.cuda.current_stream(deck.device).synchronize()
+        return n
+    chunk = 256 << 20
+    with open(fileout, 'wb') as INP:
+        for lo in range(0, n, chunk):
+            INP.write(deck[lo:lo + chunk].cpu().numpy().tobytes())
+    logging.info('Model with {0} nodes and {1} elements written to file {fname}'.format(
+        mesh.n_points, mesh.n_el, fname=fileout))
+    return
+
+
+def matpropdictionary(proplist):
+    """Compose dictionary of material properties and property mapping GV ranges
+    (drop-in for voxelFE.py:774-819)."""
+    if proplist is None:
+        return None
+    if len(proplist) == 0:
+        return None
+    elif len(proplist) == 1:
+        if not os.path.isfile(proplist[0]):
+            raise IOError('Property file {0} does not exist.'.format(proplist[0]))
+        return {"file": [proplist[0]]}
+    if not len(proplist) % 3 == 0:
+        raise IOError('Mapping dictionary error (probably due to incorrect use of --mapping flag): each material '
+                      'property file must be followed by MIN and MAX of the corresponding GV range.')
+    matprop = {'file': [], 'range': []}
+    for i in range(len(proplist) // 3):
+        matprop['file'].append(proplist[3 * i])
+        matprop['range'].append([int(proplist[3 * i + 1]), int(proplist[3 * i + 2])])
+    return matprop

@@ -1,0 +1,179 @@
+/*
+ * ciclope_b200 -- C ABI of the B200-native CT -> CalculiX .INP hot path.
+ *
+ * This is the drop-in boundary: everything the Python facade (ciclope_b200/voxelFE.py,
+ * ciclope_b200/preprocess.py) needs from the GPU goes through these entry points, and a
+ * ciclope maintainer can bind the same symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - sizes and indices are int64_t; volumes are uint8 [Z][Y][X] (C order, x fastest);
+ *   - the last argument is the CUDA stream the work is enqueued on; nothing synchronises;
+ *   - no hidden allocation: scratch/workspace buffers are passed in by the caller;
+ *   - return 0 on success, < 0 on error (cfe_last_error() holds the message).
+ *
+ * Each entry point names the reference lines (ciclope 2.0.3, paths relative to the ciclope
+ * checkout) whose work it replaces.
+ */
+#ifndef CICLOPE_B200_H
+#define CICLOPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* cfe_stream_t; /* == cudaStream_t */
+
+#define CFE_ABI_VERSION 1
+
+int cfe_version(void);
+const char* cfe_last_error(void);
+
+/* ------------------------------------------------------------------ bit packing + scans */
+
+/* bits[row][w] bit b = (vol[row][32w+b] > thr); W = ceil(X/32) words per row, pad bits 0.
+ * `GV > GVmin` of src/ciclope/core/voxelFE.py:140-141 (thr = floor(GVmin)) and the
+ * foreground test of measure.label, src/ciclope/utils/preprocess.py:135 (thr = 0). */
+int cfe_pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t* bits, cfe_stream_t s);
+
+/* bytes of look-back workspace for a scan over n_items items */
+size_t cfe_scan_workspace_bytes(int64_t n_items);
+
+/* pref[i] = number of elements (set bits) before word i; *total = n_el.
+ * The `cell_i += 1` counter of voxelFE.py:142. */
+int cfe_scan_elements(const uint32_t* bits, int64_t n_words, uint32_t* pref, uint64_t* total, void* ws,
+                      cfe_stream_t s);
+
+/* pref[i] = number of x-run starts before word i; *total = number of runs (CCL vertices). */
+int cfe_scan_run_starts(const uint32_t* bits, int64_t rows, int64_t X, uint32_t* pref, uint64_t* total,
+                        void* ws, cfe_stream_t s);
+
+/* Used-node bitmap + numbering: nbits[(layer,row)][w] bit b = grid node (layer,row,32w+b) is
+ * a corner of >= 1 element; npref = exclusive count of used nodes; *total = used nodes.
+ * np.unique(mesh.cells_dict["hexahedron"]) of voxelFE.py:628 without building the cells.
+ * halo_below: element bits [Y][W] of the voxel plane under local slice 0 (z-slab sharding)
+ * or NULL; n_layers = node layers owned by this slab (Zl, or Zl+1 for the top slab). */
+int cfe_scan_nodes(const uint32_t* bits, const uint32_t* halo_below, int64_t Zl, int64_t Y, int64_t X,
+                   int64_t n_layers, uint32_t* nbits, uint32_t* npref, uint64_t* total, void* ws,
+                   cfe_stream_t s);
+
+/* list[pref[i] + k] = row*row_len + 32*w + (k-th set bit of word i): ascending index lists of
+ * the elements (row_len = X) or used nodes (row_len = X+1). */
+int cfe_fill_list(const uint32_t* bits, const uint32_t* pref, int64_t n_words, int64_t words_per_row,
+                  int64_t row_len, uint32_t* list, cfe_stream_t s);
+
+/* generic exclusive scan of u32 counts into u64 offsets (tile counts, histograms) */
+int cfe_scan_u32(const uint32_t* in, int64_t n, uint64_t* out, uint64_t* total, void* ws, cfe_stream_t s);
+
+/* ------------------------------------------------------------------ CCL */
+
+/* capacity (entries) of the parent / size scratch arrays for a slab of `rows` rows */
+size_t cfe_ccl_max_runs(int64_t rows, int64_t X);
+
+/* Largest 6-connected component of the slab: measure.label(bw, None, True, 1) + np.bincount +
+ * argmax + (labels == id), src/ciclope/utils/preprocess.py:135-143.  Ties go to the component
+ * whose first voxel comes first in C order.
+ *   *best = (size << 32) | (0xffffffff - root run id), 0 when there is no foreground. */
+int cfe_ccl_largest(const uint32_t* bits, const uint32_t* run_pref, const uint64_t* n_runs, int64_t Z,
+                    int64_t Y, int64_t X, uint32_t* parent, uint32_t* size, uint64_t* best,
+                    uint8_t* out_mask, cfe_stream_t s);
+
+/* ------------------------------------------------------------------ boundary sets */
+
+/* One boundary set = the candidates of a box of the node grid (kind 0/1) or voxel grid
+ * (kind 2), in raster order, kept when the predicate holds (voxelFE.py:163-192, 205-247):
+ *   kind 0/1  node (s,r,c) is kept when one of its <= 8 adjacent voxels inside the voxel box
+ *             [vs0,vs1) x [vr0,vr1) x [vc0,vc1) is an element ("plane": the locked voxel
+ *             planes; "exact": the whole volume);  value = 0-based grid node id;
+ *   kind 2    voxel (s,r,c) is kept when it is an element;  value = 1-based element id.
+ * All coordinates are GLOBAL (z-slab sharding passes z0); boxes are half-open. */
+typedef struct {
+    int32_t kind;
+    int32_t pad_;
+    int64_t s0, s1, r0, r1, c0, c1;
+    int64_t vs0, vs1, vr0, vr1, vc0, vc1;
+    int64_t n_cand;    /* (s1-s0)*(r1-r0)*(c1-c0) */
+    int64_t tile_base; /* first 256-candidate tile of this set */
+} CfeSetDesc;
+
+int cfe_sets_count(const CfeSetDesc* descs, int n_sets, int64_t n_tiles, int64_t Zl, int64_t Y, int64_t X,
+                   int64_t z0, int64_t eid_offset, const uint32_t* bits, const uint32_t* pref,
+                   const uint32_t* halo_below, uint32_t* tile_count, cfe_stream_t s);
+int cfe_sets_fill(const CfeSetDesc* descs, int n_sets, int64_t n_tiles, int64_t Zl, int64_t Y, int64_t X,
+                  int64_t z0, int64_t eid_offset, const uint32_t* bits, const uint32_t* pref,
+                  const uint32_t* halo_below, const uint64_t* tile_off, int64_t* ids, cfe_stream_t s);
+
+/* Reference-node barycentre sums (voxelFE.py:208-223, 254-268): acc[q][0..2] += coordinates of
+ * the ids of set q, float64, in ascending order (one thread per set: the reference's
+ * summation order).  xs/ys/zs index GLOBAL column / row / layer. */
+int cfe_refnode_sums(const int64_t* ids, const int64_t* first, const int64_t* count, int n_sets, int64_t Y,
+                     int64_t X, const double* xs, const double* ys, const double* zs, double* acc,
+                     cfe_stream_t s);
+
+/* ------------------------------------------------------------------ lazy-mesh materialisers */
+
+/* cells (n_el,8) int64 in C3D8 order, voxelFE.py:145-157 */
+int cfe_fill_cells(const uint32_t* elem_vox, int64_t n_el, int64_t Y, int64_t X, int64_t z0, int64_t* cells,
+                   cfe_stream_t s);
+/* cell_GV, voxelFE.py:160 */
+int cfe_gather_gv(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, uint8_t* gv, cfe_stream_t s);
+/* points (n_layers*(Y+1)*(X+1), 3) from per-axis value tables, voxelFE.py:202-203 */
+int cfe_fill_points(const void* xs, const void* ys, const void* zs, int elem_bytes, int64_t n_layers,
+                    int64_t Y, int64_t X, void* out, cfe_stream_t s);
+
+/* ------------------------------------------------------------------ deck emission */
+
+/* *NODE lines (voxelFE.py:629-630).  xtab/ytab/ztab: 16-byte slots holding the 12-character
+ * '{:12.6f}' field of every column / row / layer coordinate (formatted on the host by the
+ * same interpreter arithmetic as the reference).  Writes 53*n_nodes bytes at out. */
+int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab, const char* ytab,
+                   const char* ztab, int64_t Y, int64_t X, int64_t z0, char* out, cfe_stream_t s);
+
+/* *ELEMENT lines (voxelFE.py:639-647).  perm == NULL: raster order, one grey value
+ * (single_gv); otherwise perm holds {voxel, raster rank} pairs in GV-major order and vol is
+ * read for the grey value.  first[gv] = emission index of the first element of block gv;
+ * hdr_text/hdr_len = '*ELEMENT, TYPE=.., ELSET=SET<gv>\n' per gv in 64-byte slots.
+ * *total = bytes written; blk_off[gv] = offset of block gv's first line (optional). */
+int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
+                      const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len, int single_gv,
+                      int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, char* out, uint64_t* total,
+                      uint64_t* blk_off, void* ws, cfe_stream_t s);
+
+/* *NSET / *ELSET sections (voxelFE.py:650-688) as a stream of items. */
+typedef struct {
+    int32_t kind;     /* 0 = literal text, 1 = id list */
+    int32_t pad_;
+    int64_t item0;    /* index of the segment's first item */
+    int64_t lit_off;  /* kind 0: offset / length into `literals` */
+    int64_t lit_len;
+    int64_t id0;      /* kind 1: first entry in `ids` */
+    int64_t rank0;    /* kind 1: 0-based position of that entry inside its (global) set */
+} CfeItemSeg;
+
+int cfe_emit_items(const CfeItemSeg* segs, int n_segs, int64_t n_items, const int64_t* ids,
+                   const char* literals, char* out_base, const uint64_t* dyn_off, uint64_t* total, void* ws,
+                   cfe_stream_t s);
+
+/* literal text to out + *dyn0 + *dyn1 (either may be NULL) */
+int cfe_put_literal(const char* src, int64_t n, char* out, const uint64_t* dyn0, const uint64_t* dyn1,
+                    cfe_stream_t s);
+
+/* ------------------------------------------------------------------ grey values */
+
+/* hist256[g] = number of elements (v > thr) with grey value g: np.unique(cell_GV), voxelFE.py:570 */
+int cfe_gv_histogram(const uint8_t* vol, int64_t n_vox, int thr, uint64_t* hist256, cfe_stream_t s);
+
+/* stable partition of the element list by grey value: np.where(cell_GV == GV), voxelFE.py:645 */
+int64_t cfe_partition_tiles(int64_t n_el);
+int cfe_partition_hist(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, uint32_t* mat,
+                       cfe_stream_t s); /* mat: u32 [256][tiles] */
+int cfe_partition_scatter(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, const uint64_t* mat_off,
+                          void* perm, cfe_stream_t s); /* perm: uint2 [n_el] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

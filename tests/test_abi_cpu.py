@@ -1,0 +1,119 @@
+"""CPU-only checks of the C-ABI boundary and of the facade's host logic (no compute calls)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ciclope_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cfe_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ciclope_b200 import _lib, build
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libciclope_b200.so does not export %s" % name
+    # the ctypes table binds exactly the declared entry points
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    lib.cfe_version.restype = ctypes.c_int
+    assert lib.cfe_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from ciclope_b200._lib import CfeItemSeg, CfeSetDesc
+    assert ctypes.sizeof(CfeSetDesc) == 8 + 14 * 8
+    assert ctypes.sizeof(CfeItemSeg) == 8 + 5 * 8
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from ciclope_b200 import _lib, remove_unconnected, vol2ugrid
+    with pytest.raises(_lib.CfeError):
+        remove_unconnected(np.ones((2, 2, 2), dtype=bool))
+    with pytest.raises(_lib.CfeError):
+        vol2ugrid(np.ones((2, 2, 2), dtype=bool))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "ciclope_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no CPU fallback", ""), "%s mentions the oracle" % f
+                assert "/root/reference" not in text
+
+
+def test_matpropdictionary_matches_reference_behaviour(tmp_path):
+    from ciclope_b200 import matpropdictionary
+    errs = json.load(open(os.path.join(cases.GOLDEN_DIR, "errors.json")))
+    assert matpropdictionary(None) is None
+    assert matpropdictionary([]) is None
+    assert matpropdictionary(["a.inp", "1", "100", "b.inp", "101", "255"]) == errs["matpropdictionary_triples"]
+    assert errs["matpropdictionary_bad_len"] == "OSError"
+    with pytest.raises(IOError):
+        matpropdictionary(["a.inp", "1"])
+    assert errs["matpropdictionary_missing_file"] == "OSError"
+    with pytest.raises(IOError):
+        matpropdictionary(["/nonexistent/a.inp"])
+    assert matpropdictionary([cases.MAT_CONST]) == {"file": [cases.MAT_CONST]}
+
+
+def test_threshold_and_tables_host_logic(golden):
+    from ciclope_b200 import voxelFE as v
+    for gvmin, want in [(0, 0), (100, 100), (99.5, 99), (-1, -1), (-0.5, -1), (255, 255), (300, 255), (0.999, 0)]:
+        assert v._gv_threshold(gvmin) == want
+        x = np.arange(256)
+        assert np.array_equal(x > gvmin, x > want)
+    # coordinate tables reproduce the reference's points (dtype and values) for every golden case
+    for c in cases.deck_cases():
+        vol = np.asarray(c["vol"])
+        Z, Y, X = vol.shape
+        xs, ys, zs = v._coordinate_tables(c["u"]["voxelsize"], Z, Y, X)
+        pts = golden[c["name"] + "/points"].reshape(Z + 1, Y + 1, X + 1, 3)
+        assert xs.dtype == pts.dtype, c["name"]
+        assert np.array_equal(pts[0, 0, :, 0], xs) and np.array_equal(pts[0, :, 0, 1], ys) \
+            and np.array_equal(pts[:, 0, 0, 2], zs), c["name"]
+        tab = v._field_table(xs)
+        assert len(tab) == 16 * (X + 1)
+    with pytest.raises(NotImplementedError):
+        v._field_table(np.array([0.0, 123456.0]))
+
+
+def test_boundary_boxes_host_logic():
+    from ciclope_b200 import voxelFE as v
+    Z, Y, X = 8, 9, 12
+    b = v._boundary_boxes("plane", 2, 1, Z, Y, X)
+    assert b[0] == ((0, Z), (0, Y), (0, 2)) and b[1] == ((0, Z), (0, Y), (10, 12))
+    assert b[4] == ((0, 2), (0, Y), (0, X)) and b[5] == ((6, 8), (0, Y), (0, X))
+    b = v._boundary_boxes("plane", 20, 1, Z, Y, X)
+    assert b[0] == ((0, Z), (0, Y), (0, X)) and b[1] == ((0, Z), (0, Y), (0, X))
+    b = v._boundary_boxes("plane", 0, 1, Z, Y, X)
+    assert all(v._box_count(x) == 0 for x in b)
+    b = v._boundary_boxes("exact", 1, 1, Z, Y, X)
+    assert b[0] == ((0, Z + 1), (0, Y + 1), (0, 1)) and b[1] == ((0, Z + 1), (0, Y + 1), (12, 13))
+    b = v._boundary_boxes("exact", 1, 0, Z, Y, X)
+    assert all(v._box_count(x) == 0 for x in b)
+
+
+def test_vol2ugrid_argument_errors_before_any_gpu_work():
+    from ciclope_b200 import vol2ugrid
+    with pytest.raises(ValueError):
+        vol2ugrid(np.ones((2, 2, 2), dtype=bool), locking_strategy="both")
+    with pytest.raises(TypeError):
+        vol2ugrid(np.ones((2, 2, 2), dtype=bool), voxelsize=(1, 1, 1))

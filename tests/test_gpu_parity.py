@@ -1,0 +1,258 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C ABI against the golden vectors produced
+by the unmodified reference and against the CPU oracle on seeded inputs.  Bit-exact everywhere
+(integer / byte work); the *NODE coordinates are compared as bytes, which is stronger than the
+"parse to identical float64" bar."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+DECK_CASES = {c["name"]: c for c in cases.deck_cases()}
+
+
+@pytest.fixture(scope="module")
+def cfe():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import ciclope_b200
+    from ciclope_b200 import _lib
+    _lib.require_cuda()
+    return ciclope_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _unpack(g, name):
+    shape = tuple(g[name + "/shape"])
+    n = int(np.prod(shape))
+    return (np.unpackbits(g[name + "/in"])[:n].astype(bool).reshape(shape),
+            np.unpackbits(g[name + "/out"])[:n].astype(bool).reshape(shape))
+
+
+# ------------------------------------------------------------------ remove_unconnected
+
+@pytest.mark.parametrize("name", [n for n, _ in cases.ccl_cases()])
+def test_remove_unconnected_golden(cfe, golden_ccl, name):
+    bw, want = _unpack(golden_ccl, name)
+    got = cfe.remove_unconnected(bw)
+    assert isinstance(got, np.ndarray) and got.dtype == np.bool_ and got.shape == bw.shape
+    assert np.array_equal(got, want)
+
+
+def test_remove_unconnected_reference_known_answer(cfe):
+    bw = cases.trab() > 100          # test/test_ciclope.py:11-15
+    assert int(bw.sum()) - int(cfe.remove_unconnected(bw).sum()) == 4
+
+
+def test_remove_unconnected_torch_in_torch_out(cfe, orc):
+    import torch
+    bw = cases.blobs((16, 20, 64), 0.25, 3)
+    got = cfe.remove_unconnected(torch.from_numpy(bw).cuda())
+    assert got.is_cuda and got.dtype == torch.bool
+    assert np.array_equal(got.cpu().numpy(), orc.remove_unconnected(bw))
+
+
+def test_remove_unconnected_empty_raises(cfe):
+    with pytest.raises(ValueError):
+        cfe.remove_unconnected(np.zeros((3, 4, 5), dtype=bool))
+
+
+@pytest.mark.parametrize("shape,density,seed", [
+    ((32, 32, 32), 0.2, 1), ((32, 32, 32), 0.32, 2), ((17, 23, 129), 0.28, 3), ((40, 33, 96), 0.5, 4),
+    ((64, 64, 64), 0.31, 5), ((5, 200, 70), 0.3, 6), ((64, 48, 160), 0.26, 7)])
+def test_remove_unconnected_random_vs_oracle(cfe, orc, shape, density, seed):
+    # random noise near the 6-connectivity percolation threshold: thousands of components, many ties
+    bw = cases.rand_binary(shape, density, 1000 + seed)
+    assert np.array_equal(cfe.remove_unconnected(bw), orc.remove_unconnected(bw))
+
+
+@pytest.mark.parametrize("shape,density,seed", [((48, 64, 96), 0.3, 11), ((96, 96, 128), 0.12, 12),
+                                                ((128, 128, 128), 0.3, 13)])
+def test_remove_unconnected_blobs_vs_oracle(cfe, orc, shape, density, seed):
+    bw = cases.blobs(shape, density, seed, radius=2, passes=2)
+    assert np.array_equal(cfe.remove_unconnected(bw), orc.remove_unconnected(bw))
+
+
+# ------------------------------------------------------------------ vol2ugrid
+
+@pytest.mark.parametrize("name", list(DECK_CASES))
+def test_vol2ugrid_golden(cfe, golden, name):
+    c = DECK_CASES[name]
+    g = golden
+    mesh, refn = cfe.vol2ugrid(c["vol"], refnodes=True, **c["u"])
+    assert mesh.cells[0].type == "hexahedron" and mesh.cells[0][0] == "hexahedron"
+    assert mesh.cells[0].data.dtype == np.int64
+    assert np.array_equal(mesh.cells[0].data.reshape(-1, 8), g[name + "/cells"])
+    assert np.array_equal(mesh.cells[0][1].reshape(-1, 8), g[name + "/cells"])
+    assert np.array_equal(mesh.cells_dict["hexahedron"].reshape(-1, 8), g[name + "/cells"])
+    assert mesh.points.dtype == g[name + "/points"].dtype
+    assert mesh.points.shape == g[name + "/points"].shape
+    assert np.array_equal(mesh.points, g[name + "/points"])
+    assert list(mesh.cell_data) == ["GV"]
+    assert mesh.cell_data["GV"][0].dtype == g[name + "/gv"].dtype
+    assert np.array_equal(mesh.cell_data["GV"][0], g[name + "/gv"])
+    assert list(mesh.point_sets) == ["NODES_X0", "NODES_X1", "NODES_Y0", "NODES_Y1", "NODES_Z0", "NODES_Z1",
+                                     "NODES_X0Y0Z0", "NODES_X0Y0Z1"]
+    assert list(mesh.cell_sets) == ["CELLS_X0", "CELLS_X1", "CELLS_Y0", "CELLS_Y1", "CELLS_Z0", "CELLS_Z1"]
+    for k, v in mesh.point_sets.items():
+        assert isinstance(v, list)
+        assert v == g[name + "/ps/" + k].tolist(), k
+    for k, v in mesh.cell_sets.items():
+        assert isinstance(v, list)
+        assert v == g[name + "/cs/" + k].tolist(), k
+    for k, v in refn.items():
+        assert np.array_equal(v, g[name + "/refnode/" + k]), k
+
+
+def test_vol2ugrid_reference_known_answers(cfe):
+    # test/test_ciclope.py:75-87
+    mesh = cfe.vol2ugrid(cases.trab(), [0.12, 0.12, 0.12], GVmin=100, locking_strategy="exact",
+                         node_level_lock_num=1)
+    assert mesh.cells[0].type == "hexahedron"
+    assert mesh.cells[0].data.shape == (209, 8)
+    assert mesh.points.shape == (1331, 3)
+    assert mesh.point_sets['NODES_X0Y0Z0'] == [18, 19]
+    assert (mesh.points[100] == np.array([0.12, 1.08, 0])).all()
+
+
+# ------------------------------------------------------------------ mesh2voxelfe
+
+def _deck(cfe, c, tmp_path, **over):
+    m = dict(c["m"])
+    if "matprop" in m:
+        m["matprop"] = m["matprop"]()
+    m.update(over)
+    mesh = cfe.vol2ugrid(c["vol"], **c["u"])
+    out = str(tmp_path / "deck.inp")
+    assert cfe.mesh2voxelfe(mesh, fileout=out, **m) is None
+    return mesh, cases.mask_timestamp(open(out, "rb").read())
+
+
+@pytest.mark.parametrize("name", list(DECK_CASES))
+def test_mesh2voxelfe_golden(cfe, golden, name, tmp_path):
+    _, got = _deck(cfe, DECK_CASES[name], tmp_path)
+    want = bytes(golden[name + "/deck"])
+    if got != want:
+        gl, wl = got.split(b"\n"), want.split(b"\n")
+        for i, (a, b) in enumerate(zip(gl, wl)):
+            assert a == b, "first differing line %d: got %r want %r" % (i, a, b)
+        assert len(gl) == len(wl)
+    assert got == want
+
+
+def test_mesh2voxelfe_reference_known_answers(cfe, tmp_path):
+    # test/test_ciclope.py:89-132
+    mesh = cfe.vol2ugrid(cases.trab(), [0.12, 0.12, 0.12], GVmin=100)
+    out = str(tmp_path / "foo.inp")
+    cfe.mesh2voxelfe(mesh, cases.TEMPLATE, out)
+    lines = open(out).read().split("\n")
+    assert any('*NODE' in ln for ln in lines)
+    assert any('*ELEMENT, TYPE=C3D8, ELSET=SET255' in ln for ln in lines)
+    assert any('*ELSET, ELSET=CELLS_Z1' in ln for ln in lines)
+    assert any('*NSET, NSET=NODES_Z0' in ln for ln in lines)
+    assert any('*STEP' in ln for ln in lines)
+    assert any('NODES_T, 3, 3, -0.002' in ln for ln in lines)
+    assert list(map(float, lines[99].split(","))) == [359.0, 0.84, 1.2, 0.24]
+    assert list(map(int, lines[860].strip(',').split(','))) == [1315, 1316, 1326, 1327]
+
+
+@pytest.mark.parametrize("case", cases.midsize_cases(), ids=lambda c: c["name"])
+def test_mesh2voxelfe_midsize_hash(cfe, case, tmp_path):
+    want = json.load(open(os.path.join(cases.GOLDEN_DIR, "midsize.json")))[case["name"]]
+    mesh, got = _deck(cfe, case, tmp_path)
+    assert mesh.n_el == want["n_el"] and mesh.n_nd == want["n_used_nodes"]
+    assert len(got) == want["size"]
+    assert hashlib.sha256(got).hexdigest() == want["sha256"]
+
+
+def _oracle_deck(orc, vol, u, m, path):
+    m = dict(m)
+    if "matprop" in m:
+        m["matprop"] = m["matprop"]()
+    orc.mesh2voxelfe(orc.vol2ugrid(vol, **u), fileout=path, **m)
+    return cases.mask_timestamp(open(path, "rb").read())
+
+
+@pytest.mark.parametrize("shape,seed,grey", [((33, 47, 65), 31, False), ((64, 64, 64), 32, False),
+                                             ((30, 70, 130), 33, True), ((96, 96, 96), 34, True),
+                                             ((128, 128, 128), 35, False)])
+def test_full_path_vs_oracle(cfe, orc, shape, seed, grey, tmp_path):
+    """remove_unconnected -> vol2ugrid -> mesh2voxelfe on seeded trabecular-like volumes."""
+    bw = cases.blobs(shape, 0.3, seed)
+    L = cfe.remove_unconnected(bw)
+    L_ref = orc.remove_unconnected(bw)
+    assert np.array_equal(L, L_ref)
+    vol = cases.grey_from_mask(L, seed + 100) if grey else L
+    u = dict(voxelsize=[0.0195, 0.0195, 0.0195])
+    m = dict(templatefile=cases.TEMPLATE)
+    if grey:
+        m.update(keywords=['NSET', 'ELSET', 'PROPERTY'],
+                 matprop=lambda: {"file": [cases.MAT_LINEAR], "range": [[1, 255]]})
+    want = _oracle_deck(orc, vol, u, m, str(tmp_path / "cpu.inp"))
+    c = dict(vol=vol, u=u, m=m)
+    _, got = _deck(cfe, c, tmp_path)
+    assert len(got) == len(want)
+    assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+    assert got == want
+
+
+def test_device_tensor_input_and_host_sink(cfe, orc, tmp_path):
+    import torch
+    L = cases.blobs((32, 32, 64), 0.3, 41)
+    vol = torch.from_numpy(L).cuda()
+    mesh = cfe.vol2ugrid(vol, [0.0195] * 3)
+    sink = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    n = cfe.mesh2voxelfe(mesh, cases.TEMPLATE, sink)
+    got = cases.mask_timestamp(sink[:n].numpy().tobytes())
+    want = _oracle_deck(orc, L, dict(voxelsize=[0.0195] * 3), dict(templatefile=cases.TEMPLATE),
+                        str(tmp_path / "cpu.inp"))
+    assert got == want
+
+
+def test_notebook_cell_data_astype_pattern(cfe, golden, tmp_path):
+    # notebooks do mesh.cell_data['GV'] = mesh.cell_data['GV'][0].astype('uint8') before mesh2voxelfe
+    c = DECK_CASES["trab_bool_property"]
+    mesh = cfe.vol2ugrid(c["vol"], **c["u"])
+    mesh.cell_data['GV'] = mesh.cell_data['GV'][0].astype('uint8')
+    out = str(tmp_path / "d.inp")
+    cfe.mesh2voxelfe(mesh, cases.TEMPLATE, out, keywords=['NSET', 'ELSET', 'PROPERTY'],
+                     matprop={"file": [cases.MAT_LINEAR]})
+    text = open(out).read()
+    assert "ELSET=SET1, MATERIAL=MATSET1" in text and "SETTrue" not in text
+
+
+# ------------------------------------------------------------------ error behaviour
+
+def test_error_behaviour_matches_reference(cfe, tmp_path):
+    errs = json.load(open(os.path.join(cases.GOLDEN_DIR, "errors.json")))
+    empty = np.zeros((3, 3, 3), dtype=bool)
+    assert errs["vol2ugrid_all_background"] is None
+    mesh = cfe.vol2ugrid(empty)
+    assert mesh.n_el == 0 and mesh.cells[0].data.shape[0] == 0 and mesh.points.shape == (64, 3)
+    assert errs["mesh2voxelfe_all_background"] == "ValueError"
+    with pytest.raises(ValueError):
+        cfe.mesh2voxelfe(mesh, cases.TEMPLATE, str(tmp_path / "e.inp"))
+    g = cases.rand_grey((4, 4, 6), 0.5, 3)
+    mk = lambda: cfe.vol2ugrid(g)  # noqa: E731
+    for key, mp in [("matprop_two_files_no_range", {"file": [cases.MAT_CONST, cases.MAT_POWER]}),
+                    ("matprop_range_exceeds", {"file": [cases.MAT_CONST], "range": [[1, 300]]}),
+                    ("matprop_range_negative", {"file": [cases.MAT_CONST], "range": [[-1, 30]]}),
+                    ("matprop_overlap", {"file": [cases.MAT_CONST, cases.MAT_POWER],
+                                         "range": [[1, 100], [100, 255]]})]:
+        assert errs[key] == "OSError"
+        with pytest.raises(IOError):
+            cfe.mesh2voxelfe(mk(), cases.TEMPLATE, str(tmp_path / "e.inp"), matprop=mp)
+    with pytest.raises(TypeError):
+        cfe.vol2ugrid(np.zeros((2, 2, 2), dtype=np.float32))
+    with pytest.raises(NotImplementedError):
+        cfe.mesh2voxelfe(object(), cases.TEMPLATE, str(tmp_path / "e.inp"))
