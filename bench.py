@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the CT -> .INP hot path (remove_unconnected + vol2ugrid + mesh2voxelfe).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S]
+
+One "step" = one pass of the whole path over one synthetic trabecular-like volume (BASELINE.json
+configs[1]: S^3 binary volume, 30 % BV/TV; S = 512 per GPU by default).  `value` is voxels/s with
+the volume resident in HBM and the deck left in HBM; `e2e` is the same path fed from a pinned HOST
+volume with the deck copied back into a pinned HOST buffer inside the timed region.
+
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference
+(oracle/, single-threaded C port) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "voxels/s CT->.INP (CCL+vol2ugrid+deck)"
+VOXELSIZE = [0.0195, 0.0195, 0.0195]
+TEMPLATE = os.path.join(ROOT, "tests", "golden", "tmpl_compression.inp")
+CPU_SAMPLE = 256          # edge of the cubic sample the CPU port is timed on
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+
+def cpu_port_pass(sample):
+    """One pass of the CPU port (oracle/) over a bool numpy volume; returns seconds per stage."""
+    import tempfile
+
+    from oracle import oracle as orc
+    t0 = time.perf_counter()
+    L = orc.remove_unconnected(sample)
+    t1 = time.perf_counter()
+    mesh = orc.vol2ugrid(L, VOXELSIZE)
+    t2 = time.perf_counter()
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        orc.mesh2voxelfe(mesh, TEMPLATE, os.path.join(d, "cpu.inp"))
+        size = os.path.getsize(os.path.join(d, "cpu.inp"))
+    t3 = time.perf_counter()
+    return dict(ccl=t1 - t0, vol2ugrid=t2 - t1, mesh2voxelfe=t3 - t2, total=t3 - t0, deck_bytes=size)
+
+
+def cpu_sample(edge, seed=0):
+    import torch
+
+    from ciclope_b200 import synth
+    return synth.trabecular((edge, edge, edge), seed, 0.30, "cpu").numpy()
+
+
+def cpu_baseline_obj(edge, times):
+    vox = edge ** 3
+    return {"value": vox / times["total"], "unit": "voxels/s", "cores": 1, "kind": "port",
+            "sample": "%d^3 synthetic trabecular sample (same generator as the workload), 1 pass; "
+                      "ccl %.3fs vol2ugrid %.3fs mesh2voxelfe %.3fs" % (edge, times["ccl"], times["vol2ugrid"],
+                                                                        times["mesh2voxelfe"]),
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    edge = CPU_SAMPLE
+    sample = cpu_sample(edge)
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_pass(sample)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_port_pass(sample)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = edge ** 3 / dt
+    base = cpu_baseline_obj(edge, last)
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args.size, args.gpus, note="CPU port timed on a %d^3 sample per step" % edge),
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+
+def workload_config(size, n_gpus, note=None):
+    cfg = {"workload": "synthetic %d^3 trabecular-like binary volume (30%% BV/TV) per GPU: remove_unconnected + "
+                       "vol2ugrid + mesh2voxelfe (BASELINE.json configs[1])" % size,
+           "volume_per_gpu": [size, size, size], "voxelsize": VOXELSIZE[0], "bvtv": 0.30, "seed": 0,
+           "template": "tests/golden/tmpl_compression.inp", "keywords": ["NSET", "ELSET"],
+           "parallelism": "1 process per GPU" if n_gpus == 1 else "%d independent z-slab replicas" % n_gpus,
+           "l2": "inputs+outputs per step (0.13 GB volume, ~6 GB deck at 512^3) exceed the 126 MB L2; no flush"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def gpu_step(vol_dev):
+    """One pass of the hot path, volume and deck resident in HBM."""
+    from ciclope_b200.preprocess import remove_unconnected
+    from ciclope_b200.voxelFE import deck_to_device, vol2ugrid
+    L = remove_unconnected(vol_dev)
+    mesh = vol2ugrid(L, VOXELSIZE)
+    deck = deck_to_device(mesh, TEMPLATE)
+    return mesh, deck
+
+
+def gpu_step_e2e(vol_host, vol_dev, sink):
+    """Same path through the public API with HOST buffers: pinned volume in, pinned deck out."""
+    from ciclope_b200.preprocess import remove_unconnected
+    from ciclope_b200.voxelFE import mesh2voxelfe, vol2ugrid
+    vol_dev.copy_(vol_host, non_blocking=True)
+    L = remove_unconnected(vol_dev)
+    mesh = vol2ugrid(L, VOXELSIZE)
+    n = mesh2voxelfe(mesh, TEMPLATE, sink)
+    return mesh, n
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from ciclope_b200 import _lib, synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.require_cuda()
+    S = args.size
+    vol = synth.trabecular((S, S, S), seed=rank, bvtv=0.30, device=dev)
+    n_vox = vol.numel()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sizes the caching allocator)
+    for _ in range(max(args.warmup, 3)):
+        mesh, deck = gpu_step(vol)
+    deck_bytes = deck.numel()
+    n_el, n_nd = mesh.n_el, mesh.n_nd
+    del mesh, deck
+
+    # ---- timed region: K steps, CUDA events, max over ranks
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = lib.cfe_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mesh, deck = gpu_step(vol)
+        del mesh, deck
+    e1.record()
+    barrier()
+    launches = lib.cfe_launch_count() - l0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    ms_per_step = ms_total / args.steps
+    value = n_vox * world / (ms_per_step * 1e-3)
+
+    # ---- per-entry-point device times (separate profiled steps, CUDA events on the launch stream)
+    _lib.PROFILE = []
+    prof_steps = 3
+    for _ in range(prof_steps):
+        mesh, deck = gpu_step(vol)
+        del mesh, deck
+    torch.cuda.synchronize()
+    stage_ms = {}
+    for name, a, b in _lib.PROFILE:
+        stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / prof_steps
+    _lib.PROFILE = None
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        vol_host = torch.empty((S, S, S), dtype=torch.bool).pin_memory()
+        vol_host.copy_(vol)
+        sink = torch.empty(int(deck_bytes * 1.02) + (1 << 20), dtype=torch.uint8).pin_memory()
+        vol_dev = torch.empty_like(vol)
+        for _ in range(2):
+            gpu_step_e2e(vol_host, vol_dev, sink)
+        barrier()
+        k_e2e = max(3, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            _, n_out = gpu_step_e2e(vol_host, vol_dev, sink)
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_vox * world / dt.item(), "unit": "voxels/s", "h2d_bytes_per_step": int(n_vox),
+               "d2h_bytes_per_step": int(n_out) + 16 + 128 + 16, "ms_per_step": dt.item() * 1e3, "steps": k_e2e}
+        del sink, vol_host
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    # dominant kernel: the *ELEMENT emitter.  Algorithmic bytes per launch = element-section bytes
+    # written + 4 B/element list read.
+    elem_bytes = deck_bytes - 53 * n_nd   # everything but the *NODE lines is element lines + O(N^2) text
+    dom = max(stage_ms, key=stage_ms.get)
+    alg = {"cfe_emit_elements": elem_bytes + 4 * n_el, "cfe_emit_nodes": 57 * n_nd}
+    dom_for_roofline = "cfe_emit_elements"
+    achieved = alg[dom_for_roofline] / (stage_ms[dom_for_roofline] * 1e-3) / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tr.get("size") == S:
+            traffic = tr.get(dom_for_roofline)
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_emit_elements (cfe_emit_elements)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom_for_roofline],
+                "ms_per_launch": stage_ms[dom_for_roofline], "dominant_entry_point": dom}
+    total_alg = 2 * n_vox + deck_bytes
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_obj(CPU_SAMPLE, cpu_port_pass(cpu_sample(CPU_SAMPLE)))
+    line = {"metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(S, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu,
+            "job": {"voxels": n_vox * world, "elements_rank0": n_el, "used_nodes_rank0": n_nd,
+                    "deck_bytes_rank0": deck_bytes, "algorithmic_bytes_rank0": total_alg,
+                    "whole_path_frac_of_hbm_peak": total_alg / (ms_per_step * 1e-3) / 1e9 / peak},
+            "entry_point_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ciclope_b200", choices=["ciclope_b200", "reference"])
+    ap.add_argument("--size", type=int, default=512, help="edge of the cubic volume per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps == 20:
+            args.steps = 3
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_gpu(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,7 @@ class CfeItemSeg(ctypes.Structure):
 _SIGNATURES = {
     "cfe_version": (c_int, []),
     "cfe_last_error": (ctypes.c_char_p, []),
+    "cfe_launch_count": (ctypes.c_uint64, []),
     "cfe_pack_bits": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
     "cfe_scan_workspace_bytes": (c_sz, [c_i64]),
     "cfe_scan_elements": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
@@ -90,10 +91,23 @@ def require_cuda():
     return load()
 
 
+# When set to a list, every entry-point call is bracketed by CUDA events on the current stream and
+# (name, start_event, stop_event) is appended: bench.py's per-kernel timing.  None = off.
+PROFILE = None
+
+
 def call(name, *args):
     """Call an int-returning entry point; raise CfeError with cfe_last_error() on failure."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise CfeError("%s failed (%d): %s" % (name, rc, lib.cfe_last_error().decode()))
 

@@ -17,8 +17,10 @@ typedef long long i64;
 // ------------------------------------------------------------------------------------------
 // error plumbing (api.cu owns the storage)
 void cfe_set_error(const char* fmt, ...);
+void cfe_count_launch();
 #define CFE_CHECK_LAUNCH(name)                                                        \
     do {                                                                              \
+        cfe_count_launch();                                                           \
         cudaError_t e__ = cudaGetLastError();                                         \
         if (e__ != cudaSuccess) {                                                     \
             cfe_set_error("%s: kernel launch failed: %s", name, cudaGetErrorString(e__)); \

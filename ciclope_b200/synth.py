@@ -1,0 +1,74 @@
+"""Synthetic trabecular-like microCT volumes, bit-reproducible on CPU and GPU (integer-only
+torch ops): splitmix64 noise of the voxel index -> three passes of separable box blur (radius r,
+exact integer arithmetic) -> threshold at the level giving the requested bone volume fraction."""
+import torch
+
+_M64 = (1 << 64) - 1
+
+
+def _i64(v):
+    v &= _M64
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _lsr(x, k):
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def noise16(shape, seed, device, z0=0, full_shape=None):
+    """uint16-range white noise as int32; value depends only on (seed, global voxel index)."""
+    Z, Y, X = shape
+    fz, fy, fx = full_shape or shape
+    z = torch.arange(z0, z0 + Z, device=device, dtype=torch.int64).view(Z, 1, 1)
+    y = torch.arange(Y, device=device, dtype=torch.int64).view(1, Y, 1)
+    x = torch.arange(X, device=device, dtype=torch.int64).view(1, 1, X)
+    idx = (z * fy + y) * fx + x
+    v = idx + _i64(seed * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019)
+    v = (v ^ _lsr(v, 30)) * _i64(0xBF58476D1CE4E5B9)
+    v = (v ^ _lsr(v, 27)) * _i64(0x94D049BB133111EB)
+    v = v ^ _lsr(v, 31)
+    return (_lsr(v, 48)).to(torch.int32)
+
+
+def _box(f, axis, r):
+    """periodic box filter of width 2r+1 along `axis`, floor-divided to stay in 16 bits"""
+    n = f.shape[axis]
+    idx = torch.arange(-r - 1, n + r, device=f.device) % n
+    c = torch.cumsum(f.index_select(axis, idx).to(torch.int64), dim=axis)
+    hi = c.narrow(axis, 2 * r + 1, n)
+    lo = c.narrow(axis, 0, n)
+    return ((hi - lo) // (2 * r + 1)).to(torch.int32)
+
+
+def field(shape, seed, device, radius=4, passes=3):
+    f = noise16(shape, seed, device)
+    for _ in range(passes):
+        for axis in range(3):
+            f = _box(f, axis, radius)
+    return f
+
+
+def level_for_fraction(f, fraction):
+    """smallest integer t with mean(f > t) <= fraction"""
+    h = torch.bincount(f.reshape(-1).to(torch.int64), minlength=65536)
+    above = h.flip(0).cumsum(0).flip(0)          # above[t] = #(f >= t)
+    n = f.numel()
+    ok = (above[1:] <= int(fraction * n)).nonzero()   # #(f > t) = above[t+1]
+    return int(ok[0].item())
+
+
+def trabecular(shape, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3):
+    """bool volume [Z,Y,X] with bone volume fraction ~bvtv (smooth, mostly one connected component)."""
+    f = field(shape, seed, device, radius, passes)
+    t = level_for_fraction(f, bvtv)
+    return f > t
+
+
+def greyscale(shape, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3):
+    """uint8 volume: GV = 1 + blurred field quantised to 0..254 inside the bone mask, 0 outside
+    (the `masked[~L] = 0` pattern of ciclope example 01)."""
+    f = field(shape, seed, device, radius, passes)
+    t = level_for_fraction(f, bvtv)
+    fmax = int(f.max().item())
+    g = 1 + ((f - t).clamp(min=0).to(torch.int64) * 254 // max(fmax - t, 1)).clamp(max=254)
+    return torch.where(f > t, g.to(torch.uint8), torch.zeros((), dtype=torch.uint8, device=f.device))

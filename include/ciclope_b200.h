@@ -31,6 +31,8 @@ typedef struct CUstream_st* cfe_stream_t; /* == cudaStream_t */
 
 int cfe_version(void);
 const char* cfe_last_error(void);
+/* kernels launched by this library since it was loaded (benchmark bookkeeping) */
+uint64_t cfe_launch_count(void);
 
 /* ------------------------------------------------------------------ bit packing + scans */
 
