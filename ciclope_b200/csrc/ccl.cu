@@ -186,11 +186,12 @@ __device__ __forceinline__ u32 spread_nibble(u32 n) { return ((n & 15u) * 0x0020
 template <bool FLAT>
 __global__ void __launch_bounds__(256)
 k_ccl_write_mask(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 rows, int X, int W,
-                 const u32* __restrict__ parent, const u64* __restrict__ best, uint8_t* __restrict__ out)
+                 const u32* __restrict__ parent, const u64* __restrict__ best, const u32* __restrict__ keep_flag,
+                 uint8_t* __restrict__ out)
 {
     const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;  // 16-voxel chunk
     if (g >= rows * 2 * (i64)W) return;
-    const u64 key = *best;
+    const u64 key = keep_flag ? 1ull : *best;
     const u32 winner = 0xffffffffu - (u32)(key & 0xffffffffu);
     const i64 i = g >> 1;
     const int half = (int)(g & 1);
@@ -205,7 +206,8 @@ k_ccl_write_mask(const u32* __restrict__ bits, const u32* __restrict__ pref, i64
             const u32 shifted = rest >> b;
             const int len = (~shifted == 0u) ? 32 - b : __ffs((int)~shifted) - 1;
             const u32 seg = (len >= 32) ? 0xffffffffu : (((1u << len) - 1u) << b);
-            if (__ldg(parent + run_id(word, carry, pf, b)) == winner) keep |= seg;
+            const u32 root = __ldg(parent + run_id(word, carry, pf, b));
+            if (keep_flag ? (keep_flag[root] != 0u) : (root == winner)) keep |= seg;
             rest &= ~seg;
         }
     }
@@ -233,28 +235,24 @@ extern "C" size_t cfe_ccl_max_runs(int64_t rows, int64_t X)
     return (size_t)(rows * ((X + 1) / 2));
 }
 
-// Labels the slab and keeps the largest component.
-//   bits/pref : packed foreground bits and run-start prefixes (cfe_pack_bits, cfe_scan_run_starts)
-//   n_runs    : device scalar written by cfe_scan_run_starts
-//   parent,size : u32[cfe_ccl_max_runs] scratch
-//   best      : device u64, out: (size << 32) | (0xffffffff - root run id); 0 = no foreground
-//   out_mask  : uint8 [rows*X], 1 = voxel belongs to the largest component
-extern "C" int cfe_ccl_largest(const uint32_t* bits, const uint32_t* pref, const uint64_t* n_runs,
-                               int64_t Z, int64_t Y, int64_t X, uint32_t* parent, uint32_t* size,
-                               uint64_t* best, uint8_t* out_mask, cudaStream_t stream)
+static unsigned grid_stride_blocks()
+{
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (unsigned)(sms * 8);  // 8 CTAs of 256 threads per SM
+}
+
+// Phase 1: label the slab.  After this call parent[run] = root run id (min run id of the
+// component inside this slab) and size[root] = voxels of the component inside this slab.
+extern "C" int cfe_ccl_label(const uint32_t* bits, const uint32_t* pref, const uint64_t* n_runs, int64_t Z,
+                             int64_t Y, int64_t X, uint32_t* parent, uint32_t* size, cudaStream_t stream)
 {
     const i64 rows = Z * Y;
     if (rows <= 0 || X <= 0) return 0;
     const int W = (int)((X + 31) / 32);
     const i64 n_words = rows * W;
-    int sms = 148;
-    {
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    const unsigned gs_blocks = (unsigned)(sms * 8);  // grid-stride kernels: 8 CTAs of 256 per SM
+    const unsigned gs_blocks = grid_stride_blocks();
     const u64* nr = reinterpret_cast<const u64*>(n_runs);
-    CFE_CHECK_CUDA(cudaMemsetAsync(best, 0, sizeof(u64), stream));
     k_ccl_init<<<gs_blocks, 256, 0, stream>>>(parent, size, nr);
     CFE_CHECK_LAUNCH("k_ccl_init");
     const unsigned wb = (unsigned)((n_words + 255) / 256);
@@ -264,17 +262,137 @@ extern "C" int cfe_ccl_largest(const uint32_t* bits, const uint32_t* pref, const
     CFE_CHECK_LAUNCH("k_ccl_flatten");
     k_ccl_sizes<<<wb, 256, 0, stream>>>(bits, pref, n_words, W, parent, size);
     CFE_CHECK_LAUNCH("k_ccl_sizes");
-    k_ccl_select<<<gs_blocks, 256, 0, stream>>>(parent, size, nr, reinterpret_cast<u64*>(best));
+    return 0;
+}
+
+// Phase 2: *best = max over roots of (size << 32) | (0xffffffff - root); 0 = no foreground.
+extern "C" int cfe_ccl_select(const uint32_t* parent, const uint32_t* size, const uint64_t* n_runs,
+                              uint64_t* best, cudaStream_t stream)
+{
+    CFE_CHECK_CUDA(cudaMemsetAsync(best, 0, sizeof(u64), stream));
+    k_ccl_select<<<grid_stride_blocks(), 256, 0, stream>>>(parent, size, reinterpret_cast<const u64*>(n_runs),
+                                                           reinterpret_cast<u64*>(best));
     CFE_CHECK_LAUNCH("k_ccl_select");
-    const i64 chunks = n_words * 2;
+    return 0;
+}
+
+// Phase 3: out_mask = 1 where the voxel's run has root (0xffffffff - low32(*best)).
+// With `keep` != NULL the test is keep[root] != 0 instead (z-slab sharding: the winning global
+// component may be the union of several slab-local components).
+extern "C" int cfe_ccl_write_mask(const uint32_t* bits, const uint32_t* pref, int64_t Z, int64_t Y, int64_t X,
+                                  const uint32_t* parent, const uint64_t* best, const uint32_t* keep,
+                                  uint8_t* out_mask, cudaStream_t stream)
+{
+    const i64 rows = Z * Y;
+    if (rows <= 0 || X <= 0) return 0;
+    const int W = (int)((X + 31) / 32);
+    const i64 chunks = rows * W * 2;
     const unsigned cb = (unsigned)((chunks + 255) / 256);
     const bool flat = (X % 32 == 0) && ((reinterpret_cast<uintptr_t>(out_mask) & 15u) == 0);
-    if (flat)
-        k_ccl_write_mask<true><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent,
-                                                      reinterpret_cast<const u64*>(best), out_mask);
-    else
-        k_ccl_write_mask<false><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent,
-                                                       reinterpret_cast<const u64*>(best), out_mask);
+    const u64* b = reinterpret_cast<const u64*>(best);
+    if (flat) k_ccl_write_mask<true><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, out_mask);
+    else k_ccl_write_mask<false><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, out_mask);
     CFE_CHECK_LAUNCH("k_ccl_write_mask");
+    return 0;
+}
+
+// Labels the slab and keeps the largest component (single-GPU path = phases 1-3 back to back).
+//   bits/pref : packed foreground bits and run-start prefixes (cfe_pack_bits, cfe_scan_run_starts)
+//   n_runs    : device scalar written by cfe_scan_run_starts
+//   parent,size : u32[cfe_ccl_max_runs] scratch
+//   best      : device u64, out: (size << 32) | (0xffffffff - root run id); 0 = no foreground
+//   out_mask  : uint8 [rows*X], 1 = voxel belongs to the largest component
+extern "C" int cfe_ccl_largest(const uint32_t* bits, const uint32_t* pref, const uint64_t* n_runs,
+                               int64_t Z, int64_t Y, int64_t X, uint32_t* parent, uint32_t* size,
+                               uint64_t* best, uint8_t* out_mask, cudaStream_t stream)
+{
+    if (Z * Y <= 0 || X <= 0) return 0;
+    int rc = cfe_ccl_label(bits, pref, n_runs, Z, Y, X, parent, size, stream);
+    if (rc) return rc;
+    rc = cfe_ccl_select(parent, size, n_runs, best, stream);
+    if (rc) return rc;
+    return cfe_ccl_write_mask(bits, pref, Z, Y, X, parent, best, nullptr, out_mask, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// z-slab sharding: cross-slab merge support.
+
+// roots[k] = root of the k-th run (raster order) of the voxel plane made of rows
+// [row0, row0 + Y); *count = number of runs in the plane.
+__global__ void __launch_bounds__(256)
+k_ccl_plane_roots(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 word0, i64 n_plane_words,
+                  int W, const u32* __restrict__ parent, u32* __restrict__ roots, u32* __restrict__ count)
+{
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_plane_words) return;
+    const i64 i = word0 + t;
+    const u32 w = __ldg(bits + i);
+    const u32 base = __ldg(pref + word0);
+    const u32 pf = __ldg(pref + i);
+    const u32 carry = (i % W) ? (__ldg(bits + i - 1) >> 31) : 0u;
+    u32 starts = w & ~((w << 1) | carry);
+    u32 k = pf - base;
+    if (t == n_plane_words - 1) *count = k + (u32)__popc(starts);
+    u32 id = pf;
+    while (starts) {
+        starts &= starts - 1;
+        roots[k++] = __ldg(parent + id++);
+    }
+}
+
+extern "C" int cfe_ccl_plane_roots(const uint32_t* bits, const uint32_t* pref, int64_t plane, int64_t Y,
+                                   int64_t X, const uint32_t* parent, uint32_t* roots, uint32_t* count,
+                                   cudaStream_t stream)
+{
+    const int W = (int)((X + 31) / 32);
+    const i64 n = Y * W;
+    if (n <= 0) return 0;
+    k_ccl_plane_roots<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bits, pref, plane * n, n, W, parent, roots,
+                                                                      count);
+    CFE_CHECK_LAUNCH("k_ccl_plane_roots");
+    return 0;
+}
+
+// Interface between the top plane A of the slab below (bitsA, plane-local run prefixes prefA and
+// the roots of its runs, all received from the neighbour rank) and this slab's bottom plane B:
+// one edge (rootA, rootB) per pair of overlapping runs, appended in arbitrary order.
+__global__ void __launch_bounds__(256)
+k_ccl_interface_edges(const u32* __restrict__ bitsA, const u32* __restrict__ prefA,
+                      const u32* __restrict__ rootsA, const u32* __restrict__ bitsB,
+                      const u32* __restrict__ prefB, const u32* __restrict__ parentB, i64 n_plane_words, int W,
+                      u32* __restrict__ edges, u32* __restrict__ count, u32 capacity)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_plane_words) return;
+    const u32 a = __ldg(bitsA + i), b = __ldg(bitsB + i);
+    const u32 both = a & b;
+    if (!both) return;
+    const bool inner = (i % W) != 0;
+    const u32 a_prev = inner ? __ldg(bitsA + i - 1) : 0u;
+    const u32 b_prev = inner ? __ldg(bitsB + i - 1) : 0u;
+    const u32 pa = __ldg(prefA + i), pb = __ldg(prefB + i);
+    u32 pair_starts = both & ~((both << 1) | ((a_prev & b_prev) >> 31));
+    while (pair_starts) {
+        const int bit = __ffs((int)pair_starts) - 1;
+        pair_starts &= pair_starts - 1;
+        const u32 ra = __ldg(rootsA + run_id(a, a_prev >> 31, pa, bit));
+        const u32 rb = __ldg(parentB + run_id(b, b_prev >> 31, pb, bit));
+        const u32 slot = atomicAdd(count, 1u);
+        if (slot < capacity) { edges[2 * slot] = ra; edges[2 * slot + 1] = rb; }
+    }
+}
+
+extern "C" int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* prefA, const uint32_t* rootsA,
+                                       const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* parentB,
+                                       int64_t Y, int64_t X, uint32_t* edges, uint32_t* count, int64_t capacity,
+                                       cudaStream_t stream)
+{
+    const int W = (int)((X + 31) / 32);
+    const i64 n = Y * W;
+    CFE_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(u32), stream));
+    if (n <= 0) return 0;
+    k_ccl_interface_edges<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        bitsA, prefA, rootsA, bitsB, prefB, parentB, n, W, edges, count, (u32)capacity);
+    CFE_CHECK_LAUNCH("k_ccl_interface_edges");
     return 0;
 }

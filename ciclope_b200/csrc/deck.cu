@@ -150,7 +150,7 @@ struct ElemEmitParams {
     i64 SN, RN, z0, eid_offset;
     char* out;               // start of the element lines
     u64* total;              // out: bytes written
-    u64* blk_off;            // out [256]: byte offset (from `out`) of the first line of each GV block
+    u64* blk_off;            // out [256]: byte offset (from `out`) where each GV block (header included) starts
     u64* ws;                 // look-back workspace
 };
 
@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_elements(ElemEmitParams P
     u64 val[9];
     int nd[9];
     u32 len = 0, hl = 0;
+    bool is_first = false;
     int gv = P.single_gv;
     if (j < P.n_el) {
         u32 v, rank;
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_elements(ElemEmitParams P
         len = 9;
 #pragma unroll
         for (int q = 0; q < 9; ++q) { nd[q] = digits_u64(val[q]); len += (u32)nd[q]; }
-        if ((u64)j == __ldg(P.first + gv)) hl = __ldg(P.hdr_len + gv);
+        is_first = ((u64)j == __ldg(P.first + gv));
+        if (is_first) hl = __ldg(P.hdr_len + gv);
     }
     u32 tile_total;
     const u32 excl = block_exclusive_scan<u32>(len + hl, s_scan, tile_total);
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_elements(ElemEmitParams P
     __syncthreads();
     char* dst = P.out + s_base;
     const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
-    if (hl && P.blk_off) P.blk_off[gv] = s_base + excl + hl;
+    if (is_first && P.blk_off) P.blk_off[gv] = s_base + excl;
     // A tile normally fits the staging buffer; a pathological tile (hundreds of block headers)
     // falls back to direct global writes.
     const bool staged = (pad + tile_total) <= (u32)ELEM_STAGE_BYTES;
@@ -261,7 +263,7 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
 
 __global__ void __launch_bounds__(EMIT_THREADS)
 k_emit_items(const CfeItemSeg* __restrict__ segs, int n_segs, i64 n_items, const i64* __restrict__ ids,
-             const char* __restrict__ lit, char* out_base, const u64* dyn_off, u64* total, u64* ws)
+             const char* __restrict__ lit, char* out_base, const u64* dyn_off, u64* total, u64* seg_off, u64* ws)
 {
     extern __shared__ __align__(16) char stage[];
     __shared__ u32 s_scan[33];
@@ -273,10 +275,12 @@ k_emit_items(const CfeItemSeg* __restrict__ segs, int n_segs, i64 n_items, const
     u64 id = 0;
     char sep = 0;
     const char* src = nullptr;
+    int seg_first = -1;
     if (t < n_items) {
         int q = 0;
         while (q + 1 < n_segs && t >= segs[q + 1].item0) ++q;
         const CfeItemSeg sg = segs[q];
+        if (t == sg.item0) seg_first = q;
         if (sg.kind == 0) {
             src = lit + sg.lit_off;
             len = (u32)sg.lit_len;
@@ -301,6 +305,7 @@ k_emit_items(const CfeItemSeg* __restrict__ segs, int n_segs, i64 n_items, const
     __syncthreads();
     char* dst = out_base + (dyn_off ? *dyn_off : 0ull) + s_base;
     const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    if (seg_first >= 0 && seg_off) seg_off[seg_first] = s_base + excl;
     const bool staged = (pad + tile_total) <= (u32)ITEM_STAGE_BYTES;
     if (t < n_items) {
         char* p = staged ? (stage + pad + excl) : (dst + excl);
@@ -317,7 +322,7 @@ k_emit_items(const CfeItemSeg* __restrict__ segs, int n_segs, i64 n_items, const
 
 extern "C" int cfe_emit_items(const CfeItemSeg* segs_dev, int n_segs, int64_t n_items, const int64_t* ids,
                               const char* literals, char* out_base, const uint64_t* dyn_off, uint64_t* total,
-                              void* ws, cudaStream_t stream)
+                              uint64_t* seg_off, void* ws, cudaStream_t stream)
 {
     const i64 tiles = (n_items + EMIT_THREADS - 1) / EMIT_THREADS;
     CFE_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(tiles + 2) * sizeof(u64), stream));
@@ -331,7 +336,8 @@ extern "C" int cfe_emit_items(const CfeItemSeg* segs_dev, int n_segs, int64_t n_
     }
     k_emit_items<<<(unsigned)tiles, EMIT_THREADS, ITEM_STAGE_BYTES, stream>>>(
         segs_dev, n_segs, n_items, reinterpret_cast<const i64*>(ids), literals, out_base,
-        reinterpret_cast<const u64*>(dyn_off), reinterpret_cast<u64*>(total), reinterpret_cast<u64*>(ws));
+        reinterpret_cast<const u64*>(dyn_off), reinterpret_cast<u64*>(total), reinterpret_cast<u64*>(seg_off),
+        reinterpret_cast<u64*>(ws));
     CFE_CHECK_LAUNCH("k_emit_items");
     return 0;
 }

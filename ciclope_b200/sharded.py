@@ -1,0 +1,739 @@
+"""Z-slab sharding of the CT -> .INP hot path over the GPUs of one box.
+
+The global volume [Z,Y,X] is cut into contiguous z-slabs, one per rank (one process per GPU under
+torchrun).  Every voxel / node / text loop is the same CUDA kernel the single-GPU path uses; the
+kernels take the slab's global slice offset ``z0``, the global element-id offset and the global
+position of every set entry, so their output bytes are the bytes of the single-GPU deck.
+
+Exchange steps (NCCL over NVLink; all latency-bound, O(plane) or O(1) sized):
+
+* ``shift_up``     one voxel plane of packed bits (Y*W words) to the rank above: node flags /
+                   plane-set membership on a slab's first node layer, and the CCL interface;
+* ``all_gather``   per-slab element / node / set counts and byte totals -> global numbering and
+                   file offsets; CCL boundary vertices, sizes and cross-slab edges;
+* the CCL winner is the max over (merged size, min global run id), computed identically on every
+  rank from the gathered boundary graph.
+
+Each rank's logic is written ONCE as a generator that yields its collective requests; the same
+program runs under ``torch.distributed`` (``DistRunner``) or as N emulated ranks inside one
+process on one GPU (``LocalRunner``), which is how the single-GPU test box exercises N = 2..8.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import voxelFE as vfe
+from ._lib import CfeItemSeg, CfeSetDesc
+from ._util import empty_u32, scan_workspace
+
+
+# --------------------------------------------------------------------------------------------
+# slab geometry (pure host logic)
+
+def slab_ranges(Z, n):
+    """Contiguous z ranges [z0, z1) of n slabs; the first Z % n slabs get one extra slice."""
+    if n < 1:
+        raise ValueError("need at least one slab")
+    if Z < n:
+        raise ValueError("cannot cut %d slices into %d non-empty slabs" % (Z, n))
+    base, extra = divmod(Z, n)
+    out, z = [], 0
+    for k in range(n):
+        h = base + (1 if k < extra else 0)
+        out.append((z, z + h))
+        z += h
+    return out
+
+
+def exclusive_offsets(counts):
+    """[sum(counts[:k]) for k] and the total."""
+    out, acc = [], 0
+    for c in counts:
+        out.append(acc)
+        acc += int(c)
+    return out, acc
+
+
+def clip_box_z(box, lo, hi):
+    (s0, s1), r, c = box
+    s0, s1 = max(s0, lo), min(s1, hi)
+    if s1 <= s0:
+        return ((0, 0), (0, 0), (0, 0))
+    return ((s0, s1), r, c)
+
+
+# --------------------------------------------------------------------------------------------
+# collectives as generator requests
+
+class Ctx:
+    """Per-rank context handed to the rank programs."""
+
+    def __init__(self, rank, size, device):
+        self.rank, self.size, self.device = rank, size, device
+
+    def all_gather(self, t):
+        """same-shape tensor from every rank -> list of tensors (index = rank)"""
+        return (yield ("all_gather", t))
+
+    def all_gather_var(self, t):
+        """1-D tensors of different lengths -> list of tensors"""
+        return (yield ("all_gather_var", t))
+
+    def shift_up(self, t):
+        """send `t` to rank+1; returns the tensor of rank-1 (None on rank 0).  Same shape on all ranks."""
+        return (yield ("shift_up", t))
+
+    def barrier(self):
+        return (yield ("barrier", None))
+
+
+class LocalRunner:
+    """Runs N rank programs in lock-step inside one process (all on the current device)."""
+
+    def __init__(self, size, device=None):
+        self.size = size
+        self.device = device
+
+    def ctxs(self):
+        return [Ctx(k, self.size, self.device) for k in range(self.size)]
+
+    def run(self, programs):
+        gens = list(programs)
+        results = [None] * len(gens)
+        reqs = []
+        for k, g in enumerate(gens):
+            try:
+                reqs.append(next(g))
+            except StopIteration as e:
+                results[k] = e.value
+                reqs.append(None)
+        while any(r is not None for r in reqs):
+            if any(r is None for r in reqs):
+                raise RuntimeError("rank programs diverged (some finished while others wait on a collective)")
+            kinds = {r[0] for r in reqs}
+            if len(kinds) != 1:
+                raise RuntimeError("rank programs issued different collectives: %s" % kinds)
+            kind = kinds.pop()
+            vals = [r[1] for r in reqs]
+            if kind in ("all_gather", "all_gather_var"):
+                answers = [[v.clone() for v in vals] for _ in gens]
+            elif kind == "shift_up":
+                answers = [None] + [vals[k - 1].clone() for k in range(1, len(gens))]
+            elif kind == "barrier":
+                answers = [None] * len(gens)
+            else:
+                raise RuntimeError("unknown collective %s" % kind)
+            new = []
+            for k, g in enumerate(gens):
+                try:
+                    new.append(g.send(answers[k]))
+                except StopIteration as e:
+                    results[k] = e.value
+                    new.append(None)
+            reqs = new
+        return results
+
+
+class DistRunner:
+    """Runs one rank program per process over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        self.device = device
+
+    def ctx(self):
+        return Ctx(self.rank, self.size, self.device)
+
+    def _fulfil(self, kind, t):
+        dist = self.dist
+        if kind == "all_gather":
+            out = [torch.empty_like(t) for _ in range(self.size)]
+            dist.all_gather(out, t.contiguous(), group=self.group)
+            return out
+        if kind == "all_gather_var":
+            n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+            ns = [torch.empty_like(n) for _ in range(self.size)]
+            dist.all_gather(ns, n, group=self.group)
+            ns = [int(v.item()) for v in ns]
+            m = max(max(ns), 1)
+            pad = torch.zeros(m, dtype=t.dtype, device=t.device)
+            pad[: t.numel()] = t.reshape(-1)
+            out = [torch.empty_like(pad) for _ in range(self.size)]
+            dist.all_gather(out, pad, group=self.group)
+            return [o[:k] for o, k in zip(out, ns)]
+        if kind == "shift_up":
+            ops, recv = [], None
+            if self.rank + 1 < self.size:
+                ops.append(dist.P2POp(dist.isend, t.contiguous(), self.rank + 1, group=self.group))
+            if self.rank > 0:
+                recv = torch.empty_like(t)
+                ops.append(dist.P2POp(dist.irecv, recv, self.rank - 1, group=self.group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            return recv
+        if kind == "barrier":
+            dist.barrier(group=self.group)
+            return None
+        raise RuntimeError("unknown collective %s" % kind)
+
+    def run(self, program):
+        try:
+            req = next(program)
+            while True:
+                req = program.send(self._fulfil(*req))
+        except StopIteration as e:
+            return e.value
+
+
+# --------------------------------------------------------------------------------------------
+# cross-slab component merge (device-agnostic torch ops on O(boundary) data)
+
+def solve_boundary_components(keys, sizes, edges):
+    """Connected components of the boundary graph.
+
+    keys  : int64 [V] sorted unique vertex keys (rank << 32 | slab-local root run id)
+    sizes : int64 [V] voxels of each slab-local component
+    edges : int64 [E,2] vertex keys of overlapping runs across slab interfaces
+    Returns (label [V] = index of the smallest-key vertex of the component, comp_size [V] (valid at
+    label positions)).  Label propagation with pointer jumping; O(log diameter) rounds."""
+    V = keys.numel()
+    lab = torch.arange(V, dtype=torch.int64, device=keys.device)
+    if V == 0:
+        return lab, sizes.clone()
+    if edges.numel():
+        a = torch.searchsorted(keys, edges[:, 0].contiguous())
+        b = torch.searchsorted(keys, edges[:, 1].contiguous())
+        while True:
+            m = torch.minimum(lab[a], lab[b])
+            new = lab.clone()
+            new.scatter_reduce_(0, a, m, reduce="amin")
+            new.scatter_reduce_(0, b, m, reduce="amin")
+            for _ in range(3):
+                new = new[new]
+            if torch.equal(new, lab):
+                break
+            lab = new
+        while True:           # full compression
+            nxt = lab[lab]
+            if torch.equal(nxt, lab):
+                break
+            lab = nxt
+    comp = torch.zeros(V, dtype=torch.int64, device=keys.device)
+    comp.scatter_add_(0, lab, sizes)
+    return lab, comp
+
+
+def pick_winner(cands):
+    """cands: iterable of (size, key); largest size, ties -> smallest key.  None if empty/zero."""
+    best = None
+    for size, key in cands:
+        if size <= 0:
+            continue
+        if best is None or size > best[0] or (size == best[0] and key < best[1]):
+            best = (size, key)
+    return best
+
+
+# --------------------------------------------------------------------------------------------
+# rank programs
+
+def _u32_to_i64(t):
+    return t.to(torch.int64) & 0xFFFFFFFF
+
+
+def ccl_program(ctx, vol):
+    """remove_unconnected of the global volume; `vol` = this rank's uint8 slab [Zl,Y,X] on the GPU.
+    Returns (uint8 mask slab, winner (size, key) or None)."""
+    lib = _lib.require_cuda()
+    dev = vol.device
+    Zl, Y, X = (int(v) for v in vol.shape)
+    W = (X + 31) // 32
+    rows = Zl * Y
+    PW = Y * W
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        bits = empty_u32(rows * W, dev)
+        pref = empty_u32(rows * W, dev)
+        stats = torch.zeros(4, dtype=torch.int64, device=dev)   # n_runs, best, plane counts
+        ws = scan_workspace(max(rows * W, PW), dev)
+        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
+        _lib.call("cfe_scan_run_starts", bits.data_ptr(), rows, X, pref.data_ptr(), stats.data_ptr(),
+                  ws.data_ptr(), s)
+        max_runs = lib.cfe_ccl_max_runs(rows, X)
+        parent = empty_u32(max_runs, dev)
+        size = empty_u32(max_runs, dev)
+        _lib.call("cfe_ccl_label", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Zl, Y, X,
+                  parent.data_ptr(), size.data_ptr(), s)
+        out = torch.empty((Zl, Y, X), dtype=torch.uint8, device=dev)
+
+        # ---- boundary planes: roots of the runs of my bottom (0) and top (Zl-1) voxel planes
+        cap = Y * ((X + 1) // 2)
+        roots_bot = empty_u32(cap, dev)
+        roots_top = empty_u32(cap, dev)
+        cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+        _lib.call("cfe_ccl_plane_roots", bits.data_ptr(), pref.data_ptr(), 0, Y, X, parent.data_ptr(),
+                  roots_bot.data_ptr(), cnt.data_ptr(), s)
+        _lib.call("cfe_ccl_plane_roots", bits.data_ptr(), pref.data_ptr(), Zl - 1, Y, X, parent.data_ptr(),
+                  roots_top.data_ptr(), cnt.data_ptr() + 4, s)
+        top_bits = bits[(Zl - 1) * PW: Zl * PW]
+    # planes travel to the rank above (fixed shapes: bits PW, roots cap)
+    bitsA = yield from ctx.shift_up(top_bits)
+    rootsA = yield from ctx.shift_up(roots_top)
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        n_edges = 0
+        edges_dev = None
+        if ctx.rank > 0:
+            prefA = empty_u32(PW, dev)
+            scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.call("cfe_scan_run_starts", bitsA.data_ptr(), Y, X, prefA.data_ptr(), scratch.data_ptr(),
+                      ws.data_ptr(), s)
+            edges_dev = torch.empty((max(cap, 1), 2), dtype=torch.int32, device=dev)
+            _lib.call("cfe_ccl_interface_edges", bitsA.data_ptr(), prefA.data_ptr(), rootsA.data_ptr(),
+                      bits.data_ptr(), pref.data_ptr(), parent.data_ptr(), Y, X, edges_dev.data_ptr(),
+                      cnt.data_ptr() + 8, cap, s)
+        h = cnt.cpu().tolist()                      # sync: plane run counts, edge count
+        n_bot, n_top, n_edges = h[0], h[1], h[2]
+        if n_edges > cap:
+            raise _lib.CfeError("interface edge buffer overflow")
+        # my boundary vertices (slab-local roots that own a run in an interface plane)
+        parts = []
+        if ctx.rank > 0:
+            parts.append(roots_bot[:n_bot])
+        if ctx.rank + 1 < ctx.size:
+            parts.append(roots_top[:n_top])
+        my_roots = torch.unique(_u32_to_i64(torch.cat(parts))) if parts else torch.empty(0, dtype=torch.int64,
+                                                                                         device=dev)
+        my_sizes = _u32_to_i64(size[my_roots]) if my_roots.numel() else my_roots.clone()
+        if ctx.rank > 0 and n_edges:
+            e = _u32_to_i64(edges_dev[:n_edges])
+            my_edges = torch.stack([e[:, 0] | ((ctx.rank - 1) << 32), e[:, 1] | (ctx.rank << 32)], dim=1)
+        else:
+            my_edges = torch.empty((0, 2), dtype=torch.int64, device=dev)
+    all_roots = yield from ctx.all_gather_var(my_roots)
+    all_sizes = yield from ctx.all_gather_var(my_sizes)
+    all_edges = yield from ctx.all_gather_var(my_edges.reshape(-1))
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        keys = torch.cat([r | (k << 32) for k, r in enumerate(all_roots)])     # sorted: ranks ascending
+        sizes = torch.cat(all_sizes)
+        edges = torch.cat(all_edges).reshape(-1, 2)
+        lab, comp = solve_boundary_components(keys, sizes, edges)
+        # best slab-internal component of this rank: hide the boundary vertices from the arg-max
+        if my_roots.numel():
+            saved = size[my_roots].clone()
+            size[my_roots] = 0
+        _lib.call("cfe_ccl_select", parent.data_ptr(), size.data_ptr(), stats.data_ptr(), stats.data_ptr() + 8, s)
+        if my_roots.numel():
+            size[my_roots] = saved
+        best_internal = stats[1:2].clone()
+    all_best = yield from ctx.all_gather(best_internal)
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        cands = []
+        for k, b in enumerate(all_best):
+            v = int(b.item()) & 0xFFFFFFFFFFFFFFFF
+            cands.append((v >> 32, (k << 32) | (0xFFFFFFFF - (v & 0xFFFFFFFF))))
+        if keys.numel():
+            is_rep = lab == torch.arange(keys.numel(), device=dev)
+            rep_sizes = comp[is_rep]
+            rep_keys = keys[is_rep]
+            top = int(rep_sizes.max().item())
+            cands.append((top, int(rep_keys[rep_sizes == top].min().item())))
+        winner = pick_winner(cands)
+        if winner is None:
+            out.zero_()
+            return out, None
+        wsize, wkey = winner
+        # which of MY roots belong to the winning component
+        off = sum(r.numel() for r in all_roots[: ctx.rank])
+        mine = slice(off, off + my_roots.numel())
+        idx = (keys == wkey).nonzero()
+        kept_roots = []
+        if idx.numel():                      # the winner is a merged (boundary) component
+            wlab = int(idx[0].item())
+            if lab[wlab].item() != wlab:
+                raise _lib.CfeError("internal error: winner is not a component representative")
+            kept_roots = my_roots[lab[mine] == wlab]
+        elif (wkey >> 32) == ctx.rank:       # a slab-internal component of this rank
+            kept_roots = torch.tensor([wkey & 0xFFFFFFFF], dtype=torch.int64, device=dev)
+        # keep flags live in the (no longer needed) size array
+        n_runs = int(stats[0].item())
+        size[: max(n_runs, 1)] = 0
+        if len(kept_roots):
+            size[kept_roots] = 1
+        _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
+                  stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), s)
+    return out, winner
+
+
+class SlabMesh:
+    """One rank's part of the global voxel mesh (device-resident)."""
+
+
+def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_num=1, node_level_lock_num=1,
+                      locking_strategy="plane"):
+    """vol2ugrid of the global volume [Zg,Y,X]; `vol` = this rank's uint8 slab starting at slice z0."""
+    _lib.require_cuda()
+    if locking_strategy not in ("plane", "exact"):
+        raise ValueError("locking_strategy must be 'plane' or 'exact'")
+    p = vfe._int_lock(plane_lock_num, "plane_lock_num")
+    kk = vfe._int_lock(node_level_lock_num, "node_level_lock_num")
+    dev = vol.device
+    Zl, Y, X = (int(v) for v in vol.shape)
+    last = ctx.rank == ctx.size - 1
+    n_layers = Zl + (1 if last else 0)
+    thr = vfe._gv_threshold(GVmin)
+    W, WN = (X + 31) // 32, (X + 32) // 32
+    rows, nrows = Zl * Y, n_layers * (Y + 1)
+    PW = Y * W
+    m = SlabMesh()
+    m.rank, m.size = ctx.rank, ctx.size
+    m.vol, m.is_bool, m.thr = vol, is_bool, thr
+    m.Zg, m.Zl, m.Y, m.X, m.z0, m.n_layers = Zg, Zl, Y, X, z0, n_layers
+    m.xs, m.ys, m.zs = vfe._coordinate_tables(voxelsize, Zg, Y, X)
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        bits = empty_u32(rows * W, dev)
+        epref = empty_u32(rows * W, dev)
+        nbits = empty_u32(nrows * WN, dev)
+        npref = empty_u32(nrows * WN, dev)
+        ws = scan_workspace(max(rows * W, nrows * WN), dev)
+        stats = torch.zeros(4, dtype=torch.int64, device=dev)
+        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
+        top_bits = bits[(Zl - 1) * PW: Zl * PW]
+    halo = yield from ctx.shift_up(top_bits)
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        _lib.call("cfe_scan_elements", bits.data_ptr(), rows * W, epref.data_ptr(), stats.data_ptr(),
+                  ws.data_ptr(), s)
+        _lib.call("cfe_scan_nodes", bits.data_ptr(), _lib.ptr(halo), Zl, Y, X, n_layers, nbits.data_ptr(),
+                  npref.data_ptr(), stats.data_ptr() + 8, ws.data_ptr(), s)
+        # boundary sets: global boxes clipped to the layers this slab owns
+        boxes = vfe._boundary_boxes(locking_strategy, p, kk, Zg, Y, X)
+        descs = (CfeSetDesc * 12)()
+        tile_base = 0
+        for q in range(12):
+            d = descs[q]
+            b = boxes[q % 6]
+            if locking_strategy == "plane":
+                if q < 6:
+                    d.kind = 0
+                    cand = tuple((lo, hi + 1) if hi > lo else (0, 0) for lo, hi in b)
+                    vbox = b
+                    cand = clip_box_z(cand, z0, z0 + n_layers) if vfe._box_count(cand) else cand
+                else:
+                    d.kind = 2
+                    cand = clip_box_z(b, z0, z0 + Zl) if vfe._box_count(b) else b
+                    vbox = b
+            else:
+                if q < 6:
+                    d.kind = 1
+                    cand = clip_box_z(b, z0, z0 + n_layers) if vfe._box_count(b) else b
+                    vbox = ((0, Zg), (0, Y), (0, X))
+                else:
+                    d.kind = 2
+                    cand = ((0, 0), (0, 0), (0, 0))
+                    vbox = cand
+            (d.s0, d.s1), (d.r0, d.r1), (d.c0, d.c1) = cand
+            (d.vs0, d.vs1), (d.vr0, d.vr1), (d.vc0, d.vc1) = vbox
+            d.n_cand = vfe._box_count(cand)
+            d.tile_base = tile_base
+            tile_base += (d.n_cand + 255) // 256
+        n_tiles = tile_base
+        descs_dev = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev)
+        tile_count = empty_u32(n_tiles, dev)
+        tile_off = torch.empty(max(n_tiles, 1) + 1, dtype=torch.int64, device=dev)
+        bases = torch.tensor([descs[q].tile_base for q in range(12)], dtype=torch.int64, device=dev)
+        # element ids need the global offset -> counts first, ids after the all-gather
+        _lib.call("cfe_sets_count", descs_dev.data_ptr(), 12, n_tiles, Zl, Y, X, z0, 0, bits.data_ptr(),
+                  epref.data_ptr(), _lib.ptr(halo), tile_count.data_ptr(), s)
+        _lib.call("cfe_scan_u32", tile_count.data_ptr(), n_tiles, tile_off.data_ptr(), stats.data_ptr() + 16,
+                  ws.data_ptr(), s)
+        tile_off[n_tiles] = stats[2]
+        first_t = tile_off[bases.clamp(max=n_tiles)]
+        count_t = torch.cat([first_t[1:], stats[2:3]]) - first_t
+        mine = torch.cat([stats[:2], count_t])          # n_el, n_nd, 12 set counts
+    gathered = yield from ctx.all_gather(mine)
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        table = torch.stack(gathered).cpu().tolist()    # the one host sync: [rank][14]
+        n_el_r = [t[0] for t in table]
+        n_nd_r = [t[1] for t in table]
+        m.n_el, m.n_nd = n_el_r[ctx.rank], n_nd_r[ctx.rank]
+        m.eid_offset = sum(n_el_r[: ctx.rank])
+        m.node_rank_offset = sum(n_nd_r[: ctx.rank])
+        m.n_el_global, m.n_nd_global = sum(n_el_r), sum(n_nd_r)
+        m.set_count = [int(c) for c in table[ctx.rank][2:]]
+        m.set_first, n_ids = exclusive_offsets(m.set_count)
+        m.set_rank0 = [sum(t[2 + q] for t in table[: ctx.rank]) for q in range(12)]
+        m.set_count_global = [sum(t[2 + q] for t in table) for q in range(12)]
+        m.elem_vox = empty_u32(m.n_el, dev)
+        m.node_list = empty_u32(m.n_nd, dev)
+        m.set_ids = torch.empty(max(n_ids, 1), dtype=torch.int64, device=dev)
+        _lib.call("cfe_fill_list", bits.data_ptr(), epref.data_ptr(), rows * W, W, X, m.elem_vox.data_ptr(), s)
+        _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
+                  m.node_list.data_ptr(), s)
+        _lib.call("cfe_sets_fill", descs_dev.data_ptr(), 12, n_tiles, Zl, Y, X, z0, m.eid_offset, bits.data_ptr(),
+                  epref.data_ptr(), _lib.ptr(halo), tile_off.data_ptr(), m.set_ids.data_ptr(), s)
+    m.bits, m.epref = bits, epref
+    return m
+
+
+class SlabDeck:
+    """One rank's deck pieces: device buffers + (file offset, buffer, lo, hi) write list."""
+
+
+def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'], eltype='C3D8', matpropbits=8,
+                 refnode=None):
+    """mesh2voxelfe of the global mesh.  Every rank formats its own elements / nodes / set entries
+    into HBM; the all-gathered byte totals give each piece its offset in the single .INP file."""
+    lib = _lib.require_cuda()
+    dev = m.vol.device
+    Zl, Y, X = m.Zl, m.Y, m.X
+    rank = ctx.rank
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        hist_dev = torch.zeros(256, dtype=torch.int64, device=dev)
+        if m.is_bool:
+            hist_dev[1] = m.n_el
+        else:
+            _lib.call("cfe_gv_histogram", m.vol.data_ptr(), Zl * Y * X, m.thr, hist_dev.data_ptr(), s)
+    hists = yield from ctx.all_gather(hist_dev)
+    hist_r = torch.stack(hists).cpu().numpy()            # [rank][256]
+    hist = hist_r.sum(axis=0)
+    if m.n_el_global == 0:
+        raise ValueError("min() iterable argument is empty")
+    gv_dtype = np.bool_ if m.is_bool else np.uint8
+    gvs = np.flatnonzero(hist)
+    existing_GV = gvs.astype(gv_dtype)
+    GVmax = 2 ** matpropbits - 1
+    binary_model = bool(gvs.min() == 0) and bool(gvs.max() == 1) and issubclass(gv_dtype, np.integer)
+    if max(existing_GV) > GVmax:
+        GVmax = max(existing_GV)
+    prop_GV = {0: (1, 1)} if binary_model else vfe._resolve_matprop(matprop, GVmax)
+
+    from datetime import datetime
+    head = ('** ---------------------------------------------------------\n'
+            '** Abaqus .INP file written by Voxel_FEM script on {}\n'
+            '** ---------------------------------------------------------\n'
+            '** Node coordinates from input model\n'
+            '*NODE\n').format(datetime.now()).encode()
+    elem_comment = b'** Elements and Element sets from input model\n'
+    tail = ''
+    if 'PROPERTY' in keywords:
+        tail += vfe._property_cards(matprop, prop_GV, existing_GV)
+    tail += vfe._template_text(templatefile, refnode)
+    tail = tail.encode()
+    hdrs = {int(g): '*ELEMENT, TYPE={0}, ELSET={1}\n'.format(eltype, 'SET' + str(int(g))).encode() for g in gvs}
+
+    my_hist = hist_r[rank]
+    first = np.zeros(256, dtype=np.int64)
+    first[1:] = np.cumsum(my_hist)[:-1]
+    first[my_hist == 0] = -1
+    blob = vfe._Blob()
+    o_first = blob.add(first.tobytes())
+    o_hdr = blob.add(bytes(256 * vfe._ELEM_HDR_SLOT))
+    o_hlen = blob.add(bytes(256))                      # no headers inside the slab buffers
+    o_xt = blob.add(vfe._field_table(m.xs))
+    o_yt = blob.add(vfe._field_table(m.ys))
+    o_zt = blob.add(vfe._field_table(m.zs[m.z0: m.z0 + m.n_layers]))
+
+    # id-list segments of this rank, one per non-empty set, in file order
+    set_names = []
+    if 'NSET' in keywords:
+        set_names += [("N", q) for q in range(8)]
+    if 'ELSET' in keywords:
+        set_names += [("E", q) for q in range(6)]
+    segs, seg_sets, n_items = [], [], 0
+    for kind, q in set_names:
+        if kind == "N" and q >= 6:       # corner sets: first two entries of the GLOBAL NODES_Z0 / Z1
+            src = 4 if q == 6 else 5
+            before = m.set_rank0[src]
+            cnt = max(0, min(2 - before, m.set_count[src]))
+            f, r0 = m.set_first[src], before
+        else:
+            src = q if kind == "N" else 6 + q
+            cnt, f, r0 = m.set_count[src], m.set_first[src], m.set_rank0[src]
+        if cnt:
+            segs.append((1, n_items, 0, 0, f, r0))
+            seg_sets.append((kind, q))
+            n_items += cnt
+    seg_arr = (CfeItemSeg * max(len(segs), 1))()
+    for i, sg in enumerate(segs):
+        a = seg_arr[i]
+        a.kind, a.item0, a.lit_off, a.lit_len, a.id0, a.rank0 = sg
+    o_segs = blob.add(bytes(seg_arr))
+
+    max_node_id = (m.Zg + 1) * (Y + 1) * (X + 1) - 1
+    if max_node_id >= 10 ** 10:
+        raise NotImplementedError("node ids wider than the 10-character field are not supported")
+    max_line = len(str(m.n_el_global)) + 8 * len(str(max_node_id)) + 9
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        dblob = blob.to_device(dev)
+        base = dblob.data_ptr()
+        nodes_buf = torch.empty(max(53 * m.n_nd, 1), dtype=torch.uint8, device=dev)
+        elem_buf = torch.empty(max(m.n_el * max_line, 1) + 64, dtype=torch.uint8, device=dev)
+        items_buf = torch.empty(n_items * (len(str(max(max_node_id, m.n_el_global))) + 1) + 64, dtype=torch.uint8,
+                                device=dev)
+        totals = torch.zeros(2, dtype=torch.int64, device=dev)
+        blk_off = torch.zeros(256, dtype=torch.int64, device=dev)
+        seg_off = torch.zeros(max(len(segs), 1), dtype=torch.int64, device=dev)
+        ws = scan_workspace(max(m.n_el, n_items, 1), dev)
+        _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, base + o_xt, base + o_yt, base + o_zt,
+                  Y, X, m.z0, nodes_buf.data_ptr(), s)
+        perm = None
+        single_gv = int(gvs[0])
+        if len(gvs) > 1:
+            n_ptiles = lib.cfe_partition_tiles(m.n_el)
+            mat = empty_u32(256 * n_ptiles, dev)
+            mat_off = torch.empty(max(256 * n_ptiles, 1), dtype=torch.int64, device=dev)
+            perm = torch.empty((max(m.n_el, 1), 2), dtype=torch.int32, device=dev)
+            _lib.call("cfe_partition_hist", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, mat.data_ptr(), s)
+            ws_p = scan_workspace(256 * n_ptiles, dev)
+            scratch = torch.empty(1, dtype=torch.int64, device=dev)
+            _lib.call("cfe_scan_u32", mat.data_ptr(), 256 * n_ptiles, mat_off.data_ptr(), scratch.data_ptr(),
+                      ws_p.data_ptr(), s)
+            _lib.call("cfe_partition_scatter", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el,
+                      mat_off.data_ptr(), perm.data_ptr(), s)
+            single_gv = -1
+        _lib.call("cfe_emit_elements", m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(),
+                  base + o_first, base + o_hdr, base + o_hlen, single_gv if single_gv >= 0 else 0, Y, X, m.z0,
+                  m.eid_offset, elem_buf.data_ptr(), totals.data_ptr(), blk_off.data_ptr(), ws.data_ptr(), s)
+        _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base, items_buf.data_ptr(),
+                  None, totals.data_ptr() + 8, seg_off.data_ptr(), ws.data_ptr(), s)
+        # byte sizes of my (gv) element blocks and of my set segments
+        host = torch.cat([totals, blk_off, seg_off]).cpu().tolist()
+    el_total, it_total = host[0], host[1]
+    blk = host[2:258]
+    sgo = host[258:258 + len(segs)]
+    my_gvs = [int(g) for g in gvs if my_hist[g]]
+    gv_bytes = np.zeros(256, dtype=np.int64)
+    for i, g in enumerate(my_gvs):
+        end = blk[my_gvs[i + 1]] if i + 1 < len(my_gvs) else el_total
+        gv_bytes[g] = end - blk[g]
+    set_bytes = np.zeros(14, dtype=np.int64)
+    seg_local = {}
+    for i, (kind, q) in enumerate(seg_sets):
+        end = sgo[i + 1] if i + 1 < len(segs) else it_total
+        col = q if kind == "N" else 8 + q
+        set_bytes[col] = end - sgo[i]
+        seg_local[col] = (sgo[i], end)
+    mine = torch.from_numpy(np.concatenate([gv_bytes, set_bytes, [53 * m.n_nd]])).to(dev)
+    allb = yield from ctx.all_gather(mine)
+    allb = torch.stack(allb).cpu().numpy()             # [rank][256 + 14 + 1]
+
+    # ---- global file layout (identical on every rank)
+    writes = []        # (file offset, device tensor, lo, hi)
+    lits = []          # (file offset, bytes) -- written by rank 0
+    pos = 0
+    lits.append((pos, head)); pos += len(head)
+    for k in range(ctx.size):
+        nb = int(allb[k, 270])
+        if k == rank and nb:
+            writes.append((pos, nodes_buf, 0, nb))
+        pos += nb
+    lits.append((pos, elem_comment)); pos += len(elem_comment)
+    for g in gvs.tolist():
+        lits.append((pos, hdrs[g])); pos += len(hdrs[g])
+        for k in range(ctx.size):
+            nb = int(allb[k, g])
+            if k == rank and nb:
+                writes.append((pos, elem_buf, blk[g], blk[g] + nb))
+            pos += nb
+
+    def set_block(names, prologue, header_fmt, col0):
+        nonlocal pos
+        lits.append((pos, prologue)); pos += len(prologue)
+        for q, name in enumerate(names):
+            h = header_fmt.format(name).encode()
+            lits.append((pos, h)); pos += len(h)
+            for k in range(ctx.size):
+                nb = int(allb[k, 256 + col0 + q])
+                if k == rank and nb:
+                    lo, hi = seg_local[col0 + q]
+                    writes.append((pos, items_buf, lo, hi))
+                pos += nb
+            lits.append((pos, b'\n')); pos += 1
+
+    if 'NSET' in keywords:
+        set_block(vfe.NODE_SET_NAMES + ["NODES_X0Y0Z0", "NODES_X0Y0Z1"],
+                  ('** Additional nset from voxel model. New generated nsets are:\n'
+                   '** {}, \n'.format(vfe.NODE_SET_NAMES[0])).encode(), '*NSET, NSET={0}\n', 0)
+    if 'ELSET' in keywords:
+        set_block(vfe.CELL_SET_NAMES,
+                  ('** Additional elset from voxel model. New generated elsets are:\n'
+                   '** {}, \n'.format(vfe.CELL_SET_NAMES[0])).encode(), '*ELSET, ELSET={}\n', 8)
+    lits.append((pos, tail)); pos += len(tail)
+
+    d = SlabDeck()
+    d.rank, d.size = rank, ctx.size
+    d.total_bytes = pos
+    d.writes = writes
+    d.literals = lits if rank == 0 else []
+    d.buffers = (nodes_buf, elem_buf, items_buf, dblob)
+    d.local_bytes = sum(hi - lo for _, _, lo, hi in writes)
+    return d
+
+
+def write_deck_program(ctx, deck, fileout):
+    """All ranks write their pieces into ONE file at the offsets of the global layout."""
+    if ctx.rank == 0:
+        with open(fileout, "wb") as f:
+            f.truncate(deck.total_bytes)
+    yield from ctx.barrier()
+    fd = os.open(fileout, os.O_WRONLY)
+    try:
+        chunk = 256 << 20
+        for off, buf, lo, hi in deck.writes:
+            for a in range(lo, hi, chunk):
+                b = min(a + chunk, hi)
+                os.pwrite(fd, buf[a:b].cpu().numpy().tobytes(), off + (a - lo))
+        for off, data in deck.literals:
+            os.pwrite(fd, data, off)
+    finally:
+        os.close(fd)
+    yield from ctx.barrier()
+    return deck.total_bytes
+
+
+# --------------------------------------------------------------------------------------------
+# convenience drivers
+
+def _slab_inputs(vol, n):
+    """Cut a global (host or device) volume into n device slabs: [(uint8 slab tensor, z0)], is_bool."""
+    from ._util import as_device_volume
+    t, is_bool, _ = as_device_volume(vol)
+    return [(t[a:b].contiguous(), a) for a, b in slab_ranges(int(t.shape[0]), n)], is_bool, int(t.shape[0])
+
+
+def emulate_remove_unconnected(vol, n):
+    """N emulated ranks on one GPU: returns the global bool mask (numpy) and the winner."""
+    slabs, _, _ = _slab_inputs(vol, n)
+    runner = LocalRunner(n)
+    res = runner.run([ccl_program(c, s) for c, (s, _) in zip(runner.ctxs(), slabs)])
+    if res[0][1] is None:
+        raise ValueError("attempt to get argmax of an empty sequence")
+    mask = torch.cat([r[0] for r in res]).view(torch.bool)
+    return mask, res[0][1]
+
+
+def emulate_ct2inp(vol, n, voxelsize, templatefile, fileout, u_kwargs=None, m_kwargs=None):
+    """vol2ugrid + mesh2voxelfe on N emulated ranks of one GPU, written to `fileout`."""
+    slabs, is_bool, Zg = _slab_inputs(vol, n)
+    runner = LocalRunner(n)
+    meshes = runner.run([vol2ugrid_program(c, s, is_bool, Zg, z0, voxelsize, **(u_kwargs or {}))
+                         for c, (s, z0) in zip(runner.ctxs(), slabs)])
+    mk = dict(m_kwargs or {})
+    decks = runner.run([deck_program(c, m, templatefile, **{k: (v() if callable(v) else v) for k, v in mk.items()})
+                        for c, m in zip(runner.ctxs(), meshes)])
+    runner.run([write_deck_program(c, d, fileout) for c, d in zip(runner.ctxs(), decks)])
+    return meshes, decks

@@ -634,7 +634,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
                   base + o_first, base + o_hdr, base + o_hlen, single_gv, Y, X, 0, 0,
                   out.data_ptr() + off_elem, totals.data_ptr(), None, ws.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base + o_lits,
-                  out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, ws.data_ptr(), s)
+                  out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, None, ws.data_ptr(), s)
         _lib.call("cfe_put_literal", base + o_tail, len(tail), out.data_ptr() + off_elem, totals.data_ptr(),
                   totals.data_ptr() + 8, s)
         t = totals.cpu().tolist()

@@ -83,6 +83,26 @@ int cfe_ccl_largest(const uint32_t* bits, const uint32_t* run_pref, const uint64
                     int64_t Y, int64_t X, uint32_t* parent, uint32_t* size, uint64_t* best,
                     uint8_t* out_mask, cfe_stream_t s);
 
+/* The same work in three phases, for z-slab sharding (the cross-slab merge sits between 1 and 2):
+ *   cfe_ccl_label       parent[run] = slab-local root, size[root] = voxels inside the slab
+ *   cfe_ccl_select      *best = max over roots of (size << 32) | (0xffffffff - root)
+ *   cfe_ccl_write_mask  mask = runs whose root is the winner (keep == NULL) or has keep[root] != 0 */
+int cfe_ccl_label(const uint32_t* bits, const uint32_t* run_pref, const uint64_t* n_runs, int64_t Z, int64_t Y,
+                  int64_t X, uint32_t* parent, uint32_t* size, cfe_stream_t s);
+int cfe_ccl_select(const uint32_t* parent, const uint32_t* size, const uint64_t* n_runs, uint64_t* best,
+                   cfe_stream_t s);
+int cfe_ccl_write_mask(const uint32_t* bits, const uint32_t* run_pref, int64_t Z, int64_t Y, int64_t X,
+                       const uint32_t* parent, const uint64_t* best, const uint32_t* keep, uint8_t* out_mask,
+                       cfe_stream_t s);
+/* roots[k] = slab-local root of the k-th run of voxel plane `plane`; *count = runs in the plane */
+int cfe_ccl_plane_roots(const uint32_t* bits, const uint32_t* run_pref, int64_t plane, int64_t Y, int64_t X,
+                        const uint32_t* parent, uint32_t* roots, uint32_t* count, cfe_stream_t s);
+/* edges (rootA, rootB) between the neighbour slab's top plane A (bits, plane-local run prefixes,
+ * run roots: received over NCCL) and this slab's bottom plane B; *count may exceed capacity */
+int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* prefA, const uint32_t* rootsA,
+                            const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* parentB, int64_t Y,
+                            int64_t X, uint32_t* edges, uint32_t* count, int64_t capacity, cfe_stream_t s);
+
 /* ------------------------------------------------------------------ boundary sets */
 
 /* One boundary set = the candidates of a box of the node grid (kind 0/1) or voxel grid
@@ -138,7 +158,7 @@ int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab,
  * (single_gv); otherwise perm holds {voxel, raster rank} pairs in GV-major order and vol is
  * read for the grey value.  first[gv] = emission index of the first element of block gv;
  * hdr_text/hdr_len = '*ELEMENT, TYPE=.., ELSET=SET<gv>\n' per gv in 64-byte slots.
- * *total = bytes written; blk_off[gv] = offset of block gv's first line (optional). */
+ * *total = bytes written; blk_off[gv] = offset where block gv (header included) starts (optional). */
 int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
                       const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len, int single_gv,
                       int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, char* out, uint64_t* total,
@@ -155,9 +175,10 @@ typedef struct {
     int64_t rank0;    /* kind 1: 0-based position of that entry inside its (global) set */
 } CfeItemSeg;
 
+/* seg_off (optional, [n_segs]): byte offset of every segment inside the emitted stream */
 int cfe_emit_items(const CfeItemSeg* segs, int n_segs, int64_t n_items, const int64_t* ids,
-                   const char* literals, char* out_base, const uint64_t* dyn_off, uint64_t* total, void* ws,
-                   cfe_stream_t s);
+                   const char* literals, char* out_base, const uint64_t* dyn_off, uint64_t* total,
+                   uint64_t* seg_off, void* ws, cfe_stream_t s);
 
 /* literal text to out + *dyn0 + *dyn1 (either may be NULL) */
 int cfe_put_literal(const char* src, int64_t n, char* out, const uint64_t* dyn0, const uint64_t* dyn1,

@@ -1,0 +1,169 @@
+"""GPU tests (-m gpu) of the z-slab sharded path.  On a one-GPU box the N ranks are emulated in
+lock-step inside one process (sharded.LocalRunner): same kernels, same offsets, same collectives'
+results.  With >= 2 GPUs a real 2-rank NCCL run is compared with the single-GPU deck as well."""
+import hashlib
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sh():
+    import torch
+    assert torch.cuda.is_available()
+    from ciclope_b200 import sharded
+    return sharded
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+CCL_NAMES = [n for n, v in cases.ccl_cases() if v.shape[0] >= 2]
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 8])
+@pytest.mark.parametrize("name", CCL_NAMES)
+def test_sharded_ccl_golden(sh, golden_ccl, name, n):
+    shape = tuple(golden_ccl[name + "/shape"])
+    if shape[0] < n:
+        pytest.skip("fewer slices than slabs")
+    k = int(np.prod(shape))
+    bw = np.unpackbits(golden_ccl[name + "/in"])[:k].astype(bool).reshape(shape)
+    want = np.unpackbits(golden_ccl[name + "/out"])[:k].astype(bool).reshape(shape)
+    mask, _ = sh.emulate_remove_unconnected(bw, n)
+    assert np.array_equal(mask.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+@pytest.mark.parametrize("shape,density,seed,kind", [
+    ((16, 24, 64), 0.3, 1, "rand"), ((24, 32, 96), 0.22, 2, "rand"), ((32, 48, 64), 0.3, 3, "blobs"),
+    ((64, 64, 64), 0.12, 4, "blobs"), ((33, 20, 70), 0.4, 5, "rand"), ((48, 48, 128), 0.3, 6, "blobs")])
+def test_sharded_ccl_vs_oracle(sh, orc, shape, density, seed, kind, n):
+    bw = cases.rand_binary(shape, density, 500 + seed) if kind == "rand" else cases.blobs(shape, density, seed)
+    mask, winner = sh.emulate_remove_unconnected(bw, n)
+    want = orc.remove_unconnected(bw)
+    assert np.array_equal(mask.cpu().numpy(), want)
+    assert winner[0] == int(want.sum())
+
+
+def test_sharded_ccl_u_shape_across_slabs(sh, orc):
+    # two prongs that only join in the LAST slab: slab-local components must be merged globally, and a
+    # bigger slab-internal blob must not win against the merged component
+    bw = np.zeros((16, 12, 40), dtype=bool)
+    bw[0:15, 2, 5] = True
+    bw[0:15, 9, 30] = True
+    bw[15, 2:10, 5] = True
+    bw[15, 9, 5:31] = True
+    bw[3:5, 5:8, 10:20] = True          # 60-voxel blob inside one slab (smaller than the U: 64)
+    for n in (2, 4, 8, 16):
+        mask, winner = sh.emulate_remove_unconnected(bw, n)
+        assert np.array_equal(mask.cpu().numpy(), orc.remove_unconnected(bw)), n
+    bw[3:6, 5:8, 10:20] = True          # now the blob (90) wins
+    for n in (2, 4, 8):
+        mask, _ = sh.emulate_remove_unconnected(bw, n)
+        assert np.array_equal(mask.cpu().numpy(), orc.remove_unconnected(bw)), n
+
+
+def test_sharded_ccl_empty(sh):
+    with pytest.raises(ValueError):
+        sh.emulate_remove_unconnected(np.zeros((4, 4, 8), dtype=bool), 2)
+
+
+DECK_NAMES = [c["name"] for c in cases.deck_cases() if np.asarray(c["vol"]).shape[0] >= 2]
+DECK_CASES = {c["name"]: c for c in cases.deck_cases()}
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("name", DECK_NAMES)
+def test_sharded_deck_golden(sh, golden, name, n, tmp_path):
+    c = DECK_CASES[name]
+    if np.asarray(c["vol"]).shape[0] < n:
+        pytest.skip("fewer slices than slabs")
+    u = dict(c["u"])
+    vs = u.pop("voxelsize")
+    m = dict(c["m"])
+    tmpl = m.pop("templatefile")
+    out = str(tmp_path / "deck.inp")
+    sh.emulate_ct2inp(c["vol"], n, vs, tmpl, out, u_kwargs=u, m_kwargs=m)
+    got = cases.mask_timestamp(open(out, "rb").read())
+    want = bytes(golden[name + "/deck"])
+    if got != want:
+        for i, (a, b) in enumerate(zip(got.split(b"\n"), want.split(b"\n"))):
+            assert a == b, "first differing line %d: got %r want %r" % (i, a, b)
+    assert got == want
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+@pytest.mark.parametrize("grey", [False, True])
+def test_sharded_full_path_vs_oracle(sh, orc, n, grey, tmp_path):
+    bw = cases.blobs((40, 48, 96), 0.3, 77)
+    mask, _ = sh.emulate_remove_unconnected(bw, n)
+    L = mask.cpu().numpy()
+    L_ref = orc.remove_unconnected(bw)
+    assert np.array_equal(L, L_ref)
+    vol = cases.grey_from_mask(L, 78) if grey else L
+    m = {}
+    if grey:
+        m = dict(keywords=['NSET', 'ELSET', 'PROPERTY'],
+                 matprop=lambda: {"file": [cases.MAT_LINEAR], "range": [[1, 255]]})
+    out = str(tmp_path / "gpu.inp")
+    meshes, decks = sh.emulate_ct2inp(vol, n, [0.0195] * 3, cases.TEMPLATE, out, m_kwargs=m)
+    mm = {k: (v() if callable(v) else v) for k, v in m.items()}
+    orc.mesh2voxelfe(orc.vol2ugrid(vol, [0.0195] * 3), cases.TEMPLATE, str(tmp_path / "cpu.inp"), **mm)
+    got = cases.mask_timestamp(open(out, "rb").read())
+    want = cases.mask_timestamp(open(str(tmp_path / "cpu.inp"), "rb").read())
+    assert len(got) == len(want) == decks[0].total_bytes
+    assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+    assert sum(mesh.n_el for mesh in meshes) == int(L.sum())
+
+
+_NCCL_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from ciclope_b200 import sharded
+from tests import cases
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+bw = cases.blobs((40, 48, 96), 0.3, 77)
+a, b = sharded.slab_ranges(bw.shape[0], world)[rank]
+slab = torch.from_numpy(bw[a:b].copy()).cuda().view(torch.uint8)
+runner = sharded.DistRunner()
+mask, winner = runner.run(sharded.ccl_program(runner.ctx(), slab))
+mesh = runner.run(sharded.vol2ugrid_program(runner.ctx(), mask, True, bw.shape[0], a, [0.0195] * 3))
+deck = runner.run(sharded.deck_program(runner.ctx(), mesh, cases.TEMPLATE))
+runner.run(sharded.write_deck_program(runner.ctx(), deck, {out!r}))
+dist.destroy_process_group()
+"""
+
+
+def test_real_nccl_two_ranks(orc, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "nccl.inp")
+    script = tmp_path / "worker.py"
+    script.write_text(_NCCL_WORKER.format(root=ROOT, out=out))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       cwd=ROOT, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]
+    bw = cases.blobs((40, 48, 96), 0.3, 77)
+    L = orc.remove_unconnected(bw)
+    orc.mesh2voxelfe(orc.vol2ugrid(L, [0.0195] * 3), cases.TEMPLATE, str(tmp_path / "cpu.inp"))
+    assert cases.mask_timestamp(open(out, "rb").read()) == \
+        cases.mask_timestamp(open(str(tmp_path / "cpu.inp"), "rb").read())
