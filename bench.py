@@ -95,7 +95,9 @@ def workload_config(size, n_gpus, note=None):
                        "vol2ugrid + mesh2voxelfe (BASELINE.json configs[1])" % size,
            "volume_per_gpu": [size, size, size], "voxelsize": VOXELSIZE[0], "bvtv": 0.30, "seed": 0,
            "template": "tests/golden/tmpl_compression.inp", "keywords": ["NSET", "ELSET"],
-           "parallelism": "1 process per GPU" if n_gpus == 1 else "%d independent z-slab replicas" % n_gpus,
+           "parallelism": "1 GPU" if n_gpus == 1 else
+           "z-slabs: global volume [%d,%d,%d] cut into %d slabs of %d slices, one process per GPU, NCCL "
+           "plane shifts + count/byte all-gathers" % (size * n_gpus, size, size, n_gpus, size),
            "l2": "inputs+outputs per step (0.13 GB volume, ~6 GB deck at 512^3) exceed the 126 MB L2; no flush"}
     if note:
         cfg["note"] = note
@@ -173,6 +175,42 @@ def gpu_step_e2e(vol_host, vol_dev, sink):
     return mesh, n
 
 
+class _Sized:
+    """what the bookkeeping below needs from a step's result"""
+
+    def __init__(self, n_el, n_nd, nbytes):
+        self.n_el, self.n_nd, self.nbytes = n_el, n_nd, nbytes
+
+    def numel(self):
+        return self.nbytes
+
+
+def make_sharded_steps(runner, Zg, z0):
+    """N > 1: the same path as rank programs over torch.distributed (ciclope_b200.sharded)."""
+    from ciclope_b200 import sharded
+
+    def step(vol_dev):
+        u8 = vol_dev.view(__import__("torch").uint8)
+        mask, winner = runner.run(sharded.ccl_program(runner.ctx(), u8))
+        if winner is None:
+            raise ValueError("attempt to get argmax of an empty sequence")
+        mesh = runner.run(sharded.vol2ugrid_program(runner.ctx(), mask, True, Zg, z0, VOXELSIZE))
+        deck = runner.run(sharded.deck_program(runner.ctx(), mesh, TEMPLATE))
+        return mesh, deck
+
+    def step_e2e(vol_host, vol_dev, sink):
+        vol_dev.copy_(vol_host, non_blocking=True)
+        mesh, deck = step(vol_dev)
+        pos = 0
+        for _, buf, lo, hi in deck.writes:       # this rank's pieces of the global deck
+            sink[pos:pos + hi - lo].copy_(buf[lo:hi], non_blocking=True)
+            pos += hi - lo
+        __import__("torch").cuda.current_stream().synchronize()
+        return mesh, pos
+
+    return step, step_e2e
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -183,7 +221,19 @@ def run_gpu(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     lib = _lib.require_cuda()
     S = args.size
-    vol = synth.trabecular((S, S, S), seed=rank, bvtv=0.30, device=dev)
+    global gpu_step, gpu_step_e2e
+    if world == 1:
+        vol = synth.trabecular((S, S, S), seed=0, bvtv=0.30, device=dev)
+    else:
+        from ciclope_b200 import sharded
+        Zg, z0 = S * world, S * rank
+        vol = synth.trabecular_slab((Zg, S, S), z0, z0 + S, seed=0, bvtv=0.30, device=dev)
+        sh_step, sh_step_e2e = make_sharded_steps(sharded.DistRunner(), Zg, z0)
+
+        def gpu_step(v):
+            mesh, deck = sh_step(v)
+            return mesh, _Sized(mesh.n_el, mesh.n_nd, deck.local_bytes)
+        gpu_step_e2e = sh_step_e2e
     n_vox = vol.numel()
 
     def barrier():

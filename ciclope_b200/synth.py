@@ -72,3 +72,43 @@ def greyscale(shape, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3):
     fmax = int(f.max().item())
     g = 1 + ((f - t).clamp(min=0).to(torch.int64) * 254 // max(fmax - t, 1)).clamp(max=254)
     return torch.where(f > t, g.to(torch.uint8), torch.zeros((), dtype=torch.uint8, device=f.device))
+
+
+def trabecular_slab(global_shape, z0, z1, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3, group=None):
+    """Slab [z0, z1) of the GLOBAL trabecular volume of shape `global_shape`, generated without ever
+    holding the global field: the noise is a pure function of the global voxel index and the z-blur
+    only needs a halo of radius*passes slices (periodic in the global z).  The threshold comes from
+    the all-reduced histogram when a process group is initialised; every rank then holds exactly
+    the slab that `trabecular(global_shape, ...)[z0:z1]` would give."""
+    Zg, Y, X = global_shape
+    h = radius * passes
+    if Zg < z1 - z0 + 2 * h:
+        f = field(global_shape, seed, device, radius, passes)[z0:z1]
+    else:
+        zs = (torch.arange(z0 - h, z1 + h, device=device, dtype=torch.int64) % Zg).view(-1, 1, 1)
+        y = torch.arange(Y, device=device, dtype=torch.int64).view(1, Y, 1)
+        x = torch.arange(X, device=device, dtype=torch.int64).view(1, 1, X)
+        idx = (zs * Y + y) * X + x
+        v = idx + _i64(seed * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019)
+        v = (v ^ _lsr(v, 30)) * _i64(0xBF58476D1CE4E5B9)
+        v = (v ^ _lsr(v, 27)) * _i64(0x94D049BB133111EB)
+        v = v ^ _lsr(v, 31)
+        f = _lsr(v, 48).to(torch.int32)
+        del v, idx
+        for _ in range(passes):
+            for axis in range(3):
+                f = _box(f, axis, radius)
+        f = f[h: h + (z1 - z0)].contiguous()
+    hist = torch.bincount(f.reshape(-1).to(torch.int64), minlength=65536)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, group=group)
+        n = Zg * Y * X
+    else:
+        n = f.numel() if (z0, z1) == (0, Zg) else None
+        if n is None:
+            raise RuntimeError("trabecular_slab needs an initialised process group to threshold a partial volume")
+    above = hist.flip(0).cumsum(0).flip(0)
+    ok = (above[1:] <= int(bvtv * n)).nonzero()
+    t = int(ok[0].item())
+    return f > t
