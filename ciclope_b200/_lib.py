@@ -56,7 +56,7 @@ _SIGNATURES = {
     "cfe_fill_points": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_emit_nodes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_emit_elements": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,
-                                  c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                  c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cfe_emit_items": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cfe_put_literal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_gv_histogram": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),

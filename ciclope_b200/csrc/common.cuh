@@ -54,8 +54,14 @@ __device__ __forceinline__ u32 scan_next_tile(u64* ws)
     return s_tile;
 }
 
-// Must be called by every lane of warp 0.  Returns the exclusive prefix of `tile` (sum of the
-// aggregates of tiles 0..tile-1) in every lane of warp 0 and publishes the inclusive prefix.
+// Must be called by every lane of ONE warp.  Returns the exclusive prefix of `tile` (sum of the
+// aggregates of tiles 0..tile-1) in every lane of that warp and publishes the inclusive prefix.
+//
+// The window is 32 * SCAN_LB_DEPTH predecessors per round trip to L2: with small, fast tiles the
+// nearest published prefix is "number of tiles in flight" (hundreds) behind, and a 32-wide window
+// makes the whole kernel wait on (tiles in flight / 32) serial L2 latencies per tile.
+#define SCAN_LB_DEPTH 2
+
 __device__ __forceinline__ u64 scan_lookback(u64* ws, u32 tile, u64 aggregate)
 {
     volatile u64* status = ws + 1;
@@ -67,23 +73,32 @@ __device__ __forceinline__ u64 scan_lookback(u64* ws, u32 tile, u64 aggregate)
     if (lane == 0) status[tile] = SCAN_FLAG_A | aggregate;
     u64 excl = 0;
     int base = (int)tile - 1;
-    while (true) {
-        int idx = base - (int)lane;
-        u64 v = SCAN_FLAG_P;  // virtual predecessors (index < 0) are an inclusive prefix of 0
-        if (idx >= 0) {
-            do { v = status[idx]; } while ((v >> 62) == 0ull);
-        }
-        u32 pmask = __ballot_sync(CFE_FULL_MASK, (v >> 62) == 2ull);
-        u64 val = v & SCAN_VAL_MASK;
-        if (pmask) {
-            u32 first = (u32)__ffs((int)pmask) - 1u;  // nearest predecessor holding a prefix
-            if (lane > first) val = 0;
+    bool done = false;
+    while (!done) {
+        u64 v[SCAN_LB_DEPTH];
+#pragma unroll
+        for (int k = 0; k < SCAN_LB_DEPTH; ++k) {
+            const int idx = base - (int)lane - 32 * k;
+            v[k] = idx >= 0 ? status[idx] : SCAN_FLAG_P;  // virtual predecessors: inclusive prefix 0
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(CFE_FULL_MASK, val, o);
-        excl += val;
-        if (pmask) break;
-        base -= 32;
+        for (int k = 0; k < SCAN_LB_DEPTH; ++k) {
+            if (!done) {                                   // warp-uniform
+                const int idx = base - (int)lane - 32 * k;
+                while ((v[k] >> 62) == 0ull) v[k] = status[idx];   // not published yet: spin
+                const u32 pmask = __ballot_sync(CFE_FULL_MASK, (v[k] >> 62) == 2ull);
+                u64 val = v[k] & SCAN_VAL_MASK;
+                if (pmask) {
+                    const u32 first = (u32)__ffs((int)pmask) - 1u;  // nearest predecessor holding a prefix
+                    if (lane > first) val = 0;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(CFE_FULL_MASK, val, o);
+                excl += val;
+                if (pmask) done = true;
+            }
+        }
+        base -= 32 * SCAN_LB_DEPTH;
     }
     if (lane == 0) status[tile] = SCAN_FLAG_P | (excl + aggregate);
     return excl;
@@ -167,6 +182,17 @@ __device__ __forceinline__ int digits_u64(u64 v)
     if (w >= 100u) return d + 2;
     if (w >= 10u) return d + 1;
     return d;
+}
+
+// decimal digits of a 32-bit value by binary search (4 compares)
+__device__ __forceinline__ int digits_u32(u32 v)
+{
+    if (v >= 100000u) {
+        if (v >= 10000000u) return v >= 1000000000u ? 10 : (v >= 100000000u ? 9 : 8);
+        return v >= 1000000u ? 7 : 6;
+    }
+    if (v >= 100u) return v >= 10000u ? 5 : (v >= 1000u ? 4 : 3);
+    return v >= 10u ? 2 : 1;
 }
 
 __device__ __forceinline__ u32 mask_lt(int b) { return (b >= 32) ? 0xffffffffu : ((1u << b) - 1u); }

@@ -60,6 +60,52 @@ __device__ __forceinline__ void flush_stage(const char* stage, u32 pad, u32 n, c
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// SWAR decimal formatting.  raw4(g): the four decimal digits of g < 10000, one per byte, most
+// significant digit in the LOW byte (= first in memory); add 0x30303030 for ASCII.
+__device__ __forceinline__ u32 raw4(u32 g)
+{
+    const u32 hi = (g * 5243u) >> 19;                    // g / 100   (exact for g < 10000)
+    const u32 lo = g - hi * 100u;
+    const u32 x = hi | (lo << 16);
+    const u32 t = ((x * 103u) >> 10) & 0x000F000Fu;      // tens digit of each pair
+    const u32 o = x - t * 10u;                           // ones digit of each pair
+    return t | (o << 8);
+}
+
+// 12 zero-padded decimal digits of v (< 10^12) as three raw4 words, first word = most significant.
+template <bool WIDE>
+__device__ __forceinline__ void raw12(u64 v, u32& r0, u32& r1, u32& r2, u32& low4)
+{
+    u32 a, rem;
+    if (WIDE) {
+        const u64 q = v / 100000000ull;
+        a = (u32)q;
+        rem = (u32)(v - q * 100000000ull);
+    } else {
+        const u32 vv = (u32)v;
+        a = vv / 100000000u;
+        rem = vv - a * 100000000u;
+    }
+    const u32 b = rem / 10000u;
+    low4 = rem - b * 10000u;
+    r0 = raw4(a);
+    r1 = raw4(b);
+    r2 = raw4(low4);
+}
+
+// number of significant digits (>= 1) of the 12-digit raw representation
+__device__ __forceinline__ int raw12_digits(u32 r0, u32 r1, u32 r2)
+{
+    int lz;
+    if (r0) lz = (__ffs((int)r0) - 1) >> 3;
+    else if (r1) lz = 4 + ((__ffs((int)r1) - 1) >> 3);
+    else if (r2) lz = 8 + ((__ffs((int)r2) - 1) >> 3);
+    else lz = 11;
+    return 12 - lz;
+}
+
 // ------------------------------------------------------------------------------------------
 // *NODE section: fixed 53-byte lines, one thread per used node.
 
@@ -113,6 +159,87 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_nodes(NodeEmitParams P)
     flush_stage(stage, pad, n_here * 53u, dst);
 }
 
+
+// Fast path: one thread formats FOUR consecutive node lines (212 bytes = 53 words), so every byte
+// position inside the thread's block is a compile-time constant and the staging buffer is filled
+// with aligned 32-bit stores (stride 53 words between threads: bank-conflict free).  Requires a
+// 4-byte aligned destination (the callers align the *NODE section to 16 bytes).
+#define NODE4_THREADS 128
+#define NODE4_PER_CTA (NODE4_THREADS * 4)
+
+__device__ __forceinline__ void node_line_words(const NodeEmitParams& P, u32 v, u32 (&L)[14])
+{
+    const u32 s = fd_div(v, P.dSN);
+    const u32 rem = v - s * P.SN32;
+    const u32 r = fd_div(rem, P.dRN);
+    const u32 c = rem - r * P.RN32;
+    const u64 id = (u64)P.SN32 * (u64)((i64)s + P.z0) + (u64)rem;
+    u32 r0, r1, r2, low4;
+    raw12<true>(id, r0, r1, r2, low4);
+    const int nd = raw12_digits(r0, r1, r2);
+    // '{:10d}': blank the leading zeros (chars [0, 12-nd)) -> ' ' = '0' - 0x10
+    const int blank = 12 - nd;
+    u32 I[3] = {r0 + 0x30303030u, r1 + 0x30303030u, r2 + 0x30303030u};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int bc = blank - 4 * i;
+        const u32 m = bc >= 4 ? 0x10101010u : (bc <= 0 ? 0u : (0x10101010u & ((1u << (8 * bc)) - 1u)));
+        I[i] -= m;
+    }
+    const uint4 fx = __ldg(reinterpret_cast<const uint4*>(P.xtab) + c);
+    const uint4 fy = __ldg(reinterpret_cast<const uint4*>(P.ytab) + r);
+    const uint4 fz = __ldg(reinterpret_cast<const uint4*>(P.ztab) + s);
+    const u32 CS = 0x0000202Cu;   // ", "
+    L[0] = __byte_perm(I[0], I[1], 0x5432);   // id chars 2..5
+    L[1] = __byte_perm(I[1], I[2], 0x5432);   // id chars 6..9
+    L[2] = __byte_perm(I[2], CS, 0x5432);     // id chars 10,11 + ", "
+    L[3] = fx.x; L[4] = fx.y; L[5] = fx.z;
+    L[6] = __byte_perm(CS, fy.x, 0x5410);     // ", " + y chars 0,1
+    L[7] = __byte_perm(fy.x, fy.y, 0x5432);
+    L[8] = __byte_perm(fy.y, fy.z, 0x5432);
+    L[9] = __byte_perm(fy.z, CS, 0x5432);     // y chars 10,11 + ", "
+    L[10] = fz.x; L[11] = fz.y; L[12] = fz.z;
+    L[13] = 0x0000000Au;                      // '\n'
+}
+
+__global__ void __launch_bounds__(NODE4_THREADS) k_emit_nodes4(NodeEmitParams P)
+{
+    __shared__ __align__(16) u32 stage[NODE4_THREADS * 53];
+    const i64 k0 = (i64)blockIdx.x * NODE4_PER_CTA;           // first node of this CTA
+    const i64 k = k0 + (i64)threadIdx.x * 4;
+    u32* B = stage + threadIdx.x * 53;
+    if (k + 3 < P.n_nodes) {
+        const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(P.node_list + k));
+        const u32 vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        u32 pending = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            u32 L[14];
+            node_line_words(P, vv[q], L);
+            const int sh = 8 * q;                              // (53 q) mod 4 == q
+            B[13 * q] = pending | (L[0] << sh);
+#pragma unroll
+            for (int i = 1; i < 13; ++i) B[13 * q + i] = sh ? __funnelshift_l(L[i - 1], L[i], sh) : L[i];
+            pending = sh ? __funnelshift_l(L[12], L[13], sh) : L[13];
+        }
+        B[52] = pending;
+    }
+    __syncthreads();
+    i64 n_here = P.n_nodes - k0;
+    if (n_here > NODE4_PER_CTA) n_here = NODE4_PER_CTA;
+    const u32 nbytes = (u32)n_here * 53u;                      // n_here is a multiple of 4
+    char* dst = P.out + k0 * 53;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const u32 n16 = nbytes >> 4;
+        for (u32 c = threadIdx.x; c < n16; c += blockDim.x)
+            reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(stage)[c];
+        for (u32 c = (n16 << 2) + threadIdx.x; c < (nbytes >> 2); c += blockDim.x)
+            reinterpret_cast<u32*>(dst)[c] = stage[c];
+    } else {
+        for (u32 c = threadIdx.x; c < (nbytes >> 2); c += blockDim.x) reinterpret_cast<u32*>(dst)[c] = stage[c];
+    }
+}
+
 extern "C" int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab, const char* ytab,
                               const char* ztab, int64_t Y, int64_t X, int64_t z0, char* out,
                               cudaStream_t stream)
@@ -123,9 +250,24 @@ extern "C" int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const 
     P.SN32 = (u32)((X + 1) * (Y + 1)); P.RN32 = (u32)(X + 1);
     P.dSN = make_fastdiv(P.SN32); P.dRN = make_fastdiv(P.RN32);
     P.z0 = z0; P.out = out;
-    const i64 blocks = (n_nodes + EMIT_THREADS - 1) / EMIT_THREADS;
-    k_emit_nodes<<<(unsigned)blocks, EMIT_THREADS, 0, stream>>>(P);
-    CFE_CHECK_LAUNCH("k_emit_nodes");
+    i64 done = 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(out) & 3u) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(node_list) & 15u) == 0);
+    if (aligned && n_nodes >= 4) {
+        P.n_nodes = n_nodes & ~3ll;
+        const i64 blocks = (P.n_nodes + NODE4_PER_CTA - 1) / NODE4_PER_CTA;
+        k_emit_nodes4<<<(unsigned)blocks, NODE4_THREADS, 0, stream>>>(P);
+        CFE_CHECK_LAUNCH("k_emit_nodes4");
+        done = P.n_nodes;
+    }
+    if (done < n_nodes) {   // generic byte-wise kernel: unaligned destination or the last n % 4 nodes
+        P.node_list = node_list + done;
+        P.n_nodes = n_nodes - done;
+        P.out = out + done * 53;
+        const i64 blocks = (P.n_nodes + EMIT_THREADS - 1) / EMIT_THREADS;
+        k_emit_nodes<<<(unsigned)blocks, EMIT_THREADS, 0, stream>>>(P);
+        CFE_CHECK_LAUNCH("k_emit_nodes");
+    }
     return 0;
 }
 
@@ -134,7 +276,7 @@ extern "C" int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const 
 
 #define ELEM_HDR_SLOT 64      // bytes reserved per '*ELEMENT, TYPE=..., ELSET=SET<gv>\n' header
 #define ELEM_MAX_LINE 192     // eid (<= 20) + 8 node ids (<= 20 each) + 9 separators
-#define ELEM_STAGE_BYTES (EMIT_THREADS * 100 + 4096 + 32)
+#define ELEM_STAGE_BYTES (EMIT_THREADS * 100 + 2048 + 32)
 
 struct ElemEmitParams {
     const u32* elem_vox;     // raster-ordered local voxel indices (PERM = false)
@@ -154,20 +296,142 @@ struct ElemEmitParams {
     u64* ws;                 // look-back workspace
 };
 
-template <bool PERM>
-__global__ void __launch_bounds__(EMIT_THREADS) k_emit_elements(ElemEmitParams P)
+// Line builder: bytes are appended to a 32-bit accumulator and leave as aligned 32-bit
+// shared-memory stores; only the first and last partial words of a line use byte stores.
+struct LineWriter {
+    char* wp;      // 4-byte aligned staging address of the word being assembled
+    u32 acc;       // its low `d` bytes are valid
+    u32 d;         // 0..3
+    u32 lead;      // > 0 until the first word has been stored: bytes [0, lead) of it belong to the
+                   // previous line and must not be overwritten (only looked at when FIRST)
+};
+
+// append the nd significant digits of a raw12 number followed by `sep`.  FIRST = the line's first
+// word may still be pending (fields 0 and 1); later fields use plain predicated word stores.
+template <bool FIRST>
+__device__ __forceinline__ void lw_append(LineWriter& w, u32 r0, u32 r1, u32 r2, int nd, u32 sep)
+{
+    const u32 W0 = r0 + 0x30303030u, W1 = r1 + 0x30303030u, W2 = r2 + 0x30303030u;
+    const int skip = 12 - nd;                 // leading characters to drop (2..11)
+    const u32 sb = (u32)(skip & 3) * 8u;
+    // x0..x3 = the 16-byte string W0 W1 W2 sep shifted left by (skip / 4) words
+    const bool s1 = skip >= 4, s2 = skip >= 8;
+    const u32 x0 = s2 ? W2 : (s1 ? W1 : W0);
+    const u32 x1 = s2 ? sep : (s1 ? W2 : W1);
+    const u32 x2 = s2 ? 0u : (s1 ? sep : W2);
+    const u32 x3 = s1 ? 0u : sep;
+    // left-aligned field: nd digits, separator, zeros
+    const u32 A0 = __funnelshift_r(x0, x1, sb), A1 = __funnelshift_r(x1, x2, sb), A2 = __funnelshift_r(x2, x3, sb);
+    const u32 s8 = w.d * 8u;
+    const u32 O0 = w.acc | (A0 << s8);
+    const u32 O1 = __funnelshift_l(A0, A1, s8);
+    const u32 O2 = __funnelshift_l(A1, A2, s8);
+    const u32 O3 = __funnelshift_l(A2, 0u, s8);
+    const u32 tot = w.d + (u32)nd + 1u;       // bytes now held by O0..O3 (<= 14)
+    u32* p = reinterpret_cast<u32*>(w.wp);
+    if (FIRST) {
+        if (tot >= 4u) {
+            if (w.lead) {
+#pragma unroll
+                for (u32 k = 1; k < 4; ++k)
+                    if (k >= w.lead) w.wp[k] = (char)(O0 >> (8 * k));
+                w.lead = 0;
+            } else {
+                p[0] = O0;
+            }
+        }
+    } else {
+        if (tot >= 4u) p[0] = O0;
+    }
+    if (tot >= 8u) p[1] = O1;
+    if (tot >= 12u) p[2] = O2;
+    w.acc = tot >= 8u ? (tot >= 12u ? O3 : O2) : (tot >= 4u ? O1 : O0);
+    w.wp += tot & ~3u;
+    w.d = tot & 3u;
+}
+
+__device__ __forceinline__ void lw_finish(LineWriter& w)
+{
+    // the last partial word shares its upper bytes with the next line: byte stores
+#pragma unroll
+    for (u32 k = 0; k < 3; ++k)
+        if (k < w.d) w.wp[k] = (char)(w.acc >> (8 * k));
+}
+
+// Copy n staged bytes (stage[0..n), stage 16-byte aligned) to an arbitrarily aligned global dst:
+// aligned 16-byte global stores assembled from two aligned 16-byte shared loads and a byte funnel.
+__device__ __forceinline__ void flush_unaligned(const char* stage, u32 n, char* dst)
+{
+    const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    char* gbase = dst - pad;                       // 16-byte aligned; chunk c = [gbase+16c, +16)
+    const u32 end = pad + n;
+    const u32 c_first = pad ? 1u : 0u;             // first chunk fully inside the span
+    const u32 c_last = end >> 4;                   // one past the last full chunk
+    // chunk c takes staged bytes [16c - pad, 16c - pad + 16) = 16(c-1) + (16 - pad) when pad > 0
+    const u32 off = (16u - pad) & 15u;             // byte offset inside the aligned staged block
+    const u32 wsel = off >> 2, bs = (off & 3u) * 8u;
+    const uint4* sv = reinterpret_cast<const uint4*>(stage);
+    for (u32 c = c_first + threadIdx.x; c < c_last; c += blockDim.x) {
+        const u32 blk = pad ? c - 1u : c;
+        const uint4 a = sv[blk];
+        uint4 o;
+        if (off == 0) {
+            o = a;
+        } else {
+            const uint4 b = sv[blk + 1];
+            u32 x0, x1, x2, x3, x4;
+            if (wsel == 0) { x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w; x4 = b.x; }
+            else if (wsel == 1) { x0 = a.y; x1 = a.z; x2 = a.w; x3 = b.x; x4 = b.y; }
+            else if (wsel == 2) { x0 = a.z; x1 = a.w; x2 = b.x; x3 = b.y; x4 = b.z; }
+            else { x0 = a.w; x1 = b.x; x2 = b.y; x3 = b.z; x4 = b.w; }
+            o.x = __funnelshift_r(x0, x1, bs); o.y = __funnelshift_r(x1, x2, bs);
+            o.z = __funnelshift_r(x2, x3, bs); o.w = __funnelshift_r(x3, x4, bs);
+        }
+        *reinterpret_cast<uint4*>(gbase + 16u * c) = o;
+    }
+    // partial head / tail chunks: bytes
+    if (pad) {
+        const u32 hb = (16u - pad) < n ? (16u - pad) : n;
+        for (u32 k = threadIdx.x; k < hb; k += blockDim.x) dst[k] = stage[k];
+    }
+    if (c_last >= c_first && (c_last << 4) < end && (c_last << 4) >= pad) {
+        const u32 s0 = (c_last << 4) - pad;        // first staged byte of the tail chunk
+        for (u32 k = s0 + threadIdx.x; k < n; k += blockDim.x) dst[k] = stage[k];
+    }
+}
+
+// 8 worker warps format one element each; a 9th warp only runs the decoupled look-back.
+// Phase 0 computes nothing but the line LENGTHS (digit counts of the ids) so that the tile's
+// aggregate is published within a few hundred cycles of the CTA's start -- successors spin on it.
+// Phase 1 (digit generation, staging) then overlaps the look-back; lines are staged at their
+// tile-local offsets and the flush realigns them to the destination.
+#define ELEM_CTA_THREADS (EMIT_THREADS + 32)
+
+template <bool WIDE>
+__device__ __forceinline__ int id_digits(u64 v)
+{
+    if (WIDE && (v >> 32)) return digits_u64(v);
+    return digits_u32((u32)v);
+}
+
+// PERM: elements come from the GV-major permutation; WIDE: ids may exceed 32 bits.
+template <bool PERM, bool WIDE>
+__global__ void __launch_bounds__(ELEM_CTA_THREADS) k_emit_elements(ElemEmitParams P)
 {
     extern __shared__ __align__(16) char stage[];
     __shared__ u32 s_scan[33];
     __shared__ u64 s_base;
     const u32 tile = scan_next_tile(P.ws);
+    const bool worker = threadIdx.x < EMIT_THREADS;
     const i64 j = (i64)tile * EMIT_THREADS + threadIdx.x;
-    u64 val[9];
-    int nd[9];
+    const bool active = worker && j < P.n_el;
+    // ---- phase 0: line lengths
+    u64 b = 0, eid = 0;
+    int nd0 = 0, nlo = 0, nhi = 0;
     u32 len = 0, hl = 0;
     bool is_first = false;
     int gv = P.single_gv;
-    if (j < P.n_el) {
+    if (active) {
         u32 v, rank;
         if (PERM) { const uint2 e = __ldg(P.perm + j); v = e.x; rank = e.y; gv = (int)__ldg(P.vol + v); }
         else { v = __ldg(P.elem_vox + j); rank = (u32)j; }
@@ -175,55 +439,103 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit_elements(ElemEmitParams P
         const u32 rem = v - s * P.YX32;
         const u32 r = fd_div(rem, P.dX);
         const u32 c = rem - r * P.X32;
-        const u64 b = (u64)(P.SN * ((i64)s + P.z0) + P.RN * (i64)r + (i64)c);
-        val[0] = (u64)(P.eid_offset + (i64)rank + 1);
-        val[1] = b;                 val[2] = b + 1;
-        val[3] = b + P.RN + 1;      val[4] = b + P.RN;
-        val[5] = b + P.SN;          val[6] = b + P.SN + 1;
-        val[7] = b + P.SN + P.RN + 1; val[8] = b + P.SN + P.RN;
-        len = 9;
-#pragma unroll
-        for (int q = 0; q < 9; ++q) { nd[q] = digits_u64(val[q]); len += (u32)nd[q]; }
+        b = (u64)(P.SN * ((i64)s + P.z0) + P.RN * (i64)r + (i64)c);
+        eid = (u64)(P.eid_offset + (i64)rank + 1);
+        nd0 = id_digits<WIDE>(eid);
+        nlo = id_digits<WIDE>(b);
+        nhi = id_digits<WIDE>(b + P.SN + P.RN + 1);       // the largest of the eight node ids
+        if (nlo == nhi) {
+            len = 9u + (u32)nd0 + 8u * (u32)nlo;
+        } else {                                          // the ids straddle a power of ten (rare)
+            len = 9u + (u32)nd0 + (u32)nlo + (u32)nhi + (u32)id_digits<WIDE>(b + 1) +
+                  (u32)id_digits<WIDE>(b + P.RN) + (u32)id_digits<WIDE>(b + P.RN + 1) +
+                  (u32)id_digits<WIDE>(b + P.SN) + (u32)id_digits<WIDE>(b + P.SN + 1) +
+                  (u32)id_digits<WIDE>(b + P.SN + P.RN);
+        }
         is_first = ((u64)j == __ldg(P.first + gv));
         if (is_first) hl = __ldg(P.hdr_len + gv);
     }
     u32 tile_total;
     const u32 excl = block_exclusive_scan<u32>(len + hl, s_scan, tile_total);
-    if (threadIdx.x < 32) {
+    const bool staged = tile_total <= (u32)(ELEM_STAGE_BYTES - 32);
+    if (!worker) {
+        // ---- the look-back warp
         const u64 e = scan_lookback(P.ws, tile, (u64)tile_total);
-        if (threadIdx.x == 0) {
+        if ((threadIdx.x & 31u) == 0) {
             s_base = e;
             if ((i64)(tile + 1) * EMIT_THREADS >= P.n_el) *P.total = e + tile_total;
         }
+    } else if (active && staged) {
+        // ---- phase 1: digits and staging (C3D8 order, voxelFE.py:145-154):
+        //   eid, b, b+1, b+RN+1, b+RN, b+SN, b+SN+1, b+SN+RN+1, b+SN+RN
+        u32 o = excl;
+        if (hl) {
+            const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
+            for (u32 q = 0; q < hl; ++q) stage[o + q] = __ldg(h + q);
+            o += hl;
+        }
+        LineWriter w;
+        w.lead = o & 3u;
+        w.d = w.lead;
+        w.acc = 0;
+        w.wp = stage + (o - w.lead);
+        u32 r0, r1, r2, low4;
+        raw12<WIDE>(eid, r0, r1, r2, low4);
+        lw_append<true>(w, r0, r1, r2, nd0, 0x2Cu);
+        const bool same = nlo == nhi;
+        // the four (v, v+1) pairs share everything but the low four digits (unless those wrap)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u64 v0 = b + ((q & 1) ? P.RN : 0) + ((q & 2) ? P.SN : 0);
+            raw12<WIDE>(v0, r0, r1, r2, low4);
+            u32 h0 = r0, h1 = r1, h2;
+            if (low4 != 9999u) {
+                h2 = raw4(low4 + 1u);
+            } else {
+                u32 dummy;
+                raw12<WIDE>(v0 + 1, h0, h1, h2, dummy);
+            }
+            const int n0 = same ? nlo : raw12_digits(r0, r1, r2);
+            const int n1 = same ? nlo : raw12_digits(h0, h1, h2);
+            const u32 last = (q == 3) ? 0x0Au : 0x2Cu;
+            if ((q & 1) == 0) {          // order: v, v+1
+                if (q == 0) lw_append<true>(w, r0, r1, r2, n0, 0x2Cu);
+                else lw_append<false>(w, r0, r1, r2, n0, 0x2Cu);
+                lw_append<false>(w, h0, h1, h2, n1, 0x2Cu);
+            } else {                     // order: v+1, v
+                lw_append<false>(w, h0, h1, h2, n1, 0x2Cu);
+                lw_append<false>(w, r0, r1, r2, n0, last);
+            }
+        }
+        lw_finish(w);
     }
     __syncthreads();
     char* dst = P.out + s_base;
-    const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
     if (is_first && P.blk_off) P.blk_off[gv] = s_base + excl;
-    // A tile normally fits the staging buffer; a pathological tile (hundreds of block headers)
-    // falls back to direct global writes.
-    const bool staged = (pad + tile_total) <= (u32)ELEM_STAGE_BYTES;
-    if (j < P.n_el) {
-        char* p = staged ? (stage + pad + excl) : (dst + excl);
+    if (staged) {
+        flush_unaligned(stage, tile_total, dst);
+    } else if (active) {
+        char* p = dst + excl;
         if (hl) {
             const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
             for (u32 q = 0; q < hl; ++q) p[q] = __ldg(h + q);
             p += hl;
         }
-#pragma unroll
-        for (int q = 0; q < 9; ++q) {
-            p += nd[q];
-            put_u64_back(p, val[q], nd[q]);
-            *p++ = (q == 8) ? '\n' : ',';
+        const u64 vals[9] = {eid, b, b + 1, b + P.RN + 1, b + P.RN, b + P.SN, b + P.SN + 1, b + P.SN + P.RN + 1,
+                             b + P.SN + P.RN};
+#pragma unroll 1
+        for (int f = 0; f < 9; ++f) {
+            const int n = digits_u64(vals[f]);
+            p += n;
+            put_u64_back(p, vals[f], n);
+            *p++ = (f == 8) ? '\n' : ',';
         }
     }
-    __syncthreads();
-    if (staged) flush_stage(stage, pad, tile_total, dst);
 }
 
 extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
                                  const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len,
-                                 int single_gv, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset,
+                                 int single_gv, int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset,
                                  char* out, uint64_t* total, uint64_t* blk_off, void* ws, cudaStream_t stream)
 {
     const i64 tiles = (n_el + EMIT_THREADS - 1) / EMIT_THREADS;
@@ -239,18 +551,26 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
     P.RN = X + 1; P.SN = (X + 1) * (Y + 1); P.z0 = z0; P.eid_offset = eid_offset;
     P.out = out; P.total = reinterpret_cast<u64*>(total); P.blk_off = reinterpret_cast<u64*>(blk_off);
     P.ws = reinterpret_cast<u64*>(ws);
+    // largest id that can appear in this slab's lines: node ids up to the top corner of the slab's
+    // last voxel, element ids up to eid_offset + n_el
+    const unsigned long long max_node = (unsigned long long)P.SN * (unsigned long long)(z0 + Zl + 1);
+    const bool wide = (max_node >= 0xffffffffull) || ((unsigned long long)(eid_offset + n_el) >= 0xffffffffull);
     static bool attr_set = false;
     if (!attr_set) {
-        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            ELEM_STAGE_BYTES));
-        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            ELEM_STAGE_BYTES));
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ELEM_STAGE_BYTES));
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ELEM_STAGE_BYTES));
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ELEM_STAGE_BYTES));
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ELEM_STAGE_BYTES));
         attr_set = true;
     }
-    if (perm)
-        k_emit_elements<true><<<(unsigned)tiles, EMIT_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
-    else
-        k_emit_elements<false><<<(unsigned)tiles, EMIT_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
+    const unsigned g = (unsigned)tiles;
+    if (perm) {
+        if (wide) k_emit_elements<true, true><<<g, ELEM_CTA_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
+        else k_emit_elements<true, false><<<g, ELEM_CTA_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
+    } else {
+        if (wide) k_emit_elements<false, true><<<g, ELEM_CTA_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
+        else k_emit_elements<false, false><<<g, ELEM_CTA_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
+    }
     CFE_CHECK_LAUNCH("k_emit_elements");
     return 0;
 }

@@ -606,7 +606,7 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
                       mat_off.data_ptr(), perm.data_ptr(), s)
             single_gv = -1
         _lib.call("cfe_emit_elements", m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(),
-                  base + o_first, base + o_hdr, base + o_hlen, single_gv if single_gv >= 0 else 0, Y, X, m.z0,
+                  base + o_first, base + o_hdr, base + o_hlen, single_gv if single_gv >= 0 else 0, Zl, Y, X, m.z0,
                   m.eid_offset, elem_buf.data_ptr(), totals.data_ptr(), blk_off.data_ptr(), ws.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base, items_buf.data_ptr(),
                   None, totals.data_ptr() + 8, seg_off.data_ptr(), ws.data_ptr(), s)

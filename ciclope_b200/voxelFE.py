@@ -608,7 +608,9 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         s = _lib.stream()
         dblob = blob.to_device(dev)
         base = dblob.data_ptr()
-        out = torch.empty(cap, dtype=torch.uint8, device=dev)
+        # the *NODE section starts 16-byte aligned in memory (word stores in k_emit_nodes4)
+        out_full = torch.empty(cap + 16, dtype=torch.uint8, device=dev)
+        out = out_full[(-(out_full.data_ptr() + off_nodes)) % 16:]
         totals = torch.zeros(2, dtype=torch.int64, device=dev)   # element bytes, set bytes
         ws = scan_workspace(max(m.n_el, n_items, 1), dev)
         _lib.call("cfe_put_literal", base + o_head, len(head), out.data_ptr(), None, None, s)
@@ -631,7 +633,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
                       mat_off.data_ptr(), perm.data_ptr(), s)
             single_gv = -1
         _lib.call("cfe_emit_elements", m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(),
-                  base + o_first, base + o_hdr, base + o_hlen, single_gv, Y, X, 0, 0,
+                  base + o_first, base + o_hdr, base + o_hlen, single_gv, Z, Y, X, 0, 0,
                   out.data_ptr() + off_elem, totals.data_ptr(), None, ws.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base + o_lits,
                   out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, None, ws.data_ptr(), s)

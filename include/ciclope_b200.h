@@ -161,8 +161,8 @@ int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab,
  * *total = bytes written; blk_off[gv] = offset where block gv (header included) starts (optional). */
 int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
                       const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len, int single_gv,
-                      int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, char* out, uint64_t* total,
-                      uint64_t* blk_off, void* ws, cfe_stream_t s);
+                      int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, char* out,
+                      uint64_t* total, uint64_t* blk_off, void* ws, cfe_stream_t s);
 
 /* *NSET / *ELSET sections (voxelFE.py:650-688) as a stream of items. */
 typedef struct {
