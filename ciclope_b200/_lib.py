@@ -54,6 +54,7 @@ _SIGNATURES = {
     "cfe_fill_cells": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_gather_gv": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "cfe_fill_points": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "cfe_format_coords": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cfe_emit_nodes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_emit_elements": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,
                                   c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -360,42 +360,50 @@ __device__ __forceinline__ void lw_finish(LineWriter& w)
 
 // Copy n staged bytes (stage[0..n), stage 16-byte aligned) to an arbitrarily aligned global dst:
 // aligned 16-byte global stores assembled from two aligned 16-byte shared loads and a byte funnel.
+// The word / byte shifts are uniform for the whole tile, so the loop is specialised on them.
+template <int WSEL>
+__device__ __forceinline__ void flush_loop(const uint4* sv, char* gbase, u32 c_first, u32 c_last, u32 bs)
+{
+    for (u32 c = c_first + threadIdx.x; c < c_last; c += blockDim.x) {
+        const uint4 a = sv[c - 1u];
+        const uint4 b = sv[c];
+        u32 x0, x1, x2, x3, x4;
+        if (WSEL == 0) { x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w; x4 = b.x; }
+        else if (WSEL == 1) { x0 = a.y; x1 = a.z; x2 = a.w; x3 = b.x; x4 = b.y; }
+        else if (WSEL == 2) { x0 = a.z; x1 = a.w; x2 = b.x; x3 = b.y; x4 = b.z; }
+        else { x0 = a.w; x1 = b.x; x2 = b.y; x3 = b.z; x4 = b.w; }
+        uint4 o;
+        o.x = __funnelshift_r(x0, x1, bs); o.y = __funnelshift_r(x1, x2, bs);
+        o.z = __funnelshift_r(x2, x3, bs); o.w = __funnelshift_r(x3, x4, bs);
+        *reinterpret_cast<uint4*>(gbase + 16u * c) = o;
+    }
+}
+
 __device__ __forceinline__ void flush_unaligned(const char* stage, u32 n, char* dst)
 {
     const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
     char* gbase = dst - pad;                       // 16-byte aligned; chunk c = [gbase+16c, +16)
     const u32 end = pad + n;
-    const u32 c_first = pad ? 1u : 0u;             // first chunk fully inside the span
     const u32 c_last = end >> 4;                   // one past the last full chunk
-    // chunk c takes staged bytes [16c - pad, 16c - pad + 16) = 16(c-1) + (16 - pad) when pad > 0
-    const u32 off = (16u - pad) & 15u;             // byte offset inside the aligned staged block
-    const u32 wsel = off >> 2, bs = (off & 3u) * 8u;
     const uint4* sv = reinterpret_cast<const uint4*>(stage);
-    for (u32 c = c_first + threadIdx.x; c < c_last; c += blockDim.x) {
-        const u32 blk = pad ? c - 1u : c;
-        const uint4 a = sv[blk];
-        uint4 o;
-        if (off == 0) {
-            o = a;
-        } else {
-            const uint4 b = sv[blk + 1];
-            u32 x0, x1, x2, x3, x4;
-            if (wsel == 0) { x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w; x4 = b.x; }
-            else if (wsel == 1) { x0 = a.y; x1 = a.z; x2 = a.w; x3 = b.x; x4 = b.y; }
-            else if (wsel == 2) { x0 = a.z; x1 = a.w; x2 = b.x; x3 = b.y; x4 = b.z; }
-            else { x0 = a.w; x1 = b.x; x2 = b.y; x3 = b.z; x4 = b.w; }
-            o.x = __funnelshift_r(x0, x1, bs); o.y = __funnelshift_r(x1, x2, bs);
-            o.z = __funnelshift_r(x2, x3, bs); o.w = __funnelshift_r(x3, x4, bs);
+    if (pad == 0) {
+        for (u32 c = threadIdx.x; c < c_last; c += blockDim.x) reinterpret_cast<uint4*>(gbase)[c] = sv[c];
+    } else {
+        // chunk c (>= 1) takes staged bytes [16(c-1) + off, +16), off = 16 - pad
+        const u32 off = 16u - pad;
+        const u32 bs = (off & 3u) * 8u;
+        switch (off >> 2) {
+        case 0: flush_loop<0>(sv, gbase, 1u, c_last, bs); break;
+        case 1: flush_loop<1>(sv, gbase, 1u, c_last, bs); break;
+        case 2: flush_loop<2>(sv, gbase, 1u, c_last, bs); break;
+        default: flush_loop<3>(sv, gbase, 1u, c_last, bs); break;
         }
-        *reinterpret_cast<uint4*>(gbase + 16u * c) = o;
-    }
-    // partial head / tail chunks: bytes
-    if (pad) {
-        const u32 hb = (16u - pad) < n ? (16u - pad) : n;
+        const u32 hb = off < n ? off : n;          // partial head chunk: bytes
         for (u32 k = threadIdx.x; k < hb; k += blockDim.x) dst[k] = stage[k];
     }
-    if (c_last >= c_first && (c_last << 4) < end && (c_last << 4) >= pad) {
-        const u32 s0 = (c_last << 4) - pad;        // first staged byte of the tail chunk
+    // partial tail chunk: bytes [16 c_last - pad, n)
+    if ((c_last << 4) >= pad && (c_last << 4) < end && (pad == 0 || c_last >= 1u)) {
+        const u32 s0 = (c_last << 4) - pad;
         for (u32 k = s0 + threadIdx.x; k < n; k += blockDim.x) dst[k] = stage[k];
     }
 }
@@ -850,5 +858,67 @@ extern "C" int cfe_partition_scatter(const uint8_t* vol, const uint32_t* elem_vo
                                                                    reinterpret_cast<const u64*>(mat_off),
                                                                    reinterpret_cast<uint2*>(perm));
     CFE_CHECK_LAUNCH("k_part_scatter");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// '{:12.6f}'.format(v) of the per-axis node coordinates (voxelFE.py:630) -- exact: the binary
+// value times 10^6 is rounded half-to-even in 128-bit integer arithmetic, which is what CPython's
+// correctly rounded float formatting does.  One thread per value, 16-byte output slots.
+// *overflow is set when a field would be wider than 12 characters (|v| >= 1e5) or v is not finite.
+
+__global__ void __launch_bounds__(128)
+k_format_coords(const double* __restrict__ vals, i64 n, char* __restrict__ out16, int* __restrict__ overflow)
+{
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u64 bits = (u64)__double_as_longlong(vals[t]);
+    const bool neg = (bits >> 63) != 0;
+    const int ex = (int)((bits >> 52) & 0x7ffu);
+    u64 m = bits & 0xfffffffffffffull;
+    int e;
+    if (ex == 0) e = -1074; else { m |= 1ull << 52; e = ex - 1075; }
+    char* o = out16 + 16 * t;
+    u64 N = 0;
+    bool bad = (ex == 0x7ff);
+    if (!bad && m) {
+        const unsigned __int128 P = (unsigned __int128)m * 1000000u;   // < 2^73
+        if (e >= 0) {
+            bad = true;                                               // >= 2^52: far beyond 1e5
+        } else {
+            const int sft = -e;
+            if (sft < 128) {
+                unsigned __int128 q = P >> sft;
+                const unsigned __int128 rem = P - (q << sft);
+                const unsigned __int128 half = (unsigned __int128)1 << (sft - 1);
+                if (rem > half || (rem == half && ((u64)q & 1ull))) q += 1;
+                if (q >= (unsigned __int128)100000000000ull) bad = true; else N = (u64)q;
+            }
+        }
+    }
+    if (N >= 100000000000ull) bad = true;                             // 100000.000000 needs 13 chars
+    const u64 ip = N / 1000000ull;
+    u32 fp = (u32)(N - ip * 1000000ull);
+    if (neg && ip >= 10000ull) bad = true;                            // '-' + 5 digits + 7 = 13 chars
+    if (bad) { *overflow = 1; return; }
+    char buf[12];
+#pragma unroll
+    for (int k = 11; k >= 6; --k) { buf[k] = (char)('0' + fp % 10u); fp /= 10u; }
+    buf[5] = '.';
+    u32 iv = (u32)ip;
+    int k = 4;
+    do { buf[k--] = (char)('0' + iv % 10u); iv /= 10u; } while (iv && k >= 0);
+    if (neg) buf[k--] = '-';
+    while (k >= 0) buf[k--] = ' ';
+#pragma unroll
+    for (int q = 0; q < 12; ++q) o[q] = buf[q];
+    o[12] = 0; o[13] = 0; o[14] = 0; o[15] = 0;
+}
+
+extern "C" int cfe_format_coords(const double* vals, int64_t n, char* out16, int* overflow, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    k_format_coords<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(vals, n, out16, overflow);
+    CFE_CHECK_LAUNCH("k_format_coords");
     return 0;
 }

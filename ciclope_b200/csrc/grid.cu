@@ -230,31 +230,61 @@ extern "C" int cfe_scan_nodes(const uint32_t* bits, const uint32_t* halo_below, 
 // K9: expand set bits into an index list: list[pref[i] + k] = row*rowlen + 32*w + b
 // (elements: rowlen = X, words per row W; nodes: rowlen = X+1, words per row WN).
 
-__global__ void __launch_bounds__(256)
-k_fill_list(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 n_words, int wpr, int rowlen,
-            u32* __restrict__ list)
+// One CTA expands 256 consecutive words (<= 8192 entries) into shared memory at their final
+// relative positions, then streams the contiguous span to HBM with coalesced stores.
+#define FILL_WORDS 256
+
+__global__ void __launch_bounds__(FILL_WORDS)
+k_fill_list(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_words, FastDiv d_wpr, u32 wpr,
+            u32 rowlen, u32* __restrict__ list)
 {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_words) return;
-    u32 word = __ldg(bits + i);
-    if (!word) return;
-    const i64 row = i / wpr;
-    const int w = (int)(i - row * wpr);
-    const u32 base = (u32)(row * rowlen + (i64)w * 32);
-    u32 o = __ldg(pref + i);
-    while (word) {
-        const int b = __ffs((int)word) - 1;
-        word &= word - 1;
-        list[o++] = base + (u32)b;
+    __shared__ u32 sm[FILL_WORDS * 32];
+    __shared__ u32 s_total;
+    const u32 i0 = blockIdx.x * FILL_WORDS;
+    const u32 i = i0 + threadIdx.x;
+    const u32 base0 = __ldg(pref + i0);
+    u32 word = 0, p = 0;
+    if (i < n_words) {
+        word = __ldg(bits + i);
+        p = __ldg(pref + i) - base0;
     }
+    const u32 last = (n_words - i0 < FILL_WORDS ? n_words - i0 : FILL_WORDS) - 1u;
+    if (threadIdx.x == last) s_total = p + (u32)__popc(word);
+    if (word) {
+        const u32 row = fd_div(i, d_wpr);
+        const u32 w = i - row * wpr;
+        const u32 base = row * rowlen + w * 32u;
+        while (word) {
+            const int b = __ffs((int)word) - 1;
+            word &= word - 1;
+            sm[p++] = base + (u32)b;
+        }
+    }
+    __syncthreads();
+    const u32 total = s_total;
+    u32* dst = list + base0;
+    // align the destination to 16 bytes, then 16-byte stores
+    const u32 head = (u32)((16u - ((uintptr_t)dst & 15u)) & 15u) >> 2;
+    const u32 h = head < total ? head : total;
+    if (threadIdx.x < h) dst[threadIdx.x] = sm[threadIdx.x];
+    const u32 n4 = (total - h) >> 2;
+    for (u32 k = threadIdx.x; k < n4; k += FILL_WORDS) {
+        uint4 v;
+        v.x = sm[h + 4 * k]; v.y = sm[h + 4 * k + 1]; v.z = sm[h + 4 * k + 2]; v.w = sm[h + 4 * k + 3];
+        reinterpret_cast<uint4*>(dst + h)[k] = v;
+    }
+    for (u32 k = h + 4 * n4 + threadIdx.x; k < total; k += FILL_WORDS) dst[k] = sm[k];
 }
 
 extern "C" int cfe_fill_list(const uint32_t* bits, const uint32_t* pref, int64_t n_words,
                              int64_t words_per_row, int64_t row_len, uint32_t* list, cudaStream_t stream)
 {
     if (n_words <= 0) return 0;
-    const i64 blocks = (n_words + 255) / 256;
-    k_fill_list<<<(unsigned)blocks, 256, 0, stream>>>(bits, pref, n_words, (int)words_per_row, (int)row_len, list);
+    if (n_words >= (1LL << 32)) { cfe_set_error("cfe_fill_list: too many words"); return -1; }
+    const i64 blocks = (n_words + FILL_WORDS - 1) / FILL_WORDS;
+    k_fill_list<<<(unsigned)blocks, FILL_WORDS, 0, stream>>>(bits, pref, (u32)n_words,
+                                                             make_fastdiv((u32)words_per_row), (u32)words_per_row,
+                                                             (u32)row_len, list);
     CFE_CHECK_LAUNCH("k_fill_list");
     return 0;
 }

@@ -457,10 +457,11 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
                   epref.data_ptr(), _lib.ptr(halo), tile_count.data_ptr(), s)
         _lib.call("cfe_scan_u32", tile_count.data_ptr(), n_tiles, tile_off.data_ptr(), stats.data_ptr() + 16,
                   ws.data_ptr(), s)
+        m.ftab = vfe._format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
         tile_off[n_tiles] = stats[2]
         first_t = tile_off[bases.clamp(max=n_tiles)]
         count_t = torch.cat([first_t[1:], stats[2:3]]) - first_t
-        mine = torch.cat([stats[:2], count_t])          # n_el, n_nd, 12 set counts
+        mine = torch.cat([stats[:2], count_t, stats[3:4]])   # n_el, n_nd, 12 set counts, field overflow
     gathered = yield from ctx.all_gather(mine)
     with torch.cuda.device(dev):
         s = _lib.stream()
@@ -471,7 +472,8 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         m.eid_offset = sum(n_el_r[: ctx.rank])
         m.node_rank_offset = sum(n_nd_r[: ctx.rank])
         m.n_el_global, m.n_nd_global = sum(n_el_r), sum(n_nd_r)
-        m.set_count = [int(c) for c in table[ctx.rank][2:]]
+        m.set_count = [int(c) for c in table[ctx.rank][2:14]]
+        m.field_overflow = any(t[14] for t in table)
         m.set_first, n_ids = exclusive_offsets(m.set_count)
         m.set_rank0 = [sum(t[2 + q] for t in table[: ctx.rank]) for q in range(12)]
         m.set_count_global = [sum(t[2 + q] for t in table) for q in range(12)]
@@ -542,9 +544,12 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     o_first = blob.add(first.tobytes())
     o_hdr = blob.add(bytes(256 * vfe._ELEM_HDR_SLOT))
     o_hlen = blob.add(bytes(256))                      # no headers inside the slab buffers
-    o_xt = blob.add(vfe._field_table(m.xs))
-    o_yt = blob.add(vfe._field_table(m.ys))
-    o_zt = blob.add(vfe._field_table(m.zs[m.z0: m.z0 + m.n_layers]))
+    if m.field_overflow:
+        raise NotImplementedError("node coordinates wider than the 12-character field (|coord| >= 1e5) are not "
+                                  "supported by the CUDA deck writer yet")
+    p_xt = m.ftab.data_ptr()
+    p_yt = p_xt + 16 * (X + 1)
+    p_zt = p_yt + 16 * (Y + 1) + 16 * m.z0      # this slab's node layers
 
     # id-list segments of this rank, one per non-empty set, in file order
     set_names = []
@@ -588,7 +593,7 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         blk_off = torch.zeros(256, dtype=torch.int64, device=dev)
         seg_off = torch.zeros(max(len(segs), 1), dtype=torch.int64, device=dev)
         ws = scan_workspace(max(m.n_el, n_items, 1), dev)
-        _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, base + o_xt, base + o_yt, base + o_zt,
+        _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
                   Y, X, m.z0, nodes_buf.data_ptr(), s)
         perm = None
         single_gv = int(gvs[0])

@@ -70,6 +70,21 @@ def _field_table(values):
     return b"".join(f.encode("ascii") + b"\0\0\0\0" for f in fields)
 
 
+def _format_tables_device(xs, ys, zs, dev, overflow_ptr, stream):
+    """'{:12.6f}' fields of every per-axis coordinate, formatted exactly on the GPU (16-byte slots,
+    x then y then z).  The values are float64 copies of what np.asarray(nodes) holds, which is what
+    format() sees (np.float32 / np.int64 scalars are widened exactly by their __format__)."""
+    vals = []
+    for a in (xs, ys, zs):
+        if a.dtype.kind in "iu" and a.size and int(np.abs(a).max()) >= 2 ** 53:
+            raise NotImplementedError("integer node coordinates beyond 2^53 are not supported")
+        vals.append(np.asarray(a, dtype=np.float64))
+    tab = torch.from_numpy(np.concatenate(vals)).to(dev, non_blocking=True)
+    out = torch.empty(16 * tab.numel(), dtype=torch.uint8, device=dev)
+    _lib.call("cfe_format_coords", tab.data_ptr(), tab.numel(), out.data_ptr(), overflow_ptr, stream)
+    return out
+
+
 def _int_lock(v, name):
     if isinstance(v, (bool, np.bool_)) or int(v) != v:
         raise TypeError("%s must be an integer" % name)
@@ -260,7 +275,6 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
     m.vol, m.is_bool, m.thr = vol, is_bool, thr
     m.Z, m.Y, m.X = Z, Y, X
     m.strategy, m.plane_lock_num, m.node_level_lock_num = locking_strategy, p, k
-    m.xs, m.ys, m.zs = _coordinate_tables(voxelsize, Z, Y, X)
 
     logging.info('Calculating cell array')
     with torch.cuda.device(dev):
@@ -321,10 +335,14 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
                   epref.data_ptr(), None, tile_count.data_ptr(), s)
         _lib.call("cfe_scan_u32", tile_count.data_ptr(), n_tiles, tile_off.data_ptr(), stats.data_ptr() + 16,
                   ws.data_ptr(), s)
+        # host work that overlaps the kernels above: per-axis coordinate values and their text fields
+        m.xs, m.ys, m.zs = _coordinate_tables(voxelsize, Z, Y, X)
+        m.ftab = _format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
         # one device->host read: counts + first id of every set
         tile_off[n_tiles] = stats[2]
         host = torch.cat([stats, tile_off[bases.clamp(max=n_tiles)]]).cpu().tolist()
         n_el, n_nd, n_ids = host[0], host[1], host[2]
+        m.field_overflow = bool(host[3])
         first = host[4:16]
         count = [(first[q + 1] if q < 11 else n_ids) - first[q] for q in range(12)]
 
@@ -544,9 +562,12 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     o_hdr = blob.add(bytes(hdr_text))
     o_hlen = blob.add(hdr_len.tobytes())
     o_first = blob.add(first.tobytes())
-    o_xt = blob.add(_field_table(m.xs))
-    o_yt = blob.add(_field_table(m.ys))
-    o_zt = blob.add(_field_table(m.zs))
+    if m.field_overflow:
+        raise NotImplementedError("node coordinates wider than the 12-character field (|coord| >= 1e5) are not "
+                                  "supported by the CUDA deck writer yet")
+    p_xt = m.ftab.data_ptr()
+    p_yt = p_xt + 16 * (X + 1)
+    p_zt = p_yt + 16 * (Y + 1)
 
     # NSET / ELSET item stream (voxelFE.py:650-688)
     lits = bytearray()
@@ -614,7 +635,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         totals = torch.zeros(2, dtype=torch.int64, device=dev)   # element bytes, set bytes
         ws = scan_workspace(max(m.n_el, n_items, 1), dev)
         _lib.call("cfe_put_literal", base + o_head, len(head), out.data_ptr(), None, None, s)
-        _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, base + o_xt, base + o_yt, base + o_zt,
+        _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
                   Y, X, 0, out.data_ptr() + off_nodes, s)
         _lib.call("cfe_put_literal", base + o_cmt, len(elem_comment), out.data_ptr() + off_cmt, None, None, s)
         perm = None

@@ -148,6 +148,11 @@ int cfe_fill_points(const void* xs, const void* ys, const void* zs, int elem_byt
 
 /* ------------------------------------------------------------------ deck emission */
 
+/* '{:12.6f}'.format(v) for every per-axis node coordinate (voxelFE.py:630), exact (round-half-even
+ * of the binary value in 128-bit integers, as CPython does): 16-byte slots, 12 characters each.
+ * *overflow (device int, caller-zeroed) is set when a field needs more than 12 characters. */
+int cfe_format_coords(const double* vals, int64_t n, char* out16, int* overflow, cfe_stream_t s);
+
 /* *NODE lines (voxelFE.py:629-630).  xtab/ytab/ztab: 16-byte slots holding the 12-character
  * '{:12.6f}' field of every column / row / layer coordinate (formatted on the host by the
  * same interpreter arithmetic as the reference).  Writes 53*n_nodes bytes at out. */

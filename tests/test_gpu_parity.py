@@ -256,3 +256,44 @@ def test_error_behaviour_matches_reference(cfe, tmp_path):
         cfe.vol2ugrid(np.zeros((2, 2, 2), dtype=np.float32))
     with pytest.raises(NotImplementedError):
         cfe.mesh2voxelfe(object(), cases.TEMPLATE, str(tmp_path / "e.inp"))
+
+
+# ------------------------------------------------------------------ coordinate formatting kernel
+
+def test_format_coords_matches_cpython(cfe):
+    """cfe_format_coords must print exactly what '{:12.6f}'.format does (voxelFE.py:630)."""
+    import torch
+    from ciclope_b200 import _lib
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([
+        rng.uniform(-9999.0, 99999.0, 20000),
+        rng.uniform(-1e-5, 1e-5, 5000),
+        np.arange(-640, 6400) / 128.0,                      # exact ties of the 6th decimal: half-to-even
+        np.arange(1, 4000) / 128.0 + 1000.0,
+        np.arange(0, 3000) * 0.0195, np.arange(0, 3000) * 0.0000005, np.arange(0, 3000) * np.float64(np.float32(0.1)),
+        np.array([0.0, -0.0, 99999.9999994, 99999.999999, -9999.9999994, 5e-324, -5e-324, 1e-7, 4.9999999e-7,
+                  5e-7, 5.0000001e-7, 1.5e-6, 2.5e-6, 0.1, 0.2, 0.3, 1 / 3, 2 / 3, 12345.678901, 12345.6789015]),
+    ]).astype(np.float64)
+    t = torch.from_numpy(vals).cuda()
+    out = torch.zeros(16 * len(vals), dtype=torch.uint8, device="cuda")
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.call("cfe_format_coords", t.data_ptr(), len(vals), out.data_ptr(), flag.data_ptr(), _lib.stream())
+    got = out.cpu().numpy().reshape(-1, 16)
+    assert int(flag.item()) == 0
+    for i, v in enumerate(vals.tolist()):
+        want = format(v, "12.6f")
+        assert len(want) == 12
+        assert bytes(got[i, :12]).decode() == want, (i, v, want, bytes(got[i, :12]))
+    for bad in (100000.0, 99999.9999996, -10000.0, float("inf"), float("nan"), 1e300):
+        flag.zero_()
+        t = torch.tensor([bad], dtype=torch.float64, device="cuda")
+        _lib.call("cfe_format_coords", t.data_ptr(), 1, out.data_ptr(), flag.data_ptr(), _lib.stream())
+        assert int(flag.item()) == 1, bad
+        assert len(format(bad, "12.6f")) != 12 or bad != bad or abs(bad) == float("inf")
+
+
+def test_wide_coordinate_fields_raise(cfe, tmp_path):
+    mesh = cfe.vol2ugrid(np.ones((2, 2, 3), dtype=bool), voxelsize=[50000.0, 1.0, 1.0])
+    assert mesh.points[2, 0] == 100000.0           # the mesh itself is fine
+    with pytest.raises(NotImplementedError):
+        cfe.mesh2voxelfe(mesh, cases.TEMPLATE, str(tmp_path / "w.inp"))
