@@ -56,6 +56,7 @@ _SIGNATURES = {
     "cfe_fill_points": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_format_coords": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cfe_emit_nodes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "cfe_emit_elements_workspace_bytes": (c_sz, [c_i64]),
     "cfe_emit_elements": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,
                                   c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cfe_emit_items": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -60,9 +60,8 @@ __device__ __forceinline__ u32 scan_next_tile(u64* ws)
 // The window is 32 * SCAN_LB_DEPTH predecessors per round trip to L2: with small, fast tiles the
 // nearest published prefix is "number of tiles in flight" (hundreds) behind, and a 32-wide window
 // makes the whole kernel wait on (tiles in flight / 32) serial L2 latencies per tile.
-#define SCAN_LB_DEPTH 2
-
-__device__ __forceinline__ u64 scan_lookback(u64* ws, u32 tile, u64 aggregate)
+template <int SCAN_LB_DEPTH>
+__device__ __forceinline__ u64 scan_lookback_d(u64* ws, u32 tile, u64 aggregate)
 {
     volatile u64* status = ws + 1;
     const u32 lane = threadIdx.x & 31u;
@@ -102,6 +101,11 @@ __device__ __forceinline__ u64 scan_lookback(u64* ws, u32 tile, u64 aggregate)
     }
     if (lane == 0) status[tile] = SCAN_FLAG_P | (excl + aggregate);
     return excl;
+}
+
+__device__ __forceinline__ u64 scan_lookback(u64* ws, u32 tile, u64 aggregate)
+{
+    return scan_lookback_d<1>(ws, tile, aggregate);
 }
 
 // ------------------------------------------------------------------------------------------

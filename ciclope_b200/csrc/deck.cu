@@ -16,6 +16,8 @@
 
 #define EMIT_THREADS 256
 
+extern "C" size_t cfe_scan_workspace_bytes(int64_t n_items);
+
 // ------------------------------------------------------------------------------------------
 // staging helpers
 
@@ -291,9 +293,12 @@ struct ElemEmitParams {
     u32 YX32, X32;
     i64 SN, RN, z0, eid_offset;
     char* out;               // start of the element lines
-    u64* total;              // out: bytes written
     u64* blk_off;            // out [256]: byte offset (from `out`) where each GV block (header included) starts
-    u64* ws;                 // look-back workspace
+    uint8_t* len8;           // [n_el] line length (block header included) in emission order
+    uint8_t* nd8;            // [n_el] digit-count flags (see k_elem_lengths)
+    u32* warp_total;         // [n_warp_tiles] bytes of every 32-element tile
+    const u64* warp_off;     // [n_warp_tiles] exclusive scan of warp_total
+    i64 n_warp_tiles;
 };
 
 // Line builder: bytes are appended to a 32-bit accumulator and leave as aligned 32-bit
@@ -350,6 +355,84 @@ __device__ __forceinline__ void lw_append(LineWriter& w, u32 r0, u32 r1, u32 r2,
     w.d = tot & 3u;
 }
 
+// Four consecutive node-id fields of an element line when all eight ids have the same number of
+// digits N (the usual case: the ids of one element differ by < 2 slices of the node grid).  Every
+// byte position of the 4*(N+1)-byte half-block is then a compile-time constant: it is assembled
+// with immediate funnel shifts from the 12-digit words of the fields (F[k] = ASCII words of field
+// k, most significant first) and appended with ONE runtime shift.  LAST: the half-block ends the
+// line ('\n' after its fourth field).
+template <bool LAST>
+__device__ __forceinline__ u32 field_word(const u32 (&F)[4][3], int k, int j)
+{
+    // word j of the 16-byte string "12 digits, separator, zeros" of field k
+    return j < 3 ? F[k][j] : (j == 3 ? ((LAST && k == 3) ? 0x0Au : 0x2Cu) : 0u);
+}
+
+template <bool LAST>
+__device__ __forceinline__ u32 field_chars(const u32 (&F)[4][3], int k, int c)
+{
+    // characters c .. c+3 of that string (c is a compile-time constant after unrolling)
+    const u32 lo = field_word<LAST>(F, k, c >> 2), hi = field_word<LAST>(F, k, (c >> 2) + 1);
+    return (c & 3) ? __funnelshift_r(lo, hi, 8 * (c & 3)) : lo;
+}
+
+template <int N, bool LAST>
+__device__ __forceinline__ void lw_append_block(LineWriter& w, const u32 (&F)[4][3])
+{
+    constexpr int NB = N + 1;        // bytes per field (digits + separator); 4 * NB bytes = NB words
+    const u32 s8 = w.d * 8u;
+    u32 prev = 0;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        u32 Bm = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int fs = k * NB - 4 * m;          // where field k starts relative to this word
+            if (fs <= -NB || fs >= 4) continue;     // no overlap
+            if (fs <= 0) Bm |= field_chars<LAST>(F, k, 12 - N - fs);
+            else Bm |= field_chars<LAST>(F, k, 12 - N) << (8 * fs);
+        }
+        const u32 outw = (m == 0) ? (w.acc | (Bm << s8)) : __funnelshift_l(prev, Bm, s8);
+        if (m == 0 && w.lead) {
+#pragma unroll
+            for (u32 q = 1; q < 4; ++q)
+                if (q >= w.lead) w.wp[q] = (char)(outw >> (8 * q));
+            w.lead = 0;
+        } else {
+            reinterpret_cast<u32*>(w.wp)[m] = outw;
+        }
+        prev = Bm;
+    }
+    w.acc = __funnelshift_l(prev, 0u, s8);
+    w.wp += 4 * NB;
+}
+
+template <bool LAST>
+__device__ __forceinline__ void lw_append_half(LineWriter& w, const u32 (&F)[4][3], int n, bool same)
+{
+    if (same) {
+        switch (n) {
+        case 1: lw_append_block<1, LAST>(w, F); break;
+        case 2: lw_append_block<2, LAST>(w, F); break;
+        case 3: lw_append_block<3, LAST>(w, F); break;
+        case 4: lw_append_block<4, LAST>(w, F); break;
+        case 5: lw_append_block<5, LAST>(w, F); break;
+        case 6: lw_append_block<6, LAST>(w, F); break;
+        case 7: lw_append_block<7, LAST>(w, F); break;
+        case 8: lw_append_block<8, LAST>(w, F); break;
+        case 9: lw_append_block<9, LAST>(w, F); break;
+        default: lw_append_block<10, LAST>(w, F); break;   // ids are < 10^10 (checked by the host)
+        }
+    } else {
+        // ids straddle a power of ten: per-field appends
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const u32 a0 = F[k][0] - 0x30303030u, a1 = F[k][1] - 0x30303030u, a2 = F[k][2] - 0x30303030u;
+            lw_append<true>(w, a0, a1, a2, raw12_digits(a0, a1, a2), (LAST && k == 3) ? 0x0Au : 0x2Cu);
+        }
+    }
+}
+
 __device__ __forceinline__ void lw_finish(LineWriter& w)
 {
     // the last partial word shares its upper bytes with the next line: byte stores
@@ -364,6 +447,7 @@ __device__ __forceinline__ void lw_finish(LineWriter& w)
 template <int WSEL>
 __device__ __forceinline__ void flush_loop(const uint4* sv, char* gbase, u32 c_first, u32 c_last, u32 bs)
 {
+#pragma unroll 1
     for (u32 c = c_first + threadIdx.x; c < c_last; c += blockDim.x) {
         const uint4 a = sv[c - 1u];
         const uint4 b = sv[c];
@@ -387,6 +471,7 @@ __device__ __forceinline__ void flush_unaligned(const char* stage, u32 n, char* 
     const u32 c_last = end >> 4;                   // one past the last full chunk
     const uint4* sv = reinterpret_cast<const uint4*>(stage);
     if (pad == 0) {
+#pragma unroll 1
         for (u32 c = threadIdx.x; c < c_last; c += blockDim.x) reinterpret_cast<uint4*>(gbase)[c] = sv[c];
     } else {
         // chunk c (>= 1) takes staged bytes [16(c-1) + off, +16), off = 16 - pad
@@ -408,13 +493,13 @@ __device__ __forceinline__ void flush_unaligned(const char* stage, u32 n, char* 
     }
 }
 
-// 8 worker warps format one element each; a 9th warp only runs the decoupled look-back.
-// Phase 0 computes nothing but the line LENGTHS (digit counts of the ids) so that the tile's
-// aggregate is published within a few hundred cycles of the CTA's start -- successors spin on it.
-// Phase 1 (digit generation, staging) then overlaps the look-back; lines are staged at their
-// tile-local offsets and the flush realigns them to the destination.
-#define ELEM_CTA_THREADS (EMIT_THREADS + 32)
-
+// The *ELEMENT section is emitted in two kernels so that no CTA ever waits on another:
+//   k_elem_lengths  line length of every element (digit counts only) -> len8[j], and the byte
+//                   total of every 32-element warp tile -> warp_total[w]
+//   (exclusive scan of warp_total: cfe_scan_u32 machinery)
+//   k_emit_elements each WARP formats its 32 lines into a private shared-memory region that is
+//                   congruent mod 16 with its destination span and streams it out with 16-byte
+//                   stores; there is no block-level barrier anywhere.
 template <bool WIDE>
 __device__ __forceinline__ int id_digits(u64 v)
 {
@@ -422,123 +507,171 @@ __device__ __forceinline__ int id_digits(u64 v)
     return digits_u32((u32)v);
 }
 
-// PERM: elements come from the GV-major permutation; WIDE: ids may exceed 32 bits.
-template <bool PERM, bool WIDE>
-__global__ void __launch_bounds__(ELEM_CTA_THREADS) k_emit_elements(ElemEmitParams P)
+template <bool PERM>
+__device__ __forceinline__ void elem_ids(const ElemEmitParams& P, i64 j, u64& b, u64& eid, int& gv)
 {
-    extern __shared__ __align__(16) char stage[];
-    __shared__ u32 s_scan[33];
-    __shared__ u64 s_base;
-    const u32 tile = scan_next_tile(P.ws);
-    const bool worker = threadIdx.x < EMIT_THREADS;
-    const i64 j = (i64)tile * EMIT_THREADS + threadIdx.x;
-    const bool active = worker && j < P.n_el;
-    // ---- phase 0: line lengths
-    u64 b = 0, eid = 0;
-    int nd0 = 0, nlo = 0, nhi = 0;
-    u32 len = 0, hl = 0;
-    bool is_first = false;
-    int gv = P.single_gv;
-    if (active) {
-        u32 v, rank;
-        if (PERM) { const uint2 e = __ldg(P.perm + j); v = e.x; rank = e.y; gv = (int)__ldg(P.vol + v); }
-        else { v = __ldg(P.elem_vox + j); rank = (u32)j; }
-        const u32 s = fd_div(v, P.dYX);
-        const u32 rem = v - s * P.YX32;
-        const u32 r = fd_div(rem, P.dX);
-        const u32 c = rem - r * P.X32;
-        b = (u64)(P.SN * ((i64)s + P.z0) + P.RN * (i64)r + (i64)c);
-        eid = (u64)(P.eid_offset + (i64)rank + 1);
-        nd0 = id_digits<WIDE>(eid);
-        nlo = id_digits<WIDE>(b);
-        nhi = id_digits<WIDE>(b + P.SN + P.RN + 1);       // the largest of the eight node ids
+    u32 v, rank;
+    if (PERM) { const uint2 e = __ldg(P.perm + j); v = e.x; rank = e.y; gv = (int)__ldg(P.vol + v); }
+    else { v = __ldg(P.elem_vox + j); rank = (u32)j; gv = P.single_gv; }
+    const u32 s = fd_div(v, P.dYX);
+    const u32 rem = v - s * P.YX32;
+    const u32 r = fd_div(rem, P.dX);
+    const u32 c = rem - r * P.X32;
+    b = (u64)(P.SN * ((i64)s + P.z0) + P.RN * (i64)r + (i64)c);
+    eid = (u64)(P.eid_offset + (i64)rank + 1);
+}
+
+template <bool PERM, bool WIDE>
+__global__ void __launch_bounds__(256) k_elem_lengths(ElemEmitParams P)
+{
+    const i64 j = (i64)blockIdx.x * 256 + threadIdx.x;
+    u32 len = 0;
+    if (j < P.n_el) {
+        u64 b, eid;
+        int gv;
+        elem_ids<PERM>(P, j, b, eid, gv);
+        const int nd0 = id_digits<WIDE>(eid);
+        const int nlo = id_digits<WIDE>(b);
+        const int nhi = id_digits<WIDE>(b + P.SN + P.RN + 1);       // the largest of the eight node ids
         if (nlo == nhi) {
             len = 9u + (u32)nd0 + 8u * (u32)nlo;
-        } else {                                          // the ids straddle a power of ten (rare)
+        } else {                                                  // the ids straddle a power of ten
             len = 9u + (u32)nd0 + (u32)nlo + (u32)nhi + (u32)id_digits<WIDE>(b + 1) +
                   (u32)id_digits<WIDE>(b + P.RN) + (u32)id_digits<WIDE>(b + P.RN + 1) +
                   (u32)id_digits<WIDE>(b + P.SN) + (u32)id_digits<WIDE>(b + P.SN + 1) +
                   (u32)id_digits<WIDE>(b + P.SN + P.RN);
         }
-        is_first = ((u64)j == __ldg(P.first + gv));
-        if (is_first) hl = __ldg(P.hdr_len + gv);
+        // flags byte: low nibble = digit count of the smallest node id, bit 7 = all eight counts equal
+        P.nd8[j] = (uint8_t)((nlo == nhi ? 0x80u : 0u) | (u32)nlo);
+        if ((u64)j == __ldg(P.first + gv)) len += __ldg(P.hdr_len + gv);
+        P.len8[j] = (uint8_t)len;
     }
-    u32 tile_total;
-    const u32 excl = block_exclusive_scan<u32>(len + hl, s_scan, tile_total);
-    const bool staged = tile_total <= (u32)(ELEM_STAGE_BYTES - 32);
-    if (!worker) {
-        // ---- the look-back warp
-        const u64 e = scan_lookback(P.ws, tile, (u64)tile_total);
-        if ((threadIdx.x & 31u) == 0) {
-            s_base = e;
-            if ((i64)(tile + 1) * EMIT_THREADS >= P.n_el) *P.total = e + tile_total;
-        }
-    } else if (active && staged) {
-        // ---- phase 1: digits and staging (C3D8 order, voxelFE.py:145-154):
-        //   eid, b, b+1, b+RN+1, b+RN, b+SN, b+SN+1, b+SN+RN+1, b+SN+RN
-        u32 o = excl;
-        if (hl) {
-            const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
-            for (u32 q = 0; q < hl; ++q) stage[o + q] = __ldg(h + q);
-            o += hl;
-        }
-        LineWriter w;
-        w.lead = o & 3u;
-        w.d = w.lead;
-        w.acc = 0;
-        w.wp = stage + (o - w.lead);
-        u32 r0, r1, r2, low4;
-        raw12<WIDE>(eid, r0, r1, r2, low4);
-        lw_append<true>(w, r0, r1, r2, nd0, 0x2Cu);
-        const bool same = nlo == nhi;
-        // the four (v, v+1) pairs share everything but the low four digits (unless those wrap)
+    const u32 tot = __reduce_add_sync(CFE_FULL_MASK, len);
+    if ((threadIdx.x & 31u) == 0 && (j >> 5) < P.n_warp_tiles) P.warp_total[j >> 5] = tot;
+}
+
+#define ELEM_WARP_STAGE 3584     // bytes of staging per warp: 32 lines of <= 99 bytes + headers + pad
+
+// PERM: elements come from the GV-major permutation; WIDE: ids may exceed 32 bits.
+template <bool PERM, bool WIDE>
+__global__ void __launch_bounds__(256) k_emit_elements(ElemEmitParams P)
+{
+    __shared__ __align__(16) char stage_all[8 * ELEM_WARP_STAGE];
+    const u32 lane = threadIdx.x & 31u;
+    char* stage = stage_all + (threadIdx.x >> 5) * ELEM_WARP_STAGE;
+    const i64 wt = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);       // warp tile
+    if (wt >= P.n_warp_tiles) return;
+    const i64 j = wt * 32 + lane;
+    const bool active = j < P.n_el;
+    const u32 len = active ? (u32)__ldg(P.len8 + j) : 0u;
+    // warp exclusive scan of the line lengths
+    u32 incl = len;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const u64 v0 = b + ((q & 1) ? P.RN : 0) + ((q & 2) ? P.SN : 0);
-            raw12<WIDE>(v0, r0, r1, r2, low4);
-            u32 h0 = r0, h1 = r1, h2;
-            if (low4 != 9999u) {
-                h2 = raw4(low4 + 1u);
-            } else {
-                u32 dummy;
-                raw12<WIDE>(v0 + 1, h0, h1, h2, dummy);
-            }
-            const int n0 = same ? nlo : raw12_digits(r0, r1, r2);
-            const int n1 = same ? nlo : raw12_digits(h0, h1, h2);
-            const u32 last = (q == 3) ? 0x0Au : 0x2Cu;
-            if ((q & 1) == 0) {          // order: v, v+1
-                if (q == 0) lw_append<true>(w, r0, r1, r2, n0, 0x2Cu);
-                else lw_append<false>(w, r0, r1, r2, n0, 0x2Cu);
-                lw_append<false>(w, h0, h1, h2, n1, 0x2Cu);
-            } else {                     // order: v+1, v
-                lw_append<false>(w, h0, h1, h2, n1, 0x2Cu);
-                lw_append<false>(w, r0, r1, r2, n0, last);
-            }
-        }
-        lw_finish(w);
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(CFE_FULL_MASK, incl, o);
+        if (lane >= (u32)o) incl += t;
     }
-    __syncthreads();
-    char* dst = P.out + s_base;
-    if (is_first && P.blk_off) P.blk_off[gv] = s_base + excl;
-    if (staged) {
-        flush_unaligned(stage, tile_total, dst);
-    } else if (active) {
-        char* p = dst + excl;
-        if (hl) {
-            const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
-            for (u32 q = 0; q < hl; ++q) p[q] = __ldg(h + q);
-            p += hl;
+    const u32 excl = incl - len;
+    const u32 total = __shfl_sync(CFE_FULL_MASK, incl, 31);
+    const u64 base = __ldg(P.warp_off + wt);
+    char* dst = P.out + base;
+    const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    const bool staged = pad + total <= (u32)ELEM_WARP_STAGE;
+    if (active) {
+        u64 b, eid;
+        int gv;
+        elem_ids<PERM>(P, j, b, eid, gv);
+        const u32 flags = __ldg(P.nd8 + j);
+        u32 hl = 0;
+        if ((u64)j == __ldg(P.first + gv)) {
+            hl = __ldg(P.hdr_len + gv);
+            if (P.blk_off) P.blk_off[gv] = base + excl;
         }
-        const u64 vals[9] = {eid, b, b + 1, b + P.RN + 1, b + P.RN, b + P.SN, b + P.SN + 1, b + P.SN + P.RN + 1,
-                             b + P.SN + P.RN};
+        if (staged) {
+            // eid, b, b+1, b+RN+1, b+RN | b+SN, b+SN+1, b+SN+RN+1, b+SN+RN   (voxelFE.py:145-154)
+            u32 o = pad + excl;
+            if (hl) {
+                const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
+                for (u32 q = 0; q < hl; ++q) stage[o + q] = __ldg(h + q);
+                o += hl;
+            }
+            LineWriter w;
+            w.lead = o & 3u;
+            w.d = w.lead;
+            w.acc = 0;
+            w.wp = stage + (o - w.lead);
+            u32 r0, r1, r2, low4;
+            raw12<WIDE>(eid, r0, r1, r2, low4);
+            lw_append<true>(w, r0, r1, r2, raw12_digits(r0, r1, r2), 0x2Cu);
+            const bool same = (flags & 0x80u) != 0;
+            const int nlo = (int)(flags & 15u);
+            // the four (v, v+1) pairs share everything but the low four digits (unless those wrap)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                u32 F[4][3];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const u64 v0 = b + (q ? P.RN : 0) + (h ? P.SN : 0);
+                    const int f_lo = q ? 3 : 0;               // slot of v
+                    const int f_hi = q ? 2 : 1;               // slot of v + 1
+                    raw12<WIDE>(v0, r0, r1, r2, low4);
+                    F[f_lo][0] = r0 + 0x30303030u; F[f_lo][1] = r1 + 0x30303030u; F[f_lo][2] = r2 + 0x30303030u;
+                    if (low4 != 9999u) {
+                        F[f_hi][0] = F[f_lo][0]; F[f_hi][1] = F[f_lo][1];
+                        F[f_hi][2] = raw4(low4 + 1u) + 0x30303030u;
+                    } else {
+                        u32 dummy;
+                        raw12<WIDE>(v0 + 1, r0, r1, r2, dummy);
+                        F[f_hi][0] = r0 + 0x30303030u; F[f_hi][1] = r1 + 0x30303030u; F[f_hi][2] = r2 + 0x30303030u;
+                    }
+                }
+                if (h == 0) lw_append_half<false>(w, F, nlo, same);
+                else lw_append_half<true>(w, F, nlo, same);
+            }
+            lw_finish(w);
+        } else {
+            // pathological warp tile (dozens of block headers): direct byte writes
+            char* p = dst + excl;
+            if (hl) {
+                const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
+                for (u32 q = 0; q < hl; ++q) p[q] = __ldg(h + q);
+                p += hl;
+            }
+            const u64 vals[9] = {eid, b, b + 1, b + P.RN + 1, b + P.RN, b + P.SN, b + P.SN + 1,
+                                 b + P.SN + P.RN + 1, b + P.SN + P.RN};
 #pragma unroll 1
-        for (int f = 0; f < 9; ++f) {
-            const int n = digits_u64(vals[f]);
-            p += n;
-            put_u64_back(p, vals[f], n);
-            *p++ = (f == 8) ? '\n' : ',';
+            for (int f = 0; f < 9; ++f) {
+                const int n = digits_u64(vals[f]);
+                p += n;
+                put_u64_back(p, vals[f], n);
+                *p++ = (f == 8) ? '\n' : ',';
+            }
         }
     }
+    __syncwarp();
+    if (!staged) return;
+    // stream the warp's span [pad, pad + total) to dst: aligned 16-byte chunks, bytes at the edges
+    char* gbase = dst - pad;
+    const u32 end = pad + total;
+    const u32 c0 = pad ? 1u : 0u, c1 = end >> 4;
+#pragma unroll 1
+    for (u32 c = c0 + lane; c < c1; c += 32u)
+        *reinterpret_cast<uint4*>(gbase + 16u * c) = *reinterpret_cast<const uint4*>(stage + 16u * c);
+    if (pad) {
+        const u32 hb = end < 16u ? end : 16u;
+        for (u32 k = pad + lane; k < hb; k += 32u) gbase[k] = stage[k];
+    }
+    if ((c1 << 4) < end && c1 >= c0) {
+        for (u32 k = (c1 << 4) + lane; k < end; k += 32u) gbase[k] = stage[k];
+    }
+}
+
+extern "C" size_t cfe_emit_elements_workspace_bytes(int64_t n_el)
+{
+    // len8 + nd8 (1 byte each, 16-byte aligned), warp_total (u32), warp_off (u64), scan workspace
+    const size_t nw = (size_t)((n_el + 31) / 32);
+    const size_t a = ((size_t)n_el + 15) & ~(size_t)15;
+    return 2 * a + ((nw * 4 + 15) & ~(size_t)15) + nw * 8 + 16 + cfe_scan_workspace_bytes((int64_t)nw) + 64;
 }
 
 extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
@@ -546,10 +679,9 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
                                  int single_gv, int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset,
                                  char* out, uint64_t* total, uint64_t* blk_off, void* ws, cudaStream_t stream)
 {
-    const i64 tiles = (n_el + EMIT_THREADS - 1) / EMIT_THREADS;
-    CFE_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(tiles + 2) * sizeof(u64), stream));
     CFE_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(u64), stream));
-    if (tiles == 0) return 0;
+    if (n_el <= 0) return 0;
+    const i64 nw = (n_el + 31) / 32;
     ElemEmitParams P;
     P.elem_vox = elem_vox; P.perm = reinterpret_cast<const uint2*>(perm); P.n_el = n_el; P.vol = vol;
     P.first = reinterpret_cast<const u64*>(first); P.hdr_text = hdr_text; P.hdr_len = hdr_len;
@@ -557,27 +689,38 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
     P.YX32 = (u32)(Y * X); P.X32 = (u32)X;
     P.dYX = make_fastdiv(P.YX32); P.dX = make_fastdiv(P.X32);
     P.RN = X + 1; P.SN = (X + 1) * (Y + 1); P.z0 = z0; P.eid_offset = eid_offset;
-    P.out = out; P.total = reinterpret_cast<u64*>(total); P.blk_off = reinterpret_cast<u64*>(blk_off);
-    P.ws = reinterpret_cast<u64*>(ws);
-    // largest id that can appear in this slab's lines: node ids up to the top corner of the slab's
-    // last voxel, element ids up to eid_offset + n_el
+    P.out = out; P.blk_off = reinterpret_cast<u64*>(blk_off);
+    // carve the workspace
+    char* w = reinterpret_cast<char*>(ws);
+    const size_t a = ((size_t)n_el + 15) & ~(size_t)15;
+    P.len8 = reinterpret_cast<uint8_t*>(w); w += a;
+    P.nd8 = reinterpret_cast<uint8_t*>(w); w += a;
+    P.warp_total = reinterpret_cast<u32*>(w); w += ((size_t)nw * 4 + 15) & ~(size_t)15;
+    u64* warp_off = reinterpret_cast<u64*>(w); w += (size_t)nw * 8 + 16;
+    void* scan_ws = w;
+    P.warp_off = warp_off;
+    P.n_warp_tiles = nw;
+    // largest id that can appear in this slab's lines
     const unsigned long long max_node = (unsigned long long)P.SN * (unsigned long long)(z0 + Zl + 1);
     const bool wide = (max_node >= 0xffffffffull) || ((unsigned long long)(eid_offset + n_el) >= 0xffffffffull);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ELEM_STAGE_BYTES));
-        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ELEM_STAGE_BYTES));
-        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ELEM_STAGE_BYTES));
-        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ELEM_STAGE_BYTES));
-        attr_set = true;
-    }
-    const unsigned g = (unsigned)tiles;
+    const unsigned g1 = (unsigned)((n_el + 255) / 256);
     if (perm) {
-        if (wide) k_emit_elements<true, true><<<g, ELEM_CTA_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
-        else k_emit_elements<true, false><<<g, ELEM_CTA_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
+        if (wide) k_elem_lengths<true, true><<<g1, 256, 0, stream>>>(P);
+        else k_elem_lengths<true, false><<<g1, 256, 0, stream>>>(P);
     } else {
-        if (wide) k_emit_elements<false, true><<<g, ELEM_CTA_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
-        else k_emit_elements<false, false><<<g, ELEM_CTA_THREADS, ELEM_STAGE_BYTES, stream>>>(P);
+        if (wide) k_elem_lengths<false, true><<<g1, 256, 0, stream>>>(P);
+        else k_elem_lengths<false, false><<<g1, 256, 0, stream>>>(P);
+    }
+    CFE_CHECK_LAUNCH("k_elem_lengths");
+    int rc = cfe_scan_u32(P.warp_total, nw, reinterpret_cast<uint64_t*>(warp_off), total, scan_ws, stream);
+    if (rc) return rc;
+    const unsigned g2 = (unsigned)((nw + 7) / 8);
+    if (perm) {
+        if (wide) k_emit_elements<true, true><<<g2, 256, 0, stream>>>(P);
+        else k_emit_elements<true, false><<<g2, 256, 0, stream>>>(P);
+    } else {
+        if (wide) k_emit_elements<false, true><<<g2, 256, 0, stream>>>(P);
+        else k_emit_elements<false, false><<<g2, 256, 0, stream>>>(P);
     }
     CFE_CHECK_LAUNCH("k_emit_elements");
     return 0;

@@ -592,7 +592,8 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         totals = torch.zeros(2, dtype=torch.int64, device=dev)
         blk_off = torch.zeros(256, dtype=torch.int64, device=dev)
         seg_off = torch.zeros(max(len(segs), 1), dtype=torch.int64, device=dev)
-        ws = scan_workspace(max(m.n_el, n_items, 1), dev)
+        ws = scan_workspace(max(n_items, 1), dev)
+        ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(m.n_el) + 16, dtype=torch.uint8, device=dev)
         _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
                   Y, X, m.z0, nodes_buf.data_ptr(), s)
         perm = None
@@ -612,7 +613,7 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             single_gv = -1
         _lib.call("cfe_emit_elements", m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(),
                   base + o_first, base + o_hdr, base + o_hlen, single_gv if single_gv >= 0 else 0, Zl, Y, X, m.z0,
-                  m.eid_offset, elem_buf.data_ptr(), totals.data_ptr(), blk_off.data_ptr(), ws.data_ptr(), s)
+                  m.eid_offset, elem_buf.data_ptr(), totals.data_ptr(), blk_off.data_ptr(), ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base, items_buf.data_ptr(),
                   None, totals.data_ptr() + 8, seg_off.data_ptr(), ws.data_ptr(), s)
         # byte sizes of my (gv) element blocks and of my set segments

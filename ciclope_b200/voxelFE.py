@@ -633,7 +633,8 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         out_full = torch.empty(cap + 16, dtype=torch.uint8, device=dev)
         out = out_full[(-(out_full.data_ptr() + off_nodes)) % 16:]
         totals = torch.zeros(2, dtype=torch.int64, device=dev)   # element bytes, set bytes
-        ws = scan_workspace(max(m.n_el, n_items, 1), dev)
+        ws = scan_workspace(max(n_items, 1), dev)
+        ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(m.n_el) + 16, dtype=torch.uint8, device=dev)
         _lib.call("cfe_put_literal", base + o_head, len(head), out.data_ptr(), None, None, s)
         _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
                   Y, X, 0, out.data_ptr() + off_nodes, s)
@@ -655,7 +656,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             single_gv = -1
         _lib.call("cfe_emit_elements", m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(),
                   base + o_first, base + o_hdr, base + o_hlen, single_gv, Z, Y, X, 0, 0,
-                  out.data_ptr() + off_elem, totals.data_ptr(), None, ws.data_ptr(), s)
+                  out.data_ptr() + off_elem, totals.data_ptr(), None, ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base + o_lits,
                   out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, None, ws.data_ptr(), s)
         _lib.call("cfe_put_literal", base + o_tail, len(tail), out.data_ptr() + off_elem, totals.data_ptr(),

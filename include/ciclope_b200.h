@@ -163,7 +163,10 @@ int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab,
  * (single_gv); otherwise perm holds {voxel, raster rank} pairs in GV-major order and vol is
  * read for the grey value.  first[gv] = emission index of the first element of block gv;
  * hdr_text/hdr_len = '*ELEMENT, TYPE=.., ELSET=SET<gv>\n' per gv in 64-byte slots.
- * *total = bytes written; blk_off[gv] = offset where block gv (header included) starts (optional). */
+ * *total = bytes written; blk_off[gv] = offset where block gv (header included) starts (optional).
+ * Three launches: line lengths, exclusive scan of the 32-line tile totals, formatting.
+ * ws: cfe_emit_elements_workspace_bytes(n_el) bytes of scratch. */
+size_t cfe_emit_elements_workspace_bytes(int64_t n_el);
 int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
                       const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len, int single_gv,
                       int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, char* out,
