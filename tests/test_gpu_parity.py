@@ -69,7 +69,9 @@ def test_remove_unconnected_empty_raises(cfe):
 
 @pytest.mark.parametrize("shape,density,seed", [
     ((32, 32, 32), 0.2, 1), ((32, 32, 32), 0.32, 2), ((17, 23, 129), 0.28, 3), ((40, 33, 96), 0.5, 4),
-    ((64, 64, 64), 0.31, 5), ((5, 200, 70), 0.3, 6), ((64, 48, 160), 0.26, 7)])
+    ((64, 64, 64), 0.31, 5), ((5, 200, 70), 0.3, 6), ((64, 48, 160), 0.26, 7),
+    # > 8192 runs per (8 slices x 32 rows) tile: the block-local union-find hands the tile to the global kernel
+    ((8, 32, 512), 0.5, 8), ((16, 64, 300), 0.45, 9), ((9, 33, 1024), 0.33, 10)])
 def test_remove_unconnected_random_vs_oracle(cfe, orc, shape, density, seed):
     # random noise near the 6-connectivity percolation threshold: thousands of components, many ties
     bw = cases.rand_binary(shape, density, 1000 + seed)
