@@ -111,56 +111,63 @@ k_ccl_merge(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 n_wo
 // the local forest and writes parent[run] = tile-local root.  Local run indices follow the global
 // raster order restricted to the tile, so the smallest local index is also the smallest global id.
 // Tiles holding more than CCL_LOCAL_CAP runs are left to the global kernel (tile_flag = 0).
-__global__ void __launch_bounds__(CCL_TILE_ROWS)
+#define CCL_LOCAL_THREADS 512
+
+__global__ void __launch_bounds__(CCL_LOCAL_THREADS)
 k_ccl_local(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64* __restrict__ n_runs_p,
-            int Z, int Y, int W, u32* __restrict__ parent, u32* __restrict__ tile_flag, int tiles_r)
+            int Z, int Y, int W, FastDiv dW, u32* __restrict__ parent, u32* __restrict__ tile_flag, int tiles_r)
 {
     __shared__ u32 sp[CCL_LOCAL_CAP];
     __shared__ u32 rb_g[CCL_TILE_ROWS + 1];   // global run id at the start of each tile row
     __shared__ u32 rb_l[CCL_TILE_ROWS + 1];   // local run index at the start of each tile row
+    __shared__ u32 rw[CCL_TILE_ROWS];         // global word index of each tile row (0xffffffff: outside)
     __shared__ u32 s_scan[33];
     const int tile_s = blockIdx.x / tiles_r, tile_r = blockIdx.x - tile_s * tiles_r;
     const int t = threadIdx.x;
-    // tile row t  <->  slice s0 + t / TR, row r0 + t % TR
-    const int s = tile_s * CCL_TS + t / CCL_TR, r = tile_r * CCL_TR + (t % CCL_TR);
-    const bool valid = s < Z && r < Y;
-    const i64 row = (i64)s * Y + r;
-    const i64 n_rows = (i64)Z * Y;
     u32 g0 = 0, cnt = 0;
-    if (valid) {
-        g0 = __ldg(pref + row * W);
-        const u32 g1 = (row + 1 < n_rows) ? __ldg(pref + (row + 1) * W) : (u32)(*n_runs_p);
-        cnt = g1 - g0;
+    if (t < CCL_TILE_ROWS) {
+        // tile row t  <->  slice s0 + t / TR, row r0 + t % TR
+        const int s = tile_s * CCL_TS + t / CCL_TR, r = tile_r * CCL_TR + (t % CCL_TR);
+        const bool valid = s < Z && r < Y;
+        const i64 row = (i64)s * Y + r;
+        const i64 n_rows = (i64)Z * Y;
+        if (valid) {
+            g0 = __ldg(pref + row * W);
+            const u32 g1 = (row + 1 < n_rows) ? __ldg(pref + (row + 1) * W) : (u32)(*n_runs_p);
+            cnt = g1 - g0;
+        }
+        rw[t] = valid ? (u32)(row * W) : 0xffffffffu;
+        rb_g[t] = g0;
     }
     u32 total;
     const u32 l0 = block_exclusive_scan<u32>(cnt, s_scan, total);
-    rb_g[t] = g0;
-    rb_l[t] = l0;
+    if (t < CCL_TILE_ROWS) rb_l[t] = l0;
     if (t == 0) { rb_l[CCL_TILE_ROWS] = total; tile_flag[blockIdx.x] = total <= CCL_LOCAL_CAP ? 1u : 0u; }
     if (total > CCL_LOCAL_CAP || total == 0) return;   // uniform for the CTA
-    for (u32 l = t; l < total; l += CCL_TILE_ROWS) sp[l] = l;
+    for (u32 l = t; l < total; l += CCL_LOCAL_THREADS) sp[l] = l;
     __syncthreads();
     // unions between rows of the tile
-    const int tile_words = CCL_TILE_ROWS * W;
-    for (int wt = t; wt < tile_words; wt += CCL_TILE_ROWS) {
-        const int tr = wt / W, w = wt - tr * W;
-        const int ss = tile_s * CCL_TS + tr / CCL_TR, rr = tile_r * CCL_TR + (tr % CCL_TR);
-        if (ss >= Z || rr >= Y) continue;
-        const i64 i = ((i64)ss * Y + rr) * W + w;
+    const u32 tile_words = (u32)CCL_TILE_ROWS * (u32)W;
+    const u32 slice_words = (u32)W * (u32)Y;
+    for (u32 wt = t; wt < tile_words; wt += CCL_LOCAL_THREADS) {
+        const u32 tr = fd_div(wt, dW), w = wt - tr * (u32)W;
+        const u32 rbase = rw[tr];
+        if (rbase == 0xffffffffu) continue;
+        const u32 i = rbase + w;
         const u32 cur = __ldg(bits + i);
         if (!cur) continue;
+        const bool up = (tr % CCL_TR) != 0, back = tr >= CCL_TR;
+        // issue every load of this word before the first use
         const u32 cur_prev = w ? __ldg(bits + i - 1) : 0u;
         const u32 cur_pref = __ldg(pref + i);
+        const u32 nbw[2] = {up ? __ldg(bits + i - W) : 0u, back ? __ldg(bits + i - slice_words) : 0u};
         const u32 cur_off = rb_l[tr] - rb_g[tr];           // local = global + off (mod 2^32)
 #pragma unroll
         for (int dir = 0; dir < 2; ++dir) {
-            int tn;
-            i64 j;
-            if (dir == 0) { if ((tr % CCL_TR) == 0) continue; tn = tr - 1; j = i - W; }
-            else { if (tr < CCL_TR) continue; tn = tr - CCL_TR; j = i - (i64)W * Y; }
-            const u32 nb = __ldg(bits + j);
-            const u32 both = cur & nb;
+            const u32 both = cur & nbw[dir];
             if (!both) continue;
+            const u32 j = dir == 0 ? i - (u32)W : i - slice_words;
+            const u32 tn = dir == 0 ? tr - 1 : tr - CCL_TR;
             const u32 nb_prev = w ? __ldg(bits + j - 1) : 0u;
             const u32 nb_pref = __ldg(pref + j);
             const u32 nb_off = rb_l[tn] - rb_g[tn];
@@ -169,22 +176,27 @@ k_ccl_local(const u32* __restrict__ bits, const u32* __restrict__ pref, const u6
                 const int b = __ffs((int)pair_starts) - 1;
                 pair_starts &= pair_starts - 1;
                 uf_union(sp, run_id(cur, cur_prev >> 31, cur_pref, b) + cur_off,
-                         run_id(nb, nb_prev >> 31, nb_pref, b) + nb_off);
+                         run_id(nbw[dir], nb_prev >> 31, nb_pref, b) + nb_off);
             }
         }
     }
     __syncthreads();
-    // flatten locally and publish global parents
-    for (u32 l = t; l < total; l += CCL_TILE_ROWS) {
-        u32 x = l, q;
-        while ((q = sp[x]) != x) x = q;
-        // tile row of l and of its root: binary search in rb_l (rows with zero runs are skipped by <=)
-        int lo = 0, hi = CCL_TILE_ROWS;          // invariant: rb_l[lo] <= x < rb_l[hi]
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rb_l[mid] <= x) lo = mid; else hi = mid; }
-        const u32 groot = rb_g[lo] + (x - rb_l[lo]);
-        lo = 0; hi = CCL_TILE_ROWS;
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rb_l[mid] <= l) lo = mid; else hi = mid; }
-        parent[rb_g[lo] + (l - rb_l[lo])] = groot;
+    // flatten and publish: thread t owns tile row t; the root's global id is found by a binary
+    // search over the row starts, memoised because consecutive runs mostly share their root
+    if (t < CCL_TILE_ROWS) {
+        const u32 lbeg = rb_l[t], lend = rb_l[t + 1], gbeg = rb_g[t];
+        u32 last_root = 0xffffffffu, last_gid = 0;
+        for (u32 l = lbeg; l < lend; ++l) {
+            u32 x = l, q;
+            while ((q = sp[x]) != x) x = q;
+            if (x != last_root) {
+                int lo = 0, hi = CCL_TILE_ROWS;      // invariant: rb_l[lo] <= x < rb_l[hi]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rb_l[mid] <= x) lo = mid; else hi = mid; }
+                last_root = x;
+                last_gid = rb_g[lo] + (x - rb_l[lo]);
+            }
+            parent[gbeg + (l - lbeg)] = last_gid;
+        }
     }
 }
 
@@ -354,8 +366,8 @@ extern "C" int cfe_ccl_label(const uint32_t* bits, const uint32_t* pref, const u
     // tile flags live behind the n_runs <= rows*ceil(X/2) entries of `size` (see cfe_ccl_max_runs)
     const int tiles_s = (int)((Z + CCL_TS - 1) / CCL_TS), tiles_r = (int)((Y + CCL_TR - 1) / CCL_TR);
     u32* tile_flag = size + (size_t)rows * (size_t)((X + 1) / 2);
-    k_ccl_local<<<(unsigned)(tiles_s * tiles_r), CCL_TILE_ROWS, 0, stream>>>(bits, pref, nr, (int)Z, (int)Y, W, parent,
-                                                                            tile_flag, tiles_r);
+    k_ccl_local<<<(unsigned)(tiles_s * tiles_r), CCL_LOCAL_THREADS, 0, stream>>>(
+        bits, pref, nr, (int)Z, (int)Y, W, make_fastdiv((u32)W), parent, tile_flag, tiles_r);
     CFE_CHECK_LAUNCH("k_ccl_local");
     k_ccl_merge<<<wb, 256, 0, stream>>>(bits, pref, n_words, W, (int)Y, parent, tile_flag, tiles_r);
     CFE_CHECK_LAUNCH("k_ccl_merge");
