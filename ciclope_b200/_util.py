@@ -50,3 +50,19 @@ def check_slab_size(Z, Y, X):
     if (Z + 1) * (Y + 1) * (X + 1) >= 2 ** 32:
         raise ValueError("a single-GPU slab must hold fewer than 2^32 grid nodes; shard the volume as "
                          "z-slabs over more GPUs")
+
+
+def to_device_async(data, dtype, device):
+    """Small host data -> device tensor without a blocking copy: staged in pinned memory (torch's
+    caching host allocator) and copied with non_blocking=True on the current stream.
+    torch.tensor(..., device=cuda) would block the host until everything queued before it is done."""
+    if isinstance(data, torch.Tensor):
+        host = data.to(dtype)
+    else:
+        host = torch.tensor(data, dtype=dtype)
+    return host.pin_memory().to(device, non_blocking=True)
+
+
+def bytes_to_device_async(raw, device):
+    host = torch.frombuffer(bytearray(raw) if len(raw) else bytearray(b"\0"), dtype=torch.uint8)
+    return host.pin_memory().to(device, non_blocking=True)

@@ -509,3 +509,48 @@ extern "C" int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* pr
     CFE_CHECK_LAUNCH("k_ccl_interface_edges");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Boundary graph of the cross-slab merge: vertices = slab-local components that touch an
+// interface plane (dense indices, sorted by global key), edges = overlapping run pairs.
+// label[v] = smallest vertex index of v's component (same union-find as the voxel kernels).
+
+__global__ void __launch_bounds__(256)
+k_uf_edges(u32* __restrict__ label, const i64* __restrict__ ea, const i64* __restrict__ eb, i64 n_edges)
+{
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_edges) uf_union(label, (u32)ea[e], (u32)eb[e]);
+}
+
+__global__ void __launch_bounds__(256) k_uf_flatten(u32* __restrict__ label, i64 n)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 r = (u32)i, p;
+    while ((p = label[r]) != r) r = p;
+    label[i] = r;
+}
+
+__global__ void __launch_bounds__(256) k_uf_iota(u32* __restrict__ label, i64 n)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) label[i] = (u32)i;
+}
+
+// label: u32 [n_vertices] (initialised here); ea/eb: int64 dense endpoints of the n_edges edges
+extern "C" int cfe_uf_solve(uint32_t* label, int64_t n_vertices, const int64_t* ea, const int64_t* eb,
+                            int64_t n_edges, cudaStream_t stream)
+{
+    if (n_vertices <= 0) return 0;
+    const unsigned vb = (unsigned)((n_vertices + 255) / 256);
+    k_uf_iota<<<vb, 256, 0, stream>>>(label, n_vertices);
+    CFE_CHECK_LAUNCH("k_uf_iota");
+    if (n_edges > 0) {
+        k_uf_edges<<<(unsigned)((n_edges + 255) / 256), 256, 0, stream>>>(label, reinterpret_cast<const i64*>(ea),
+                                                                          reinterpret_cast<const i64*>(eb), n_edges);
+        CFE_CHECK_LAUNCH("k_uf_edges");
+        k_uf_flatten<<<vb, 256, 0, stream>>>(label, n_vertices);
+        CFE_CHECK_LAUNCH("k_uf_flatten");
+    }
+    return 0;
+}

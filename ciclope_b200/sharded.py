@@ -26,7 +26,7 @@ import torch
 from . import _lib
 from . import voxelFE as vfe
 from ._lib import CfeItemSeg, CfeSetDesc
-from ._util import empty_u32, scan_workspace
+from ._util import bytes_to_device_async, empty_u32, scan_workspace, to_device_async
 
 
 # --------------------------------------------------------------------------------------------
@@ -150,24 +150,31 @@ class DistRunner:
     def ctx(self):
         return Ctx(self.rank, self.size, self.device)
 
+    def _gather(self, t):
+        """all_gather_into_tensor: one flat output, far less Python / launch overhead than the list API"""
+        t = t.contiguous()
+        flat = t.reshape(-1)
+        out = torch.empty(self.size * flat.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, flat, group=self.group)
+        return out.reshape((self.size,) + tuple(t.shape))
+
     def _fulfil(self, kind, t):
         dist = self.dist
         if kind == "all_gather":
-            out = [torch.empty_like(t) for _ in range(self.size)]
-            dist.all_gather(out, t.contiguous(), group=self.group)
-            return out
+            return list(self._gather(t).unbind(0))
         if kind == "all_gather_var":
             n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
-            ns = [torch.empty_like(n) for _ in range(self.size)]
-            dist.all_gather(ns, n, group=self.group)
-            ns = [int(v.item()) for v in ns]
+            ns = [int(v) for v in self._gather(n).reshape(-1).tolist()]
             m = max(max(ns), 1)
             pad = torch.zeros(m, dtype=t.dtype, device=t.device)
             pad[: t.numel()] = t.reshape(-1)
-            out = [torch.empty_like(pad) for _ in range(self.size)]
-            dist.all_gather(out, pad, group=self.group)
-            return [o[:k] for o, k in zip(out, ns)]
+            out = self._gather(pad)
+            return [out[k, :c] for k, c in enumerate(ns)]
         if kind == "shift_up":
+            if t.numel() * t.element_size() <= self.SHIFT_VIA_GATHER_BYTES:
+                # small planes: one all-gather is cheaper to issue than a send/recv pair
+                out = self._gather(t)
+                return out[self.rank - 1] if self.rank > 0 else None
             ops, recv = [], None
             if self.rank + 1 < self.size:
                 ops.append(dist.P2POp(dist.isend, t.contiguous(), self.rank + 1, group=self.group))
@@ -182,6 +189,8 @@ class DistRunner:
             dist.barrier(group=self.group)
             return None
         raise RuntimeError("unknown collective %s" % kind)
+
+    SHIFT_VIA_GATHER_BYTES = 4 << 20
 
     def run(self, program):
         try:
@@ -202,7 +211,8 @@ def solve_boundary_components(keys, sizes, edges):
     sizes : int64 [V] voxels of each slab-local component
     edges : int64 [E,2] vertex keys of overlapping runs across slab interfaces
     Returns (label [V] = index of the smallest-key vertex of the component, comp_size [V] (valid at
-    label positions)).  Label propagation with pointer jumping; O(log diameter) rounds."""
+    label positions)).  On CUDA tensors the components come from the library's union-find kernels
+    (cfe_uf_solve); on CPU tensors (unit tests, gloo) from label propagation with pointer jumping."""
     V = keys.numel()
     lab = torch.arange(V, dtype=torch.int64, device=keys.device)
     if V == 0:
@@ -210,21 +220,27 @@ def solve_boundary_components(keys, sizes, edges):
     if edges.numel():
         a = torch.searchsorted(keys, edges[:, 0].contiguous())
         b = torch.searchsorted(keys, edges[:, 1].contiguous())
-        while True:
-            m = torch.minimum(lab[a], lab[b])
-            new = lab.clone()
-            new.scatter_reduce_(0, a, m, reduce="amin")
-            new.scatter_reduce_(0, b, m, reduce="amin")
-            for _ in range(3):
-                new = new[new]
-            if torch.equal(new, lab):
-                break
-            lab = new
-        while True:           # full compression
-            nxt = lab[lab]
-            if torch.equal(nxt, lab):
-                break
-            lab = nxt
+        if keys.is_cuda:
+            lab32 = torch.empty(V, dtype=torch.int32, device=keys.device)
+            with torch.cuda.device(keys.device):
+                _lib.call("cfe_uf_solve", lab32.data_ptr(), V, a.data_ptr(), b.data_ptr(), a.numel(), _lib.stream())
+            lab = lab32.to(torch.int64)
+        else:
+            while True:
+                m = torch.minimum(lab[a], lab[b])
+                new = lab.clone()
+                new.scatter_reduce_(0, a, m, reduce="amin")
+                new.scatter_reduce_(0, b, m, reduce="amin")
+                for _ in range(3):
+                    new = new[new]
+                if torch.equal(new, lab):
+                    break
+                lab = new
+            while True:           # full compression
+                nxt = lab[lab]
+                if torch.equal(nxt, lab):
+                    break
+                lab = nxt
     comp = torch.zeros(V, dtype=torch.int64, device=keys.device)
     comp.scatter_add_(0, lab, sizes)
     return lab, comp
@@ -283,14 +299,13 @@ def ccl_program(ctx, vol):
         _lib.call("cfe_ccl_plane_roots", bits.data_ptr(), pref.data_ptr(), Zl - 1, Y, X, parent.data_ptr(),
                   roots_top.data_ptr(), cnt.data_ptr() + 4, s)
         top_bits = bits[(Zl - 1) * PW: Zl * PW]
-    # planes travel to the rank above (fixed shapes: bits PW, roots cap)
-    bitsA = yield from ctx.shift_up(top_bits)
-    rootsA = yield from ctx.shift_up(roots_top)
+    # the top plane (bits + run roots) travels to the rank above in one message
+    recv = yield from ctx.shift_up(torch.cat([top_bits, roots_top]))
     with torch.cuda.device(dev):
         s = _lib.stream()
-        n_edges = 0
         edges_dev = None
         if ctx.rank > 0:
+            bitsA, rootsA = recv[:PW], recv[PW:]
             prefA = empty_u32(PW, dev)
             scratch = torch.zeros(1, dtype=torch.int64, device=dev)
             _lib.call("cfe_scan_run_starts", bitsA.data_ptr(), Y, X, prefA.data_ptr(), scratch.data_ptr(),
@@ -299,8 +314,8 @@ def ccl_program(ctx, vol):
             _lib.call("cfe_ccl_interface_edges", bitsA.data_ptr(), prefA.data_ptr(), rootsA.data_ptr(),
                       bits.data_ptr(), pref.data_ptr(), parent.data_ptr(), Y, X, edges_dev.data_ptr(),
                       cnt.data_ptr() + 8, cap, s)
-        h = cnt.cpu().tolist()                      # sync: plane run counts, edge count
-        n_bot, n_top, n_edges = h[0], h[1], h[2]
+        h = torch.cat([cnt[:3].to(torch.int64), stats[:1]]).cpu().tolist()   # sync: plane runs, edges, runs
+        n_bot, n_top, n_edges, n_runs = h
         if n_edges > cap:
             raise _lib.CfeError("interface edge buffer overflow")
         # my boundary vertices (slab-local roots that own a run in an interface plane)
@@ -317,58 +332,59 @@ def ccl_program(ctx, vol):
             my_edges = torch.stack([e[:, 0] | ((ctx.rank - 1) << 32), e[:, 1] | (ctx.rank << 32)], dim=1)
         else:
             my_edges = torch.empty((0, 2), dtype=torch.int64, device=dev)
-    all_roots = yield from ctx.all_gather_var(my_roots)
-    all_sizes = yield from ctx.all_gather_var(my_sizes)
-    all_edges = yield from ctx.all_gather_var(my_edges.reshape(-1))
-    with torch.cuda.device(dev):
-        s = _lib.stream()
-        keys = torch.cat([r | (k << 32) for k, r in enumerate(all_roots)])     # sorted: ranks ascending
-        sizes = torch.cat(all_sizes)
-        edges = torch.cat(all_edges).reshape(-1, 2)
-        lab, comp = solve_boundary_components(keys, sizes, edges)
+        nr, ne = my_roots.numel(), my_edges.shape[0]
         # best slab-internal component of this rank: hide the boundary vertices from the arg-max
-        if my_roots.numel():
+        if nr:
             saved = size[my_roots].clone()
             size[my_roots] = 0
         _lib.call("cfe_ccl_select", parent.data_ptr(), size.data_ptr(), stats.data_ptr(), stats.data_ptr() + 8, s)
-        if my_roots.numel():
+        if nr:
             size[my_roots] = saved
-        best_internal = stats[1:2].clone()
-    all_best = yield from ctx.all_gather(best_internal)
+        head = to_device_async([nr, ne], torch.int64, dev)
+        head = torch.cat([head, stats[1:2]])             # + packed best internal component
+    heads = yield from ctx.all_gather(head)
+    hh = torch.stack(heads).cpu().tolist()               # sync: everybody's sizes
+    maxlen = max(max(2 * a + 2 * b for a, b, _ in hh), 1)
+    with torch.cuda.device(dev):
+        pack = torch.zeros(maxlen, dtype=torch.int64, device=dev)
+        pack[:nr] = my_roots
+        pack[nr:2 * nr] = my_sizes
+        pack[2 * nr:2 * nr + 2 * ne] = my_edges.reshape(-1)
+    packs = yield from ctx.all_gather(pack)
     with torch.cuda.device(dev):
         s = _lib.stream()
+        keys = torch.cat([packs[k][:a] | (k << 32) for k, (a, b, _) in enumerate(hh)])   # sorted by rank, root
+        sizes = torch.cat([packs[k][a:2 * a] for k, (a, b, _) in enumerate(hh)])
+        edges = torch.cat([packs[k][2 * a:2 * a + 2 * b] for k, (a, b, _) in enumerate(hh)]).reshape(-1, 2)
+        lab, comp = solve_boundary_components(keys, sizes, edges)
         cands = []
-        for k, b in enumerate(all_best):
-            v = int(b.item()) & 0xFFFFFFFFFFFFFFFF
+        for k, (_, _, best) in enumerate(hh):
+            v = best & 0xFFFFFFFFFFFFFFFF
             cands.append((v >> 32, (k << 32) | (0xFFFFFFFF - (v & 0xFFFFFFFF))))
+        wlab = -1
         if keys.numel():
             is_rep = lab == torch.arange(keys.numel(), device=dev)
-            rep_sizes = comp[is_rep]
-            rep_keys = keys[is_rep]
-            top = int(rep_sizes.max().item())
-            cands.append((top, int(rep_keys[rep_sizes == top].min().item())))
+            rep_size = torch.where(is_rep, comp, torch.zeros_like(comp))
+            top = rep_size.max()
+            top_idx = torch.where(rep_size == top, torch.arange(keys.numel(), device=dev),
+                                  torch.full_like(lab, keys.numel())).min()      # smallest key among the largest
+            t = torch.stack([top, keys[top_idx.clamp(max=keys.numel() - 1)], top_idx]).cpu().tolist()   # sync
+            cands.append((t[0], t[1]))
         winner = pick_winner(cands)
         if winner is None:
             out.zero_()
             return out, None
         wsize, wkey = winner
-        # which of MY roots belong to the winning component
-        off = sum(r.numel() for r in all_roots[: ctx.rank])
-        mine = slice(off, off + my_roots.numel())
-        idx = (keys == wkey).nonzero()
-        kept_roots = []
-        if idx.numel():                      # the winner is a merged (boundary) component
-            wlab = int(idx[0].item())
-            if lab[wlab].item() != wlab:
-                raise _lib.CfeError("internal error: winner is not a component representative")
-            kept_roots = my_roots[lab[mine] == wlab]
-        elif (wkey >> 32) == ctx.rank:       # a slab-internal component of this rank
-            kept_roots = torch.tensor([wkey & 0xFFFFFFFF], dtype=torch.int64, device=dev)
+        if keys.numel() and wkey == t[1] and wsize == t[0]:
+            wlab = t[2]
         # keep flags live in the (no longer needed) size array
-        n_runs = int(stats[0].item())
         size[: max(n_runs, 1)] = 0
-        if len(kept_roots):
-            size[kept_roots] = 1
+        off = sum(a for a, _, _ in hh[: ctx.rank])
+        if wlab >= 0:                        # the winner is a merged (boundary) component
+            if nr:
+                size[my_roots] = (lab[off: off + nr] == wlab).to(torch.int32)
+        elif (wkey >> 32) == ctx.rank:       # a slab-internal component of this rank
+            size[wkey & 0xFFFFFFFF] = 1
         _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
                   stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), s)
     return out, winner
@@ -448,10 +464,10 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
             d.tile_base = tile_base
             tile_base += (d.n_cand + 255) // 256
         n_tiles = tile_base
-        descs_dev = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev)
+        descs_dev = bytes_to_device_async(bytes(descs), dev)
         tile_count = empty_u32(n_tiles, dev)
         tile_off = torch.empty(max(n_tiles, 1) + 1, dtype=torch.int64, device=dev)
-        bases = torch.tensor([descs[q].tile_base for q in range(12)], dtype=torch.int64, device=dev)
+        bases = to_device_async([descs[q].tile_base for q in range(12)], torch.int64, dev)
         # element ids need the global offset -> counts first, ids after the all-gather
         _lib.call("cfe_sets_count", descs_dev.data_ptr(), 12, n_tiles, Zl, Y, X, z0, 0, bits.data_ptr(),
                   epref.data_ptr(), _lib.ptr(halo), tile_count.data_ptr(), s)
@@ -472,6 +488,7 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         m.eid_offset = sum(n_el_r[: ctx.rank])
         m.node_rank_offset = sum(n_nd_r[: ctx.rank])
         m.n_el_global, m.n_nd_global = sum(n_el_r), sum(n_nd_r)
+        m.n_el_by_rank = [int(v) for v in n_el_r]
         m.set_count = [int(c) for c in table[ctx.rank][2:14]]
         m.field_overflow = any(t[14] for t in table)
         m.set_first, n_ids = exclusive_offsets(m.set_count)
@@ -501,15 +518,18 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     dev = m.vol.device
     Zl, Y, X = m.Zl, m.Y, m.X
     rank = ctx.rank
-    with torch.cuda.device(dev):
-        s = _lib.stream()
-        hist_dev = torch.zeros(256, dtype=torch.int64, device=dev)
-        if m.is_bool:
-            hist_dev[1] = m.n_el
-        else:
+    if m.is_bool:
+        # a boolean volume has one grey value (True -> SET1): the histogram is the element count,
+        # which every rank already knows from vol2ugrid's all-gather
+        hist_r = np.zeros((ctx.size, 256), dtype=np.int64)
+        hist_r[:, 1] = m.n_el_by_rank
+    else:
+        with torch.cuda.device(dev):
+            s = _lib.stream()
+            hist_dev = torch.zeros(256, dtype=torch.int64, device=dev)
             _lib.call("cfe_gv_histogram", m.vol.data_ptr(), Zl * Y * X, m.thr, hist_dev.data_ptr(), s)
-    hists = yield from ctx.all_gather(hist_dev)
-    hist_r = torch.stack(hists).cpu().numpy()            # [rank][256]
+        hists = yield from ctx.all_gather(hist_dev)
+        hist_r = torch.stack(hists).cpu().numpy()        # [rank][256]
     hist = hist_r.sum(axis=0)
     if m.n_el_global == 0:
         raise ValueError("min() iterable argument is empty")
@@ -616,26 +636,30 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
                   m.eid_offset, elem_buf.data_ptr(), totals.data_ptr(), blk_off.data_ptr(), ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base, items_buf.data_ptr(),
                   None, totals.data_ptr() + 8, seg_off.data_ptr(), ws.data_ptr(), s)
-        # byte sizes of my (gv) element blocks and of my set segments
-        host = torch.cat([totals, blk_off, seg_off]).cpu().tolist()
-    el_total, it_total = host[0], host[1]
-    blk = host[2:258]
-    sgo = host[258:258 + len(segs)]
-    my_gvs = [int(g) for g in gvs if my_hist[g]]
-    gv_bytes = np.zeros(256, dtype=np.int64)
-    for i, g in enumerate(my_gvs):
-        end = blk[my_gvs[i + 1]] if i + 1 < len(my_gvs) else el_total
-        gv_bytes[g] = end - blk[g]
-    set_bytes = np.zeros(14, dtype=np.int64)
-    seg_local = {}
-    for i, (kind, q) in enumerate(seg_sets):
-        end = sgo[i + 1] if i + 1 < len(segs) else it_total
-        col = q if kind == "N" else 8 + q
-        set_bytes[col] = end - sgo[i]
-        seg_local[col] = (sgo[i], end)
-    mine = torch.from_numpy(np.concatenate([gv_bytes, set_bytes, [53 * m.n_nd]])).to(dev)
+        # byte sizes of my (gv) element blocks and of my set segments, computed on the device
+        my_gvs = [int(g) for g in gvs if my_hist[g]]
+        gv_bytes = torch.zeros(256, dtype=torch.int64, device=dev)
+        if my_gvs:
+            gi = to_device_async(my_gvs, torch.int64, dev)
+            starts = blk_off[gi]
+            gv_bytes[gi] = torch.cat([starts[1:], totals[0:1]]) - starts
+        set_bytes = torch.zeros(14, dtype=torch.int64, device=dev)
+        cols = [(q if kind == "N" else 8 + q) for kind, q in seg_sets]
+        if cols:
+            ci = to_device_async(cols, torch.int64, dev)
+            st = seg_off[: len(cols)]
+            set_bytes[ci] = torch.cat([st[1:], totals[1:2]]) - st
+        mine = torch.cat([gv_bytes, set_bytes, to_device_async([53 * m.n_nd], torch.int64, dev)])
     allb = yield from ctx.all_gather(mine)
-    allb = torch.stack(allb).cpu().numpy()             # [rank][256 + 14 + 1]
+    host = torch.cat([torch.stack(allb).reshape(-1), totals, blk_off, seg_off]).cpu().numpy()   # the one sync
+    nb = ctx.size * 271
+    allb = host[:nb].reshape(ctx.size, 271)             # [rank][256 + 14 + 1]
+    blk = host[nb + 2: nb + 258].tolist()
+    sgo = host[nb + 258: nb + 258 + len(segs)].tolist()
+    it_total = int(host[nb + 1])
+    seg_local = {}
+    for i, col in enumerate(cols):
+        seg_local[col] = (sgo[i], sgo[i + 1] if i + 1 < len(cols) else it_total)
 
     # ---- global file layout (identical on every rank)
     writes = []        # (file offset, device tensor, lo, hi)

@@ -26,7 +26,8 @@ import torch
 
 from . import _lib
 from ._lib import CfeItemSeg, CfeSetDesc
-from ._util import as_device_volume, check_slab_size, empty_u32, scan_workspace
+from ._util import (as_device_volume, bytes_to_device_async, check_slab_size, empty_u32, scan_workspace,
+                    to_device_async)
 
 CellBlock = collections.namedtuple("CellBlock", ["type", "data"])  # meshio 5.0.0 CellBlock
 
@@ -79,7 +80,7 @@ def _format_tables_device(xs, ys, zs, dev, overflow_ptr, stream):
         if a.dtype.kind in "iu" and a.size and int(np.abs(a).max()) >= 2 ** 53:
             raise NotImplementedError("integer node coordinates beyond 2^53 are not supported")
         vals.append(np.asarray(a, dtype=np.float64))
-    tab = torch.from_numpy(np.concatenate(vals)).to(dev, non_blocking=True)
+    tab = torch.from_numpy(np.concatenate(vals)).pin_memory().to(dev, non_blocking=True)
     out = torch.empty(16 * tab.numel(), dtype=torch.uint8, device=dev)
     _lib.call("cfe_format_coords", tab.data_ptr(), tab.numel(), out.data_ptr(), overflow_ptr, stream)
     return out
@@ -318,12 +319,11 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
             d.tile_base = tile_base
             tile_base += (d.n_cand + 255) // 256
         n_tiles = tile_base
-        descs_host = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
-        descs_dev = descs_host.to(dev, non_blocking=False)
+        descs_dev = bytes_to_device_async(bytes(descs), dev)
         tile_count = empty_u32(n_tiles, dev)
         tile_off = torch.empty(max(n_tiles, 1) + 1, dtype=torch.int64, device=dev)
         stats = torch.zeros(4, dtype=torch.int64, device=dev)   # n_el, n_nd, n_set_ids
-        bases = torch.tensor([descs[q].tile_base for q in range(12)], dtype=torch.int64, device=dev)
+        bases = to_device_async([descs[q].tile_base for q in range(12)], torch.int64, dev)
 
         _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
         _lib.call("cfe_scan_elements", bits.data_ptr(), rows * W, epref.data_ptr(), stats.data_ptr(),
@@ -373,8 +373,8 @@ def _refnodes(m):
     dev = m.vol.device
     with torch.cuda.device(dev):
         tabs = [torch.from_numpy(np.asarray(a, dtype=np.float64)).to(dev) for a in (m.xs, m.ys, m.zs)]
-        first = torch.tensor(m.set_first[:6], dtype=torch.int64, device=dev)
-        count = torch.tensor(m.set_count[:6], dtype=torch.int64, device=dev)
+        first = to_device_async(m.set_first[:6], torch.int64, dev)
+        count = to_device_async(m.set_count[:6], torch.int64, dev)
         acc = torch.zeros((6, 3), dtype=torch.float64, device=dev)
         _lib.call("cfe_refnode_sums", m.set_ids.data_ptr(), first.data_ptr(), count.data_ptr(), 6, m.Y, m.X,
                   tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(), acc.data_ptr(), _lib.stream())
@@ -475,8 +475,7 @@ class _Blob:
         return off
 
     def to_device(self, dev):
-        host = torch.frombuffer(bytearray(b"".join(self.parts) or b"\0"), dtype=torch.uint8)
-        return host.to(dev)
+        return bytes_to_device_async(b"".join(self.parts), dev)
 
 
 def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'], eltype='C3D8', matpropbits=8,

@@ -103,6 +103,11 @@ int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* prefA, const 
                             const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* parentB, int64_t Y,
                             int64_t X, uint32_t* edges, uint32_t* count, int64_t capacity, cfe_stream_t s);
 
+/* connected components of the (small) cross-slab boundary graph: label[v] = smallest vertex index
+ * of v's component; ea/eb = dense int64 endpoints of the edges */
+int cfe_uf_solve(uint32_t* label, int64_t n_vertices, const int64_t* ea, const int64_t* eb, int64_t n_edges,
+                 cfe_stream_t s);
+
 /* ------------------------------------------------------------------ boundary sets */
 
 /* One boundary set = the candidates of a box of the node grid (kind 0/1) or voxel grid
