@@ -313,24 +313,29 @@ def run_gpu(args, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    # dominant kernel: the *ELEMENT emitter.  Algorithmic bytes per launch = element-section bytes
-    # written + 4 B/element list read.
+    # dominant kernel: k_emit_elements (entry point cfe_emit_elements = that one launch).  Algorithmic
+    # bytes per launch = element-section bytes written + 6 B/element read (voxel index, line length,
+    # digit flags) -- DESIGN.md section 4.
     elem_bytes = deck_bytes - 53 * n_nd   # everything but the *NODE lines is element lines + O(N^2) text
     dom = max(stage_ms, key=stage_ms.get)
-    alg = {"cfe_emit_elements": elem_bytes + 4 * n_el, "cfe_emit_nodes": 57 * n_nd}
+    alg = {"cfe_emit_elements": elem_bytes + 6 * n_el, "cfe_emit_nodes": 57 * n_nd}
     dom_for_roofline = "cfe_emit_elements"
     achieved = alg[dom_for_roofline] / (stage_ms[dom_for_roofline] * 1e-3) / 1e9
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if tr.get("size") == S:
-            traffic = tr.get(dom_for_roofline)
+            traffic = tr.get("k_emit_elements")
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "kernel": "k_emit_elements (cfe_emit_elements)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    roofline = {"bound": "hbm", "kernel": "k_emit_elements (entry point cfe_emit_elements, one launch per deck)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom_for_roofline],
-                "ms_per_launch": stage_ms[dom_for_roofline], "dominant_entry_point": dom}
+                "ms_per_launch": stage_ms[dom_for_roofline], "dominant_entry_point": dom,
+                "other_kernels": {"k_emit_nodes4": {"achieved": alg["cfe_emit_nodes"] / (stage_ms["cfe_emit_nodes"] * 1e-3) / 1e9,
+                                                    "frac": alg["cfe_emit_nodes"] / (stage_ms["cfe_emit_nodes"] * 1e-3) / 1e9 / peak,
+                                                    "algorithmic_bytes_per_launch": alg["cfe_emit_nodes"],
+                                                    "ms_per_launch": stage_ms["cfe_emit_nodes"]}}}
     total_alg = 2 * n_vox + deck_bytes
     cpu = None
     if world == 1 and not args.no_cpu:

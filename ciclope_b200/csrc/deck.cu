@@ -297,7 +297,7 @@ struct ElemEmitParams {
     uint8_t* len8;           // [n_el] line length (block header included) in emission order
     uint8_t* nd8;            // [n_el] digit-count flags (see k_elem_lengths)
     u32* warp_total;         // [n_warp_tiles] bytes of every 32-element tile
-    const u64* warp_off;     // [n_warp_tiles] exclusive scan of warp_total
+    u64* warp_off;           // [n_warp_tiles] exclusive scan of warp_total
     i64 n_warp_tiles;
 };
 
@@ -674,15 +674,12 @@ extern "C" size_t cfe_emit_elements_workspace_bytes(int64_t n_el)
     return 2 * a + ((nw * 4 + 15) & ~(size_t)15) + nw * 8 + 16 + cfe_scan_workspace_bytes((int64_t)nw) + 64;
 }
 
-extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
-                                 const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len,
-                                 int single_gv, int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset,
-                                 char* out, uint64_t* total, uint64_t* blk_off, void* ws, cudaStream_t stream)
+static void elem_params(ElemEmitParams& P, const uint32_t* elem_vox, const void* perm, int64_t n_el,
+                        const uint8_t* vol, const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len,
+                        int single_gv, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, char* out,
+                        uint64_t* blk_off, void* ws, void** scan_ws)
 {
-    CFE_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(u64), stream));
-    if (n_el <= 0) return 0;
     const i64 nw = (n_el + 31) / 32;
-    ElemEmitParams P;
     P.elem_vox = elem_vox; P.perm = reinterpret_cast<const uint2*>(perm); P.n_el = n_el; P.vol = vol;
     P.first = reinterpret_cast<const u64*>(first); P.hdr_text = hdr_text; P.hdr_len = hdr_len;
     P.single_gv = single_gv;
@@ -696,13 +693,32 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
     P.len8 = reinterpret_cast<uint8_t*>(w); w += a;
     P.nd8 = reinterpret_cast<uint8_t*>(w); w += a;
     P.warp_total = reinterpret_cast<u32*>(w); w += ((size_t)nw * 4 + 15) & ~(size_t)15;
-    u64* warp_off = reinterpret_cast<u64*>(w); w += (size_t)nw * 8 + 16;
-    void* scan_ws = w;
-    P.warp_off = warp_off;
+    P.warp_off = reinterpret_cast<u64*>(w); w += (size_t)nw * 8 + 16;
+    *scan_ws = w;
     P.n_warp_tiles = nw;
+}
+
+static bool elem_wide(const ElemEmitParams& P, int64_t Zl)
+{
     // largest id that can appear in this slab's lines
-    const unsigned long long max_node = (unsigned long long)P.SN * (unsigned long long)(z0 + Zl + 1);
-    const bool wide = (max_node >= 0xffffffffull) || ((unsigned long long)(eid_offset + n_el) >= 0xffffffffull);
+    const unsigned long long max_node = (unsigned long long)P.SN * (unsigned long long)(P.z0 + Zl + 1);
+    return (max_node >= 0xffffffffull) || ((unsigned long long)(P.eid_offset + P.n_el) >= 0xffffffffull);
+}
+
+// Pass 1 of the *ELEMENT section: line lengths, 32-line tile totals and their exclusive scan.
+// *total = bytes of the section (block headers included).  Same arguments as cfe_emit_elements.
+extern "C" int cfe_element_lengths(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
+                                   const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len,
+                                   int single_gv, int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset,
+                                   uint64_t* total, void* ws, cudaStream_t stream)
+{
+    CFE_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(u64), stream));
+    if (n_el <= 0) return 0;
+    ElemEmitParams P;
+    void* scan_ws;
+    elem_params(P, elem_vox, perm, n_el, vol, first, hdr_text, hdr_len, single_gv, Y, X, z0, eid_offset, nullptr,
+                nullptr, ws, &scan_ws);
+    const bool wide = elem_wide(P, Zl);
     const unsigned g1 = (unsigned)((n_el + 255) / 256);
     if (perm) {
         if (wide) k_elem_lengths<true, true><<<g1, 256, 0, stream>>>(P);
@@ -712,9 +728,23 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
         else k_elem_lengths<false, false><<<g1, 256, 0, stream>>>(P);
     }
     CFE_CHECK_LAUNCH("k_elem_lengths");
-    int rc = cfe_scan_u32(P.warp_total, nw, reinterpret_cast<uint64_t*>(warp_off), total, scan_ws, stream);
-    if (rc) return rc;
-    const unsigned g2 = (unsigned)((nw + 7) / 8);
+    return cfe_scan_u32(P.warp_total, P.n_warp_tiles, reinterpret_cast<uint64_t*>(P.warp_off),
+                        total, scan_ws, stream);
+}
+
+// Pass 2: format the lines (requires cfe_element_lengths on the same workspace).
+extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
+                                 const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len,
+                                 int single_gv, int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset,
+                                 char* out, uint64_t* blk_off, void* ws, cudaStream_t stream)
+{
+    if (n_el <= 0) return 0;
+    ElemEmitParams P;
+    void* scan_ws;
+    elem_params(P, elem_vox, perm, n_el, vol, first, hdr_text, hdr_len, single_gv, Y, X, z0, eid_offset, out,
+                blk_off, ws, &scan_ws);
+    const bool wide = elem_wide(P, Zl);
+    const unsigned g2 = (unsigned)((P.n_warp_tiles + 7) / 8);
     if (perm) {
         if (wide) k_emit_elements<true, true><<<g2, 256, 0, stream>>>(P);
         else k_emit_elements<true, false><<<g2, 256, 0, stream>>>(P);

@@ -340,17 +340,30 @@ def ccl_program(ctx, vol):
         _lib.call("cfe_ccl_select", parent.data_ptr(), size.data_ptr(), stats.data_ptr(), stats.data_ptr() + 8, s)
         if nr:
             size[my_roots] = saved
-        head = to_device_async([nr, ne], torch.int64, dev)
-        head = torch.cat([head, stats[1:2]])             # + packed best internal component
-    heads = yield from ctx.all_gather(head)
-    hh = torch.stack(heads).cpu().tolist()               # sync: everybody's sizes
-    maxlen = max(max(2 * a + 2 * b for a, b, _ in hh), 1)
-    with torch.cuda.device(dev):
-        pack = torch.zeros(maxlen, dtype=torch.int64, device=dev)
-        pack[:nr] = my_roots
-        pack[nr:2 * nr] = my_sizes
-        pack[2 * nr:2 * nr + 2 * ne] = my_edges.reshape(-1)
+        # one message per rank: [n_roots, n_edges, best internal component, roots, sizes, edges]; the
+        # capacity is a guess that covers ordinary volumes -- when some rank overflows it, every rank
+        # sees that in the gathered headers and the exchange is repeated at the exact size
+        capacity = min(1 << 16, 6 * cap + 8)
+        need = 3 + 2 * nr + 2 * ne
+
+        def make_pack(n):
+            pk = torch.zeros(n, dtype=torch.int64, device=dev)
+            pk[0:2] = to_device_async([nr, ne], torch.int64, dev)
+            pk[2] = stats[1]
+            if need <= n:
+                pk[3:3 + nr] = my_roots
+                pk[3 + nr:3 + 2 * nr] = my_sizes
+                pk[3 + 2 * nr:need] = my_edges.reshape(-1)
+            return pk
+        pack = make_pack(capacity)
     packs = yield from ctx.all_gather(pack)
+    hh = torch.stack([pk[:3] for pk in packs]).cpu().tolist()      # sync: everybody's sizes + best internal
+    maxneed = max(3 + 2 * a + 2 * b for a, b, _ in hh)
+    if maxneed > capacity:
+        with torch.cuda.device(dev):
+            pack = make_pack(maxneed)
+        packs = yield from ctx.all_gather(pack)
+    packs = [pk[3:] for pk in packs]
     with torch.cuda.device(dev):
         s = _lib.stream()
         keys = torch.cat([packs[k][:a] | (k << 32) for k, (a, b, _) in enumerate(hh)])   # sorted by rank, root
@@ -631,9 +644,10 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             _lib.call("cfe_partition_scatter", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el,
                       mat_off.data_ptr(), perm.data_ptr(), s)
             single_gv = -1
-        _lib.call("cfe_emit_elements", m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(),
-                  base + o_first, base + o_hdr, base + o_hlen, single_gv if single_gv >= 0 else 0, Zl, Y, X, m.z0,
-                  m.eid_offset, elem_buf.data_ptr(), totals.data_ptr(), blk_off.data_ptr(), ws_el.data_ptr(), s)
+        el_args = (m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(), base + o_first, base + o_hdr,
+                   base + o_hlen, single_gv if single_gv >= 0 else 0, Zl, Y, X, m.z0, m.eid_offset)
+        _lib.call("cfe_element_lengths", *el_args, totals.data_ptr(), ws_el.data_ptr(), s)
+        _lib.call("cfe_emit_elements", *el_args, elem_buf.data_ptr(), blk_off.data_ptr(), ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base, items_buf.data_ptr(),
                   None, totals.data_ptr() + 8, seg_off.data_ptr(), ws.data_ptr(), s)
         # byte sizes of my (gv) element blocks and of my set segments, computed on the device

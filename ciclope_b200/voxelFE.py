@@ -653,9 +653,10 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             _lib.call("cfe_partition_scatter", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el,
                       mat_off.data_ptr(), perm.data_ptr(), s)
             single_gv = -1
-        _lib.call("cfe_emit_elements", m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(),
-                  base + o_first, base + o_hdr, base + o_hlen, single_gv, Z, Y, X, 0, 0,
-                  out.data_ptr() + off_elem, totals.data_ptr(), None, ws_el.data_ptr(), s)
+        el_args = (m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(), base + o_first, base + o_hdr,
+                   base + o_hlen, single_gv, Z, Y, X, 0, 0)
+        _lib.call("cfe_element_lengths", *el_args, totals.data_ptr(), ws_el.data_ptr(), s)
+        _lib.call("cfe_emit_elements", *el_args, out.data_ptr() + off_elem, None, ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base + o_lits,
                   out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, None, ws.data_ptr(), s)
         _lib.call("cfe_put_literal", base + o_tail, len(tail), out.data_ptr() + off_elem, totals.data_ptr(),

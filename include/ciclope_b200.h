@@ -169,13 +169,20 @@ int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab,
  * read for the grey value.  first[gv] = emission index of the first element of block gv;
  * hdr_text/hdr_len = '*ELEMENT, TYPE=.., ELSET=SET<gv>\n' per gv in 64-byte slots.
  * *total = bytes written; blk_off[gv] = offset where block gv (header included) starts (optional).
- * Three launches: line lengths, exclusive scan of the 32-line tile totals, formatting.
- * ws: cfe_emit_elements_workspace_bytes(n_el) bytes of scratch. */
+ * Two entry points (three launches): cfe_element_lengths (line lengths + exclusive scan of the
+ * 32-line tile totals) then cfe_emit_elements (formatting); ws = cfe_emit_elements_workspace_bytes(n_el)
+ * bytes of scratch shared by both. */
 size_t cfe_emit_elements_workspace_bytes(int64_t n_el);
+/* pass 1: line lengths + tile offsets; *total = bytes of the section */
+int cfe_element_lengths(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
+                        const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len, int single_gv,
+                        int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, uint64_t* total,
+                        void* ws, cfe_stream_t s);
+/* pass 2: the lines themselves (same arguments, same workspace) */
 int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
                       const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len, int single_gv,
                       int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, char* out,
-                      uint64_t* total, uint64_t* blk_off, void* ws, cfe_stream_t s);
+                      uint64_t* blk_off, void* ws, cfe_stream_t s);
 
 /* *NSET / *ELSET sections (voxelFE.py:650-688) as a stream of items. */
 typedef struct {
