@@ -260,13 +260,13 @@ k_ccl_sizes(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 n_wo
 // K3b: arg-max over roots of (size, then smallest id)  ->  best = (size << 32) | ~id
 __global__ void __launch_bounds__(256)
 k_ccl_select(const u32* __restrict__ parent, const u32* __restrict__ size, const u64* __restrict__ n_runs,
-             u64* __restrict__ best)
+             u64* __restrict__ best, const u32* __restrict__ exclude)
 {
     __shared__ u64 s_best[8];
     const u64 n = *n_runs;
     u64 key = 0;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        if (parent[i] == (u32)i) {
+        if (parent[i] == (u32)i && !(exclude && exclude[i] != 0xffffffffu)) {
             const u64 k = ((u64)size[i] << 32) | (u64)(0xffffffffu - (u32)i);
             key = k > key ? k : key;
         }
@@ -312,7 +312,7 @@ k_ccl_write_mask(const u32* __restrict__ bits, const u32* __restrict__ pref, i64
             const int len = (~shifted == 0u) ? 32 - b : __ffs((int)~shifted) - 1;
             const u32 seg = (len >= 32) ? 0xffffffffu : (((1u << len) - 1u) << b);
             const u32 root = __ldg(parent + run_id(word, carry, pf, b));
-            if (keep_flag ? (keep_flag[root] != 0u) : (root == winner)) keep |= seg;
+            if (keep_flag ? (keep_flag[root] == 0xffffffffu) : (root == winner)) keep |= seg;
             rest &= ~seg;
         }
     }
@@ -384,14 +384,14 @@ extern "C" int cfe_ccl_select(const uint32_t* parent, const uint32_t* size, cons
 {
     CFE_CHECK_CUDA(cudaMemsetAsync(best, 0, sizeof(u64), stream));
     k_ccl_select<<<grid_stride_blocks(), 256, 0, stream>>>(parent, size, reinterpret_cast<const u64*>(n_runs),
-                                                           reinterpret_cast<u64*>(best));
+                                                           reinterpret_cast<u64*>(best), nullptr);
     CFE_CHECK_LAUNCH("k_ccl_select");
     return 0;
 }
 
 // Phase 3: out_mask = 1 where the voxel's run has root (0xffffffff - low32(*best)).
-// With `keep` != NULL the test is keep[root] != 0 instead (z-slab sharding: the winning global
-// component may be the union of several slab-local components).
+// With `keep` != NULL the test is keep[root] == 0xffffffff instead (z-slab sharding: the winning
+// global component may be the union of several slab-local components; the marker cannot be a size).
 extern "C" int cfe_ccl_write_mask(const uint32_t* bits, const uint32_t* pref, int64_t Z, int64_t Y, int64_t X,
                                   const uint32_t* parent, const uint64_t* best, const uint32_t* keep,
                                   uint8_t* out_mask, cudaStream_t stream)
@@ -552,5 +552,200 @@ extern "C" int cfe_uf_solve(uint32_t* label, int64_t n_vertices, const int64_t* 
         k_uf_flatten<<<vb, 256, 0, stream>>>(label, n_vertices);
         CFE_CHECK_LAUNCH("k_uf_flatten");
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Device-side cross-slab merge (z-slab sharding).  Per rank a fixed-capacity message
+//   pack[0] = n_vertices, pack[1] = n_edges, pack[2..3] = best slab-internal component (u64),
+//   pack[4 .. 4+Cv) vertex roots, pack[4+Cv .. 4+2Cv) vertex sizes, then Ce (a, b) edge pairs
+// is built by three launches, all-gathered over NCCL, and solved identically on every rank by
+// one single-CTA kernel that also writes the keep markers; the host reads 4 words at the end.
+
+__global__ void __launch_bounds__(256) k_fill_u32(u32* __restrict__ a, const u64* __restrict__ n, u32 value)
+{
+    const u64 m = *n;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) a[i] = value;
+}
+
+// Boundary vertices = slab-local roots owning a run in an interface plane.  vfirst[] (SENT-filled
+// over the run ids) receives the smallest plane-run index of every such root; those first
+// occurrences are numbered densely (plane-run order) and every plane run learns its vertex.
+__global__ void __launch_bounds__(1024)
+k_boundary_vertices(const u32* __restrict__ roots_bot, const u32* __restrict__ roots_top,
+                    const u32* __restrict__ cnt, int use_bot, int use_top, u32* __restrict__ vfirst,
+                    u32* __restrict__ didx, const u32* __restrict__ size, u32 Cv, u32* __restrict__ pack,
+                    u32* __restrict__ vbot, u32* __restrict__ vtop)
+{
+    __shared__ u32 s_scan[33];
+    const u32 n_bot = use_bot ? cnt[0] : 0u, n_top = use_top ? cnt[1] : 0u, n = n_bot + n_top;
+    const u32 t = threadIdx.x;
+    for (u32 k = t; k < n; k += 1024u) {
+        const u32 r = k < n_bot ? roots_bot[k] : roots_top[k - n_bot];
+        atomicMin(vfirst + r, k);
+    }
+    __syncthreads();
+    u32 carry = 0;
+    for (u32 base = 0; base < n; base += 1024u) {
+        const u32 k = base + t;
+        u32 r = 0;
+        bool flag = false;
+        if (k < n) {
+            r = k < n_bot ? roots_bot[k] : roots_top[k - n_bot];
+            flag = vfirst[r] == k;
+        }
+        u32 tot;
+        const u32 d = carry + block_exclusive_scan<u32>(flag ? 1u : 0u, s_scan, tot);
+        if (flag) {
+            didx[k] = d;
+            if (d < Cv) { pack[4 + d] = r; pack[4 + Cv + d] = size[r]; }
+        }
+        carry += tot;
+        __syncthreads();
+    }
+    if (t == 0) pack[0] = carry;
+    __syncthreads();
+    for (u32 k = t; k < n; k += 1024u) {
+        const u32 r = k < n_bot ? roots_bot[k] : roots_top[k - n_bot];
+        const u32 v = didx[vfirst[r]];
+        if (k < n_bot) vbot[k] = v; else vtop[k - n_bot] = v;
+    }
+}
+
+extern "C" int cfe_ccl_boundary_vertices(const uint32_t* roots_bot, const uint32_t* roots_top, const uint32_t* cnt,
+                                         int use_bot, int use_top, const uint64_t* n_runs, uint32_t* vfirst,
+                                         uint32_t* didx, const uint32_t* parent, const uint32_t* size,
+                                         int64_t Cv, uint32_t* pack, uint32_t* vbot, uint32_t* vtop,
+                                         cudaStream_t stream)
+{
+    k_fill_u32<<<grid_stride_blocks(), 256, 0, stream>>>(vfirst, reinterpret_cast<const u64*>(n_runs), 0xffffffffu);
+    CFE_CHECK_LAUNCH("k_fill_u32");
+    k_boundary_vertices<<<1, 1024, 0, stream>>>(roots_bot, roots_top, cnt, use_bot, use_top, vfirst, didx, size,
+                                                (u32)Cv, pack, vbot, vtop);
+    CFE_CHECK_LAUNCH("k_boundary_vertices");
+    // best slab-internal component: roots that are boundary vertices are excluded
+    CFE_CHECK_CUDA(cudaMemsetAsync(pack + 2, 0, sizeof(u64), stream));
+    k_ccl_select<<<grid_stride_blocks(), 256, 0, stream>>>(parent, size, reinterpret_cast<const u64*>(n_runs),
+                                                           reinterpret_cast<u64*>(pack + 2), vfirst);
+    CFE_CHECK_LAUNCH("k_ccl_select");
+    return 0;
+}
+
+struct BCand { u64 size; u64 key; u32 rep; };
+
+__device__ __forceinline__ bool bcand_better(const BCand& a, const BCand& b)
+{
+    // larger component first; ties -> smaller key (rank << 32 | root) = earlier in raster order
+    return a.size > b.size || (a.size == b.size && a.key < b.key);
+}
+
+__global__ void __launch_bounds__(1024)
+k_boundary_solve(const u32* __restrict__ packs, int N, u32 Cv, u32 Ce, int rank, u32* __restrict__ label,
+                 u64* __restrict__ comp, u64* __restrict__ ckey, u32* __restrict__ size, i64* __restrict__ result)
+{
+    __shared__ u32 s_nr[64], s_ne[64];
+    __shared__ int s_ovf;
+    __shared__ BCand s_c[32];
+    __shared__ BCand s_win;
+    const u32 PS = 4u + 2u * Cv + 2u * Ce;
+    const u32 t = threadIdx.x;
+    if (t == 0) s_ovf = 0;
+    __syncthreads();
+    if (t < (u32)N) {
+        s_nr[t] = packs[(size_t)t * PS];
+        s_ne[t] = packs[(size_t)t * PS + 1];
+        if (s_nr[t] > Cv || s_ne[t] > Ce) s_ovf = 1;
+    }
+    __syncthreads();
+    if (s_ovf) {
+        if (t == 0) { result[0] = 0; result[1] = 0; result[2] = 1; result[3] = 0; }
+        return;
+    }
+    for (int k = 0; k < N; ++k)
+        for (u32 i = t; i < s_nr[k]; i += 1024u) {
+            const u32 v = (u32)k * Cv + i;
+            label[v] = v; comp[v] = 0; ckey[v] = ~0ull;
+        }
+    __syncthreads();
+    for (int k = 1; k < N; ++k) {
+        const u32* e = packs + (size_t)k * PS + 4u + 2u * Cv;
+        for (u32 i = t; i < s_ne[k]; i += 1024u) {
+            const u32 a = e[2 * i], b = e[2 * i + 1];
+            if (a < s_nr[k - 1] && b < s_nr[k]) uf_union(label, (u32)(k - 1) * Cv + a, (u32)k * Cv + b);
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < N; ++k) {
+        const u32* pk = packs + (size_t)k * PS;
+        for (u32 i = t; i < s_nr[k]; i += 1024u) {
+            const u32 v = (u32)k * Cv + i;
+            u32 r = v, p;
+            while ((p = label[r]) != r) r = p;
+            atomicAdd(reinterpret_cast<unsigned long long*>(comp + r), (unsigned long long)pk[4 + Cv + i]);
+            atomicMin(reinterpret_cast<unsigned long long*>(ckey + r), ((unsigned long long)k << 32) | pk[4 + i]);
+        }
+    }
+    __syncthreads();
+    // flatten (second pass so that the accumulation above saw a stable forest)
+    for (int k = 0; k < N; ++k)
+        for (u32 i = t; i < s_nr[k]; i += 1024u) {
+            const u32 v = (u32)k * Cv + i;
+            u32 r = v, p;
+            while ((p = label[r]) != r) r = p;
+            if (r != v) label[v] = r;
+        }
+    __syncthreads();
+    BCand best = {0ull, ~0ull, 0xffffffffu};
+    for (int k = 0; k < N; ++k)
+        for (u32 i = t; i < s_nr[k]; i += 1024u) {
+            const u32 v = (u32)k * Cv + i;
+            if (label[v] == v) {
+                const BCand c = {comp[v], ckey[v], v};
+                if (bcand_better(c, best)) best = c;
+            }
+        }
+    if (t < (u32)N) {
+        const u64 b = *reinterpret_cast<const u64*>(packs + (size_t)t * PS + 2);
+        const BCand c = {b >> 32, ((u64)t << 32) | (u64)(0xffffffffu - (u32)(b & 0xffffffffu)), 0xffffffffu};
+        if (c.size > 0 && bcand_better(c, best)) best = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        BCand other;
+        other.size = __shfl_xor_sync(CFE_FULL_MASK, best.size, o);
+        other.key = __shfl_xor_sync(CFE_FULL_MASK, best.key, o);
+        other.rep = __shfl_xor_sync(CFE_FULL_MASK, best.rep, o);
+        if (bcand_better(other, best)) best = other;
+    }
+    if ((t & 31u) == 0) s_c[t >> 5] = best;
+    __syncthreads();
+    if (t == 0) {
+        for (int w = 1; w < 32; ++w) if (bcand_better(s_c[w], best)) best = s_c[w];
+        s_win = best;
+        result[0] = (i64)best.size; result[1] = (i64)best.key; result[2] = 0; result[3] = (i64)best.rep;
+    }
+    __syncthreads();
+    const BCand w = s_win;
+    if (w.size == 0) return;
+    if (w.rep != 0xffffffffu) {
+        const u32* pk = packs + (size_t)rank * PS;
+        for (u32 i = t; i < s_nr[rank]; i += 1024u)
+            if (label[(u32)rank * Cv + i] == w.rep) size[pk[4 + i]] = 0xffffffffu;
+    } else if ((int)(w.key >> 32) == rank) {
+        if (t == 0) size[(u32)(w.key & 0xffffffffu)] = 0xffffffffu;
+    }
+}
+
+// packs: the all-gathered messages [N][4 + 2 Cv + 2 Ce] u32; label u32 [N*Cv], comp / ckey u64 [N*Cv]
+// scratch; size: this rank's size array (keep markers are written into it); result: i64[4] =
+// {winner size, winner key (rank << 32 | root), capacity overflow flag, winner vertex or -1}
+extern "C" int cfe_ccl_boundary_solve(const uint32_t* packs, int N, int64_t Cv, int64_t Ce, int rank,
+                                      uint32_t* label, uint64_t* comp, uint64_t* ckey, uint32_t* size,
+                                      int64_t* result, cudaStream_t stream)
+{
+    if (N > 64) { cfe_set_error("cfe_ccl_boundary_solve: at most 64 slabs"); return -1; }
+    k_boundary_solve<<<1, 1024, 0, stream>>>(packs, N, (u32)Cv, (u32)Ce, rank, label, reinterpret_cast<u64*>(comp),
+                                             reinterpret_cast<u64*>(ckey), size, reinterpret_cast<i64*>(result));
+    CFE_CHECK_LAUNCH("k_boundary_solve");
     return 0;
 }

@@ -264,20 +264,30 @@ def _u32_to_i64(t):
     return t.to(torch.int64) & 0xFFFFFFFF
 
 
-def ccl_program(ctx, vol):
+BOUNDARY_VERTS = 1 << 15      # per-rank capacity of the device-side cross-slab merge (vertices)
+BOUNDARY_EDGES = 1 << 16      # ... and interface edges; larger cases take the host-driven path
+_MARK = -1                    # 0xffffffff in the u32 size array = "keep this root"
+
+
+def ccl_program(ctx, vol, force_host_merge=False):
     """remove_unconnected of the global volume; `vol` = this rank's uint8 slab [Zl,Y,X] on the GPU.
-    Returns (uint8 mask slab, winner (size, key) or None)."""
+    Returns (uint8 mask slab, winner (size, key) or None).
+
+    The cross-slab merge runs entirely on the device with fixed-capacity buffers (one plane shift,
+    one all-gather, ONE host read at the end); when a rank has more boundary components / edges
+    than the capacity, the flag in that read sends every rank through `_ccl_host_merge`."""
     lib = _lib.require_cuda()
     dev = vol.device
     Zl, Y, X = (int(v) for v in vol.shape)
     W = (X + 31) // 32
     rows = Zl * Y
     PW = Y * W
+    N, rank = ctx.size, ctx.rank
     with torch.cuda.device(dev):
         s = _lib.stream()
         bits = empty_u32(rows * W, dev)
         pref = empty_u32(rows * W, dev)
-        stats = torch.zeros(4, dtype=torch.int64, device=dev)   # n_runs, best, plane counts
+        stats = torch.zeros(4, dtype=torch.int64, device=dev)   # n_runs, best
         ws = scan_workspace(max(rows * W, PW), dev)
         _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
         _lib.call("cfe_scan_run_starts", bits.data_ptr(), rows, X, pref.data_ptr(), stats.data_ptr(),
@@ -288,8 +298,14 @@ def ccl_program(ctx, vol):
         _lib.call("cfe_ccl_label", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Zl, Y, X,
                   parent.data_ptr(), size.data_ptr(), s)
         out = torch.empty((Zl, Y, X), dtype=torch.uint8, device=dev)
+        if N == 1:
+            _lib.call("cfe_ccl_select", parent.data_ptr(), size.data_ptr(), stats.data_ptr(), stats.data_ptr() + 8, s)
+            _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
+                      stats.data_ptr() + 8, None, out.data_ptr(), s)
+            best = int(stats[1].item()) & 0xFFFFFFFFFFFFFFFF
+            return (out, None) if best == 0 else (out, (best >> 32, 0xFFFFFFFF - (best & 0xFFFFFFFF)))
 
-        # ---- boundary planes: roots of the runs of my bottom (0) and top (Zl-1) voxel planes
+        # ---- roots of the runs of my bottom (0) and top (Zl-1) voxel planes
         cap = Y * ((X + 1) // 2)
         roots_bot = empty_u32(cap, dev)
         roots_top = empty_u32(cap, dev)
@@ -299,10 +315,82 @@ def ccl_program(ctx, vol):
         _lib.call("cfe_ccl_plane_roots", bits.data_ptr(), pref.data_ptr(), Zl - 1, Y, X, parent.data_ptr(),
                   roots_top.data_ptr(), cnt.data_ptr() + 4, s)
         top_bits = bits[(Zl - 1) * PW: Zl * PW]
-    # the top plane (bits + run roots) travels to the rank above in one message
+        state = dict(bits=bits, pref=pref, parent=parent, size=size, stats=stats, cnt=cnt, out=out, ws=ws,
+                     roots_bot=roots_bot, roots_top=roots_top, top_bits=top_bits, cap=cap, max_runs=max_runs,
+                     dims=(Zl, Y, X))
+    if force_host_merge:
+        return (yield from _ccl_host_merge(ctx, state))
+
+    Cv, Ce = BOUNDARY_VERTS, BOUNDARY_EDGES
+    PS = 4 + 2 * Cv + 2 * Ce
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        pack = torch.zeros(PS, dtype=torch.int32, device=dev)
+        vfirst = empty_u32(max_runs, dev)
+        didx = empty_u32(2 * cap, dev)
+        vbot = empty_u32(cap, dev)
+        vtop = torch.zeros(cap, dtype=torch.int32, device=dev)
+        # dense numbering of my boundary components, their roots / sizes, the per-run vertex indices
+        # and the best slab-internal component -- three launches, nothing read back
+        _lib.call("cfe_ccl_boundary_vertices", roots_bot.data_ptr(), roots_top.data_ptr(), cnt.data_ptr(),
+                  1 if rank > 0 else 0, 1 if rank + 1 < N else 0, stats.data_ptr(), vfirst.data_ptr(),
+                  didx.data_ptr(), parent.data_ptr(), size.data_ptr(), Cv, pack.data_ptr(), vbot.data_ptr(),
+                  vtop.data_ptr(), s)
+    recv = yield from ctx.shift_up(torch.cat([top_bits, vtop]))
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        if rank > 0:
+            bitsA, vA = recv[:PW], recv[PW:]
+            prefA = empty_u32(PW, dev)
+            scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+            _lib.call("cfe_scan_run_starts", bitsA.data_ptr(), Y, X, prefA.data_ptr(), scratch.data_ptr(),
+                      ws.data_ptr(), s)
+            # plane B is this slab's first plane: its run ids are 0..n_bot-1, so `vbot` stands in for
+            # the parent array and the kernel emits (vertex of A's run, vertex of B's run) straight
+            # into the message
+            _lib.call("cfe_ccl_interface_edges", bitsA.data_ptr(), prefA.data_ptr(), vA.data_ptr(),
+                      bits.data_ptr(), pref.data_ptr(), vbot.data_ptr(), Y, X,
+                      pack.data_ptr() + 4 * (4 + 2 * Cv), pack.data_ptr() + 4, Ce, s)
+    packs = yield from ctx.all_gather(pack)
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        P = torch.stack(packs).contiguous()                     # [N, PS]
+        label = empty_u32(N * Cv, dev)
+        comp = torch.empty(N * Cv, dtype=torch.int64, device=dev)
+        ckey = torch.empty(N * Cv, dtype=torch.int64, device=dev)
+        result = torch.zeros(4, dtype=torch.int64, device=dev)
+        _lib.call("cfe_ccl_boundary_solve", P.data_ptr(), N, Cv, Ce, rank, label.data_ptr(), comp.data_ptr(),
+                  ckey.data_ptr(), size.data_ptr(), result.data_ptr(), s)
+        _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
+                  stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), s)
+        res = result.cpu().tolist()                             # the one host read of the stage
+    if res[2]:
+        # some rank has more boundary components / edges than the fixed capacity: every rank sees the
+        # same flag (nothing was marked) and redoes the merge host-driven at exact sizes
+        return (yield from _ccl_host_merge(ctx, state))
+    if res[0] <= 0:
+        return out, None
+    return out, (int(res[0]), int(res[1]))
+
+
+def _ccl_host_merge(ctx, st):
+    """Host-driven cross-slab merge (exact sizes, a few host reads): the fallback of ccl_program."""
+    dev = st["bits"].device
+    bits, pref, parent, size, stats, cnt, out, ws = (st[k] for k in
+                                                      ("bits", "pref", "parent", "size", "stats", "cnt", "out", "ws"))
+    Zl, Y, X = st["dims"]
+    cap = st["cap"]
+    PW = Y * ((X + 31) // 32)
+    if st.get("needs_relabel"):
+        # the device path overwrote a few sizes with markers: recompute them
+        with torch.cuda.device(dev):
+            _lib.call("cfe_ccl_label", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Zl, Y, X,
+                      parent.data_ptr(), size.data_ptr(), _lib.stream())
+    roots_bot, roots_top, top_bits = st["roots_bot"], st["roots_top"], st["top_bits"]
     recv = yield from ctx.shift_up(torch.cat([top_bits, roots_top]))
     with torch.cuda.device(dev):
         s = _lib.stream()
+        cnt[2] = 0
         edges_dev = None
         if ctx.rank > 0:
             bitsA, rootsA = recv[:PW], recv[PW:]
@@ -318,7 +406,6 @@ def ccl_program(ctx, vol):
         n_bot, n_top, n_edges, n_runs = h
         if n_edges > cap:
             raise _lib.CfeError("interface edge buffer overflow")
-        # my boundary vertices (slab-local roots that own a run in an interface plane)
         parts = []
         if ctx.rank > 0:
             parts.append(roots_bot[:n_bot])
@@ -333,37 +420,22 @@ def ccl_program(ctx, vol):
         else:
             my_edges = torch.empty((0, 2), dtype=torch.int64, device=dev)
         nr, ne = my_roots.numel(), my_edges.shape[0]
-        # best slab-internal component of this rank: hide the boundary vertices from the arg-max
         if nr:
             saved = size[my_roots].clone()
             size[my_roots] = 0
         _lib.call("cfe_ccl_select", parent.data_ptr(), size.data_ptr(), stats.data_ptr(), stats.data_ptr() + 8, s)
         if nr:
             size[my_roots] = saved
-        # one message per rank: [n_roots, n_edges, best internal component, roots, sizes, edges]; the
-        # capacity is a guess that covers ordinary volumes -- when some rank overflows it, every rank
-        # sees that in the gathered headers and the exchange is repeated at the exact size
-        capacity = min(1 << 16, 6 * cap + 8)
-        need = 3 + 2 * nr + 2 * ne
-
-        def make_pack(n):
-            pk = torch.zeros(n, dtype=torch.int64, device=dev)
-            pk[0:2] = to_device_async([nr, ne], torch.int64, dev)
-            pk[2] = stats[1]
-            if need <= n:
-                pk[3:3 + nr] = my_roots
-                pk[3 + nr:3 + 2 * nr] = my_sizes
-                pk[3 + 2 * nr:need] = my_edges.reshape(-1)
-            return pk
-        pack = make_pack(capacity)
+        head = torch.cat([to_device_async([nr, ne], torch.int64, dev), stats[1:2]])
+    heads = yield from ctx.all_gather(head)
+    hh = torch.stack(heads).cpu().tolist()               # sync: everybody's sizes + best internal
+    maxlen = max(max(2 * a + 2 * b for a, b, _ in hh), 1)
+    with torch.cuda.device(dev):
+        pack = torch.zeros(maxlen, dtype=torch.int64, device=dev)
+        pack[:nr] = my_roots
+        pack[nr:2 * nr] = my_sizes
+        pack[2 * nr:2 * nr + 2 * ne] = my_edges.reshape(-1)
     packs = yield from ctx.all_gather(pack)
-    hh = torch.stack([pk[:3] for pk in packs]).cpu().tolist()      # sync: everybody's sizes + best internal
-    maxneed = max(3 + 2 * a + 2 * b for a, b, _ in hh)
-    if maxneed > capacity:
-        with torch.cuda.device(dev):
-            pack = make_pack(maxneed)
-        packs = yield from ctx.all_gather(pack)
-    packs = [pk[3:] for pk in packs]
     with torch.cuda.device(dev):
         s = _lib.stream()
         keys = torch.cat([packs[k][:a] | (k << 32) for k, (a, b, _) in enumerate(hh)])   # sorted by rank, root
@@ -375,12 +447,12 @@ def ccl_program(ctx, vol):
             v = best & 0xFFFFFFFFFFFFFFFF
             cands.append((v >> 32, (k << 32) | (0xFFFFFFFF - (v & 0xFFFFFFFF))))
         wlab = -1
+        t = None
         if keys.numel():
-            is_rep = lab == torch.arange(keys.numel(), device=dev)
-            rep_size = torch.where(is_rep, comp, torch.zeros_like(comp))
+            iota = torch.arange(keys.numel(), device=dev)
+            rep_size = torch.where(lab == iota, comp, torch.zeros_like(comp))
             top = rep_size.max()
-            top_idx = torch.where(rep_size == top, torch.arange(keys.numel(), device=dev),
-                                  torch.full_like(lab, keys.numel())).min()      # smallest key among the largest
+            top_idx = torch.where(rep_size == top, iota, torch.full_like(lab, keys.numel())).min()
             t = torch.stack([top, keys[top_idx.clamp(max=keys.numel() - 1)], top_idx]).cpu().tolist()   # sync
             cands.append((t[0], t[1]))
         winner = pick_winner(cands)
@@ -388,16 +460,14 @@ def ccl_program(ctx, vol):
             out.zero_()
             return out, None
         wsize, wkey = winner
-        if keys.numel() and wkey == t[1] and wsize == t[0]:
+        if t is not None and wkey == t[1] and wsize == t[0]:
             wlab = t[2]
-        # keep flags live in the (no longer needed) size array
-        size[: max(n_runs, 1)] = 0
         off = sum(a for a, _, _ in hh[: ctx.rank])
         if wlab >= 0:                        # the winner is a merged (boundary) component
             if nr:
-                size[my_roots] = (lab[off: off + nr] == wlab).to(torch.int32)
+                size[my_roots] = torch.where(lab[off: off + nr] == wlab, torch.full_like(saved, _MARK), saved)
         elif (wkey >> 32) == ctx.rank:       # a slab-internal component of this rank
-            size[wkey & 0xFFFFFFFF] = 1
+            size[wkey & 0xFFFFFFFF] = _MARK
         _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
                   stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), s)
     return out, winner
@@ -759,11 +829,11 @@ def _slab_inputs(vol, n):
     return [(t[a:b].contiguous(), a) for a, b in slab_ranges(int(t.shape[0]), n)], is_bool, int(t.shape[0])
 
 
-def emulate_remove_unconnected(vol, n):
+def emulate_remove_unconnected(vol, n, force_host_merge=False):
     """N emulated ranks on one GPU: returns the global bool mask (numpy) and the winner."""
     slabs, _, _ = _slab_inputs(vol, n)
     runner = LocalRunner(n)
-    res = runner.run([ccl_program(c, s) for c, (s, _) in zip(runner.ctxs(), slabs)])
+    res = runner.run([ccl_program(c, s, force_host_merge) for c, (s, _) in zip(runner.ctxs(), slabs)])
     if res[0][1] is None:
         raise ValueError("attempt to get argmax of an empty sequence")
     mask = torch.cat([r[0] for r in res]).view(torch.bool)

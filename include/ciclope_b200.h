@@ -86,7 +86,7 @@ int cfe_ccl_largest(const uint32_t* bits, const uint32_t* run_pref, const uint64
 /* The same work in three phases, for z-slab sharding (the cross-slab merge sits between 1 and 2):
  *   cfe_ccl_label       parent[run] = slab-local root, size[root] = voxels inside the slab
  *   cfe_ccl_select      *best = max over roots of (size << 32) | (0xffffffff - root)
- *   cfe_ccl_write_mask  mask = runs whose root is the winner (keep == NULL) or has keep[root] != 0 */
+ *   cfe_ccl_write_mask  mask = runs whose root is the winner (keep == NULL) or has keep[root] == 0xffffffff */
 int cfe_ccl_label(const uint32_t* bits, const uint32_t* run_pref, const uint64_t* n_runs, int64_t Z, int64_t Y,
                   int64_t X, uint32_t* parent, uint32_t* size, cfe_stream_t s);
 int cfe_ccl_select(const uint32_t* parent, const uint32_t* size, const uint64_t* n_runs, uint64_t* best,
@@ -102,6 +102,20 @@ int cfe_ccl_plane_roots(const uint32_t* bits, const uint32_t* run_pref, int64_t 
 int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* prefA, const uint32_t* rootsA,
                             const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* parentB, int64_t Y,
                             int64_t X, uint32_t* edges, uint32_t* count, int64_t capacity, cfe_stream_t s);
+
+/* Device-side cross-slab merge.  cfe_ccl_boundary_vertices numbers this slab's boundary components
+ * (roots owning a run of voxel plane 0 / Zl-1), fills the per-rank message
+ *   pack = [n_vertices, n_edges, best internal (u64), roots[Cv], sizes[Cv], edges[Ce][2]]  (u32)
+ * and the per-run vertex indices vbot / vtop; cfe_ccl_interface_edges (with vA / vbot standing in
+ * for rootsA / parentB) appends the edges; after the all-gather cfe_ccl_boundary_solve merges the
+ * graph, picks the winner (largest, ties -> first in raster order) and writes the keep markers.
+ * result = {size, key = rank << 32 | root, capacity-overflow flag, winner vertex or -1}. */
+int cfe_ccl_boundary_vertices(const uint32_t* roots_bot, const uint32_t* roots_top, const uint32_t* cnt,
+                              int use_bot, int use_top, const uint64_t* n_runs, uint32_t* vfirst,
+                              uint32_t* didx, const uint32_t* parent, const uint32_t* size, int64_t Cv,
+                              uint32_t* pack, uint32_t* vbot, uint32_t* vtop, cfe_stream_t s);
+int cfe_ccl_boundary_solve(const uint32_t* packs, int N, int64_t Cv, int64_t Ce, int rank, uint32_t* label,
+                           uint64_t* comp, uint64_t* ckey, uint32_t* size, int64_t* result, cfe_stream_t s);
 
 /* connected components of the (small) cross-slab boundary graph: label[v] = smallest vertex index
  * of v's component; ea/eb = dense int64 endpoints of the edges */

@@ -76,6 +76,21 @@ def test_sharded_ccl_u_shape_across_slabs(sh, orc):
         assert np.array_equal(mask.cpu().numpy(), orc.remove_unconnected(bw)), n
 
 
+@pytest.mark.parametrize("mode", ["host", "overflow"])
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_sharded_ccl_fallback_paths(sh, orc, n, mode, monkeypatch):
+    """the host-driven merge, directly and through the capacity-overflow flag of the device path"""
+    if mode == "overflow":
+        monkeypatch.setattr(sh, "BOUNDARY_VERTS", 4)
+        monkeypatch.setattr(sh, "BOUNDARY_EDGES", 8)
+    for bw in (cases.rand_binary((16, 24, 64), 0.3, 501), cases.blobs((32, 48, 64), 0.3, 3),
+               cases.blobs((64, 64, 64), 0.12, 4)):
+        mask, winner = sh.emulate_remove_unconnected(bw, n, force_host_merge=(mode == "host"))
+        want = orc.remove_unconnected(bw)
+        assert np.array_equal(mask.cpu().numpy(), want)
+        assert winner[0] == int(want.sum())
+
+
 def test_sharded_ccl_empty(sh):
     with pytest.raises(ValueError):
         sh.emulate_remove_unconnected(np.zeros((4, 4, 8), dtype=bool), 2)
