@@ -62,7 +62,8 @@ _SIGNATURES = {
     "cfe_emit_nodes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_emit_elements_workspace_bytes": (c_sz, [c_i64]),
     "cfe_element_lengths": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,
-                                    c_i64, c_vp, c_vp, c_vp]),
+                                    c_i64, c_int, c_vp, c_vp, c_vp]),
+    "cfe_fill_elements": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "cfe_emit_elements": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,
                                   c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_emit_items": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

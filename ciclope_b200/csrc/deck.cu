@@ -543,11 +543,35 @@ __global__ void __launch_bounds__(256) k_elem_lengths(ElemEmitParams P)
         }
         // flags byte: low nibble = digit count of the smallest node id, bit 7 = all eight counts equal
         P.nd8[j] = (uint8_t)((nlo == nhi ? 0x80u : 0u) | (u32)nlo);
-        if ((u64)j == __ldg(P.first + gv)) len += __ldg(P.hdr_len + gv);
-        P.len8[j] = (uint8_t)len;
+        P.len8[j] = (uint8_t)len;                                  // the line only
+        if ((u64)j == __ldg(P.first + gv)) len += __ldg(P.hdr_len + gv);   // + the block header in the tile total
     }
     const u32 tot = __reduce_add_sync(CFE_FULL_MASK, len);
     if ((threadIdx.x & 31u) == 0 && (j >> 5) < P.n_warp_tiles) P.warp_total[j >> 5] = tot;
+}
+
+// 32-line tile totals from precomputed lengths (cfe_fill_elements): one thread sums 16 lengths
+// (one 16-byte load), two threads make a tile; the first element of a grey-value block also
+// carries its '*ELEMENT ...' header.
+__global__ void __launch_bounds__(256) k_tile_totals(ElemEmitParams P)
+{
+    const i64 t = (i64)blockIdx.x * 256 + threadIdx.x;      // 16-element chunk
+    const i64 j0 = t * 16;
+    u32 sum = 0;
+    if (j0 < P.n_el) {
+        if (j0 + 16 <= P.n_el) {
+            const uint4 v = *reinterpret_cast<const uint4*>(P.len8 + j0);
+            const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sum += __dp4a(w[q], 0x01010101u, 0u);
+        } else {
+            for (i64 j = j0; j < P.n_el; ++j) sum += P.len8[j];
+        }
+        const u64 f = __ldg(P.first + P.single_gv);
+        if (f >= (u64)j0 && f < (u64)(j0 + 16)) sum += __ldg(P.hdr_len + P.single_gv);
+    }
+    const u32 other = __shfl_xor_sync(CFE_FULL_MASK, sum, 1);
+    if (!(threadIdx.x & 1) && (t >> 1) < P.n_warp_tiles) P.warp_total[t >> 1] = sum + other;
 }
 
 #define ELEM_WARP_STAGE 3584     // bytes of staging per warp: 32 lines of <= 99 bytes + headers + pad
@@ -563,8 +587,18 @@ __global__ void __launch_bounds__(256) k_emit_elements(ElemEmitParams P)
     if (wt >= P.n_warp_tiles) return;
     const i64 j = wt * 32 + lane;
     const bool active = j < P.n_el;
-    const u32 len = active ? (u32)__ldg(P.len8 + j) : 0u;
-    // warp exclusive scan of the line lengths
+    u64 b = 0, eid = 0;
+    int gv = P.single_gv;
+    u32 len = 0, hl = 0, flags = 0;
+    bool is_first = false;
+    if (active) {
+        elem_ids<PERM>(P, j, b, eid, gv);
+        flags = __ldg(P.nd8 + j);
+        is_first = (u64)j == __ldg(P.first + gv);
+        if (is_first) hl = __ldg(P.hdr_len + gv);
+        len = (u32)__ldg(P.len8 + j) + hl;          // len8 holds the line; the block header rides along
+    }
+    // warp exclusive scan of the byte counts
     u32 incl = len;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -578,15 +612,7 @@ __global__ void __launch_bounds__(256) k_emit_elements(ElemEmitParams P)
     const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
     const bool staged = pad + total <= (u32)ELEM_WARP_STAGE;
     if (active) {
-        u64 b, eid;
-        int gv;
-        elem_ids<PERM>(P, j, b, eid, gv);
-        const u32 flags = __ldg(P.nd8 + j);
-        u32 hl = 0;
-        if ((u64)j == __ldg(P.first + gv)) {
-            hl = __ldg(P.hdr_len + gv);
-            if (P.blk_off) P.blk_off[gv] = base + excl;
-        }
+        if (is_first && P.blk_off) P.blk_off[gv] = base + excl;
         if (staged) {
             // eid, b, b+1, b+RN+1, b+RN | b+SN, b+SN+1, b+SN+RN+1, b+SN+RN   (voxelFE.py:145-154)
             u32 o = pad + excl;
@@ -710,7 +736,7 @@ static bool elem_wide(const ElemEmitParams& P, int64_t Zl)
 extern "C" int cfe_element_lengths(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
                                    const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len,
                                    int single_gv, int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset,
-                                   uint64_t* total, void* ws, cudaStream_t stream)
+                                   int have_lengths, uint64_t* total, void* ws, cudaStream_t stream)
 {
     CFE_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(u64), stream));
     if (n_el <= 0) return 0;
@@ -720,14 +746,20 @@ extern "C" int cfe_element_lengths(const uint32_t* elem_vox, const void* perm, i
                 nullptr, ws, &scan_ws);
     const bool wide = elem_wide(P, Zl);
     const unsigned g1 = (unsigned)((n_el + 255) / 256);
-    if (perm) {
-        if (wide) k_elem_lengths<true, true><<<g1, 256, 0, stream>>>(P);
-        else k_elem_lengths<true, false><<<g1, 256, 0, stream>>>(P);
+    if (have_lengths && !perm) {
+        // len8 / nd8 were written by cfe_fill_elements (same z0 / eid_offset): only the tile totals
+        k_tile_totals<<<(unsigned)(((n_el + 15) / 16 + 255) / 256), 256, 0, stream>>>(P);
+        CFE_CHECK_LAUNCH("k_tile_totals");
     } else {
-        if (wide) k_elem_lengths<false, true><<<g1, 256, 0, stream>>>(P);
-        else k_elem_lengths<false, false><<<g1, 256, 0, stream>>>(P);
+        if (perm) {
+            if (wide) k_elem_lengths<true, true><<<g1, 256, 0, stream>>>(P);
+            else k_elem_lengths<true, false><<<g1, 256, 0, stream>>>(P);
+        } else {
+            if (wide) k_elem_lengths<false, true><<<g1, 256, 0, stream>>>(P);
+            else k_elem_lengths<false, false><<<g1, 256, 0, stream>>>(P);
+        }
+        CFE_CHECK_LAUNCH("k_elem_lengths");
     }
-    CFE_CHECK_LAUNCH("k_elem_lengths");
     return cfe_scan_u32(P.warp_total, P.n_warp_tiles, reinterpret_cast<uint64_t*>(P.warp_off),
                         total, scan_ws, stream);
 }

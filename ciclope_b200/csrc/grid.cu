@@ -289,6 +289,113 @@ extern "C" int cfe_fill_list(const uint32_t* bits, const uint32_t* pref, int64_t
     return 0;
 }
 
+// Element list + line lengths in one pass (raster order): besides the voxel index of every element
+// the kernel writes what the *ELEMENT emitter needs to place the element's text line
+//   len8[j] = 9 + digits(eid) + sum of the digits of the 8 node ids     (voxelFE.py:647)
+//   nd8[j]  = 0x80 | n when all eight node ids have n digits, else the digit count of the smallest
+// A 32-voxel word holds x-consecutive voxels, so the digit counts are computed once per word (first
+// and last set bit) and only re-derived per element when the ids straddle a power of ten.
+#define FILLE_WORDS 128
+
+__device__ __forceinline__ int nd64(u64 v) { return (v >> 32) ? digits_u64(v) : digits_u32((u32)v); }
+
+__global__ void __launch_bounds__(FILLE_WORDS)
+k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_words, FastDiv d_wpr, u32 wpr,
+                u32 X, FastDiv dY, u32 Y, i64 SN, i64 RN, i64 z0, i64 eid_offset, u32* __restrict__ list,
+                uint8_t* __restrict__ len8, uint8_t* __restrict__ nd8)
+{
+    __shared__ u32 sm[FILLE_WORDS * 32];
+    __shared__ uint8_t sl[FILLE_WORDS * 32];
+    __shared__ uint8_t sn[FILLE_WORDS * 32];
+    __shared__ u32 s_total;
+    const u32 i0 = blockIdx.x * FILLE_WORDS;
+    const u32 i = i0 + threadIdx.x;
+    const u32 base0 = __ldg(pref + i0);
+    u32 word = 0, p = 0;
+    if (i < n_words) {
+        word = __ldg(bits + i);
+        p = __ldg(pref + i) - base0;
+    }
+    const u32 last = (n_words - i0 < FILLE_WORDS ? n_words - i0 : FILLE_WORDS) - 1u;
+    if (threadIdx.x == last) s_total = p + (u32)__popc(word);
+    if (word) {
+        const u32 row = fd_div(i, d_wpr);
+        const u32 w = i - row * wpr;
+        const u32 s = fd_div(row, dY);
+        const u32 r = row - s * Y;
+        const u32 vbase = row * X + w * 32u;
+        const u64 b0 = (u64)(SN * ((i64)s + z0) + RN * (i64)r + (i64)(w * 32u));
+        const u64 eid0 = (u64)(eid_offset + (i64)base0 + (i64)p + 1);
+        const int f = __ffs((int)word) - 1, l = 31 - __clz((int)word);
+        const int nlo = nd64(b0 + f), nhi = nd64(b0 + l + SN + RN + 1);
+        const int ne0 = nd64(eid0), ne1 = nd64(eid0 + (u64)__popc(word) - 1);
+        if (nlo == nhi && ne0 == ne1) {
+            // the usual case: every element of the word has the same line length
+            const uint8_t len = (uint8_t)(9 + ne0 + 8 * nlo), flags = (uint8_t)(0x80 | nlo);
+            while (word) {
+                const int bit = __ffs((int)word) - 1;
+                word &= word - 1;
+                sm[p] = vbase + (u32)bit;
+                sl[p] = len;
+                sn[p] = flags;
+                ++p;
+            }
+        } else {
+            u32 k = 0;
+            while (word) {
+                const int bit = __ffs((int)word) - 1;
+                word &= word - 1;
+                const int nde = nd64(eid0 + k);
+                const u64 b = b0 + bit;
+                const int n0 = nd64(b), n7 = nd64(b + SN + RN + 1);
+                u32 len, flags;
+                if (n0 == n7) {
+                    len = 9u + (u32)nde + 8u * (u32)n0;
+                    flags = 0x80u | (u32)n0;
+                } else {
+                    len = 9u + (u32)nde + (u32)n0 + (u32)n7 + (u32)nd64(b + 1) + (u32)nd64(b + RN) +
+                          (u32)nd64(b + RN + 1) + (u32)nd64(b + SN) + (u32)nd64(b + SN + 1) + (u32)nd64(b + SN + RN);
+                    flags = (u32)n0;
+                }
+                sm[p] = vbase + (u32)bit;
+                sl[p] = (uint8_t)len;
+                sn[p] = (uint8_t)flags;
+                ++p;
+                ++k;
+            }
+        }
+    }
+    __syncthreads();
+    const u32 total = s_total;
+    u32* dst = list + base0;
+    for (u32 q = threadIdx.x; q < total; q += FILLE_WORDS) {
+        dst[q] = sm[q];
+        len8[base0 + q] = sl[q];
+        nd8[base0 + q] = sn[q];
+    }
+}
+
+extern "C" size_t cfe_emit_elements_workspace_bytes(int64_t n_el);
+
+// Raster-ordered element list AND the emitter's per-line lengths (written into the element
+// workspace `ws`, which cfe_element_lengths(have_lengths = 1) / cfe_emit_elements then use).
+extern "C" int cfe_fill_elements(const uint32_t* bits, const uint32_t* pref, int64_t n_words, int64_t Y, int64_t X,
+                                 int64_t z0, int64_t eid_offset, int64_t n_el, uint32_t* list, void* ws,
+                                 cudaStream_t stream)
+{
+    if (n_words <= 0 || n_el <= 0) return 0;
+    if (n_words >= (1LL << 32)) { cfe_set_error("cfe_fill_elements: too many words"); return -1; }
+    const u32 wpr = (u32)((X + 31) / 32);
+    uint8_t* len8 = reinterpret_cast<uint8_t*>(ws);
+    uint8_t* nd8 = len8 + (((size_t)n_el + 15) & ~(size_t)15);
+    const i64 blocks = (n_words + FILLE_WORDS - 1) / FILLE_WORDS;
+    k_fill_elements<<<(unsigned)blocks, FILLE_WORDS, 0, stream>>>(
+        bits, pref, (u32)n_words, make_fastdiv(wpr), wpr, (u32)X, make_fastdiv((u32)Y), (u32)Y, (X + 1) * (Y + 1),
+        X + 1, z0, eid_offset, list, len8, nd8);
+    CFE_CHECK_LAUNCH("k_fill_elements");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // K6: boundary sets (voxelFE.py:163-192, 205-251).  Every set is "candidates in a box of the
 // node / voxel grid, kept when a predicate holds", enumerated in raster order (ascending id).

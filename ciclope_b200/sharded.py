@@ -580,7 +580,10 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         m.elem_vox = empty_u32(m.n_el, dev)
         m.node_list = empty_u32(m.n_nd, dev)
         m.set_ids = torch.empty(max(n_ids, 1), dtype=torch.int64, device=dev)
-        _lib.call("cfe_fill_list", bits.data_ptr(), epref.data_ptr(), rows * W, W, X, m.elem_vox.data_ptr(), s)
+        lib = _lib.load()
+        m.ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(m.n_el) + 16, dtype=torch.uint8, device=dev)
+        _lib.call("cfe_fill_elements", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, z0, m.eid_offset, m.n_el,
+                  m.elem_vox.data_ptr(), m.ws_el.data_ptr(), s)
         _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
                   m.node_list.data_ptr(), s)
         _lib.call("cfe_sets_fill", descs_dev.data_ptr(), 12, n_tiles, Zl, Y, X, z0, m.eid_offset, bits.data_ptr(),
@@ -696,7 +699,7 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         blk_off = torch.zeros(256, dtype=torch.int64, device=dev)
         seg_off = torch.zeros(max(len(segs), 1), dtype=torch.int64, device=dev)
         ws = scan_workspace(max(n_items, 1), dev)
-        ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(m.n_el) + 16, dtype=torch.uint8, device=dev)
+        ws_el = m.ws_el
         _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
                   Y, X, m.z0, nodes_buf.data_ptr(), s)
         perm = None
@@ -716,7 +719,8 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             single_gv = -1
         el_args = (m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(), base + o_first, base + o_hdr,
                    base + o_hlen, single_gv if single_gv >= 0 else 0, Zl, Y, X, m.z0, m.eid_offset)
-        _lib.call("cfe_element_lengths", *el_args, totals.data_ptr(), ws_el.data_ptr(), s)
+        _lib.call("cfe_element_lengths", *el_args, 0 if perm is not None else 1, totals.data_ptr(),
+                  ws_el.data_ptr(), s)
         _lib.call("cfe_emit_elements", *el_args, elem_buf.data_ptr(), blk_off.data_ptr(), ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base, items_buf.data_ptr(),
                   None, totals.data_ptr() + 8, seg_off.data_ptr(), ws.data_ptr(), s)

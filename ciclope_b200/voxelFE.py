@@ -288,6 +288,12 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         npref = empty_u32(nrows * WN, dev)
         ws = scan_workspace(max(rows * W, nrows * WN), dev)
 
+        stats = torch.zeros(4, dtype=torch.int64, device=dev)   # n_el, n_nd, n_set_ids, field overflow
+        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
+        _lib.call("cfe_scan_elements", bits.data_ptr(), rows * W, epref.data_ptr(), stats.data_ptr(),
+                  ws.data_ptr(), s)
+        _lib.call("cfe_scan_nodes", bits.data_ptr(), None, Z, Y, X, Z + 1, nbits.data_ptr(), npref.data_ptr(),
+                  stats.data_ptr() + 8, ws.data_ptr(), s)
         # boundary-set descriptors: node sets X0..Z1 then cell sets X0..Z1
         boxes = _boundary_boxes(locking_strategy, p, k, Z, Y, X)
         descs = (CfeSetDesc * 12)()
@@ -322,14 +328,8 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         descs_dev = bytes_to_device_async(bytes(descs), dev)
         tile_count = empty_u32(n_tiles, dev)
         tile_off = torch.empty(max(n_tiles, 1) + 1, dtype=torch.int64, device=dev)
-        stats = torch.zeros(4, dtype=torch.int64, device=dev)   # n_el, n_nd, n_set_ids
         bases = to_device_async([descs[q].tile_base for q in range(12)], torch.int64, dev)
 
-        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
-        _lib.call("cfe_scan_elements", bits.data_ptr(), rows * W, epref.data_ptr(), stats.data_ptr(),
-                  ws.data_ptr(), s)
-        _lib.call("cfe_scan_nodes", bits.data_ptr(), None, Z, Y, X, Z + 1, nbits.data_ptr(), npref.data_ptr(),
-                  stats.data_ptr() + 8, ws.data_ptr(), s)
         logging.info('Detecting node coordinates and boundary nodes')
         _lib.call("cfe_sets_count", descs_dev.data_ptr(), 12, n_tiles, Z, Y, X, 0, 0, bits.data_ptr(),
                   epref.data_ptr(), None, tile_count.data_ptr(), s)
@@ -349,7 +349,12 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         elem_vox = empty_u32(n_el, dev)
         node_list = empty_u32(n_nd, dev)
         set_ids = torch.empty(max(n_ids, 1), dtype=torch.int64, device=dev)
-        _lib.call("cfe_fill_list", bits.data_ptr(), epref.data_ptr(), rows * W, W, X, elem_vox.data_ptr(), s)
+        # element list fused with the *ELEMENT emitter's line-length pass
+        lib = _lib.load()
+        ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(n_el) + 16, dtype=torch.uint8, device=dev)
+        _lib.call("cfe_fill_elements", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, 0, 0, n_el,
+                  elem_vox.data_ptr(), ws_el.data_ptr(), s)
+        m.ws_el = ws_el
         _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
                   node_list.data_ptr(), s)
         _lib.call("cfe_sets_fill", descs_dev.data_ptr(), 12, n_tiles, Z, Y, X, 0, 0, bits.data_ptr(),
@@ -633,7 +638,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         out = out_full[(-(out_full.data_ptr() + off_nodes)) % 16:]
         totals = torch.zeros(2, dtype=torch.int64, device=dev)   # element bytes, set bytes
         ws = scan_workspace(max(n_items, 1), dev)
-        ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(m.n_el) + 16, dtype=torch.uint8, device=dev)
+        ws_el = m.ws_el
         _lib.call("cfe_put_literal", base + o_head, len(head), out.data_ptr(), None, None, s)
         _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
                   Y, X, 0, out.data_ptr() + off_nodes, s)
@@ -655,7 +660,8 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             single_gv = -1
         el_args = (m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(), base + o_first, base + o_hdr,
                    base + o_hlen, single_gv, Z, Y, X, 0, 0)
-        _lib.call("cfe_element_lengths", *el_args, totals.data_ptr(), ws_el.data_ptr(), s)
+        _lib.call("cfe_element_lengths", *el_args, 0 if perm is not None else 1, totals.data_ptr(),
+                  ws_el.data_ptr(), s)
         _lib.call("cfe_emit_elements", *el_args, out.data_ptr() + off_elem, None, ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base + o_lits,
                   out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, None, ws.data_ptr(), s)

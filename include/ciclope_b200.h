@@ -67,6 +67,12 @@ int cfe_scan_nodes(const uint32_t* bits, const uint32_t* halo_below, int64_t Zl,
 int cfe_fill_list(const uint32_t* bits, const uint32_t* pref, int64_t n_words, int64_t words_per_row,
                   int64_t row_len, uint32_t* list, cfe_stream_t s);
 
+/* cfe_fill_list for the elements, fused with the *ELEMENT emitter's line-length pass: also writes
+ * len8 / nd8 into the element workspace `ws` (cfe_emit_elements_workspace_bytes(n_el) bytes) so that
+ * cfe_element_lengths(have_lengths = 1) only has to sum tile totals (raster order, same z0/eid_offset). */
+int cfe_fill_elements(const uint32_t* bits, const uint32_t* pref, int64_t n_words, int64_t Y, int64_t X,
+                      int64_t z0, int64_t eid_offset, int64_t n_el, uint32_t* list, void* ws, cfe_stream_t s);
+
 /* generic exclusive scan of u32 counts into u64 offsets (tile counts, histograms) */
 int cfe_scan_u32(const uint32_t* in, int64_t n, uint64_t* out, uint64_t* total, void* ws, cfe_stream_t s);
 
@@ -190,8 +196,8 @@ size_t cfe_emit_elements_workspace_bytes(int64_t n_el);
 /* pass 1: line lengths + tile offsets; *total = bytes of the section */
 int cfe_element_lengths(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
                         const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len, int single_gv,
-                        int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, uint64_t* total,
-                        void* ws, cfe_stream_t s);
+                        int64_t Zl, int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, int have_lengths,
+                        uint64_t* total, void* ws, cfe_stream_t s);
 /* pass 2: the lines themselves (same arguments, same workspace) */
 int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
                       const uint64_t* first, const char* hdr_text, const uint8_t* hdr_len, int single_gv,

@@ -299,3 +299,25 @@ def test_wide_coordinate_fields_raise(cfe, tmp_path):
     assert mesh.points[2, 0] == 100000.0           # the mesh itself is fine
     with pytest.raises(NotImplementedError):
         cfe.mesh2voxelfe(mesh, cases.TEMPLATE, str(tmp_path / "w.inp"))
+
+
+def test_mesh2voxelfe_is_repeatable_on_one_mesh(cfe, golden, tmp_path):
+    """the lazy mesh keeps device state between calls: emitting twice (and with another element type)
+    must give the reference bytes each time"""
+    c = DECK_CASES["blobs_bool"]
+    mesh = cfe.vol2ugrid(c["vol"], **c["u"])
+    outs = []
+    for i, kw in enumerate([{}, {}, {"eltype": "C3D8R"}, {}]):
+        p = str(tmp_path / ("d%d.inp" % i))
+        cfe.mesh2voxelfe(mesh, cases.TEMPLATE, p, **kw)
+        outs.append(cases.mask_timestamp(open(p, "rb").read()))
+    want = bytes(golden["blobs_bool/deck"])
+    assert outs[0] == want and outs[1] == want and outs[3] == want
+    assert outs[2] == want.replace(b"TYPE=C3D8,", b"TYPE=C3D8R,")
+    g = DECK_CASES["blobs_grey_property"]
+    mesh = cfe.vol2ugrid(g["vol"], **g["u"])
+    for i in range(2):
+        p = str(tmp_path / ("g%d.inp" % i))
+        m = dict(g["m"]); m["matprop"] = m["matprop"]()
+        cfe.mesh2voxelfe(mesh, fileout=p, **m)
+        assert cases.mask_timestamp(open(p, "rb").read()) == bytes(golden["blobs_grey_property/deck"])
