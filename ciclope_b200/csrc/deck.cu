@@ -92,7 +92,13 @@ __device__ __forceinline__ void raw12(u64 v, u32& r0, u32& r1, u32& r2, u32& low
     }
     const u32 b = rem / 10000u;
     low4 = rem - b * 10000u;
-    r0 = raw4(a);
+    if (WIDE) {
+        r0 = raw4(a);
+    } else {
+        // a 32-bit value has at most two digits above 10^8: tens and ones go to bytes 2 and 3
+        const u32 t = (a * 103u) >> 10;
+        r0 = (t << 16) | ((a - t * 10u) << 24);
+    }
     r1 = raw4(b);
     r2 = raw4(low4);
 }
@@ -680,15 +686,21 @@ __global__ void __launch_bounds__(256) k_emit_elements(ElemEmitParams P)
     char* gbase = dst - pad;
     const u32 end = pad + total;
     const u32 c0 = pad ? 1u : 0u, c1 = end >> 4;
-#pragma unroll 1
-    for (u32 c = c0 + lane; c < c1; c += 32u)
-        *reinterpret_cast<uint4*>(gbase + 16u * c) = *reinterpret_cast<const uint4*>(stage + 16u * c);
-    if (pad) {
-        const u32 hb = end < 16u ? end : 16u;
-        for (u32 k = pad + lane; k < hb; k += 32u) gbase[k] = stage[k];
+    {
+        const char* sp = stage + 16u * (c0 + lane);
+        char* gp = gbase + 16u * (c0 + lane);
+#pragma unroll 2
+        for (u32 c = c0 + lane; c < c1; c += 32u, sp += 512, gp += 512)
+            *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
     }
-    if ((c1 << 4) < end && c1 >= c0) {
-        for (u32 k = (c1 << 4) + lane; k < end; k += 32u) gbase[k] = stage[k];
+    // partial head / tail chunks: fewer than 16 bytes each, one byte per lane
+    if (pad) {
+        const u32 k = pad + lane;
+        if (k < 16u && k < end) gbase[k] = stage[k];
+    }
+    if (c1 >= c0) {
+        const u32 k = (c1 << 4) + lane;
+        if (k < end) gbase[k] = stage[k];
     }
 }
 
