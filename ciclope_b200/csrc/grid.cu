@@ -424,11 +424,15 @@ __device__ __forceinline__ bool voxel_bit(const SetGeom& g, int s, int r, int c)
 __device__ __forceinline__ bool set_candidate(const CfeSetDesc& d, const SetGeom& g, i64 k, i64& id)
 {
     // candidate k of the box -> (s, r, c) in GLOBAL coordinates
-    const i64 nr = d.r1 - d.r0, nc = d.c1 - d.c0;
-    const i64 s = d.s0 + k / (nr * nc);
-    const i64 rem = k % (nr * nc);
-    const int r = (int)(d.r0 + rem / nc);
-    const int c = (int)(d.c0 + rem % nc);
+    // (a box never has 2^32 candidates: it is a subset of one slab's node grid)
+    const u32 nc = (u32)(d.c1 - d.c0), plane = (u32)(d.r1 - d.r0) * nc;
+    const u32 k32 = (u32)k;
+    const u32 ks = k32 / plane;
+    const u32 rem = k32 - ks * plane;
+    const u32 kr = rem / nc;
+    const i64 s = d.s0 + (i64)ks;
+    const int r = (int)d.r0 + (int)kr;
+    const int c = (int)d.c0 + (int)(rem - kr * nc);
     const int sl = (int)(s - g.z0);
     if (d.kind == 2) {
         if (!voxel_bit(g, sl, r, c)) return false;
