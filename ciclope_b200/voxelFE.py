@@ -463,6 +463,24 @@ def _template_text(templatefile, refnode):
     return ''.join(lines)
 
 
+def _tail_bound(templatefile, refnode, matprop, n_gv):
+    """Upper bound (bytes) of the PROPERTY section + template copy, from file sizes only."""
+    with open(templatefile, 'r') as f:
+        t = f.read()
+    bound = len(t.encode()) + 64
+    if refnode is not None:
+        bound += 32 * (t.count('refnodeX') + t.count('refnodeY') + t.count('refnodeZ'))
+    if matprop is not None:
+        bound += 256
+        for fname in matprop["file"]:
+            with open(fname, 'r') as f:
+                lines = f.readlines()
+            # per output line: substitutions at most double it; every eval'ed field prints < 32 chars
+            per_gv = sum(2 * len(ln.encode()) + 32 * (ln.count(',') + 1) + 16 for ln in lines)
+            bound += n_gv * per_gv
+    return bound
+
+
 class _Blob:
     """Host byte blob with 16-byte aligned pieces, shipped to the device in one copy."""
 
@@ -541,11 +559,10 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             '** Node coordinates from input model\n'
             '*NODE\n').format(datetime.now()).encode()
     elem_comment = b'** Elements and Element sets from input model\n'
-    tail = ''
-    if 'PROPERTY' in keywords:
-        tail += _property_cards(matprop, prop_GV, existing_GV)
-    tail += _template_text(templatefile, refnode)
-    tail = tail.encode()
+    # The PROPERTY cards + template (host string work, O(#GV) lines with eval) are generated AFTER
+    # the emit kernels have been enqueued so that they overlap the GPU; only a bound on their size
+    # is needed to reserve the deck buffer.
+    tail_bound = _tail_bound(templatefile, refnode, matprop if 'PROPERTY' in keywords else None, len(gvs))
 
     hdr_text = bytearray(256 * _ELEM_HDR_SLOT)
     hdr_len = np.zeros(256, dtype=np.uint8)
@@ -562,7 +579,6 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     blob = _Blob()
     o_head = blob.add(head)
     o_cmt = blob.add(elem_comment)
-    o_tail = blob.add(tail)
     o_hdr = blob.add(bytes(hdr_text))
     o_hlen = blob.add(hdr_len.tobytes())
     o_first = blob.add(first.tobytes())
@@ -627,7 +643,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     off_cmt = off_nodes + 53 * m.n_nd
     off_elem = off_cmt + len(elem_comment)
     cap = (off_elem + m.n_el * max_line + int(hdr_len.astype(np.int64).sum())
-           + n_set_ids * (len(str(max(max_node_id, m.n_el))) + 1) + len(lits) + len(tail) + 64)
+           + n_set_ids * (len(str(max(max_node_id, m.n_el))) + 1) + len(lits) + tail_bound + 64)
 
     with torch.cuda.device(dev):
         s = _lib.stream()
@@ -665,13 +681,23 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         _lib.call("cfe_emit_elements", *el_args, out.data_ptr() + off_elem, None, ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base + o_lits,
                   out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, None, ws.data_ptr(), s)
-        _lib.call("cfe_put_literal", base + o_tail, len(tail), out.data_ptr() + off_elem, totals.data_ptr(),
+        # host text while the GPU formats: PROPERTY cards (voxelFE.py:691-746) + template (:748-768)
+        tail = ''
+        if 'PROPERTY' in keywords:
+            tail += _property_cards(matprop, prop_GV, existing_GV)
+        tail += _template_text(templatefile, refnode)
+        tail = tail.encode()
+        if len(tail) > tail_bound:
+            raise _lib.CfeError("internal error: PROPERTY/template text (%d bytes) exceeds its reserved bound (%d)"
+                                % (len(tail), tail_bound))
+        dtail = bytes_to_device_async(tail, dev)
+        _lib.call("cfe_put_literal", dtail.data_ptr(), len(tail), out.data_ptr() + off_elem, totals.data_ptr(),
                   totals.data_ptr() + 8, s)
         t = totals.cpu().tolist()
     length = off_elem + t[0] + t[1] + len(tail)
     if length > cap:
         raise _lib.CfeError("internal error: deck length %d exceeds the reserved capacity %d" % (length, cap))
-    mesh._last_keepalive = (dblob,)
+    mesh._last_keepalive = (dblob, dtail)
     return out[:length]
 
 
