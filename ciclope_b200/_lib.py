@@ -59,6 +59,9 @@ _SIGNATURES = {
     "cfe_gather_gv": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "cfe_fill_points": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_format_coords": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_format_coords_wide": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_node_lengths_wide": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_emit_nodes_wide": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_emit_nodes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_emit_elements_workspace_bytes": (c_sz, [c_i64]),
     "cfe_element_lengths": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,

@@ -1139,3 +1139,178 @@ extern "C" int cfe_format_coords(const double* vals, int64_t n, char* out16, int
     CFE_CHECK_LAUNCH("k_format_coords");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Wide coordinate fields: '{:12.6f}' grows beyond 12 characters when |coord| >= 1e5 (voxel sizes in
+// micrometres on large scans), which makes the *NODE lines variable-length.  General (slower) path:
+// exact formatting into 32-byte slots (slot[0] = length), per-node line lengths, tile offsets by
+// cfe_scan_u32, byte-wise staging.
+
+__global__ void __launch_bounds__(128)
+k_format_coords_wide(const double* __restrict__ vals, i64 n, char* __restrict__ out32, int* __restrict__ bad)
+{
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const u64 bits = (u64)__double_as_longlong(vals[t]);
+    const bool neg = (bits >> 63) != 0;
+    const int ex = (int)((bits >> 52) & 0x7ffu);
+    u64 m = bits & 0xfffffffffffffull;
+    int e;
+    if (ex == 0) e = -1074; else { m |= 1ull << 52; e = ex - 1075; }
+    if (ex == 0x7ff || e > 7) { *bad = 1; return; }                 // inf / nan / >= 2^60
+    unsigned __int128 q = (unsigned __int128)m * 1000000u;            // < 2^73
+    if (e >= 0) {
+        q <<= e;
+    } else {
+        const int sft = -e;
+        if (sft >= 128) q = 0;
+        else {
+            const unsigned __int128 P = q;
+            q = P >> sft;
+            const unsigned __int128 rem = P - (q << sft);
+            const unsigned __int128 half = (unsigned __int128)1 << (sft - 1);
+            if (rem > half || (rem == half && ((u64)q & 1ull))) q += 1;
+        }
+    }
+    const unsigned __int128 lim = (unsigned __int128)1000000000000000000ull * 1000000u;   // 1e24
+    if (q >= lim) { *bad = 1; return; }
+    u64 ip = (u64)(q / 1000000u);
+    u32 fp = (u32)(q - (unsigned __int128)ip * 1000000u);
+    char buf[32];
+    int p = 32;
+    for (int k = 0; k < 6; ++k) { buf[--p] = (char)('0' + fp % 10u); fp /= 10u; }
+    buf[--p] = '.';
+    do { buf[--p] = (char)('0' + (int)(ip % 10ull)); ip /= 10ull; } while (ip);
+    if (neg) buf[--p] = '-';
+    while (32 - p < 12) buf[--p] = ' ';
+    const int len = 32 - p;                                           // 12 .. 26
+    char* o = out32 + 32 * t;
+    o[0] = (char)len;
+    for (int k = 0; k < len; ++k) o[1 + k] = buf[p + k];
+}
+
+extern "C" int cfe_format_coords_wide(const double* vals, int64_t n, char* out32, int* bad, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    k_format_coords_wide<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(vals, n, out32, bad);
+    CFE_CHECK_LAUNCH("k_format_coords_wide");
+    return 0;
+}
+
+struct NodeWideParams {
+    const u32* node_list;
+    i64 n_nodes;
+    const char* xtab;        // [X+1][32]
+    const char* ytab;        // [Y+1][32]
+    const char* ztab;        // [layers][32]
+    FastDiv dSN, dRN;
+    u32 SN32, RN32;
+    i64 z0;
+    uint8_t* len8;           // [n_nodes] line lengths
+    u32* tile_tot;           // [tiles of 256 nodes]
+    const u64* tile_off;
+    char* out;
+};
+
+__device__ __forceinline__ void node_wide_fields(const NodeWideParams& P, u32 v, u64& id, u32& s, u32& r, u32& c)
+{
+    s = fd_div(v, P.dSN);
+    const u32 rem = v - s * P.SN32;
+    r = fd_div(rem, P.dRN);
+    c = rem - r * P.RN32;
+    id = (u64)P.SN32 * (u64)((i64)s + P.z0) + (u64)rem;
+}
+
+__global__ void __launch_bounds__(256) k_node_lengths_wide(NodeWideParams P)
+{
+    const i64 k = (i64)blockIdx.x * 256 + threadIdx.x;
+    u32 len = 0;
+    if (k < P.n_nodes) {
+        u64 id; u32 s, r, c;
+        node_wide_fields(P, __ldg(P.node_list + k), id, s, r, c);
+        const int nd = digits_u64(id);
+        len = (u32)(nd < 10 ? 10 : nd) + 2u + (u32)(uint8_t)P.xtab[32 * (size_t)c] + 2u +
+              (u32)(uint8_t)P.ytab[32 * (size_t)r] + 2u + (u32)(uint8_t)P.ztab[32 * (size_t)s] + 1u;
+        P.len8[k] = (uint8_t)len;
+    }
+    __shared__ u32 s_scan[33];
+    u32 tot;
+    block_exclusive_scan<u32>(len, s_scan, tot);
+    if (threadIdx.x == 0) P.tile_tot[blockIdx.x] = tot;
+}
+
+#define NODEW_STAGE (256 * 120 + 32)
+
+__global__ void __launch_bounds__(256) k_emit_nodes_wide(NodeWideParams P)
+{
+    extern __shared__ __align__(16) char stage[];
+    __shared__ u32 s_scan[33];
+    const i64 k = (i64)blockIdx.x * 256 + threadIdx.x;
+    const u32 len = k < P.n_nodes ? (u32)P.len8[k] : 0u;
+    u32 tot;
+    const u32 excl = block_exclusive_scan<u32>(len, s_scan, tot);
+    char* dst = P.out + P.tile_off[blockIdx.x];
+    const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    if (k < P.n_nodes) {
+        u64 id; u32 s, r, c;
+        node_wide_fields(P, __ldg(P.node_list + k), id, s, r, c);
+        char* p = stage + pad + excl;
+        const int nd = digits_u64(id), w = nd < 10 ? 10 : nd;
+        for (int q = 0; q < w - nd; ++q) *p++ = ' ';
+        p += nd;
+        put_u64_back(p, id, nd);
+        const char* f[3] = {P.xtab + 32 * (size_t)c, P.ytab + 32 * (size_t)r, P.ztab + 32 * (size_t)s};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            *p++ = ',';
+            *p++ = ' ';
+            const int fl = (int)(uint8_t)f[a][0];
+            for (int q = 0; q < fl; ++q) *p++ = f[a][1 + q];
+        }
+        *p = '\n';
+    }
+    __syncthreads();
+    flush_stage(stage, pad, tot, dst);
+}
+
+static void node_wide_params(NodeWideParams& P, const uint32_t* node_list, int64_t n_nodes, const char* xtab,
+                             const char* ytab, const char* ztab, int64_t Y, int64_t X, int64_t z0, uint8_t* len8,
+                             uint32_t* tile_tot, const uint64_t* tile_off, char* out)
+{
+    P.node_list = node_list; P.n_nodes = n_nodes; P.xtab = xtab; P.ytab = ytab; P.ztab = ztab;
+    P.SN32 = (u32)((X + 1) * (Y + 1)); P.RN32 = (u32)(X + 1);
+    P.dSN = make_fastdiv(P.SN32); P.dRN = make_fastdiv(P.RN32);
+    P.z0 = z0; P.len8 = len8; P.tile_tot = tile_tot; P.tile_off = reinterpret_cast<const u64*>(tile_off); P.out = out;
+}
+
+// line length of every used node (len8) and byte total of every 256-node tile (tile_tot)
+extern "C" int cfe_node_lengths_wide(const uint32_t* node_list, int64_t n_nodes, const char* xtab32,
+                                     const char* ytab32, const char* ztab32, int64_t Y, int64_t X, int64_t z0,
+                                     uint8_t* len8, uint32_t* tile_tot, cudaStream_t stream)
+{
+    if (n_nodes <= 0) return 0;
+    NodeWideParams P;
+    node_wide_params(P, node_list, n_nodes, xtab32, ytab32, ztab32, Y, X, z0, len8, tile_tot, nullptr, nullptr);
+    k_node_lengths_wide<<<(unsigned)((n_nodes + 255) / 256), 256, 0, stream>>>(P);
+    CFE_CHECK_LAUNCH("k_node_lengths_wide");
+    return 0;
+}
+
+// the *NODE lines with variable-width fields; tile_off = exclusive scan of tile_tot
+extern "C" int cfe_emit_nodes_wide(const uint32_t* node_list, int64_t n_nodes, const char* xtab32,
+                                   const char* ytab32, const char* ztab32, int64_t Y, int64_t X, int64_t z0,
+                                   const uint8_t* len8, const uint64_t* tile_off, char* out, cudaStream_t stream)
+{
+    if (n_nodes <= 0) return 0;
+    NodeWideParams P;
+    node_wide_params(P, node_list, n_nodes, xtab32, ytab32, ztab32, Y, X, z0, const_cast<uint8_t*>(len8), nullptr,
+                     tile_off, out);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_nodes_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, NODEW_STAGE));
+        attr_set = true;
+    }
+    k_emit_nodes_wide<<<(unsigned)((n_nodes + 255) / 256), 256, NODEW_STAGE, stream>>>(P);
+    CFE_CHECK_LAUNCH("k_emit_nodes_wide");
+    return 0;
+}

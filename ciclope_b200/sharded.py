@@ -556,7 +556,7 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
                   epref.data_ptr(), _lib.ptr(halo), tile_count.data_ptr(), s)
         _lib.call("cfe_scan_u32", tile_count.data_ptr(), n_tiles, tile_off.data_ptr(), stats.data_ptr() + 16,
                   ws.data_ptr(), s)
-        m.ftab = vfe._format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
+        m.ftab, m.coord_vals = vfe._format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
         tile_off[n_tiles] = stats[2]
         first_t = tile_off[bases.clamp(max=n_tiles)]
         count_t = torch.cat([first_t[1:], stats[2:3]]) - first_t
@@ -650,12 +650,20 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     o_first = blob.add(first.tobytes())
     o_hdr = blob.add(bytes(256 * vfe._ELEM_HDR_SLOT))
     o_hlen = blob.add(bytes(256))                      # no headers inside the slab buffers
-    if m.field_overflow:
-        raise NotImplementedError("node coordinates wider than the 12-character field (|coord| >= 1e5) are not "
-                                  "supported by the CUDA deck writer yet")
-    p_xt = m.ftab.data_ptr()
-    p_yt = p_xt + 16 * (X + 1)
-    p_zt = p_yt + 16 * (Y + 1) + 16 * m.z0      # this slab's node layers
+    wide = m.field_overflow      # variable-length *NODE lines (some '{:12.6f}' field needs > 12 characters)
+    slot = 32 if wide else 16
+    if wide:
+        with torch.cuda.device(dev):
+            s = _lib.stream()
+            nv = m.coord_vals.numel()
+            wtab = torch.empty(32 * nv, dtype=torch.uint8, device=dev)
+            nstat = torch.zeros(2, dtype=torch.int64, device=dev)          # *NODE bytes of this slab, bad flag
+            _lib.call("cfe_format_coords_wide", m.coord_vals.data_ptr(), nv, wtab.data_ptr(), nstat.data_ptr() + 8, s)
+        p_xt = wtab.data_ptr()
+    else:
+        p_xt = m.ftab.data_ptr()
+    p_yt = p_xt + slot * (X + 1)
+    p_zt = p_yt + slot * (Y + 1) + slot * m.z0      # this slab's node layers
 
     # id-list segments of this rank, one per non-empty set, in file order
     set_names = []
@@ -691,7 +699,7 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         s = _lib.stream()
         dblob = blob.to_device(dev)
         base = dblob.data_ptr()
-        nodes_buf = torch.empty(max(53 * m.n_nd, 1), dtype=torch.uint8, device=dev)
+        nodes_buf = torch.empty(max((96 if wide else 53) * m.n_nd, 1) + 64, dtype=torch.uint8, device=dev)
         elem_buf = torch.empty(max(m.n_el * max_line, 1) + 64, dtype=torch.uint8, device=dev)
         items_buf = torch.empty(n_items * (len(str(max(max_node_id, m.n_el_global))) + 1) + 64, dtype=torch.uint8,
                                 device=dev)
@@ -700,8 +708,20 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         seg_off = torch.zeros(max(len(segs), 1), dtype=torch.int64, device=dev)
         ws = scan_workspace(max(n_items, 1), dev)
         ws_el = m.ws_el
-        _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
-                  Y, X, m.z0, nodes_buf.data_ptr(), s)
+        if wide:
+            n_ntiles = (m.n_nd + 255) // 256
+            nlen8 = torch.empty(max(m.n_nd, 1), dtype=torch.uint8, device=dev)
+            ntile_tot = empty_u32(n_ntiles, dev)
+            ntile_off = torch.empty(max(n_ntiles, 1), dtype=torch.int64, device=dev)
+            _lib.call("cfe_node_lengths_wide", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt, Y, X, m.z0,
+                      nlen8.data_ptr(), ntile_tot.data_ptr(), s)
+            _lib.call("cfe_scan_u32", ntile_tot.data_ptr(), n_ntiles, ntile_off.data_ptr(), nstat.data_ptr(),
+                      scan_workspace(max(n_ntiles, 1), dev).data_ptr(), s)
+            _lib.call("cfe_emit_nodes_wide", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt, Y, X, m.z0,
+                      nlen8.data_ptr(), ntile_off.data_ptr(), nodes_buf.data_ptr(), s)
+        else:
+            _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
+                      Y, X, m.z0, nodes_buf.data_ptr(), s)
         perm = None
         single_gv = int(gvs[0])
         if len(gvs) > 1:
@@ -737,11 +757,15 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             ci = to_device_async(cols, torch.int64, dev)
             st = seg_off[: len(cols)]
             set_bytes[ci] = torch.cat([st[1:], totals[1:2]]) - st
-        mine = torch.cat([gv_bytes, set_bytes, to_device_async([53 * m.n_nd], torch.int64, dev)])
+        node_b = nstat[0:1] if wide else to_device_async([53 * m.n_nd], torch.int64, dev)
+        bad_b = nstat[1:2] if wide else torch.zeros(1, dtype=torch.int64, device=dev)
+        mine = torch.cat([gv_bytes, set_bytes, node_b, bad_b])
     allb = yield from ctx.all_gather(mine)
     host = torch.cat([torch.stack(allb).reshape(-1), totals, blk_off, seg_off]).cpu().numpy()   # the one sync
-    nb = ctx.size * 271
-    allb = host[:nb].reshape(ctx.size, 271)             # [rank][256 + 14 + 1]
+    nb = ctx.size * 272
+    allb = host[:nb].reshape(ctx.size, 272)             # [rank][256 grey values + 14 sets + nodes + bad flag]
+    if allb[:, 271].any():
+        raise NotImplementedError("node coordinates that are not finite or not below 1e18 cannot be formatted")
     blk = host[nb + 2: nb + 258].tolist()
     sgo = host[nb + 258: nb + 258 + len(segs)].tolist()
     it_total = int(host[nb + 1])

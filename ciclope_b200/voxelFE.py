@@ -62,15 +62,6 @@ def _coordinate_tables(voxelsize, Z, Y, X):
     return tuple(np.asarray(v).astype(dtype) for v in (xs, ys, zs))
 
 
-def _field_table(values):
-    """16-byte slots with the '{:12.6f}' field of each value (voxelFE.py:630)."""
-    fields = [format(v, "12.6f") for v in values.tolist()]
-    if any(len(f) != 12 for f in fields):
-        raise NotImplementedError("node coordinates wider than the 12-character field (|coord| >= 1e5) are not "
-                                  "supported by the CUDA deck writer yet")
-    return b"".join(f.encode("ascii") + b"\0\0\0\0" for f in fields)
-
-
 def _format_tables_device(xs, ys, zs, dev, overflow_ptr, stream):
     """'{:12.6f}' fields of every per-axis coordinate, formatted exactly on the GPU (16-byte slots,
     x then y then z).  The values are float64 copies of what np.asarray(nodes) holds, which is what
@@ -83,7 +74,7 @@ def _format_tables_device(xs, ys, zs, dev, overflow_ptr, stream):
     tab = torch.from_numpy(np.concatenate(vals)).pin_memory().to(dev, non_blocking=True)
     out = torch.empty(16 * tab.numel(), dtype=torch.uint8, device=dev)
     _lib.call("cfe_format_coords", tab.data_ptr(), tab.numel(), out.data_ptr(), overflow_ptr, stream)
-    return out
+    return out, tab
 
 
 def _int_lock(v, name):
@@ -337,7 +328,7 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
                   ws.data_ptr(), s)
         # host work that overlaps the kernels above: per-axis coordinate values and their text fields
         m.xs, m.ys, m.zs = _coordinate_tables(voxelsize, Z, Y, X)
-        m.ftab = _format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
+        m.ftab, m.coord_vals = _format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
         # one device->host read: counts + first id of every set
         tile_off[n_tiles] = stats[2]
         host = torch.cat([stats, tile_off[bases.clamp(max=n_tiles)]]).cpu().tolist()
@@ -582,12 +573,32 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     o_hdr = blob.add(bytes(hdr_text))
     o_hlen = blob.add(hdr_len.tobytes())
     o_first = blob.add(first.tobytes())
-    if m.field_overflow:
-        raise NotImplementedError("node coordinates wider than the 12-character field (|coord| >= 1e5) are not "
-                                  "supported by the CUDA deck writer yet")
-    p_xt = m.ftab.data_ptr()
-    p_yt = p_xt + 16 * (X + 1)
-    p_zt = p_yt + 16 * (Y + 1)
+    wide = m.field_overflow     # some '{:12.6f}' field needs more than 12 characters: variable-length *NODE lines
+    slot = 32 if wide else 16
+    node_bytes = 53 * m.n_nd
+    if wide:
+        with torch.cuda.device(dev):
+            s = _lib.stream()
+            nv = m.coord_vals.numel()
+            wtab = torch.empty(32 * nv, dtype=torch.uint8, device=dev)
+            nstat = torch.zeros(2, dtype=torch.int64, device=dev)          # *NODE bytes, bad-value flag
+            _lib.call("cfe_format_coords_wide", m.coord_vals.data_ptr(), nv, wtab.data_ptr(), nstat.data_ptr() + 8, s)
+            n_ntiles = (m.n_nd + 255) // 256
+            nlen8 = torch.empty(max(m.n_nd, 1), dtype=torch.uint8, device=dev)
+            ntile_tot = empty_u32(n_ntiles, dev)
+            ntile_off = torch.empty(max(n_ntiles, 1), dtype=torch.int64, device=dev)
+            p_xt = wtab.data_ptr()
+            _lib.call("cfe_node_lengths_wide", m.node_list.data_ptr(), m.n_nd, p_xt, p_xt + 32 * (X + 1),
+                      p_xt + 32 * (X + 1) + 32 * (Y + 1), Y, X, 0, nlen8.data_ptr(), ntile_tot.data_ptr(), s)
+            _lib.call("cfe_scan_u32", ntile_tot.data_ptr(), n_ntiles, ntile_off.data_ptr(), nstat.data_ptr(),
+                      scan_workspace(max(n_ntiles, 1), dev).data_ptr(), s)
+            node_bytes, bad = nstat.cpu().tolist()
+        if bad:
+            raise NotImplementedError("node coordinates that are not finite or not below 1e18 cannot be formatted")
+    else:
+        p_xt = m.ftab.data_ptr()
+    p_yt = p_xt + slot * (X + 1)
+    p_zt = p_yt + slot * (Y + 1)
 
     # NSET / ELSET item stream (voxelFE.py:650-688)
     lits = bytearray()
@@ -640,7 +651,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         raise NotImplementedError("node ids wider than the 10-character field are not supported")
     max_line = len(str(m.n_el)) + 8 * len(str(max_node_id)) + 9
     off_nodes = len(head)
-    off_cmt = off_nodes + 53 * m.n_nd
+    off_cmt = off_nodes + node_bytes
     off_elem = off_cmt + len(elem_comment)
     cap = (off_elem + m.n_el * max_line + int(hdr_len.astype(np.int64).sum())
            + n_set_ids * (len(str(max(max_node_id, m.n_el))) + 1) + len(lits) + tail_bound + 64)
@@ -656,8 +667,12 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         ws = scan_workspace(max(n_items, 1), dev)
         ws_el = m.ws_el
         _lib.call("cfe_put_literal", base + o_head, len(head), out.data_ptr(), None, None, s)
-        _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
-                  Y, X, 0, out.data_ptr() + off_nodes, s)
+        if wide:
+            _lib.call("cfe_emit_nodes_wide", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt, Y, X, 0,
+                      nlen8.data_ptr(), ntile_off.data_ptr(), out.data_ptr() + off_nodes, s)
+        else:
+            _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
+                      Y, X, 0, out.data_ptr() + off_nodes, s)
         _lib.call("cfe_put_literal", base + o_cmt, len(elem_comment), out.data_ptr() + off_cmt, None, None, s)
         perm = None
         single_gv = int(gvs[0])

@@ -178,6 +178,17 @@ int cfe_fill_points(const void* xs, const void* ys, const void* zs, int elem_byt
  * *overflow (device int, caller-zeroed) is set when a field needs more than 12 characters. */
 int cfe_format_coords(const double* vals, int64_t n, char* out16, int* overflow, cfe_stream_t s);
 
+/* General path for coordinates whose '{:12.6f}' field is wider than 12 characters (|v| >= 1e5): exact
+ * formatting into 32-byte slots (slot[0] = length, |v| < 1e18 else *bad = 1), per-node line lengths and
+ * 256-node tile totals, then (after cfe_scan_u32 of the totals) the variable-length *NODE lines. */
+int cfe_format_coords_wide(const double* vals, int64_t n, char* out32, int* bad, cfe_stream_t s);
+int cfe_node_lengths_wide(const uint32_t* node_list, int64_t n_nodes, const char* xtab32, const char* ytab32,
+                          const char* ztab32, int64_t Y, int64_t X, int64_t z0, uint8_t* len8,
+                          uint32_t* tile_tot, cfe_stream_t s);
+int cfe_emit_nodes_wide(const uint32_t* node_list, int64_t n_nodes, const char* xtab32, const char* ytab32,
+                        const char* ztab32, int64_t Y, int64_t X, int64_t z0, const uint8_t* len8,
+                        const uint64_t* tile_off, char* out, cfe_stream_t s);
+
 /* *NODE lines (voxelFE.py:629-630).  xtab/ytab/ztab: 16-byte slots holding the 12-character
  * '{:12.6f}' field of every column / row / layer coordinate (formatted on the host by the
  * same interpreter arithmetic as the reference).  Writes 53*n_nodes bytes at out. */

@@ -215,6 +215,10 @@ def deck_cases():
     add("vs_negative", b, dict(voxelsize=[-0.1, 0.1, -0.25]))
     add("vs_rounding", b, dict(voxelsize=[0.0000005, 0.0000015, 0.0000025]))
     add("vs_big_but_12chars", b, dict(voxelsize=[11111.11, 1234.5, 9999.999]))
+    # '{:12.6f}' overflows its 12 characters from 1e5 on: variable-length *NODE lines
+    add("vs_wide_fields", b, dict(voxelsize=[30000.5, 1e6, 123456.789]))
+    add("vs_wide_negative_mixed", b, dict(voxelsize=[-25000.25, 0.0195, 5e9]))
+    add("vs_wide_int", b, dict(voxelsize=[100000, 7, 12345678]))
 
     # greyscale with several ELSETs, GVmin, float GVmin
     g = rand_grey((6, 7, 20), 0.5, 10)

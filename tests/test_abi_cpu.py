@@ -89,10 +89,6 @@ def test_threshold_and_tables_host_logic(golden):
         assert xs.dtype == pts.dtype, c["name"]
         assert np.array_equal(pts[0, 0, :, 0], xs) and np.array_equal(pts[0, :, 0, 1], ys) \
             and np.array_equal(pts[:, 0, 0, 2], zs), c["name"]
-        tab = v._field_table(xs)
-        assert len(tab) == 16 * (X + 1)
-    with pytest.raises(NotImplementedError):
-        v._field_table(np.array([0.0, 123456.0]))
 
 
 def test_boundary_boxes_host_logic():
