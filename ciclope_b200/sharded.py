@@ -478,7 +478,7 @@ class SlabMesh:
 
 
 def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_num=1, node_level_lock_num=1,
-                      locking_strategy="plane"):
+                      locking_strategy="plane", eid_base=0):
     """vol2ugrid of the global volume [Zg,Y,X]; `vol` = this rank's uint8 slab starting at slice z0."""
     _lib.require_cuda()
     if locking_strategy not in ("plane", "exact"):
@@ -568,10 +568,11 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         n_el_r = [t[0] for t in table]
         n_nd_r = [t[1] for t in table]
         m.n_el, m.n_nd = n_el_r[ctx.rank], n_nd_r[ctx.rank]
-        m.eid_offset = sum(n_el_r[: ctx.rank])
+        m.eid_offset = eid_base + sum(n_el_r[: ctx.rank])   # eid_base: elements of slabs outside this group
         m.node_rank_offset = sum(n_nd_r[: ctx.rank])
         m.n_el_global, m.n_nd_global = sum(n_el_r), sum(n_nd_r)
         m.n_el_by_rank = [int(v) for v in n_el_r]
+        m.max_eid = eid_base + m.n_el_global                 # largest element id that can be printed
         m.set_count = [int(c) for c in table[ctx.rank][2:14]]
         m.field_overflow = any(t[14] for t in table)
         m.set_first, n_ids = exclusive_offsets(m.set_count)
@@ -694,14 +695,16 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     max_node_id = (m.Zg + 1) * (Y + 1) * (X + 1) - 1
     if max_node_id >= 10 ** 10:
         raise NotImplementedError("node ids wider than the 10-character field are not supported")
-    max_line = len(str(m.n_el_global)) + 8 * len(str(max_node_id)) + 9
+    if m.max_eid >= 10 ** 10:
+        raise NotImplementedError("element ids wider than 10 digits are not supported")
+    max_line = len(str(m.max_eid)) + 8 * len(str(max_node_id)) + 9
     with torch.cuda.device(dev):
         s = _lib.stream()
         dblob = blob.to_device(dev)
         base = dblob.data_ptr()
         nodes_buf = torch.empty(max((96 if wide else 53) * m.n_nd, 1) + 64, dtype=torch.uint8, device=dev)
         elem_buf = torch.empty(max(m.n_el * max_line, 1) + 64, dtype=torch.uint8, device=dev)
-        items_buf = torch.empty(n_items * (len(str(max(max_node_id, m.n_el_global))) + 1) + 64, dtype=torch.uint8,
+        items_buf = torch.empty(n_items * (len(str(max(max_node_id, m.max_eid))) + 1) + 64, dtype=torch.uint8,
                                 device=dev)
         totals = torch.zeros(2, dtype=torch.int64, device=dev)
         blk_off = torch.zeros(256, dtype=torch.int64, device=dev)

@@ -183,3 +183,48 @@ def test_real_nccl_two_ranks(orc, tmp_path):
     orc.mesh2voxelfe(orc.vol2ugrid(L, [0.0195] * 3), cases.TEMPLATE, str(tmp_path / "cpu.inp"))
     assert cases.mask_timestamp(open(out, "rb").read()) == \
         cases.mask_timestamp(open(str(tmp_path / "cpu.inp"), "rb").read())
+
+
+def test_ids_beyond_32_bits(sh):
+    """Node / element ids of the 2048^3-class configs exceed 2^32: a thin slab placed at a huge global
+    slice offset exercises the 64-bit formatting paths; the expected text is re-derived here from the
+    voxel coordinates with plain Python integers."""
+    import torch
+    Zl, Y, X = 6, 48, 64
+    RN, SN = X + 1, (X + 1) * (Y + 1)
+    z0 = (1 << 32) // SN + 700_000            # node ids around 6.4e9
+    Zg = z0 + Zl                               # this slab is the last one of the (virtual) global volume
+    eid_base = 5_000_000_000 - 300            # element ids cross 5e9 inside the slab
+    vs = [0.01, 0.02, 0.00003]
+    bw = cases.rand_binary((Zl, Y, X), 0.35, 77)
+    runner = sh.LocalRunner(1)
+    ctx = runner.ctxs()[0]
+    slab = torch.from_numpy(bw).cuda().view(torch.uint8)
+    mesh = runner.run([sh.vol2ugrid_program(ctx, slab, True, Zg, z0, vs, eid_base=eid_base)])[0]
+    deck = runner.run([sh.deck_program(ctx, mesh, cases.TEMPLATE)])[0]
+    pieces = {id(buf): bytes(buf[lo:hi].cpu().numpy()) for _, buf, lo, hi in deck.writes}
+    nodes_txt = pieces[id(deck.buffers[0])].decode()
+    elems_txt = pieces[id(deck.buffers[1])].decode()
+    # expected, from first principles (voxelFE.py:145-154, 202, 630, 647)
+    used = set()
+    elines = []
+    eid = eid_base
+    for s, r, c in zip(*np.nonzero(bw)):
+        s, r, c = int(s), int(r), int(c)
+        b = SN * (s + z0) + RN * r + c
+        n = [b, b + 1, b + RN + 1, b + RN, b + SN, b + SN + 1, b + SN + RN + 1, b + SN + RN]
+        used.update(n)
+        eid += 1
+        elines.append(",".join(str(v) for v in [eid] + n))
+    assert max(used) > (1 << 32) and eid > 5_000_000_000
+    nlines = []
+    for nid in sorted(used):
+        s, rem = divmod(nid, SN)
+        r, c = divmod(rem, RN)
+        nlines.append('{0:10d}, {1:12.6f}, {2:12.6f}, {3:12.6f}'.format(nid, vs[0] * c, vs[1] * r, vs[2] * s))
+    assert elems_txt == "\n".join(elines) + "\n"
+    assert nodes_txt == "\n".join(nlines) + "\n"
+    # the set ids are global too: CELLS_Z1 (last slice) holds the last elements
+    z1 = [eid_base + 1 + i for i, (s, r, c) in enumerate(zip(*np.nonzero(bw))) if s == Zl - 1]
+    got = mesh.set_ids[mesh.set_first[11]: mesh.set_first[11] + mesh.set_count[11]].cpu().tolist()
+    assert got == z1
