@@ -71,6 +71,10 @@ _SIGNATURES = {
                                   c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_emit_items": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cfe_put_literal": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_gen_node_lengths": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_gen_emit_nodes": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_gen_elem_lengths": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_gen_emit_elements": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_gv_histogram": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "cfe_partition_tiles": (c_i64, [c_i64]),
     "cfe_partition_hist": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),

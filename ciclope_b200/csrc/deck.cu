@@ -1314,3 +1314,193 @@ extern "C" int cfe_emit_nodes_wide(const uint32_t* node_list, int64_t n_nodes, c
     CFE_CHECK_LAUNCH("k_emit_nodes_wide");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// Generic (array-driven) deck emission: mesh2voxelfe accepts ANY hexahedral meshio mesh
+// (voxelFE.py:612-688 only touches points, cells, the first cell_data entry and the sets), e.g. one
+// read back from VTK or a vol2ugrid mesh whose sets were edited.  Same text, plain kernels:
+// lengths -> 256-item tile totals -> cfe_scan_u32 -> byte-wise staging + coalesced flush.
+
+struct GenNodeParams {
+    const i64* ids;          // used node ids, ascending (np.unique(cells))
+    i64 n;
+    const char* slots;       // [n][3] 32-byte coordinate fields (cfe_format_coords_wide of points[ids])
+    uint8_t* len8;
+    u32* tile_tot;
+    const u64* tile_off;
+    char* out;
+};
+
+__global__ void __launch_bounds__(256) k_node_lengths_gen(GenNodeParams P)
+{
+    const i64 k = (i64)blockIdx.x * 256 + threadIdx.x;
+    u32 len = 0;
+    if (k < P.n) {
+        const int nd = digits_u64((u64)P.ids[k]);
+        const char* f = P.slots + 96 * (size_t)k;
+        len = (u32)(nd < 10 ? 10 : nd) + 7u + (u32)(uint8_t)f[0] + (u32)(uint8_t)f[32] + (u32)(uint8_t)f[64];
+        P.len8[k] = (uint8_t)len;
+    }
+    __shared__ u32 s_scan[33];
+    u32 tot;
+    block_exclusive_scan<u32>(len, s_scan, tot);
+    if (threadIdx.x == 0) P.tile_tot[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) k_emit_nodes_gen(GenNodeParams P)
+{
+    extern __shared__ __align__(16) char stage[];
+    __shared__ u32 s_scan[33];
+    const i64 k = (i64)blockIdx.x * 256 + threadIdx.x;
+    const u32 len = k < P.n ? (u32)P.len8[k] : 0u;
+    u32 tot;
+    const u32 excl = block_exclusive_scan<u32>(len, s_scan, tot);
+    char* dst = P.out + P.tile_off[blockIdx.x];
+    const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    if (k < P.n) {
+        const u64 id = (u64)P.ids[k];
+        char* p = stage + pad + excl;
+        const int nd = digits_u64(id), w = nd < 10 ? 10 : nd;
+        for (int q = 0; q < w - nd; ++q) *p++ = ' ';
+        p += nd;
+        put_u64_back(p, id, nd);
+        const char* f = P.slots + 96 * (size_t)k;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            *p++ = ',';
+            *p++ = ' ';
+            const int fl = (int)(uint8_t)f[32 * a];
+            for (int q = 0; q < fl; ++q) *p++ = f[32 * a + 1 + q];
+        }
+        *p = '\n';
+    }
+    __syncthreads();
+    flush_stage(stage, pad, tot, dst);
+}
+
+extern "C" int cfe_gen_node_lengths(const int64_t* ids, int64_t n, const char* slots, uint8_t* len8,
+                                    uint32_t* tile_tot, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    GenNodeParams P = {reinterpret_cast<const i64*>(ids), n, slots, len8, tile_tot, nullptr, nullptr};
+    k_node_lengths_gen<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(P);
+    CFE_CHECK_LAUNCH("k_node_lengths_gen");
+    return 0;
+}
+
+extern "C" int cfe_gen_emit_nodes(const int64_t* ids, int64_t n, const char* slots, const uint8_t* len8,
+                                  const uint64_t* tile_off, char* out, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    GenNodeParams P = {reinterpret_cast<const i64*>(ids), n, slots, const_cast<uint8_t*>(len8), nullptr,
+                       reinterpret_cast<const u64*>(tile_off), out};
+    static bool attr_set = false;
+    if (!attr_set) {
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_nodes_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, NODEW_STAGE));
+        attr_set = true;
+    }
+    k_emit_nodes_gen<<<(unsigned)((n + 255) / 256), 256, NODEW_STAGE, stream>>>(P);
+    CFE_CHECK_LAUNCH("k_emit_nodes_gen");
+    return 0;
+}
+
+struct GenElemParams {
+    const i64* cells;        // [n_cells][8] node ids
+    const i64* order;        // [n] element index of every emitted line (grouped by grey value, ascending)
+    const int* group;        // [n] group of every emitted line
+    const i64* gfirst;       // [n_groups] emission index of each group's first line
+    const int* hdr_off;      // [n_groups] '*ELEMENT ...' header of each group in `lit`
+    const int* hdr_len;
+    const char* lit;
+    i64 n;
+    unsigned short* len16;
+    u32* tile_tot;
+    const u64* tile_off;
+    char* out;
+};
+
+#define GEN_ELEM_STAGE (256 * 200 + 32)
+
+__global__ void __launch_bounds__(256) k_elem_lengths_gen(GenElemParams P)
+{
+    const i64 t = (i64)blockIdx.x * 256 + threadIdx.x;
+    u32 len = 0;
+    if (t < P.n) {
+        const i64 e = P.order[t];
+        len = 9u + (u32)digits_u64((u64)(e + 1));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) len += (u32)digits_u64((u64)P.cells[8 * e + q]);
+        const int g = P.group[t];
+        if (P.gfirst[g] == t) len += (u32)P.hdr_len[g];
+        P.len16[t] = (unsigned short)len;
+    }
+    __shared__ u32 s_scan[33];
+    u32 tot;
+    block_exclusive_scan<u32>(len, s_scan, tot);
+    if (threadIdx.x == 0) P.tile_tot[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) k_emit_elements_gen(GenElemParams P)
+{
+    extern __shared__ __align__(16) char stage[];
+    __shared__ u32 s_scan[33];
+    const i64 t = (i64)blockIdx.x * 256 + threadIdx.x;
+    const u32 len = t < P.n ? (u32)P.len16[t] : 0u;
+    u32 tot;
+    const u32 excl = block_exclusive_scan<u32>(len, s_scan, tot);
+    char* dst = P.out + P.tile_off[blockIdx.x];
+    const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    const bool staged = pad + tot <= (u32)GEN_ELEM_STAGE;
+    if (t < P.n) {
+        char* p = staged ? stage + pad + excl : dst + excl;
+        const i64 e = P.order[t];
+        const int g = P.group[t];
+        if (P.gfirst[g] == t) {
+            const char* h = P.lit + P.hdr_off[g];
+            const int hl = P.hdr_len[g];
+            for (int q = 0; q < hl; ++q) *p++ = h[q];
+        }
+#pragma unroll 1
+        for (int q = 0; q < 9; ++q) {
+            const u64 v = q == 0 ? (u64)(e + 1) : (u64)P.cells[8 * e + q - 1];
+            const int nd = digits_u64(v);
+            p += nd;
+            put_u64_back(p, v, nd);
+            *p++ = q == 8 ? '\n' : ',';
+        }
+    }
+    __syncthreads();
+    if (staged) flush_stage(stage, pad, tot, dst);
+}
+
+extern "C" int cfe_gen_elem_lengths(const int64_t* cells, const int64_t* order, const int* group,
+                                    const int64_t* gfirst, const int* hdr_off, const int* hdr_len, int64_t n,
+                                    uint16_t* len16, uint32_t* tile_tot, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    GenElemParams P = {reinterpret_cast<const i64*>(cells), reinterpret_cast<const i64*>(order), group,
+                       reinterpret_cast<const i64*>(gfirst), hdr_off, hdr_len, nullptr, n, len16, tile_tot, nullptr,
+                       nullptr};
+    k_elem_lengths_gen<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(P);
+    CFE_CHECK_LAUNCH("k_elem_lengths_gen");
+    return 0;
+}
+
+extern "C" int cfe_gen_emit_elements(const int64_t* cells, const int64_t* order, const int* group,
+                                     const int64_t* gfirst, const int* hdr_off, const int* hdr_len, const char* lit,
+                                     int64_t n, const uint16_t* len16, const uint64_t* tile_off, char* out,
+                                     cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    GenElemParams P = {reinterpret_cast<const i64*>(cells), reinterpret_cast<const i64*>(order), group,
+                       reinterpret_cast<const i64*>(gfirst), hdr_off, hdr_len, lit, n,
+                       const_cast<unsigned short*>(len16), nullptr, reinterpret_cast<const u64*>(tile_off), out};
+    static bool attr_set = false;
+    if (!attr_set) {
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, GEN_ELEM_STAGE));
+        attr_set = true;
+    }
+    k_emit_elements_gen<<<(unsigned)((n + 255) / 256), 256, GEN_ELEM_STAGE, stream>>>(P);
+    CFE_CHECK_LAUNCH("k_emit_elements_gen");
+    return 0;
+}

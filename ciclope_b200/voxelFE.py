@@ -153,6 +153,8 @@ class VoxelMesh:
                 _lib.call("cfe_fill_points", tabs[0].data_ptr(), tabs[1].data_ptr(), tabs[2].data_ptr(),
                           dt.itemsize, self.Z + 1, self.Y, self.X, out.data_ptr(), _lib.stream())
                 self._points = out.cpu().numpy().view(dt)
+                self._points.flags.writeable = False      # replace, do not edit in place (_host_edited)
+                self._points_made = self._points
         return self._points
 
     @points.setter
@@ -167,12 +169,22 @@ class VoxelMesh:
                 out = torch.empty((self.n_el, 8), dtype=torch.int64, device=dev)
                 _lib.call("cfe_fill_cells", self.elem_vox.data_ptr(), self.n_el, self.Y, self.X, 0,
                           out.data_ptr(), _lib.stream())
-                self._cells = [CellBlock("hexahedron", out.cpu().numpy())]
+                data = out.cpu().numpy()
+                data.flags.writeable = False
+                self._cells = self._cells_made = [CellBlock("hexahedron", data)]
+                self._cells_block = self._cells[0]
         return self._cells
+
+    @cells.setter
+    def cells(self, value):
+        self._cells = value
 
     @property
     def cells_dict(self):
-        return {"hexahedron": self.cells[0].data}
+        d = {}
+        for blk in self.cells:
+            d.setdefault(blk[0], []).append(np.asarray(blk[1]))
+        return {k: (v[0] if len(v) == 1 else np.concatenate(v)) for k, v in d.items()}
 
     def _gv_array(self):
         dev = self.vol.device
@@ -209,7 +221,6 @@ class VoxelMesh:
             d["NODES_X0Y0Z0"] = d["NODES_Z0"][0:2]   # voxelFE.py:250-251
             d["NODES_X0Y0Z1"] = d["NODES_Z1"][0:2]
             self._point_sets = d
-            self._point_sets_snapshot = dict(d)
         return self._point_sets
 
     @property
@@ -217,19 +228,51 @@ class VoxelMesh:
         if self._cell_sets is None:
             lists = self._set_lists(self.set_first[6:], self.set_count[6:])
             self._cell_sets = dict(zip(CELL_SET_NAMES, lists))
-            self._cell_sets_snapshot = dict(self._cell_sets)
         return self._cell_sets
 
-    def _check_unmodified(self):
-        """mesh2voxelfe emits from device state; refuse meshes whose host views were edited."""
-        if self._point_sets is not None and (list(self._point_sets) != list(self._point_sets_snapshot) or any(
-                self._point_sets[k] is not self._point_sets_snapshot[k] for k in self._point_sets)):
-            raise NotImplementedError("point_sets were modified on the host; the CUDA deck writer emits the sets "
-                                      "computed by vol2ugrid")
-        if self._cell_sets is not None and (list(self._cell_sets) != list(self._cell_sets_snapshot) or any(
-                self._cell_sets[k] is not self._cell_sets_snapshot[k] for k in self._cell_sets)):
-            raise NotImplementedError("cell_sets were modified on the host; the CUDA deck writer emits the sets "
-                                      "computed by vol2ugrid")
+    def _host_edited(self):
+        """True when a host-side view (sets, grey values, points, cells) no longer shows what
+        vol2ugrid computed; mesh2voxelfe then emits from the host arrays (generic.py) instead of
+        the device state.  The big materialised arrays are handed out read-only, so they can only
+        be replaced (seen by identity); sets and grey values are compared by content."""
+        if self._points is not None and self._points is not self._points_made:
+            return True
+        if self._cells is not None and (self._cells is not self._cells_made or len(self._cells) != 1 or
+                                        self._cells[0] is not self._cells_block):
+            return True
+        ids = None
+        for d, names, first, count in ((self._point_sets, NODE_SET_NAMES + ["NODES_X0Y0Z0", "NODES_X0Y0Z1"],
+                                        self.set_first[:6], self.set_count[:6]),
+                                       (self._cell_sets, CELL_SET_NAMES, self.set_first[6:], self.set_count[6:])):
+            if d is None:
+                continue
+            if list(d) != names:
+                return True
+            if ids is None:
+                ids = self.set_ids.cpu().numpy()
+            for q, name in enumerate(names):
+                if q < 6:
+                    want = ids[first[q]:first[q] + count[q]] if count[q] else ids[:0]
+                else:   # corner sets: first two entries of Z0 / Z1
+                    want = ids[first[q - 2]:first[q - 2] + min(2, count[q - 2])] if count[q - 2] else ids[:0]
+                got = np.asarray(d[name])
+                if got.shape != want.shape or got.dtype.kind not in "iu" or not np.array_equal(got, want):
+                    return True
+        if self._cell_data is not None:
+            keys = list(self._cell_data)
+            if not keys:
+                return True
+            cell_GV = self._cell_data.get(keys[0])
+            if type(cell_GV) is list:
+                cell_GV = cell_GV[0] if len(cell_GV) else None
+            if cell_GV is None:
+                return True
+            cell_GV = np.asarray(cell_GV)
+            # the notebooks' cell_data['GV'] = cell_data['GV'][0].astype('uint8') keeps the values
+            if cell_GV.dtype not in (np.bool_, np.uint8) or cell_GV.shape != (self.n_el,) or \
+                    not np.array_equal(cell_GV, self._gv_array()):
+                return True
+        return False
 
     def __repr__(self):
         return "<ciclope_b200 voxel mesh>\n  Number of points: {}\n  Number of cells:\n    hexahedron: {}\n" \
@@ -496,10 +539,11 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
                    refnode=None):
     """Build the whole .INP deck in HBM.  Returns a uint8 CUDA tensor holding exactly the bytes
     the reference's mesh2voxelfe would write (voxelFE.py:612-768)."""
-    if not isinstance(mesh, VoxelMesh):
-        raise NotImplementedError("the CUDA deck writer consumes meshes produced by ciclope_b200.vol2ugrid; "
-                                  "generic meshio meshes are not supported (no CPU fallback)")
-    mesh._check_unmodified()
+    if not isinstance(mesh, VoxelMesh) or mesh._host_edited():
+        # foreign meshio meshes and vol2ugrid meshes edited on the host: array-driven CUDA emitters
+        from .generic import deck_generic
+        return deck_generic(mesh, templatefile, matprop=matprop, keywords=keywords, eltype=eltype,
+                            matpropbits=matpropbits, refnode=refnode)
     m = mesh
     lib = _lib.require_cuda()
     dev = m.vol.device
@@ -507,21 +551,11 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
 
     # ---- prologue (voxelFE.py:540-610)
     gv_dtype = np.bool_ if m.is_bool else np.uint8
-    if m._cell_data is not None:
-        keys = list(m._cell_data)
-        cell_GV = m._cell_data.get(keys[0])
+    if m._cell_data is not None:   # vetted by _host_edited: same values, dtype bool or uint8
+        cell_GV = m._cell_data.get(list(m._cell_data)[0])
         if type(cell_GV) is list:
             cell_GV = cell_GV[0]
-        cell_GV = np.asarray(cell_GV)
-        if cell_GV is not m._gv_host:
-            # e.g. the notebooks' cell_data['GV'] = cell_data['GV'][0].astype('uint8')
-            if cell_GV.shape != m._gv_host.shape or not np.array_equal(cell_GV, m._gv_host):
-                raise NotImplementedError("cell_data was modified on the host; the CUDA deck writer emits the "
-                                          "grey values of the volume given to vol2ugrid")
-            if cell_GV.dtype not in (np.bool_, np.uint8):
-                raise NotImplementedError("cell_data dtype %s is not supported by the CUDA deck writer"
-                                          % cell_GV.dtype)
-            gv_dtype = cell_GV.dtype.type
+        gv_dtype = np.asarray(cell_GV).dtype.type
     if m.n_el == 0:
         raise ValueError("min() iterable argument is empty")   # voxelFE.py:564
     with torch.cuda.device(dev):
@@ -741,8 +775,12 @@ def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'E
     with open(fileout, 'wb') as INP:
         for lo in range(0, n, chunk):
             INP.write(deck[lo:lo + chunk].cpu().numpy().tobytes())
+    if isinstance(mesh, VoxelMesh):
+        n_points, n_cells = mesh.n_points, mesh.n_el
+    else:
+        n_points, n_cells = len(mesh.points), len(mesh.cells[0][1])
     logging.info('Model with {0} nodes and {1} elements written to file {fname}'.format(
-        mesh.n_points, mesh.n_el, fname=fileout))
+        n_points, n_cells, fname=fileout))
     return
 
 

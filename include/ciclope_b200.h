@@ -235,6 +235,22 @@ int cfe_emit_items(const CfeItemSeg* segs, int n_segs, int64_t n_items, const in
 int cfe_put_literal(const char* src, int64_t n, char* out, const uint64_t* dyn0, const uint64_t* dyn1,
                     cfe_stream_t s);
 
+/* ------------------------------------------------------------------ generic (array-driven) meshes */
+
+/* mesh2voxelfe of ANY hexahedral meshio mesh (voxelFE.py:612-688 reads only points, cells, the first
+ * cell_data entry and the sets).  ids = np.unique(cells); slots = cfe_format_coords_wide(points[ids]);
+ * order / group = element indices grouped by ascending grey value; tile_off = cfe_scan_u32(tile_tot). */
+int cfe_gen_node_lengths(const int64_t* ids, int64_t n, const char* slots, uint8_t* len8, uint32_t* tile_tot,
+                         cfe_stream_t s);
+int cfe_gen_emit_nodes(const int64_t* ids, int64_t n, const char* slots, const uint8_t* len8,
+                       const uint64_t* tile_off, char* out, cfe_stream_t s);
+int cfe_gen_elem_lengths(const int64_t* cells, const int64_t* order, const int* group, const int64_t* gfirst,
+                         const int* hdr_off, const int* hdr_len, int64_t n, uint16_t* len16, uint32_t* tile_tot,
+                         cfe_stream_t s);
+int cfe_gen_emit_elements(const int64_t* cells, const int64_t* order, const int* group, const int64_t* gfirst,
+                          const int* hdr_off, const int* hdr_len, const char* lit, int64_t n, const uint16_t* len16,
+                          const uint64_t* tile_off, char* out, cfe_stream_t s);
+
 /* ------------------------------------------------------------------ grey values */
 
 /* hist256[g] = number of elements (v > thr) with grey value g: np.unique(cell_GV), voxelFE.py:570 */

@@ -58,7 +58,8 @@ def lib():
         L.orc_refnode.restype = None
         L.orc_refnode.argtypes = [_p_i64, _i64, _i64, _i64, _p_f64, _p_f64, _p_f64, _p_f64]
         L.orc_deck_body.restype = ctypes.c_int
-        L.orc_deck_body.argtypes = [_p_f64, _i64, _p_i64, _i64, _p_u8, ctypes.c_char_p,
+        L.orc_deck_body.argtypes = [_p_f64, _i64, _p_i64, _i64, _p_i64, _i64,
+                                    ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _p_i64, ctypes.c_char_p,
                                     ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_p_i64), _p_i64,
                                     ctypes.c_int, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_p_i64), _p_i64,
                                     ctypes.POINTER(ctypes.c_void_p), _p_i64]
@@ -283,8 +284,11 @@ def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'E
 
     L = lib()
     points = np.ascontiguousarray(mesh.points, dtype=np.float64)
-    cells = np.ascontiguousarray(mesh.cells_dict["hexahedron"], dtype=np.int64)
-    gv8 = np.ascontiguousarray(cell_GV).astype(np.uint8)
+    cells = np.ascontiguousarray(mesh.cells[0][1], dtype=np.int64)                   # voxelFE.py:647
+    allhex = np.ascontiguousarray(mesh.cells_dict["hexahedron"], dtype=np.int64)     # voxelFE.py:628
+    _, inv = np.unique(cell_GV, return_inverse=True)
+    group = np.ascontiguousarray(inv.reshape(-1), dtype=np.int32)
+    labels = np.asarray([int(GV) for GV in existing_GV], dtype=np.int64)             # 'SET' + str(int(GV))
 
     def pack(sets):
         names = list(sets)
@@ -302,8 +306,13 @@ def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'E
         en = -1
     out_p = ctypes.c_void_p()
     out_n = _i64()
-    L.orc_deck_body(_ptr(points, _p_f64), len(points), _ptr(cells, _p_i64), len(cells), _ptr(gv8, _p_u8),
-                    eltype.encode(), nn, nnames, nids, _ptr(ncnt, _p_i64), en, enames, eids, _ptr(ecnt, _p_i64),
+    if 'NSET' in keywords:
+        '** {}, \n'.format(*list(mesh.point_sets))      # voxelFE.py:652 raises IndexError on an empty dict
+    if 'ELSET' in keywords:
+        '** {}, \n'.format(*list(mesh.cell_sets))
+    L.orc_deck_body(_ptr(points, _p_f64), len(points), _ptr(cells, _p_i64), len(cells),
+                    _ptr(allhex, _p_i64), len(allhex), _ptr(group, ctypes.POINTER(ctypes.c_int32)), len(labels),
+                    _ptr(labels, _p_i64), eltype.encode(), nn, nnames, nids, _ptr(ncnt, _p_i64), en, enames, eids, _ptr(ecnt, _p_i64),
                     ctypes.byref(out_p), ctypes.byref(out_n))
     body = ctypes.string_at(out_p.value, out_n.value)
     L.orc_free(out_p)

@@ -253,3 +253,141 @@ def mask_timestamp(deck_bytes):
     if len(lines) >= 3 and lines[1].startswith(b"** Abaqus .INP file written by Voxel_FEM script on "):
         lines[1] = b"** Abaqus .INP file written by Voxel_FEM script on <timestamp>"
     return b"\n".join(lines)
+
+
+# ------------------------------------------------------------------------------------ generic meshes
+
+def _grid_mesh(vol, voxelsize=(0.5, 0.25, 2.0), thr=0):
+    """points / cells / gv of vol2ugrid's mesh, by the vectorised formulas of SURVEY appendix A.4
+    (only an input generator for the generic-mesh cases: every array is then scrambled)."""
+    vol = np.asarray(vol)
+    Z, Y, X = vol.shape
+    RN, SN = X + 1, (X + 1) * (Y + 1)
+    lin = np.flatnonzero(vol.ravel() > thr)
+    s, r, c = np.unravel_index(lin, vol.shape)
+    b = SN * s + RN * r + c
+    cells = b[:, None] + np.asarray([0, 1, RN + 1, RN, SN, SN + 1, SN + RN + 1, SN + RN])
+    zz, yy, xx = np.meshgrid(np.arange(Z + 1), np.arange(Y + 1), np.arange(X + 1), indexing="ij")
+    points = np.stack([xx.ravel() * voxelsize[0], yy.ravel() * voxelsize[1], zz.ravel() * voxelsize[2]], axis=1)
+    return points, cells.astype(np.int64), vol.ravel()[lin]
+
+
+def generic_cases():
+    """Meshes that did NOT come out of vol2ugrid unchanged (mesh2voxelfe accepts any hexahedral meshio
+    mesh, voxelFE.py:612-688).  Each case: name, points, blocks [(type, cells)], cell_data (dict),
+    point_sets, cell_sets, m (mesh2voxelfe kwargs)."""
+    C = []
+    rng = np.random.RandomState(77)
+
+    def add(name, points, blocks, cell_data, point_sets, cell_sets, m=None):
+        m = dict(m or {})
+        m.setdefault("templatefile", TEMPLATE)
+        C.append(dict(name=name, points=points, blocks=blocks, cell_data=cell_data, point_sets=point_sets,
+                      cell_sets=cell_sets, m=m))
+
+    g = rand_grey((5, 6, 13), 0.5, 31, 1, 6)
+    pts, cells, gv = _grid_mesh(g)
+    n_el, n_pt = len(cells), len(pts)
+    perm = rng.permutation(n_el)
+    std_ps = {"NODES_A": sorted(rng.choice(n_pt, 23, replace=False).tolist()), "NODES_B": [5, 3, 3, 1]}
+    std_cs = {"CELLS_A": list(range(1, 11)), "CELLS_B": []}
+
+    # cells in a scrambled order, nodes anywhere in space
+    rpts = rng.uniform(-50, 50, size=(n_pt, 3))
+    rpts[0] = [-0.0, -1e-9, 0.0000005]
+    rpts[1] = [123456789.123456789, -99999.9999996, 99999.9999994]
+    rpts[2] = [1e15 + 0.5, 2.5e-7, -2.5e-7]
+    rpts[3] = [0.1234565, 0.1234575, 1e17]
+    add("scrambled_cells_random_points", rpts, [("hexahedron", cells[perm])], {"GV": [gv[perm]]}, std_ps, std_cs)
+    # float grey values: several GVs share int(GV) -> repeated SETn headers (voxelFE.py:641)
+    fgv = np.asarray([1.5, 2.25, 2.75, 7.0])[rng.randint(0, 4, n_el)]
+    add("float_gv", pts, [("hexahedron", cells)], {"GV": [fgv]}, std_ps, std_cs)
+    add("float32_gv_property", pts, [("hexahedron", cells)], {"density": [fgv.astype(np.float32)]}, std_ps, std_cs,
+        dict(keywords=['NSET', 'ELSET', 'PROPERTY'], matprop=lambda: {"file": [MAT_LINEAR], "range": [[1, 255]]}))
+    igv = np.asarray([3, 1000, 70000, 2 ** 18], dtype=np.int64)[rng.randint(0, 4, n_el)]
+    add("int64_gv_beyond_8bit", pts, [("hexahedron", cells)], {"GV": [igv]}, std_ps, std_cs,
+        dict(keywords=['NSET', 'ELSET', 'PROPERTY'], matprop=lambda: {"file": [MAT_POWER]}))
+    add("uint16_gv", pts, [("hexahedron", cells)], {"GV": [(gv.astype(np.uint16) * 9000)]}, std_ps, std_cs)
+    add("int8_gv_negative", pts, [("hexahedron", cells)], {"GV": [gv.astype(np.int8) - 3]}, std_ps, std_cs)
+    add("bool_gv", pts, [("hexahedron", cells[perm])], {"GV": [np.ones(n_el, dtype=bool)]}, std_ps, std_cs)
+    add("binary_model_01", pts, [("hexahedron", cells)], {"GV": [(gv > 3).astype(np.uint8)]}, std_ps, std_cs,
+        dict(keywords=['NSET', 'ELSET', 'PROPERTY'], matprop=lambda: {"file": [MAT_CONST]}))
+    # the notebooks' pattern: cell_data value is an array, not a list (voxelFE.py:560-562)
+    add("cell_data_plain_array", pts, [("hexahedron", cells)], {"GV": gv.astype(np.uint8)}, std_ps, std_cs)
+    # set flavours: numpy arrays, unsorted with duplicates, wrap at 10, empty, many sets
+    ps = {"top": np.arange(10), "bottom nodes": np.asarray([7, 7, 2]), "none": [], "all": list(range(n_pt)),
+          "big_ids": [n_pt - 1, 0]}
+    cs = {"E10": list(range(1, 21)), "E_last": np.asarray([n_el]), "E_empty": np.zeros(0, dtype=np.int64)}
+    add("custom_sets", pts, [("hexahedron", cells)], {"GV": [gv]}, ps, cs)
+    add("custom_sets_nset_only", pts, [("hexahedron", cells)], {"GV": [gv]}, ps, {}, dict(keywords=['NSET']))
+    # two hexahedron blocks: lines come from block 0, used nodes from both (voxelFE.py:628 vs :647)
+    h = n_el // 2
+    add("two_hex_blocks", pts, [("hexahedron", cells[:h]), ("hexahedron", cells[h:])],
+        {"GV": [gv[:h], gv[h:]]}, std_ps, std_cs)
+    # point dtypes
+    ipts = np.stack([np.arange(n_pt) % 14, (np.arange(n_pt) // 14) % 7 * 3, np.arange(n_pt) // 98 * 100000], axis=1)
+    add("points_int64", ipts.astype(np.int64), [("hexahedron", cells)], {"GV": [gv]}, std_ps, std_cs)
+    add("points_float32", pts.astype(np.float32) * np.float32(0.1), [("hexahedron", cells)], {"GV": [gv]},
+        std_ps, std_cs)
+    add("points_wide", pts * np.asarray([30000.5, -1e6, 123456.789]), [("hexahedron", cells)], {"GV": [gv]},
+        std_ps, std_cs)
+    # a mesh using only a few of its points, ids far apart
+    few = np.asarray([[0, 1, 15, 14, 98, 99, 113, 112], [n_pt - 1, n_pt - 2, 5, 4, 3, 2, 1, 0]], dtype=np.int64)
+    add("two_cells_sparse_nodes", rpts, [("hexahedron", few)], {"GV": [np.asarray([9, 4], dtype=np.uint8)]},
+        {"N": [0]}, {"C": [2, 1]}, dict(eltype="C3D8R", keywords=['ELSET', 'NSET']))
+    add("single_cell", rpts[:8], [("hexahedron", np.arange(8, dtype=np.int64)[None, ::-1])],
+        {"GV": [np.asarray([200], dtype=np.uint8)]}, {"N": []}, {"C": []},
+        dict(templatefile=TEMPLATE_REFNODE, refnode=[1.23456, 2.0, -0.00004]))
+    return C
+
+
+def edit_mesh_sets(mesh):
+    """The host-side edit of a vol2ugrid mesh used by the `edited_*` cases (applied alike to the
+    reference's mesh and to ciclope_b200's VoxelMesh)."""
+    ps = mesh.point_sets
+    ps["NODES_EXTRA"] = ps["NODES_Z1"][::3]
+    ps["NODES_X0"] = ps["NODES_X0"][:7]
+    del ps["NODES_X0Y0Z1"]
+    mesh.cell_sets["CELLS_Z0"] = [int(v) for v in mesh.cell_sets["CELLS_Z0"]][::-1]
+    return mesh
+
+
+def edit_mesh_gv(mesh):
+    """Overwrite the grey values on the host (cell_data assignment, as the notebooks do)."""
+    gv = np.asarray(mesh.cell_data["GV"][0]).astype(np.int64)
+    mesh.cell_data["GV"] = [(gv % 5 + 1) * 300]
+    return mesh
+
+
+def edited_cases():
+    g = rand_grey((6, 7, 20), 0.5, 10)
+    return [dict(name="edited_sets", vol=g, u=dict(voxelsize=[0.0195] * 3), edit=edit_mesh_sets,
+                 m=dict(templatefile=TEMPLATE)),
+            dict(name="edited_gv", vol=g, u=dict(voxelsize=[0.0195] * 3, GVmin=50), edit=edit_mesh_gv,
+                 m=dict(templatefile=TEMPLATE, keywords=['NSET', 'ELSET', 'PROPERTY'],
+                        matprop=lambda: {"file": [MAT_POWER]}))]
+
+
+def copy_cell_data(cd):
+    return {k: ([np.array(a) for a in v] if isinstance(v, list) else np.array(v)) for k, v in cd.items()}
+
+
+class PlainMesh:
+    """Minimal meshio-5.0.0-like container (namedtuple cell blocks, cells_dict concatenating the
+    blocks of one type) used to hand generic meshes to the oracle and to ciclope_b200."""
+
+    def __init__(self, case):
+        import collections
+        CellBlock = collections.namedtuple("CellBlock", ["type", "data"])
+        self.points = np.asarray(case["points"])
+        self.cells = [CellBlock(t, np.asarray(d)) for t, d in case["blocks"]]
+        self.cell_data = copy_cell_data(case["cell_data"])
+        self.point_sets = {k: (v.copy() if isinstance(v, np.ndarray) else list(v)) for k, v in case["point_sets"].items()}
+        self.cell_sets = {k: (v.copy() if isinstance(v, np.ndarray) else list(v)) for k, v in case["cell_sets"].items()}
+
+    @property
+    def cells_dict(self):
+        d = {}
+        for t, data in self.cells:
+            d.setdefault(t, []).append(data)
+        return {k: np.concatenate(v) for k, v in d.items()}

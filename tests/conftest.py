@@ -24,3 +24,10 @@ def golden_ccl():
     import numpy as np
     from tests import cases
     return np.load(os.path.join(cases.GOLDEN_DIR, "ccl.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_generic():
+    import numpy as np
+    from tests import cases
+    return np.load(os.path.join(cases.GOLDEN_DIR, "generic.npz"), allow_pickle=False)

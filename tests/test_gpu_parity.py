@@ -233,6 +233,76 @@ def test_notebook_cell_data_astype_pattern(cfe, golden, tmp_path):
     assert "ELSET=SET1, MATERIAL=MATSET1" in text and "SETTrue" not in text
 
 
+# ------------------------------------------------------------------ generic / edited meshes
+
+@pytest.mark.parametrize("case", cases.generic_cases(), ids=lambda c: c["name"])
+def test_mesh2voxelfe_generic_mesh_golden(cfe, golden_generic, case, tmp_path):
+    # any hexahedral meshio mesh (voxelFE.py:612-688): array-driven CUDA emitters, byte-exact
+    m = dict(case["m"])
+    if "matprop" in m:
+        m["matprop"] = m["matprop"]()
+    out = str(tmp_path / "deck.inp")
+    cfe.mesh2voxelfe(cases.PlainMesh(case), fileout=out, **m)
+    assert cases.mask_timestamp(open(out, "rb").read()) == bytes(golden_generic[case["name"] + "/deck"])
+
+
+@pytest.mark.parametrize("case", cases.edited_cases(), ids=lambda c: c["name"])
+def test_mesh2voxelfe_edited_voxelmesh_golden(cfe, golden_generic, case, tmp_path):
+    # a vol2ugrid mesh whose host-side sets / grey values were changed is emitted from the host arrays
+    m = dict(case["m"])
+    if "matprop" in m:
+        m["matprop"] = m["matprop"]()
+    mesh = case["edit"](cfe.vol2ugrid(case["vol"], **case["u"]))
+    assert mesh._host_edited()
+    out = str(tmp_path / "deck.inp")
+    cfe.mesh2voxelfe(mesh, fileout=out, **m)
+    assert cases.mask_timestamp(open(out, "rb").read()) == bytes(golden_generic[case["name"] + "/deck"])
+
+
+def test_untouched_views_keep_the_fast_path(cfe, golden, tmp_path):
+    # reading every host view (as the reference's tests do) must not divert to the generic emitters,
+    # in-place edits of a set list must; the big arrays are read-only so they can only be replaced
+    c = DECK_CASES["grey_6x7x20"]
+    mesh = cfe.vol2ugrid(c["vol"], **c["u"])
+    _ = mesh.points[3], mesh.cells[0].data[0], mesh.cells_dict["hexahedron"], mesh.cell_data["GV"][0]
+    _ = mesh.point_sets["NODES_Z0"], mesh.cell_sets["CELLS_Z1"]
+    assert not mesh._host_edited()
+    with pytest.raises(ValueError):
+        mesh.points[0, 0] = 1.0
+    with pytest.raises(ValueError):
+        mesh.cells[0].data[0, 0] = 1
+    out = str(tmp_path / "a.inp")
+    cfe.mesh2voxelfe(mesh, cases.TEMPLATE, out)
+    assert cases.mask_timestamp(open(out, "rb").read()) == bytes(golden["grey_6x7x20/deck"])
+    mesh.point_sets["NODES_Z0"].append(5)
+    assert mesh._host_edited()
+    mesh.point_sets["NODES_Z0"].pop()
+    assert not mesh._host_edited()
+    mesh.points = mesh.points * 2.0
+    assert mesh._host_edited()
+    cfe.mesh2voxelfe(mesh, cases.TEMPLATE, out)
+    lines = open(out).read().split("\n")
+    want = "{0:10d}, {1:12.6f}, {2:12.6f}, {3:12.6f}".format(int(lines[6].split(",")[0]),
+                                                             *mesh.points[int(lines[6].split(",")[0])])
+    assert lines[6] == want
+
+
+def test_generic_mesh_midsize_vs_oracle(cfe, orc, tmp_path):
+    # 40x48x70 blobs, cells scrambled, random node coordinates, int32 grey values up to 4000
+    rng = np.random.RandomState(5)
+    vol = cases.grey_from_mask(cases.blobs((40, 48, 70), 0.3, 21), 22)
+    pts, cells, gv = cases._grid_mesh(vol)
+    perm = rng.permutation(len(cells))
+    case = dict(points=rng.uniform(-2e5, 2e5, size=pts.shape), blocks=[("hexahedron", cells[perm])],
+                cell_data={"GV": [(gv[perm].astype(np.int32) * 16)]},
+                point_sets={"A": rng.randint(0, len(pts), 12345), "B": []},
+                cell_sets={"C": rng.randint(1, len(cells) + 1, 30001)})
+    a, b = str(tmp_path / "a.inp"), str(tmp_path / "b.inp")
+    cfe.mesh2voxelfe(cases.PlainMesh(case), cases.TEMPLATE, a)
+    orc.mesh2voxelfe(cases.PlainMesh(case), cases.TEMPLATE, b)
+    assert cases.mask_timestamp(open(a, "rb").read()) == cases.mask_timestamp(open(b, "rb").read())
+
+
 # ------------------------------------------------------------------ error behaviour
 
 def test_error_behaviour_matches_reference(cfe, tmp_path):
@@ -256,7 +326,7 @@ def test_error_behaviour_matches_reference(cfe, tmp_path):
             cfe.mesh2voxelfe(mk(), cases.TEMPLATE, str(tmp_path / "e.inp"), matprop=mp)
     with pytest.raises(TypeError):
         cfe.vol2ugrid(np.zeros((2, 2, 2), dtype=np.float32))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AttributeError):     # not a mesh: the reference fails on mesh.cell_data too
         cfe.mesh2voxelfe(object(), cases.TEMPLATE, str(tmp_path / "e.inp"))
 
 

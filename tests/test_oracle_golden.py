@@ -67,6 +67,30 @@ def test_oracle_vol2ugrid_and_deck(golden, name, tmp_path):
     assert got == bytes(g[name + "/deck"])
 
 
+@pytest.mark.parametrize("case", cases.generic_cases(), ids=lambda c: c["name"])
+def test_oracle_generic_mesh_deck(golden_generic, case, tmp_path):
+    # mesh2voxelfe of meshes that are not an untouched vol2ugrid result (voxelFE.py:612-688)
+    from tests.golden.make_golden_generic import input_digest
+    assert input_digest(case) == str(golden_generic[case["name"] + "/digest"])
+    m = dict(case["m"])
+    if "matprop" in m:
+        m["matprop"] = m["matprop"]()
+    out = str(tmp_path / "deck.inp")
+    orc.mesh2voxelfe(cases.PlainMesh(case), fileout=out, **m)
+    assert cases.mask_timestamp(open(out, "rb").read()) == bytes(golden_generic[case["name"] + "/deck"])
+
+
+@pytest.mark.parametrize("case", cases.edited_cases(), ids=lambda c: c["name"])
+def test_oracle_edited_mesh_deck(golden_generic, case, tmp_path):
+    m = dict(case["m"])
+    if "matprop" in m:
+        m["matprop"] = m["matprop"]()
+    mesh = case["edit"](orc.vol2ugrid(case["vol"], **case["u"]))
+    out = str(tmp_path / "deck.inp")
+    orc.mesh2voxelfe(mesh, fileout=out, **m)
+    assert cases.mask_timestamp(open(out, "rb").read()) == bytes(golden_generic[case["name"] + "/deck"])
+
+
 @pytest.mark.parametrize("case", cases.midsize_cases(), ids=lambda c: c["name"])
 def test_oracle_midsize_hash(case, tmp_path):
     want = json.load(open(os.path.join(cases.GOLDEN_DIR, "midsize.json")))[case["name"]]
