@@ -10,5 +10,5 @@ mesh2voxelfe, matpropdictionary}``.  The compute is hand-written CUDA behind the
 __version__ = "0.1.0"
 
 from . import preprocess, voxelFE  # noqa: E402,F401
-from .preprocess import remove_unconnected  # noqa: E402,F401
+from .preprocess import fill_voids, remove_largest, remove_unconnected  # noqa: E402,F401
 from .voxelFE import matpropdictionary, mesh2voxelfe, vol2ugrid  # noqa: E402,F401

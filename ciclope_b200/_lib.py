@@ -34,6 +34,8 @@ _SIGNATURES = {
     "cfe_last_error": (ctypes.c_char_p, []),
     "cfe_launch_count": (ctypes.c_uint64, []),
     "cfe_pack_bits": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
+    "cfe_pack_bits_le": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
+    "cfe_max_u8": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "cfe_scan_workspace_bytes": (c_sz, [c_i64]),
     "cfe_scan_elements": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_scan_run_starts": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
@@ -45,6 +47,10 @@ _SIGNATURES = {
     "cfe_ccl_label": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "cfe_ccl_select": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cfe_ccl_write_mask": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_ccl_write_select": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp,
+                                     c_vp]),
+    "cfe_ccl_largest_select": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_vp, c_int,
+                                       c_vp, c_vp]),
     "cfe_ccl_plane_roots": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_ccl_interface_edges": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "cfe_ccl_boundary_vertices": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,

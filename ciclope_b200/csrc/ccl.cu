@@ -292,7 +292,7 @@ template <bool FLAT>
 __global__ void __launch_bounds__(256)
 k_ccl_write_mask(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 rows, int X, int W,
                  const u32* __restrict__ parent, const u64* __restrict__ best, const u32* __restrict__ keep_flag,
-                 uint8_t* __restrict__ out)
+                 int drop, const uint8_t* src, u32 fill, uint8_t* out)
 {
     const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;  // 16-voxel chunk
     if (g >= rows * 2 * (i64)W) return;
@@ -312,7 +312,7 @@ k_ccl_write_mask(const u32* __restrict__ bits, const u32* __restrict__ pref, i64
             const int len = (~shifted == 0u) ? 32 - b : __ffs((int)~shifted) - 1;
             const u32 seg = (len >= 32) ? 0xffffffffu : (((1u << len) - 1u) << b);
             const u32 root = __ldg(parent + run_id(word, carry, pf, b));
-            if (keep_flag ? (keep_flag[root] == 0xffffffffu) : (root == winner)) keep |= seg;
+            if ((keep_flag ? (keep_flag[root] == 0xffffffffu) : (root == winner)) != (drop != 0)) keep |= seg;
             rest &= ~seg;
         }
     }
@@ -322,16 +322,27 @@ k_ccl_write_mask(const u32* __restrict__ bits, const u32* __restrict__ pref, i64
     v.y = spread_nibble(k16 >> 4);
     v.z = spread_nibble(k16 >> 8);
     v.w = spread_nibble(k16 >> 12);
+    // selected voxels get `fill`, the others 0 or (fill_voids) their value in `src`; out may be src
+    const u32 f4 = (fill & 0xffu) * 0x01010101u;
     if (FLAT) {
-        reinterpret_cast<uint4*>(out)[g] = v;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (src) o = reinterpret_cast<const uint4*>(src)[g];
+        const u32 mx = v.x * 0xffu, my = v.y * 0xffu, mz = v.z * 0xffu, mw = v.w * 0xffu;
+        o.x = (o.x & ~mx) | (f4 & mx);
+        o.y = (o.y & ~my) | (f4 & my);
+        o.z = (o.z & ~mz) | (f4 & mz);
+        o.w = (o.w & ~mw) | (f4 & mw);
+        reinterpret_cast<uint4*>(out)[g] = o;
     } else {
         const i64 row = i / W;
         const int c0 = (int)(i - row * W) * 32 + 16 * half;
         uint8_t* p = out + row * (i64)X + c0;
+        const uint8_t* q = src ? src + row * (i64)X + c0 : nullptr;
         const u32 vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 16; ++k)
-            if (c0 + k < X) p[k] = (uint8_t)((vv[k >> 2] >> (8 * (k & 3))) & 1u);
+            if (c0 + k < X)
+                p[k] = ((vv[k >> 2] >> (8 * (k & 3))) & 1u) ? (uint8_t)fill : (q ? q[k] : (uint8_t)0);
     }
 }
 
@@ -396,15 +407,32 @@ extern "C" int cfe_ccl_write_mask(const uint32_t* bits, const uint32_t* pref, in
                                   const uint32_t* parent, const uint64_t* best, const uint32_t* keep,
                                   uint8_t* out_mask, cudaStream_t stream)
 {
+    return cfe_ccl_write_select(bits, pref, Z, Y, X, parent, best, keep, 0, nullptr, 1, out_mask, stream);
+}
+
+// General form of phase 3.  Selected voxels = runs whose root is the winner (drop = 0) or every
+// labelled voxel EXCEPT the winner's (drop = 1: remove_largest, preprocess.py:204-206; the voids of
+// fill_voids, :176-177).  out = fill on selected voxels, src[voxel] (0 when src is NULL) elsewhere;
+// out == src is allowed (in-place fill).
+extern "C" int cfe_ccl_write_select(const uint32_t* bits, const uint32_t* pref, int64_t Z, int64_t Y, int64_t X,
+                                    const uint32_t* parent, const uint64_t* best, const uint32_t* keep,
+                                    int drop, const uint8_t* src, int fill, uint8_t* out_mask,
+                                    cudaStream_t stream)
+{
     const i64 rows = Z * Y;
     if (rows <= 0 || X <= 0) return 0;
     const int W = (int)((X + 31) / 32);
     const i64 chunks = rows * W * 2;
     const unsigned cb = (unsigned)((chunks + 255) / 256);
-    const bool flat = (X % 32 == 0) && ((reinterpret_cast<uintptr_t>(out_mask) & 15u) == 0);
+    const bool flat = (X % 32 == 0) && ((reinterpret_cast<uintptr_t>(out_mask) & 15u) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
     const u64* b = reinterpret_cast<const u64*>(best);
-    if (flat) k_ccl_write_mask<true><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, out_mask);
-    else k_ccl_write_mask<false><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, out_mask);
+    if (flat)
+        k_ccl_write_mask<true><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, drop, src,
+                                                       (u32)fill, out_mask);
+    else
+        k_ccl_write_mask<false><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, drop, src,
+                                                        (u32)fill, out_mask);
     CFE_CHECK_LAUNCH("k_ccl_write_mask");
     return 0;
 }
@@ -419,12 +447,21 @@ extern "C" int cfe_ccl_largest(const uint32_t* bits, const uint32_t* pref, const
                                int64_t Z, int64_t Y, int64_t X, uint32_t* parent, uint32_t* size,
                                uint64_t* best, uint8_t* out_mask, cudaStream_t stream)
 {
+    return cfe_ccl_largest_select(bits, pref, n_runs, Z, Y, X, parent, size, best, 0, nullptr, 1, out_mask, stream);
+}
+
+// Same, with the general phase 3 (cfe_ccl_write_select): drop / src / fill.
+extern "C" int cfe_ccl_largest_select(const uint32_t* bits, const uint32_t* pref, const uint64_t* n_runs,
+                                      int64_t Z, int64_t Y, int64_t X, uint32_t* parent, uint32_t* size,
+                                      uint64_t* best, int drop, const uint8_t* src, int fill, uint8_t* out,
+                                      cudaStream_t stream)
+{
     if (Z * Y <= 0 || X <= 0) return 0;
     int rc = cfe_ccl_label(bits, pref, n_runs, Z, Y, X, parent, size, stream);
     if (rc) return rc;
     rc = cfe_ccl_select(parent, size, n_runs, best, stream);
     if (rc) return rc;
-    return cfe_ccl_write_mask(bits, pref, Z, Y, X, parent, best, nullptr, out_mask, stream);
+    return cfe_ccl_write_select(bits, pref, Z, Y, X, parent, best, nullptr, drop, src, fill, out, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -27,7 +27,7 @@ __device__ __forceinline__ u32 cmp_nibble(u32 x, u32 thr4, bool all)
 // FLAT: X % 32 == 0 and vol 16-byte aligned -> the volume is a flat array of 16-byte chunks.
 template <bool FLAT>
 __global__ void __launch_bounds__(256) k_pack_bits(const uint8_t* __restrict__ vol, i64 rows, int X, int W,
-                                                   int thr, u32* __restrict__ bits)
+                                                   int thr, int invert, u32* __restrict__ bits)
 {
     const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 nchunks = rows * 2 * (i64)W;
@@ -39,21 +39,22 @@ __global__ void __launch_bounds__(256) k_pack_bits(const uint8_t* __restrict__ v
             uint4 v = __ldg(reinterpret_cast<const uint4*>(vol) + g);
             m16 = cmp_nibble(v.x, thr4, all) | (cmp_nibble(v.y, thr4, all) << 4) |
                   (cmp_nibble(v.z, thr4, all) << 8) | (cmp_nibble(v.w, thr4, all) << 12);
+            if (invert) m16 ^= 0xffffu;
         } else {
             const i64 row = g / (2 * W);
             const int c0 = (int)(g - row * 2 * W) * 16;
             const uint8_t* p = vol + row * (i64)X + c0;
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-                if (c0 + k < X) m16 |= (u32)((int)p[k] > thr) << k;
+                if (c0 + k < X) m16 |= (u32)(((int)p[k] > thr) != (invert != 0)) << k;   // pad bits stay 0
         }
     }
     const u32 other = __shfl_xor_sync(CFE_FULL_MASK, m16, 1);
     if (g < nchunks && !(threadIdx.x & 1)) bits[g >> 1] = m16 | (other << 16);
 }
 
-extern "C" int cfe_pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t* bits,
-                             cudaStream_t stream)
+static int pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, int invert, uint32_t* bits,
+                     cudaStream_t stream)
 {
     if (rows <= 0 || X <= 0) return 0;
     const int W = (int)((X + 31) / 32);
@@ -62,10 +63,48 @@ extern "C" int cfe_pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int th
     if (blocks > 0x7fffffffLL) { cfe_set_error("cfe_pack_bits: volume too large"); return -1; }
     const bool flat = (X % 32 == 0) && ((reinterpret_cast<uintptr_t>(vol) & 15u) == 0);
     if (flat)
-        k_pack_bits<true><<<(unsigned)blocks, 256, 0, stream>>>(vol, rows, (int)X, W, thr, bits);
+        k_pack_bits<true><<<(unsigned)blocks, 256, 0, stream>>>(vol, rows, (int)X, W, thr, invert, bits);
     else
-        k_pack_bits<false><<<(unsigned)blocks, 256, 0, stream>>>(vol, rows, (int)X, W, thr, bits);
+        k_pack_bits<false><<<(unsigned)blocks, 256, 0, stream>>>(vol, rows, (int)X, W, thr, invert, bits);
     CFE_CHECK_LAUNCH("k_pack_bits");
+    return 0;
+}
+
+extern "C" int cfe_pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t* bits,
+                             cudaStream_t stream)
+{
+    return pack_bits(vol, rows, X, thr, 0, bits, stream);
+}
+
+// bits of the voxels with v <= thr: the background ~(I > 0) that fill_voids labels (preprocess.py:167)
+extern "C" int cfe_pack_bits_le(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t* bits,
+                                cudaStream_t stream)
+{
+    return pack_bits(vol, rows, X, thr, 1, bits, stream);
+}
+
+// *out = max(*out, max of vol[0..n)): I.max(), the default fill value of fill_voids (preprocess.py:163)
+__global__ void __launch_bounds__(256) k_max_u8(const uint8_t* __restrict__ vol, i64 n, u32* __restrict__ out)
+{
+    u32 m = 0;
+    const i64 n16 = (reinterpret_cast<uintptr_t>(vol) & 15u) ? 0 : n / 16;
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n16; g += (i64)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(vol) + g);
+        m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+    }
+    m = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
+    for (i64 g = n16 * 16 + (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x)
+        m = max(m, (u32)vol[g]);
+    m = __reduce_max_sync(CFE_FULL_MASK, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+extern "C" int cfe_max_u8(const uint8_t* vol, int64_t n, uint32_t* out, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    const i64 want = (n / 16 + 255) / 256 + 1;
+    k_max_u8<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, stream>>>(vol, n, out);
+    CFE_CHECK_LAUNCH("k_max_u8");
     return 0;
 }
 

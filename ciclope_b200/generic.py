@@ -9,6 +9,7 @@ were edited) comes here: the arrays are uploaded once and the same text is produ
 kernels (lengths -> tile totals -> scan -> staged emission).  No CPU fallback.
 """
 import logging
+import warnings
 from datetime import datetime
 
 import numpy as np
@@ -19,15 +20,22 @@ from ._lib import CfeItemSeg
 from ._util import bytes_to_device_async, empty_u32, scan_workspace, to_device_async
 
 
+def _h2d(a, dev):
+    """Host array -> device tensor (read-only arrays, e.g. VoxelMesh's materialised views, included)."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)     # "The given NumPy array is not writable": only read
+        return torch.from_numpy(a).to(dev)
+
+
 def _as_torch(a, dev):
     a = np.ascontiguousarray(a)
     if a.dtype == np.bool_:
-        return torch.from_numpy(a.view(np.uint8)).to(dev)
+        return _h2d(a.view(np.uint8), dev)
     if a.dtype.kind == "u" and a.dtype.itemsize > 1:
         a = a.astype(np.int64)
     if a.dtype.kind == "f" and a.dtype.itemsize == 2:
         a = a.astype(np.float32)
-    return torch.from_numpy(a).to(dev)
+    return _h2d(a, dev)
 
 
 def deck_generic(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'], eltype='C3D8', matpropbits=8,
@@ -148,10 +156,10 @@ def deck_generic(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'], e
     with torch.cuda.device(dev):
         s = _lib.stream()
         n_el = len(cells0)
-        cells_dev = torch.from_numpy(cells0).to(dev)
-        used = torch.unique(torch.from_numpy(allhex.reshape(-1)).to(dev))       # ascending
+        cells_dev = _h2d(cells0, dev)
+        used = torch.unique(_h2d(allhex.reshape(-1), dev))       # ascending
         n_nd = used.numel()
-        pts = torch.from_numpy(np.ascontiguousarray(points[:, :3], dtype=np.float64)).to(dev)
+        pts = _h2d(np.ascontiguousarray(points[:, :3], dtype=np.float64), dev)
         vals = pts[used].contiguous()                                            # (n_nd, 3)
         slots = torch.empty(96 * max(n_nd, 1), dtype=torch.uint8, device=dev)
         stat = torch.zeros(3, dtype=torch.int64, device=dev)                     # node bytes, element bytes, bad
@@ -194,7 +202,7 @@ def deck_generic(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'], e
         _lib.call("cfe_gen_emit_elements", cells_dev.data_ptr(), order.data_ptr(), group.data_ptr(),
                   gfirst.data_ptr(), d_hoff.data_ptr(), d_hlen.data_ptr(), d_hlit.data_ptr(), n_el, elen.data_ptr(),
                   eoff.data_ptr(), out.data_ptr() + off_elem, s)
-        d_ids = torch.from_numpy(ids_host).to(dev)
+        d_ids = _h2d(ids_host, dev)
         d_lits = bytes_to_device_async(bytes(lits), dev)
         d_segs = bytes_to_device_async(bytes(seg_arr), dev)
         itot = torch.zeros(1, dtype=torch.int64, device=dev)

@@ -1,5 +1,7 @@
-"""B200-native drop-in for ``ciclope.utils.preprocess.remove_unconnected``
-(reference: src/ciclope/utils/preprocess.py:119-143)."""
+"""B200-native drop-ins for the connected-component functions of ``ciclope.utils.preprocess``:
+``remove_unconnected`` (reference: src/ciclope/utils/preprocess.py:119-143), ``fill_voids``
+(:145-185) and ``remove_largest`` (:187-208).  All three are one labelling pass (``cfe_ccl_*``)
+followed by a different selection in the mask-writing kernel."""
 import numpy as np
 import torch
 
@@ -40,15 +42,90 @@ def remove_unconnected(bwimage):
     return out
 
 
-def largest_component_device(vol):
-    """vol: uint8 CUDA tensor [Z,Y,X].  Returns (uint8 mask tensor, best) where
-    best = (size << 32) | (0xffffffff - root run id), 0 when there is no foreground.
-    One device->host read (16 bytes) at the end."""
+def remove_largest(bwimage):
+    """Remove largest cluster of voxels in binary image (drop-in for preprocess.py:187-208).
+
+    Parameters
+    ----------
+    bwimage
+        Binary image (bool / uint8; NumPy array or CUDA tensor).
+
+    Returns
+    -------
+    bwcluster
+        Binary image in which the largest cluster of voxels is removed.
+    """
+    vol, _is_bool, from_numpy = as_device_volume(bwimage, allow_2d=True)
+    squeeze = (bwimage.ndim == 2)
+    mask, best = largest_component_device(vol, drop=True)
+    if best == 0:
+        raise ValueError("attempt to get argmax of an empty sequence")   # preprocess.py:204
+    out = mask.view(torch.bool)
+    if squeeze:
+        out = out[0]
+    return out.cpu().numpy() if from_numpy else out
+
+
+def fill_voids(I, fill_val=None, makecopy=False):  # noqa: E741 -- the reference's parameter name
+    """Fill voids within color image with given value (drop-in for preprocess.py:145-185).
+
+    The background ``~(I>0)`` is labelled with 6-connectivity; every background region except
+    the largest one (the outside) is set to ``fill_val`` (default ``I.max()``).  As in the
+    reference the input is modified in place and returned unless ``makecopy`` is true.
+
+    Parameters
+    ----------
+    I
+        Input image (bool / uint8; NumPy array or CUDA tensor).
+    fill_val
+        Filling value.
+    makecopy : bool
+        Make copy of input image.
+    """
+    vol, is_bool, from_numpy = as_device_volume(I, allow_2d=True)
+    if fill_val is not None:
+        if is_bool:
+            fill = int(bool(fill_val))
+        else:
+            fill = int(fill_val)
+            if fill != fill_val or not 0 <= fill <= 255:
+                raise ValueError("fill_val %r cannot be stored in a uint8 image" % (fill_val,))
+    else:
+        fill = None
+    in_place = isinstance(I, torch.Tensor) and I.is_cuda and I.is_contiguous() and not makecopy
+    filled, best = largest_component_device(vol, drop=True, invert=True, src=vol, fill=fill,
+                                            out=vol if in_place else None)
+    if best == 0:
+        raise ValueError("attempt to get argmax of an empty sequence")   # preprocess.py:175
+    if is_bool:
+        filled = filled.view(torch.bool)
+    filled = filled.reshape(I.shape)
+    if from_numpy:
+        res = filled.cpu().numpy()
+        if makecopy:
+            return res
+        I[...] = res
+        return I
+    if makecopy or in_place:
+        return I if in_place else filled.to(I.device)
+    I.copy_(filled)
+    return I
+
+
+def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, out=None):
+    """vol: uint8 CUDA tensor [Z,Y,X].  Returns (uint8 tensor, best) where
+    best = (size << 32) | (0xffffffff - root run id), 0 when nothing was labelled.
+
+    The tensor is the mask of the largest 6-connected component of ``vol != 0`` -- or, with
+    ``drop``, of every labelled voxel outside it; ``invert`` labels ``vol == 0`` instead; with
+    ``src`` the unselected voxels keep their ``src`` value and the selected ones get ``fill``
+    (None: the maximum of ``src``, computed on the device).  One device->host read (16 bytes)."""
     lib = _lib.require_cuda()
     Z, Y, X = (int(v) for v in vol.shape)
     check_slab_size(Z, Y, X)
     dev = vol.device
-    out = torch.empty((Z, Y, X), dtype=torch.uint8, device=dev)
+    if out is None:
+        out = torch.empty((Z, Y, X), dtype=torch.uint8, device=dev)
     if Z * Y * X == 0:
         return out, 0
     with torch.cuda.device(dev):
@@ -59,14 +136,32 @@ def largest_component_device(vol):
         pref = empty_u32(rows * W, dev)
         stats = torch.zeros(2, dtype=torch.int64, device=dev)  # [n_runs, best]
         ws = scan_workspace(rows * W, dev)
-        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
+        _lib.call("cfe_pack_bits_le" if invert else "cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
         _lib.call("cfe_scan_run_starts", bits.data_ptr(), rows, X, pref.data_ptr(), stats.data_ptr(),
                   ws.data_ptr(), s)
         max_runs = lib.cfe_ccl_max_runs(rows, X)
         parent = empty_u32(max_runs, dev)
         size = empty_u32(max_runs, dev)
-        _lib.call("cfe_ccl_largest", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
-                  parent.data_ptr(), size.data_ptr(), stats.data_ptr() + 8, out.data_ptr(), s)
+        if drop or src is not None:
+            if fill is None:
+                # I.max() on the device: the label/select kernels run first, the fill value is then read
+                # back with the winner (one synchronisation) and the selection pass launched
+                mx = torch.zeros(1, dtype=torch.int32, device=dev)
+                _lib.call("cfe_max_u8", src.data_ptr(), Z * Y * X, mx.data_ptr(), s)
+                _lib.call("cfe_ccl_label", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
+                          parent.data_ptr(), size.data_ptr(), s)
+                _lib.call("cfe_ccl_select", parent.data_ptr(), size.data_ptr(), stats.data_ptr(),
+                          stats.data_ptr() + 8, s)
+                fill = int(mx.cpu().item())
+                _lib.call("cfe_ccl_write_select", bits.data_ptr(), pref.data_ptr(), Z, Y, X, parent.data_ptr(),
+                          stats.data_ptr() + 8, None, int(drop), _lib.ptr(src), fill, out.data_ptr(), s)
+            else:
+                _lib.call("cfe_ccl_largest_select", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
+                          parent.data_ptr(), size.data_ptr(), stats.data_ptr() + 8, int(drop), _lib.ptr(src),
+                          int(fill), out.data_ptr(), s)
+        else:
+            _lib.call("cfe_ccl_largest", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
+                      parent.data_ptr(), size.data_ptr(), stats.data_ptr() + 8, out.data_ptr(), s)
         host = stats.cpu()
     best = int(host[1].item()) & 0xFFFFFFFFFFFFFFFF
     return out, best

@@ -474,7 +474,7 @@ def _property_cards(matprop, prop_GV, existing_GV):
                     continue
                 line = line.replace('SetName', setname).replace('MatName', 'MAT' + setname)
                 if 'GV' in line:
-                    fields = [str(eval(f, scope)) if 'GV' in f else f for f in line.split(',')]
+                    fields = ['{}'.format(eval(f, scope)) if 'GV' in f else f for f in line.split(',')]   # voxelFE.py:734
                     parts.append(','.join(fields) + '\n')
                 else:
                     parts.append(line + '\n')

@@ -40,6 +40,10 @@ uint64_t cfe_launch_count(void);
  * `GV > GVmin` of src/ciclope/core/voxelFE.py:140-141 (thr = floor(GVmin)) and the
  * foreground test of measure.label, src/ciclope/utils/preprocess.py:135 (thr = 0). */
 int cfe_pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t* bits, cfe_stream_t s);
+/* bit = (vol <= thr): the background `~(I>0)` labelled by fill_voids, src/ciclope/utils/preprocess.py:167 */
+int cfe_pack_bits_le(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t* bits, cfe_stream_t s);
+/* *out = max(*out, max(vol[0..n))): `I.max()`, the default fill value of fill_voids (preprocess.py:163) */
+int cfe_max_u8(const uint8_t* vol, int64_t n, uint32_t* out, cfe_stream_t s);
 
 /* bytes of look-back workspace for a scan over n_items items */
 size_t cfe_scan_workspace_bytes(int64_t n_items);
@@ -100,6 +104,16 @@ int cfe_ccl_select(const uint32_t* parent, const uint32_t* size, const uint64_t*
 int cfe_ccl_write_mask(const uint32_t* bits, const uint32_t* run_pref, int64_t Z, int64_t Y, int64_t X,
                        const uint32_t* parent, const uint64_t* best, const uint32_t* keep, uint8_t* out_mask,
                        cfe_stream_t s);
+/* General phase 3 and the matching one-call form.  Selected voxels = the winner's (drop = 0) or every
+ * labelled voxel except the winner's (drop = 1): `labels[labels == largest] = 0; labels != 0` of
+ * remove_largest (preprocess.py:204-206) and of fill_voids (:176-177).  out = fill on selected voxels,
+ * src[voxel] elsewhere (0 when src is NULL); out == src is allowed (`I[labels != 0] = fill_val`, :184). */
+int cfe_ccl_write_select(const uint32_t* bits, const uint32_t* run_pref, int64_t Z, int64_t Y, int64_t X,
+                         const uint32_t* parent, const uint64_t* best, const uint32_t* keep, int drop,
+                         const uint8_t* src, int fill, uint8_t* out, cfe_stream_t s);
+int cfe_ccl_largest_select(const uint32_t* bits, const uint32_t* run_pref, const uint64_t* n_runs, int64_t Z,
+                           int64_t Y, int64_t X, uint32_t* parent, uint32_t* size, uint64_t* best, int drop,
+                           const uint8_t* src, int fill, uint8_t* out, cfe_stream_t s);
 /* roots[k] = slab-local root of the k-th run of voxel plane `plane`; *count = runs in the plane */
 int cfe_ccl_plane_roots(const uint32_t* bits, const uint32_t* run_pref, int64_t plane, int64_t Y, int64_t X,
                         const uint32_t* parent, uint32_t* roots, uint32_t* count, cfe_stream_t s);

@@ -57,6 +57,8 @@ def lib():
         L.orc_free_sets.argtypes = [ctypes.POINTER(_Sets6)]
         L.orc_refnode.restype = None
         L.orc_refnode.argtypes = [_p_i64, _i64, _i64, _i64, _p_f64, _p_f64, _p_f64, _p_f64]
+        L.orc_drop_largest.restype = _i64
+        L.orc_drop_largest.argtypes = [_p_u8, _i64, _i64, _i64, _p_u8]
         L.orc_deck_body.restype = ctypes.c_int
         L.orc_deck_body.argtypes = [_p_f64, _i64, _p_i64, _i64, _p_i64, _i64,
                                     ctypes.POINTER(ctypes.c_int32), ctypes.c_int, _p_i64, ctypes.c_char_p,
@@ -97,6 +99,32 @@ def remove_unconnected(bwimage):
         # occurrences[1:].argmax() on an empty array (preprocess.py:141)
         raise ValueError("attempt to get argmax of an empty sequence")
     return out.view(np.bool_)
+
+
+def _drop_largest(u):
+    out = np.empty(u.shape, dtype=np.uint8)
+    Z, Y, X = u.shape
+    if lib().orc_drop_largest(_ptr(u, _p_u8), Z, Y, X, _ptr(out, _p_u8)) < 0:
+        raise ValueError("attempt to get argmax of an empty sequence")
+    return out.view(np.bool_)
+
+
+def remove_largest(bwimage):
+    """preprocess.py:187-208 -- everything but the largest 6-connected component."""
+    return _drop_largest(_u8(np.asarray(bwimage)))
+
+
+def fill_voids(I, fill_val=None, makecopy=False):  # noqa: E741 -- the reference's parameter name
+    """preprocess.py:145-185 -- background regions other than the largest one are set to fill_val."""
+    if fill_val is None:
+        fill_val = I.max()
+    voids = _drop_largest(np.ascontiguousarray(~(I > 0)).view(np.uint8))
+    if makecopy:
+        I_filled = I.copy()
+        I_filled[voids] = fill_val
+        return I_filled
+    I[voids] = fill_val
+    return I
 
 
 def count_components(bwimage):

@@ -391,3 +391,41 @@ class PlainMesh:
         for t, data in self.cells:
             d.setdefault(t, []).append(data)
         return {k: np.concatenate(v) for k, v in d.items()}
+
+
+# ------------------------------------------------------------------------------------ CCL reuse
+
+def fill_cases():
+    """(name, image, kwargs) for fill_voids (preprocess.py:145-185): images with enclosed background."""
+    C = []
+    box = np.zeros((7, 8, 40), dtype=np.uint8)
+    box[1:6, 1:7, 2:38] = 120
+    box[2:5, 2:6, 3:37] = 0          # one big cavity
+    box[3, 3, 10] = 200              # a speck inside the cavity
+    C.append(("hollow_box_u8", box, {}))
+    C.append(("hollow_box_fill77_copy", box, dict(fill_val=77, makecopy=True)))
+    C.append(("hollow_box_fill0", box, dict(fill_val=0)))
+    two = np.zeros((5, 9, 70), dtype=np.uint8)
+    two[1:4, 1:8, 1:30] = 50
+    two[2, 2:7, 2:29] = 0            # cavity A (5 x 27)
+    two[1:4, 1:8, 33:69] = 90
+    two[2, 2:7, 34:68] = 0           # cavity B larger than A, still smaller than the outside
+    C.append(("two_cavities", two, {}))
+    # the "outside" is NOT the largest background region: the reference then fills the outside instead
+    inv = np.zeros((3, 12, 34), dtype=np.uint8)
+    inv[:, 1:11, 1:33] = 255
+    inv[:, 2:10, 2:32] = 0
+    inv[:, 0, :] = 255
+    inv[:, 11, :] = 255
+    inv[:, :, 0] = 255
+    inv[:, :, 33] = 255
+    inv[0, 5, 0] = 0
+    C.append(("cavity_larger_than_outside", inv, {}))
+    C.append(("bool_image", box > 0, {}))
+    C.append(("bool_image_copy", box > 0, dict(makecopy=True)))
+    for i, (shape, dens) in enumerate([((6, 7, 33), 0.75), ((4, 9, 64), 0.8), ((9, 10, 31), 0.7),
+                                       ((12, 13, 47), 0.85), ((1, 20, 45), 0.7), ((16, 16, 96), 0.78)]):
+        C.append(("rand_dense_%dx%dx%d" % shape, rand_grey(shape, dens, 200 + i), {}))
+    m = blobs((20, 24, 70), 0.6, 9)
+    C.append(("blobs_dense_grey", grey_from_mask(m, 10), dict(fill_val=255, makecopy=True)))
+    return C

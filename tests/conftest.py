@@ -31,3 +31,10 @@ def golden_generic():
     import numpy as np
     from tests import cases
     return np.load(os.path.join(cases.GOLDEN_DIR, "generic.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_reuse():
+    import numpy as np
+    from tests import cases
+    return np.load(os.path.join(cases.GOLDEN_DIR, "reuse.npz"), allow_pickle=False)

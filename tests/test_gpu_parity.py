@@ -233,6 +233,59 @@ def test_notebook_cell_data_astype_pattern(cfe, golden, tmp_path):
     assert "ELSET=SET1, MATERIAL=MATSET1" in text and "SETTrue" not in text
 
 
+# ------------------------------------------------------------------ remove_largest / fill_voids
+
+@pytest.mark.parametrize("name", [n for n, _ in cases.ccl_cases()])
+def test_remove_largest_golden(cfe, golden_reuse, name):
+    bw = dict(cases.ccl_cases())[name]
+    want = np.unpackbits(golden_reuse["rl/" + name])[:bw.size].astype(bool).reshape(bw.shape)
+    got = cfe.remove_largest(bw)
+    assert got.dtype == np.bool_ and got.shape == bw.shape
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.fill_cases()])
+def test_fill_voids_golden(cfe, golden_reuse, name):
+    _, img, kw = [c for c in cases.fill_cases() if c[0] == name][0]
+    want = golden_reuse["fv/" + name + "/out"]
+    arg = img.copy()
+    got = cfe.fill_voids(arg, **kw)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    if kw.get("makecopy"):
+        assert got is not arg and np.array_equal(arg, img)
+    else:
+        assert got is arg                      # the reference fills in place and returns its argument
+    # CUDA tensor in, CUDA tensor out (in place unless makecopy)
+    import torch
+    t = torch.from_numpy(img.copy()).cuda()
+    r = cfe.fill_voids(t, **kw)
+    assert r.is_cuda and np.array_equal(r.cpu().numpy(), want)
+    assert (r.data_ptr() == t.data_ptr()) != bool(kw.get("makecopy"))
+    assert np.array_equal(t.cpu().numpy(), img if kw.get("makecopy") else want)
+
+
+@pytest.mark.parametrize("shape,density,seed", [((40, 48, 70), 0.7, 1), ((64, 64, 64), 0.8, 2), ((33, 65, 130), 0.75, 3)])
+def test_reuse_random_vs_oracle(cfe, orc, shape, density, seed):
+    g = cases.rand_grey(shape, density, seed)
+    assert np.array_equal(cfe.fill_voids(g.copy()), orc.fill_voids(g.copy()))
+    assert np.array_equal(cfe.fill_voids(g.copy(), fill_val=3, makecopy=True), orc.fill_voids(g.copy(), 3, True))
+    bw = cases.blobs(shape, 0.3, seed)
+    assert np.array_equal(cfe.remove_largest(bw), orc.remove_largest(bw))
+    # remove_unconnected and remove_largest partition the foreground
+    assert np.array_equal(cfe.remove_largest(bw) | cfe.remove_unconnected(bw), bw)
+
+
+def test_reuse_errors(cfe, golden_reuse):
+    assert str(golden_reuse["err/remove_largest_all_background"]) == "ValueError"
+    with pytest.raises(ValueError):
+        cfe.remove_largest(np.zeros((3, 3, 3), dtype=bool))
+    assert str(golden_reuse["err/fill_voids_all_foreground"]) == "ValueError"
+    with pytest.raises(ValueError):
+        cfe.fill_voids(np.full((3, 3, 3), 9, dtype=np.uint8))
+    with pytest.raises(ValueError):
+        cfe.fill_voids(np.zeros((3, 3, 3), dtype=np.uint8), fill_val=300)
+
+
 # ------------------------------------------------------------------ generic / edited meshes
 
 @pytest.mark.parametrize("case", cases.generic_cases(), ids=lambda c: c["name"])

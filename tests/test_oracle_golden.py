@@ -28,6 +28,34 @@ def test_oracle_remove_unconnected(golden_ccl, name):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("name", [n for n, _ in cases.ccl_cases()])
+def test_oracle_remove_largest(golden_reuse, name):
+    bw = dict(cases.ccl_cases())[name]
+    want = np.unpackbits(golden_reuse["rl/" + name])[:bw.size].astype(bool).reshape(bw.shape)
+    got = orc.remove_largest(bw)
+    assert got.dtype == np.bool_ and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.fill_cases()])
+def test_oracle_fill_voids(golden_reuse, name):
+    _, img, kw = [c for c in cases.fill_cases() if c[0] == name][0]
+    assert np.array_equal(golden_reuse["fv/" + name + "/in"], img)
+    arg = img.copy()
+    got = orc.fill_voids(arg, **kw)
+    want = golden_reuse["fv/" + name + "/out"]
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    assert (got is arg) != bool(kw.get("makecopy"))
+
+
+def test_oracle_reuse_errors(golden_reuse):
+    assert str(golden_reuse["err/remove_largest_all_background"]) == "ValueError"
+    assert str(golden_reuse["err/fill_voids_all_foreground"]) == "ValueError"
+    with pytest.raises(ValueError):
+        orc.remove_largest(np.zeros((3, 3, 3), dtype=bool))
+    with pytest.raises(ValueError):
+        orc.fill_voids(np.full((3, 3, 3), 9, dtype=np.uint8))
+
+
 def test_cases_regenerate_golden_inputs(golden, golden_ccl):
     # the seeded generators in tests/cases.py still produce the stored inputs
     for name, bw in cases.ccl_cases():
