@@ -66,3 +66,20 @@ def to_device_async(data, dtype, device):
 def bytes_to_device_async(raw, device):
     host = torch.frombuffer(bytearray(raw) if len(raw) else bytearray(b"\0"), dtype=torch.uint8)
     return host.pin_memory().to(device, non_blocking=True)
+
+
+_READBACK = {}
+
+
+def read_back(t):
+    """Small device tensor -> Python list through a persistent pinned buffer: one asynchronous copy
+    and a stream synchronisation (``.cpu()`` goes through a pageable staging copy)."""
+    key = (t.device.index, t.dtype)
+    host = _READBACK.get(key)
+    if host is None or host.numel() < t.numel():
+        host = torch.empty(max(64, t.numel()), dtype=t.dtype).pin_memory()
+        _READBACK[key] = host
+    view = host[: t.numel()]
+    view.copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return view.tolist()

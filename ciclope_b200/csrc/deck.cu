@@ -804,8 +804,11 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
 // *NSET / *ELSET sections: a stream of items, each either a literal (section comment, set
 // header, the closing '\n' of a set) or one id of a set's list followed by ',' or '\n'.
 
-#define ITEM_STAGE_BYTES (EMIT_THREADS * 24 + 8192 + 32)
+#define ITEM_PER_THREAD 8
+#define ITEM_TILE (EMIT_THREADS * ITEM_PER_THREAD)
+#define ITEM_STAGE_BYTES (ITEM_TILE * 12 + 8192 + 32)
 
+// One CTA = ITEM_TILE consecutive items (8 per thread): few, fat tiles keep the look-back chain short.
 __global__ void __launch_bounds__(EMIT_THREADS)
 k_emit_items(const CfeItemSeg* __restrict__ segs, int n_segs, i64 n_items, const i64* __restrict__ ids,
              const char* __restrict__ lit, char* out_base, const u64* dyn_off, u64* total, u64* seg_off, u64* ws)
@@ -814,52 +817,68 @@ k_emit_items(const CfeItemSeg* __restrict__ segs, int n_segs, i64 n_items, const
     __shared__ u32 s_scan[33];
     __shared__ u64 s_base;
     const u32 tile = scan_next_tile(ws);
-    const i64 t = (i64)tile * EMIT_THREADS + threadIdx.x;
-    u32 len = 0;
-    int nd = 0;
-    u64 id = 0;
-    char sep = 0;
-    const char* src = nullptr;
-    int seg_first = -1;
-    if (t < n_items) {
-        int q = 0;
-        while (q + 1 < n_segs && t >= segs[q + 1].item0) ++q;
-        const CfeItemSeg sg = segs[q];
-        if (t == sg.item0) seg_first = q;
-        if (sg.kind == 0) {
-            src = lit + sg.lit_off;
-            len = (u32)sg.lit_len;
-        } else {
-            const i64 e = t - sg.item0;
-            id = (u64)__ldg(ids + sg.id0 + e);
-            nd = digits_u64(id);
-            // voxelFE.py:657-666: ',' after entries 1-9 of a line, '\n' after the tenth
-            sep = (((sg.rank0 + e + 1) % 10) == 0) ? '\n' : ',';
-            len = (u32)nd + 1u;
+    const i64 t0 = (i64)tile * ITEM_TILE + (i64)threadIdx.x * ITEM_PER_THREAD;
+    u32 len[ITEM_PER_THREAD];
+    u64 id[ITEM_PER_THREAD];
+    int lit_seg[ITEM_PER_THREAD];       // >= 0: literal of that segment
+    u32 first_mask = 0, nl_mask = 0, sum = 0;
+    int q = 0;
+    if (t0 < n_items)
+        while (q + 1 < n_segs && t0 >= segs[q + 1].item0) ++q;
+#pragma unroll
+    for (int j = 0; j < ITEM_PER_THREAD; ++j) {
+        const i64 t = t0 + j;
+        len[j] = 0; id[j] = 0; lit_seg[j] = -1;
+        if (t < n_items) {
+            while (q + 1 < n_segs && t >= segs[q + 1].item0) ++q;
+            const i64 item0 = segs[q].item0;
+            if (t == item0) first_mask |= 1u << j;
+            if (segs[q].kind == 0) {
+                lit_seg[j] = q;
+                len[j] = (u32)segs[q].lit_len;
+            } else {
+                const i64 e = t - item0;
+                id[j] = (u64)__ldg(ids + segs[q].id0 + e);
+                // voxelFE.py:657-666: ',' after entries 1-9 of a line, '\n' after the tenth
+                if (((segs[q].rank0 + e + 1) % 10) == 0) nl_mask |= 1u << j;
+                len[j] = (u32)digits_u64(id[j]) + 1u;
+            }
         }
+        sum += len[j];
     }
     u32 tile_total;
-    const u32 excl = block_exclusive_scan<u32>(len, s_scan, tile_total);
+    u32 excl = block_exclusive_scan<u32>(sum, s_scan, tile_total);
     if (threadIdx.x < 32) {
-        const u64 e = scan_lookback(ws, tile, (u64)tile_total);
+        const u64 e = scan_lookback_d<4>(ws, tile, (u64)tile_total);
         if (threadIdx.x == 0) {
             s_base = e;
-            if ((i64)(tile + 1) * EMIT_THREADS >= n_items) *total = e + tile_total;
+            if ((i64)(tile + 1) * ITEM_TILE >= n_items) *total = e + tile_total;
         }
     }
     __syncthreads();
     char* dst = out_base + (dyn_off ? *dyn_off : 0ull) + s_base;
     const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
-    if (seg_first >= 0 && seg_off) seg_off[seg_first] = s_base + excl;
     const bool staged = (pad + tile_total) <= (u32)ITEM_STAGE_BYTES;
-    if (t < n_items) {
-        char* p = staged ? (stage + pad + excl) : (dst + excl);
-        if (src) {
-            for (u32 q = 0; q < len; ++q) p[q] = __ldg(src + q);
-        } else {
-            put_u64_back(p + nd, id, nd);
-            p[nd] = sep;
+    char* p = staged ? (stage + pad + excl) : (dst + excl);
+#pragma unroll
+    for (int j = 0; j < ITEM_PER_THREAD; ++j) {
+        if (t0 + j >= n_items) break;
+        if ((first_mask >> j) & 1u) {
+            // segment index of item j: recompute (rare path)
+            int qq = 0;
+            while (qq + 1 < n_segs && t0 + j >= segs[qq + 1].item0) ++qq;
+            if (seg_off) seg_off[qq] = s_base + excl;
         }
+        if (lit_seg[j] >= 0) {
+            const char* src = lit + segs[lit_seg[j]].lit_off;
+            for (u32 c = 0; c < len[j]; ++c) p[c] = __ldg(src + c);
+        } else {
+            const int nd = (int)len[j] - 1;
+            put_u64_back(p + nd, id[j], nd);
+            p[nd] = ((nl_mask >> j) & 1u) ? '\n' : ',';
+        }
+        p += len[j];
+        excl += len[j];
     }
     __syncthreads();
     if (staged) flush_stage(stage, pad, tile_total, dst);
@@ -869,7 +888,7 @@ extern "C" int cfe_emit_items(const CfeItemSeg* segs_dev, int n_segs, int64_t n_
                               const char* literals, char* out_base, const uint64_t* dyn_off, uint64_t* total,
                               uint64_t* seg_off, void* ws, cudaStream_t stream)
 {
-    const i64 tiles = (n_items + EMIT_THREADS - 1) / EMIT_THREADS;
+    const i64 tiles = (n_items + ITEM_TILE - 1) / ITEM_TILE;
     CFE_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(tiles + 2) * sizeof(u64), stream));
     CFE_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(u64), stream));
     if (tiles == 0) return 0;

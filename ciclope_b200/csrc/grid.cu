@@ -12,7 +12,7 @@
 #include "ciclope_b200.h"
 
 #define SCAN_THREADS 256
-#define SCAN_ITEMS 4
+#define SCAN_ITEMS 8
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
 
 // ------------------------------------------------------------------------------------------
@@ -175,20 +175,31 @@ k_scan_words(const u32* __restrict__ bits, i64 n_words, int W, NodeGeom geom, u3
             if (++w == geom.WN) { w = 0; if (++r == geom.Y + 1) { r = 0; ++s; } }
         }
     } else {
-        u32 prev = 0;
-        if (MODE == 1 && i0 > 0 && i0 < n_words && (i0 % W) != 0) prev = __ldg(bits + i0 - 1);
+        u32 word[SCAN_ITEMS];
+        if (i0 + SCAN_ITEMS <= n_words && (reinterpret_cast<uintptr_t>(bits) & 15u) == 0) {   // 16-byte loads
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            u32 word = (i0 + k < n_words) ? __ldg(bits + i0 + k) : 0u;
-            if (MODE == 1) {
-                const u32 carry = ((i0 + k) % W != 0) ? (prev >> 31) : 0u;
-                const u32 starts = word & ~((word << 1) | carry);
-                prev = word;
-                cnt[k] = __popc(starts);
-            } else {
-                cnt[k] = __popc(word);
+            for (int k = 0; k < SCAN_ITEMS; k += 4) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(bits + i0 + k));
+                word[k] = v.x; word[k + 1] = v.y; word[k + 2] = v.z; word[k + 3] = v.w;
             }
-            sum += cnt[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) word[k] = (i0 + k < n_words) ? __ldg(bits + i0 + k) : 0u;
+        }
+        if (MODE == 1) {
+            int w = (int)(i0 % W);                      // word position inside the voxel row
+            u32 prev = (w != 0 && i0 < n_words) ? __ldg(bits + i0 - 1) : 0u;
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                const u32 carry = w ? (prev >> 31) : 0u;
+                cnt[k] = __popc(word[k] & ~((word[k] << 1) | carry));
+                prev = word[k];
+                if (++w == W) w = 0;
+                sum += cnt[k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) { cnt[k] = __popc(word[k]); sum += cnt[k]; }
         }
     }
     u32 block_total;
@@ -202,10 +213,19 @@ k_scan_words(const u32* __restrict__ bits, i64 n_words, int W, NodeGeom geom, u3
     }
     __syncthreads();
     u32 run = (u32)s_excl + excl;
+    if (i0 + SCAN_ITEMS <= n_words && (reinterpret_cast<uintptr_t>(pref) & 15u) == 0) {
+        u32 o[SCAN_ITEMS];
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (i0 + k < n_words) pref[i0 + k] = run;
-        run += cnt[k];
+        for (int k = 0; k < SCAN_ITEMS; ++k) { o[k] = run; run += cnt[k]; }
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k += 4)
+            *reinterpret_cast<uint4*>(pref + i0 + k) = make_uint4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (i0 + k < n_words) pref[i0 + k] = run;
+            run += cnt[k];
+        }
     }
 }
 
@@ -520,6 +540,71 @@ k_sets(const CfeSetDesc* __restrict__ descs, int n_sets, SetGeom g, u32* __restr
         const u32 e = block_exclusive_scan<u32>(keep ? 1u : 0u, s_scan, tot);
         if (keep) ids[tile_off[tile] + e] = id;
     }
+}
+
+// Single-pass form: every tile (SETS1_TILE candidates, tile_base in those units) evaluates its predicates ONCE, gets its global position
+// by decoupled look-back over the tiles (set-major, raster order inside a set) and writes its ids.
+// first[q] = position of set q's first id (only written for sets that own at least one tile),
+// first[n_sets] = total number of ids.  `ids` must hold sum(n_cand) entries.
+#define SETS1_ITEMS 8
+#define SETS1_TILE (256 * SETS1_ITEMS)
+
+extern "C" int64_t cfe_sets_onepass_tile(void) { return SETS1_TILE; }
+
+__global__ void __launch_bounds__(256)
+k_sets_onepass(const CfeSetDesc* __restrict__ descs, int n_sets, i64 n_tiles, SetGeom g, u64* __restrict__ ws,
+               i64* __restrict__ ids, i64* __restrict__ first)
+{
+    __shared__ u32 s_scan[33];
+    __shared__ u64 s_excl;
+    const i64 tile = scan_next_tile(ws);
+    const int q = find_set(descs, n_sets, tile);
+    const CfeSetDesc d = descs[q];
+    // thread t owns candidates k0 .. k0+7 of its set (tile_base counts tiles of SETS1_TILE candidates)
+    const i64 k0 = (tile - d.tile_base) * SETS1_TILE + (i64)threadIdx.x * SETS1_ITEMS;
+    i64 id[SETS1_ITEMS];
+    u32 keep = 0;
+#pragma unroll
+    for (int j = 0; j < SETS1_ITEMS; ++j) {
+        id[j] = 0;
+        if (k0 + j < d.n_cand && set_candidate(d, g, k0 + j, id[j])) keep |= 1u << j;
+    }
+    u32 tot;
+    const u32 e = block_exclusive_scan<u32>((u32)__popc(keep), s_scan, tot);
+    if (threadIdx.x < 32) {
+        const u64 excl = scan_lookback_d<4>(ws, (u32)tile, (u64)tot);
+        if (threadIdx.x == 0) {
+            s_excl = excl;
+            if (tile == d.tile_base) first[q] = (i64)excl;
+            if (tile == n_tiles - 1) first[n_sets] = (i64)(excl + tot);
+        }
+    }
+    __syncthreads();
+    i64* dst = ids + s_excl + e;
+#pragma unroll
+    for (int j = 0; j < SETS1_ITEMS; ++j)
+        if (keep & (1u << j)) *dst++ = id[j];
+}
+
+extern "C" int cfe_sets_onepass(const CfeSetDesc* descs_dev, int n_sets, int64_t n_tiles, int64_t Zl,
+                                int64_t Y, int64_t X, int64_t z0, int64_t eid_offset, const uint32_t* bits,
+                                const uint32_t* pref, const uint32_t* halo_below, void* ws, int64_t* ids,
+                                int64_t* first, cudaStream_t stream)
+{
+    CFE_CHECK_CUDA(cudaMemsetAsync(first, 0xff, (size_t)(n_sets + 1) * sizeof(i64), stream));   // -1 = no tile
+    if (n_tiles <= 0) {
+        CFE_CHECK_CUDA(cudaMemsetAsync(first + n_sets, 0, sizeof(i64), stream));
+        return 0;
+    }
+    if (n_tiles >= (1LL << 31)) { cfe_set_error("cfe_sets_onepass: too many tiles"); return -1; }
+    CFE_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(n_tiles + 2) * sizeof(u64), stream));
+    SetGeom g;
+    g.Zl = (int)Zl; g.Y = (int)Y; g.X = (int)X; g.W = (int)((X + 31) / 32);
+    g.z0 = z0; g.eid_offset = eid_offset; g.bits = bits; g.pref = pref; g.halo_below = halo_below;
+    k_sets_onepass<<<(unsigned)n_tiles, 256, 0, stream>>>(descs_dev, n_sets, n_tiles, g, reinterpret_cast<u64*>(ws),
+                                                          reinterpret_cast<i64*>(ids), reinterpret_cast<i64*>(first));
+    CFE_CHECK_LAUNCH("k_sets_onepass");
+    return 0;
 }
 
 // generic exclusive scan u32 -> u64 (small arrays: tile counts, per-bin histograms)

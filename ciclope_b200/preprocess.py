@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._util import as_device_volume, check_slab_size, empty_u32, scan_workspace
+from ._util import as_device_volume, check_slab_size, empty_u32, read_back, scan_workspace
 
 
 def remove_unconnected(bwimage):
@@ -134,7 +134,7 @@ def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, ou
         rows = Z * Y
         bits = empty_u32(rows * W, dev)
         pref = empty_u32(rows * W, dev)
-        stats = torch.zeros(2, dtype=torch.int64, device=dev)  # [n_runs, best]
+        stats = torch.empty(2, dtype=torch.int64, device=dev)  # [n_runs, best]: both written by the kernels
         ws = scan_workspace(rows * W, dev)
         _lib.call("cfe_pack_bits_le" if invert else "cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
         _lib.call("cfe_scan_run_starts", bits.data_ptr(), rows, X, pref.data_ptr(), stats.data_ptr(),
@@ -152,7 +152,7 @@ def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, ou
                           parent.data_ptr(), size.data_ptr(), s)
                 _lib.call("cfe_ccl_select", parent.data_ptr(), size.data_ptr(), stats.data_ptr(),
                           stats.data_ptr() + 8, s)
-                fill = int(mx.cpu().item())
+                fill = int(read_back(mx)[0])
                 _lib.call("cfe_ccl_write_select", bits.data_ptr(), pref.data_ptr(), Z, Y, X, parent.data_ptr(),
                           stats.data_ptr() + 8, None, int(drop), _lib.ptr(src), fill, out.data_ptr(), s)
             else:
@@ -162,8 +162,8 @@ def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, ou
         else:
             _lib.call("cfe_ccl_largest", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
                       parent.data_ptr(), size.data_ptr(), stats.data_ptr() + 8, out.data_ptr(), s)
-        host = stats.cpu()
-    best = int(host[1].item()) & 0xFFFFFFFFFFFFFFFF
+        host = read_back(stats)
+    best = int(host[1]) & 0xFFFFFFFFFFFFFFFF
     return out, best
 
 

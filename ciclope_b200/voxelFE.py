@@ -26,8 +26,8 @@ import torch
 
 from . import _lib
 from ._lib import CfeItemSeg, CfeSetDesc
-from ._util import (as_device_volume, bytes_to_device_async, check_slab_size, empty_u32, scan_workspace,
-                    to_device_async)
+from ._util import (as_device_volume, bytes_to_device_async, check_slab_size, empty_u32, read_back,
+                    scan_workspace, to_device_async)
 
 CellBlock = collections.namedtuple("CellBlock", ["type", "data"])  # meshio 5.0.0 CellBlock
 
@@ -322,16 +322,20 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         npref = empty_u32(nrows * WN, dev)
         ws = scan_workspace(max(rows * W, nrows * WN), dev)
 
-        stats = torch.zeros(4, dtype=torch.int64, device=dev)   # n_el, n_nd, n_set_ids, field overflow
+        # n_el, n_nd, -, field overflow, then first[0..12] (position of every set's first id; [12] = n_ids)
+        stats = torch.zeros(17, dtype=torch.int64, device=dev)
         _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
         _lib.call("cfe_scan_elements", bits.data_ptr(), rows * W, epref.data_ptr(), stats.data_ptr(),
                   ws.data_ptr(), s)
         _lib.call("cfe_scan_nodes", bits.data_ptr(), None, Z, Y, X, Z + 1, nbits.data_ptr(), npref.data_ptr(),
                   stats.data_ptr() + 8, ws.data_ptr(), s)
+        # (host work from here to the read-back overlaps the kernels above)
         # boundary-set descriptors: node sets X0..Z1 then cell sets X0..Z1
         boxes = _boundary_boxes(locking_strategy, p, k, Z, Y, X)
         descs = (CfeSetDesc * 12)()
+        set_tile = _lib.load().cfe_sets_onepass_tile()
         tile_base = 0
+        n_cand = 0
         for q in range(12):
             d = descs[q]
             b = boxes[q % 6]
@@ -357,42 +361,42 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
             (d.vs0, d.vs1), (d.vr0, d.vr1), (d.vc0, d.vc1) = vbox
             d.n_cand = _box_count(cand)
             d.tile_base = tile_base
-            tile_base += (d.n_cand + 255) // 256
+            tile_base += (d.n_cand + set_tile - 1) // set_tile
+            n_cand += d.n_cand
         n_tiles = tile_base
         descs_dev = bytes_to_device_async(bytes(descs), dev)
-        tile_count = empty_u32(n_tiles, dev)
-        tile_off = torch.empty(max(n_tiles, 1) + 1, dtype=torch.int64, device=dev)
-        bases = to_device_async([descs[q].tile_base for q in range(12)], torch.int64, dev)
+        set_ids = torch.empty(max(n_cand, 1), dtype=torch.int64, device=dev)
+        ws_sets = scan_workspace(max(n_tiles, 1) * 256, dev)
 
         logging.info('Detecting node coordinates and boundary nodes')
-        _lib.call("cfe_sets_count", descs_dev.data_ptr(), 12, n_tiles, Z, Y, X, 0, 0, bits.data_ptr(),
-                  epref.data_ptr(), None, tile_count.data_ptr(), s)
-        _lib.call("cfe_scan_u32", tile_count.data_ptr(), n_tiles, tile_off.data_ptr(), stats.data_ptr() + 16,
-                  ws.data_ptr(), s)
-        # host work that overlaps the kernels above: per-axis coordinate values and their text fields
+        # one pass: predicates, look-back positions and the ids themselves (voxelFE.py:163-192, 205-247)
+        _lib.call("cfe_sets_onepass", descs_dev.data_ptr(), 12, n_tiles, Z, Y, X, 0, 0, bits.data_ptr(),
+                  epref.data_ptr(), None, ws_sets.data_ptr(), set_ids.data_ptr(), stats.data_ptr() + 32, s)
+        # per-axis coordinate values and their text fields
         m.xs, m.ys, m.zs = _coordinate_tables(voxelsize, Z, Y, X)
         m.ftab, m.coord_vals = _format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
-        # one device->host read: counts + first id of every set
-        tile_off[n_tiles] = stats[2]
-        host = torch.cat([stats, tile_off[bases.clamp(max=n_tiles)]]).cpu().tolist()
-        n_el, n_nd, n_ids = host[0], host[1], host[2]
+        # the one device->host read: counts + first id of every set
+        host = read_back(stats)
+        n_el, n_nd = host[0], host[1]
         m.field_overflow = bool(host[3])
-        first = host[4:16]
-        count = [(first[q + 1] if q < 11 else n_ids) - first[q] for q in range(12)]
+        first = host[4:17]
+        n_ids = first[12]
+        for q in range(11, -1, -1):
+            if first[q] < 0:             # a set without candidates starts where the next one does
+                first[q] = first[q + 1]
+        count = [first[q + 1] - first[q] for q in range(12)]
+        first = first[:12]
 
-        elem_vox = empty_u32(n_el, dev)
-        node_list = empty_u32(n_nd, dev)
-        set_ids = torch.empty(max(n_ids, 1), dtype=torch.int64, device=dev)
         # element list fused with the *ELEMENT emitter's line-length pass
         lib = _lib.load()
+        elem_vox = empty_u32(n_el, dev)
         ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(n_el) + 16, dtype=torch.uint8, device=dev)
         _lib.call("cfe_fill_elements", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, 0, 0, n_el,
                   elem_vox.data_ptr(), ws_el.data_ptr(), s)
         m.ws_el = ws_el
+        node_list = empty_u32(n_nd, dev)
         _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
                   node_list.data_ptr(), s)
-        _lib.call("cfe_sets_fill", descs_dev.data_ptr(), 12, n_tiles, Z, Y, X, 0, 0, bits.data_ptr(),
-                  epref.data_ptr(), None, tile_off.data_ptr(), set_ids.data_ptr(), s)
 
     m.bits, m.epref = bits, epref
     m.n_el, m.n_nd = int(n_el), int(n_nd)
@@ -455,13 +459,30 @@ def _resolve_matprop(matprop, GVmax):
     return prop_GV
 
 
+_TEXT_CACHE = {}
+
+
+def _read_lines(path):
+    """readlines() of a small text file (template, property cards), cached on (mtime, size): the deck
+    writer looks at these files twice per call (size bound, then the text)."""
+    st = os.stat(path)
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+    hit = _TEXT_CACHE.get(key)
+    if hit is None:
+        with open(path, 'r') as f:
+            hit = tuple(f.readlines())
+        if len(_TEXT_CACHE) > 64:
+            _TEXT_CACHE.clear()
+        _TEXT_CACHE[key] = hit
+    return list(hit)
+
+
 def _property_cards(matprop, prop_GV, existing_GV):
     """PROPERTY section (voxelFE.py:691-746): O(#GV) lines of host string work."""
     parts = ['** User material property definition:\n',
              '** internal variables are: "SetName", "MatName", "GV"\n']
     for n, fname in enumerate(matprop["file"]):
-        with open(fname, 'r') as f:
-            card = f.readlines()
+        card = _read_lines(fname)
         for GV in existing_GV:  # noqa: N806 -- the cards' expressions name this variable
             if not (prop_GV[n][0] <= GV <= prop_GV[n][1]):
                 continue
@@ -483,8 +504,7 @@ def _property_cards(matprop, prop_GV, existing_GV):
 
 def _template_text(templatefile, refnode):
     """Analysis template copy with refnodeX/Y/Z substitution (voxelFE.py:748-768)."""
-    with open(templatefile, 'r') as f:
-        lines = f.readlines()
+    lines = _read_lines(templatefile)
     if refnode is not None:
         subs = [('refnodeX', str(round(refnode[0], 4))), ('refnodeY', str(round(refnode[1], 4))),
                 ('refnodeZ', str(round(refnode[2], 4)))]
@@ -499,16 +519,14 @@ def _template_text(templatefile, refnode):
 
 def _tail_bound(templatefile, refnode, matprop, n_gv):
     """Upper bound (bytes) of the PROPERTY section + template copy, from file sizes only."""
-    with open(templatefile, 'r') as f:
-        t = f.read()
+    t = ''.join(_read_lines(templatefile))
     bound = len(t.encode()) + 64
     if refnode is not None:
         bound += 32 * (t.count('refnodeX') + t.count('refnodeY') + t.count('refnodeZ'))
     if matprop is not None:
         bound += 256
         for fname in matprop["file"]:
-            with open(fname, 'r') as f:
-                lines = f.readlines()
+            lines = _read_lines(fname)
             # per output line: substitutions at most double it; every eval'ed field prints < 32 chars
             per_gv = sum(2 * len(ln.encode()) + 32 * (ln.count(',') + 1) + 16 for ln in lines)
             bound += n_gv * per_gv
@@ -566,7 +584,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         else:
             hist_dev = torch.empty(256, dtype=torch.int64, device=dev)
             _lib.call("cfe_gv_histogram", m.vol.data_ptr(), Z * Y * X, m.thr, hist_dev.data_ptr(), s)
-            hist = hist_dev.cpu().numpy()
+            hist = np.asarray(read_back(hist_dev), dtype=np.int64)
     gvs = np.flatnonzero(hist)
     existing_GV = gvs.astype(gv_dtype)                        # np.unique(cell_GV), voxelFE.py:570
     GVmax = 2 ** matpropbits - 1
@@ -577,7 +595,8 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         GVmax = max(existing_GV)
     prop_GV = {0: (1, 1)} if binary_model else _resolve_matprop(matprop, GVmax)
 
-    # ---- host text
+    # ---- sizes needed to reserve the deck buffer; the *NODE emitter is launched before any other host
+    # work so that the GPU formats nodes while the host prepares the element / set sections
     head = ('** ---------------------------------------------------------\n'
             '** Abaqus .INP file written by Voxel_FEM script on {}\n'
             '** ---------------------------------------------------------\n'
@@ -588,25 +607,14 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     # the emit kernels have been enqueued so that they overlap the GPU; only a bound on their size
     # is needed to reserve the deck buffer.
     tail_bound = _tail_bound(templatefile, refnode, matprop if 'PROPERTY' in keywords else None, len(gvs))
-
-    hdr_text = bytearray(256 * _ELEM_HDR_SLOT)
-    hdr_len = np.zeros(256, dtype=np.uint8)
-    for g in gvs.tolist():
-        h = '*ELEMENT, TYPE={0}, ELSET={1}\n'.format(eltype, 'SET' + str(int(g))).encode()
-        if len(h) > _ELEM_HDR_SLOT:
-            raise ValueError("eltype too long for the element block header slot")
-        hdr_text[g * _ELEM_HDR_SLOT: g * _ELEM_HDR_SLOT + len(h)] = h
-        hdr_len[g] = len(h)
-    first = np.zeros(256, dtype=np.int64)
-    first[1:] = np.cumsum(hist)[:-1]
-    first[hist == 0] = -1        # never matches an emission index
-
-    blob = _Blob()
-    o_head = blob.add(head)
-    o_cmt = blob.add(elem_comment)
-    o_hdr = blob.add(bytes(hdr_text))
-    o_hlen = blob.add(hdr_len.tobytes())
-    o_first = blob.add(first.tobytes())
+    max_node_id = (Z + 1) * (Y + 1) * (X + 1) - 1
+    if max_node_id >= 10 ** 10:
+        raise NotImplementedError("node ids wider than the 10-character field are not supported")
+    if len('*ELEMENT, TYPE={0}, ELSET=SET255\n'.format(eltype)) > _ELEM_HDR_SLOT:
+        raise ValueError("eltype too long for the element block header slot")
+    max_line = len(str(m.n_el)) + 8 * len(str(max_node_id)) + 9
+    n_set_ids = sum(m.set_count) + 4
+    lits_bound = 1024                      # comments + 14 '*NSET, NSET=<name>' headers + separators
     wide = m.field_overflow     # some '{:12.6f}' field needs more than 12 characters: variable-length *NODE lines
     slot = 32 if wide else 16
     node_bytes = 53 * m.n_nd
@@ -626,15 +634,51 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
                       p_xt + 32 * (X + 1) + 32 * (Y + 1), Y, X, 0, nlen8.data_ptr(), ntile_tot.data_ptr(), s)
             _lib.call("cfe_scan_u32", ntile_tot.data_ptr(), n_ntiles, ntile_off.data_ptr(), nstat.data_ptr(),
                       scan_workspace(max(n_ntiles, 1), dev).data_ptr(), s)
-            node_bytes, bad = nstat.cpu().tolist()
+            node_bytes, bad = read_back(nstat)
         if bad:
             raise NotImplementedError("node coordinates that are not finite or not below 1e18 cannot be formatted")
     else:
         p_xt = m.ftab.data_ptr()
     p_yt = p_xt + slot * (X + 1)
     p_zt = p_yt + slot * (Y + 1)
+    off_nodes = len(head)
+    off_cmt = off_nodes + node_bytes
+    off_elem = off_cmt + len(elem_comment)
+    cap = (off_elem + m.n_el * max_line + len(gvs) * _ELEM_HDR_SLOT
+           + n_set_ids * (len(str(max(max_node_id, m.n_el))) + 1) + lits_bound + tail_bound + 64)
 
-    # NSET / ELSET item stream (voxelFE.py:650-688)
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        # the *NODE section starts 16-byte aligned in memory (word stores in k_emit_nodes4)
+        out_full = torch.empty(cap + 16, dtype=torch.uint8, device=dev)
+        out = out_full[(-(out_full.data_ptr() + off_nodes)) % 16:]
+        dhead = bytes_to_device_async(head + elem_comment, dev)
+        _lib.call("cfe_put_literal", dhead.data_ptr(), len(head), out.data_ptr(), None, None, s)
+        if wide:
+            _lib.call("cfe_emit_nodes_wide", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt, Y, X, 0,
+                      nlen8.data_ptr(), ntile_off.data_ptr(), out.data_ptr() + off_nodes, s)
+        else:
+            _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
+                      Y, X, 0, out.data_ptr() + off_nodes, s)
+        _lib.call("cfe_put_literal", dhead.data_ptr() + len(head), len(elem_comment), out.data_ptr() + off_cmt,
+                  None, None, s)
+
+    # ---- element block headers, NSET / ELSET item stream (host work overlapping the node emitter)
+    hdr_text = bytearray(256 * _ELEM_HDR_SLOT)
+    hdr_len = np.zeros(256, dtype=np.uint8)
+    for g in gvs.tolist():
+        h = '*ELEMENT, TYPE={0}, ELSET={1}\n'.format(eltype, 'SET' + str(int(g))).encode()
+        hdr_text[g * _ELEM_HDR_SLOT: g * _ELEM_HDR_SLOT + len(h)] = h
+        hdr_len[g] = len(h)
+    first = np.zeros(256, dtype=np.int64)
+    first[1:] = np.cumsum(hist)[:-1]
+    first[hist == 0] = -1        # never matches an emission index
+
+    blob = _Blob()
+    o_hdr = blob.add(bytes(hdr_text))
+    o_hlen = blob.add(hdr_len.tobytes())
+    o_first = blob.add(first.tobytes())
+
     lits = bytearray()
     segs = []
     n_items = 0
@@ -652,7 +696,6 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             segs.append((1, n_items, 0, 0, first_id, 0))
             n_items += cnt
 
-    n_set_ids = 0
     if 'NSET' in keywords:
         literal('** Additional nset from voxel model. New generated nsets are:\n')
         literal('** {}, \n'.format(NODE_SET_NAMES[0]))
@@ -662,7 +705,6 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             literal('*NSET, NSET={0}\n'.format(name))
             f, c = (m.set_first[q], m.set_count[q]) if q < 6 else corner[name]
             idlist(f, c)
-            n_set_ids += c
             literal('\n')
     if 'ELSET' in keywords:
         literal('** Additional elset from voxel model. New generated elsets are:\n')
@@ -670,8 +712,9 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         for q, name in enumerate(CELL_SET_NAMES):
             literal('*ELSET, ELSET={}\n'.format(name))
             idlist(m.set_first[6 + q], m.set_count[6 + q])
-            n_set_ids += m.set_count[6 + q]
             literal('\n')
+    if len(lits) > lits_bound:
+        raise _lib.CfeError("internal error: set headers exceed their reserved bound")
     seg_arr = (CfeItemSeg * max(len(segs), 1))()
     for i, (kind, item0, lo, ll, id0, rank0) in enumerate(segs):
         sg = seg_arr[i]
@@ -679,35 +722,13 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     o_lits = blob.add(bytes(lits))
     o_segs = blob.add(bytes(seg_arr))
 
-    # ---- capacity and layout
-    max_node_id = (Z + 1) * (Y + 1) * (X + 1) - 1
-    if max_node_id >= 10 ** 10:
-        raise NotImplementedError("node ids wider than the 10-character field are not supported")
-    max_line = len(str(m.n_el)) + 8 * len(str(max_node_id)) + 9
-    off_nodes = len(head)
-    off_cmt = off_nodes + node_bytes
-    off_elem = off_cmt + len(elem_comment)
-    cap = (off_elem + m.n_el * max_line + int(hdr_len.astype(np.int64).sum())
-           + n_set_ids * (len(str(max(max_node_id, m.n_el))) + 1) + len(lits) + tail_bound + 64)
-
     with torch.cuda.device(dev):
         s = _lib.stream()
         dblob = blob.to_device(dev)
         base = dblob.data_ptr()
-        # the *NODE section starts 16-byte aligned in memory (word stores in k_emit_nodes4)
-        out_full = torch.empty(cap + 16, dtype=torch.uint8, device=dev)
-        out = out_full[(-(out_full.data_ptr() + off_nodes)) % 16:]
         totals = torch.zeros(2, dtype=torch.int64, device=dev)   # element bytes, set bytes
         ws = scan_workspace(max(n_items, 1), dev)
         ws_el = m.ws_el
-        _lib.call("cfe_put_literal", base + o_head, len(head), out.data_ptr(), None, None, s)
-        if wide:
-            _lib.call("cfe_emit_nodes_wide", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt, Y, X, 0,
-                      nlen8.data_ptr(), ntile_off.data_ptr(), out.data_ptr() + off_nodes, s)
-        else:
-            _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
-                      Y, X, 0, out.data_ptr() + off_nodes, s)
-        _lib.call("cfe_put_literal", base + o_cmt, len(elem_comment), out.data_ptr() + off_cmt, None, None, s)
         perm = None
         single_gv = int(gvs[0])
         if len(gvs) > 1:
@@ -742,11 +763,11 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         dtail = bytes_to_device_async(tail, dev)
         _lib.call("cfe_put_literal", dtail.data_ptr(), len(tail), out.data_ptr() + off_elem, totals.data_ptr(),
                   totals.data_ptr() + 8, s)
-        t = totals.cpu().tolist()
+        t = read_back(totals)
     length = off_elem + t[0] + t[1] + len(tail)
     if length > cap:
         raise _lib.CfeError("internal error: deck length %d exceeds the reserved capacity %d" % (length, cap))
-    mesh._last_keepalive = (dblob, dtail)
+    mesh._last_keepalive = (dblob, dtail, dhead)
     return out[:length]
 
 

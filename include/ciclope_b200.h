@@ -167,6 +167,16 @@ int cfe_sets_fill(const CfeSetDesc* descs, int n_sets, int64_t n_tiles, int64_t 
                   int64_t z0, int64_t eid_offset, const uint32_t* bits, const uint32_t* pref,
                   const uint32_t* halo_below, const uint64_t* tile_off, int64_t* ids, cfe_stream_t s);
 
+/* Single-pass form of the two calls above (one predicate evaluation per candidate; positions by
+ * decoupled look-back over the tiles).  Tiles hold cfe_sets_onepass_tile() candidates: tile_base of the
+ * descriptors is counted in those units.  ids must hold sum(n_cand) entries, ws = look-back workspace for
+ * n_tiles items (cfe_scan_workspace_bytes), first[q] = position of set q's first id (-1 for a set without
+ * candidates), first[n_sets] = number of ids written. */
+int64_t cfe_sets_onepass_tile(void);
+int cfe_sets_onepass(const CfeSetDesc* descs, int n_sets, int64_t n_tiles, int64_t Zl, int64_t Y, int64_t X,
+                     int64_t z0, int64_t eid_offset, const uint32_t* bits, const uint32_t* pref,
+                     const uint32_t* halo_below, void* ws, int64_t* ids, int64_t* first, cfe_stream_t s);
+
 /* Reference-node barycentre sums (voxelFE.py:208-223, 254-268): acc[q][0..2] += coordinates of
  * the ids of set q, float64, in ascending order (one thread per set: the reference's
  * summation order).  xs/ys/zs index GLOBAL column / row / layer. */
