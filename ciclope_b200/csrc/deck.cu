@@ -704,6 +704,214 @@ __global__ void __launch_bounds__(256) k_emit_elements(ElemEmitParams P)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Version 2 of the element emitter: PERSISTENT CTAs that keep a 10000-entry table "four decimal
+// digits -> four ASCII bytes" in shared memory (40 KB, filled once per CTA), so that a 12-digit id
+// costs two divisions and three table reads instead of three SWAR conversions; the ids v, v+1, v+RN,
+// v+RN+1 of one node layer share their eight leading digits unless the low four wrap.  Everything else
+// (warp-autonomous staging, static-layout half blocks, 16-byte flush) is as in k_emit_elements.
+#define EE2_WARPS 16
+#define EE2_THREADS (32 * EE2_WARPS)
+#define EE2_LUT_BYTES 40000
+#define EE2_SMEM (EE2_LUT_BYTES + EE2_WARPS * ELEM_WARP_STAGE)
+
+// ASCII words of the 12 zero-padded digits of v (< 10^12), most significant word first
+template <bool WIDE>
+__device__ __forceinline__ void asc12(const u32* lut, u64 v, u32& a0, u32& a1, u32& a2, u32& low4)
+{
+    u32 a, rem;
+    if (WIDE) {
+        const u64 q = v / 100000000ull;
+        a = (u32)q;
+        rem = (u32)(v - q * 100000000ull);
+    } else {
+        const u32 vv = (u32)v;
+        a = vv / 100000000u;
+        rem = vv - a * 100000000u;
+    }
+    const u32 b = rem / 10000u;
+    low4 = rem - b * 10000u;
+    a0 = lut[a]; a1 = lut[b]; a2 = lut[low4];
+}
+
+// the four node-id fields of one node layer in line order: v, v+1, v+RN+1, v+RN
+template <bool WIDE>
+__device__ __forceinline__ void layer_fields(const u32* lut, u64 v, u32 RN, u32 (&F)[4][3])
+{
+    u32 low4;
+    asc12<WIDE>(lut, v, F[0][0], F[0][1], F[0][2], low4);
+    const u32 l2 = low4 + RN + 1u;
+    if (l2 < 10000u) {            // no carry out of the low four digits: the leading eight are shared
+#pragma unroll
+        for (int k = 1; k < 4; ++k) { F[k][0] = F[0][0]; F[k][1] = F[0][1]; }
+        F[1][2] = lut[low4 + 1u];
+        F[2][2] = lut[l2];
+        F[3][2] = lut[l2 - 1u];
+    } else {
+        u32 dummy;
+        asc12<WIDE>(lut, v + 1u, F[1][0], F[1][1], F[1][2], dummy);
+        asc12<WIDE>(lut, v + RN + 1u, F[2][0], F[2][1], F[2][2], dummy);
+        asc12<WIDE>(lut, v + RN, F[3][0], F[3][1], F[3][2], dummy);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void lw_append_line8(LineWriter& w, const u32 (&F0)[4][3], const u32 (&F1)[4][3])
+{
+    lw_append_block<N, false>(w, F0);
+    lw_append_block<N, true>(w, F1);
+}
+
+template <bool PERM, bool WIDE>
+__global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParams P)
+{
+    extern __shared__ __align__(16) char ee2_smem[];
+    u32* lut = reinterpret_cast<u32*>(ee2_smem);
+    for (u32 i = threadIdx.x; i < 10000u; i += EE2_THREADS) lut[i] = raw4(i) + 0x30303030u;
+    __syncthreads();
+    const u32 lane = threadIdx.x & 31u;
+    char* stage = ee2_smem + EE2_LUT_BYTES + (threadIdx.x >> 5) * ELEM_WARP_STAGE;
+    const u32 RN32 = (u32)P.RN;
+    const i64 stride = (i64)gridDim.x * EE2_WARPS;
+    i64 wt = (i64)blockIdx.x * EE2_WARPS + (threadIdx.x >> 5);
+    // software pipeline: the global loads of the NEXT tile are issued before the current one is formatted
+    u32 nx_v = 0, nx_rank = 0, nx_flags = 0, nx_len = 0;
+    int nx_gv = P.single_gv;
+    u64 nx_base = 0;
+    auto load_tile = [&](i64 t) {
+        const i64 jj = t * 32 + lane;
+        if (jj < P.n_el) {
+            if (PERM) { const uint2 e = __ldg(P.perm + jj); nx_v = e.x; nx_rank = e.y; nx_gv = (int)__ldg(P.vol + nx_v); }
+            else { nx_v = __ldg(P.elem_vox + jj); nx_rank = (u32)jj; }
+            nx_flags = __ldg(P.nd8 + jj);
+            nx_len = (u32)__ldg(P.len8 + jj);
+        }
+        nx_base = __ldg(P.warp_off + t);
+    };
+    if (wt < P.n_warp_tiles) load_tile(wt);
+    for (; wt < P.n_warp_tiles; wt += stride) {
+        const i64 j = wt * 32 + lane;
+        const bool active = j < P.n_el;
+        const u32 v = nx_v, rank = nx_rank, flags = nx_flags, line_len = nx_len;
+        const int gv = nx_gv;
+        const u64 base = nx_base;
+        if (wt + stride < P.n_warp_tiles) load_tile(wt + stride);
+        u64 b = 0, eid = 0;
+        u32 len = 0, hl = 0;
+        bool is_first = false;
+        if (active) {
+            const u32 s = fd_div(v, P.dYX);
+            const u32 rem = v - s * P.YX32;
+            const u32 r = fd_div(rem, P.dX);
+            const u32 c = rem - r * P.X32;
+            b = (u64)(P.SN * ((i64)s + P.z0) + P.RN * (i64)r + (i64)c);
+            eid = (u64)(P.eid_offset + (i64)rank + 1);
+            is_first = (u64)j == __ldg(P.first + gv);
+            if (is_first) hl = __ldg(P.hdr_len + gv);
+            len = line_len + hl;                       // the block header rides along with its first line
+        }
+        u32 incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(CFE_FULL_MASK, incl, o);
+            if (lane >= (u32)o) incl += t;
+        }
+        const u32 excl = incl - len;
+        const u32 total = __shfl_sync(CFE_FULL_MASK, incl, 31);
+        char* dst = P.out + base;
+        const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+        const bool staged = pad + total <= (u32)ELEM_WARP_STAGE;
+        if (active) {
+            if (is_first && P.blk_off) P.blk_off[gv] = base + excl;
+            if (staged) {
+                // eid, b, b+1, b+RN+1, b+RN | b+SN, b+SN+1, b+SN+RN+1, b+SN+RN   (voxelFE.py:145-154)
+                u32 o = pad + excl;
+                if (hl) {
+                    const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
+                    for (u32 q = 0; q < hl; ++q) stage[o + q] = __ldg(h + q);
+                    o += hl;
+                }
+                LineWriter w;
+                w.lead = o & 3u;
+                w.d = w.lead;
+                w.acc = 0;
+                w.wp = stage + (o - w.lead);
+                const bool same = (flags & 0x80u) != 0;
+                const int nlo = (int)(flags & 15u);
+                u32 e0, e1, e2, low4;
+                asc12<WIDE>(lut, eid, e0, e1, e2, low4);
+                const int nde = same ? (int)line_len - 9 - 8 * nlo : id_digits<WIDE>(eid);
+                lw_append<true>(w, e0 - 0x30303030u, e1 - 0x30303030u, e2 - 0x30303030u, nde, 0x2Cu);
+                u32 F0[4][3], F1[4][3];
+                layer_fields<WIDE>(lut, b, RN32, F0);
+                layer_fields<WIDE>(lut, b + (u64)P.SN, RN32, F1);
+                if (same) {
+                    switch (nlo) {
+                    case 1: lw_append_line8<1>(w, F0, F1); break;
+                    case 2: lw_append_line8<2>(w, F0, F1); break;
+                    case 3: lw_append_line8<3>(w, F0, F1); break;
+                    case 4: lw_append_line8<4>(w, F0, F1); break;
+                    case 5: lw_append_line8<5>(w, F0, F1); break;
+                    case 6: lw_append_line8<6>(w, F0, F1); break;
+                    case 7: lw_append_line8<7>(w, F0, F1); break;
+                    case 8: lw_append_line8<8>(w, F0, F1); break;
+                    case 9: lw_append_line8<9>(w, F0, F1); break;
+                    default: lw_append_line8<10>(w, F0, F1); break;   // ids are < 10^10 (checked by the host)
+                    }
+                } else {
+                    lw_append_half<false>(w, F0, nlo, false);
+                    lw_append_half<true>(w, F1, nlo, false);
+                }
+                lw_finish(w);
+            } else {
+                // pathological warp tile (dozens of block headers): direct byte writes
+                char* p = dst + excl;
+                if (hl) {
+                    const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
+                    for (u32 q = 0; q < hl; ++q) p[q] = __ldg(h + q);
+                    p += hl;
+                }
+#pragma unroll 1
+                for (int f = 0; f < 9; ++f) {
+                    // eid, b, b+1, b+RN+1, b+RN, b+SN, b+SN+1, b+SN+RN+1, b+SN+RN
+                    u64 val = eid;
+                    if (f) {
+                        const int q = f - 1;
+                        val = b + ((q & 4) ? (u64)P.SN : 0ull) + (((q & 3) == 1 || (q & 3) == 2) ? 1ull : 0ull) +
+                              (((q & 3) >= 2) ? (u64)P.RN : 0ull);
+                    }
+                    const int n = digits_u64(val);
+                    p += n;
+                    put_u64_back(p, val, n);
+                    *p++ = (f == 8) ? '\n' : ',';
+                }
+            }
+        }
+        __syncwarp();
+        if (staged) {
+            // stream the warp's span [pad, pad + total) to dst: aligned 16-byte chunks, bytes at the edges
+            char* gbase = dst - pad;
+            const u32 end = pad + total;
+            const u32 c0 = pad ? 1u : 0u, c1 = end >> 4;
+#pragma unroll
+            for (u32 it = 0; it < (ELEM_WARP_STAGE / 512u); ++it) {
+                const u32 c = c0 + lane + 32u * it;
+                if (c < c1)
+                    *reinterpret_cast<uint4*>(gbase + 16u * c) = *reinterpret_cast<const uint4*>(stage + 16u * c);
+            }
+            if (pad) {
+                const u32 k = pad + lane;
+                if (k < 16u && k < end) gbase[k] = stage[k];
+            }
+            if (c1 >= c0) {
+                const u32 k = (c1 << 4) + lane;
+                if (k < end) gbase[k] = stage[k];
+            }
+        }
+        __syncwarp();     // the staging region is reused by the next tile
+    }
+}
+
 extern "C" size_t cfe_emit_elements_workspace_bytes(int64_t n_el)
 {
     // len8 + nd8 (1 byte each, 16-byte aligned), warp_total (u32), warp_off (u64), scan workspace
@@ -788,15 +996,27 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
     elem_params(P, elem_vox, perm, n_el, vol, first, hdr_text, hdr_len, single_gv, Y, X, z0, eid_offset, out,
                 blk_off, ws, &scan_ws);
     const bool wide = elem_wide(P, Zl);
-    const unsigned g2 = (unsigned)((P.n_warp_tiles + 7) / 8);
-    if (perm) {
-        if (wide) k_emit_elements<true, true><<<g2, 256, 0, stream>>>(P);
-        else k_emit_elements<true, false><<<g2, 256, 0, stream>>>(P);
-    } else {
-        if (wide) k_emit_elements<false, true><<<g2, 256, 0, stream>>>(P);
-        else k_emit_elements<false, false><<<g2, 256, 0, stream>>>(P);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        CFE_CHECK_CUDA(cudaGetDevice(&dev));
+        CFE_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
     }
-    CFE_CHECK_LAUNCH("k_emit_elements");
+    // persistent CTAs: two per SM (97 KB of shared memory each), every warp strides over the warp tiles
+    i64 g2 = (P.n_warp_tiles + EE2_WARPS - 1) / EE2_WARPS;
+    if (g2 > 2 * (i64)sms) g2 = 2 * (i64)sms;
+    if (perm) {
+        if (wide) k_emit_elements2<true, true><<<(unsigned)g2, EE2_THREADS, EE2_SMEM, stream>>>(P);
+        else k_emit_elements2<true, false><<<(unsigned)g2, EE2_THREADS, EE2_SMEM, stream>>>(P);
+    } else {
+        if (wide) k_emit_elements2<false, true><<<(unsigned)g2, EE2_THREADS, EE2_SMEM, stream>>>(P);
+        else k_emit_elements2<false, false><<<(unsigned)g2, EE2_THREADS, EE2_SMEM, stream>>>(P);
+    }
+    CFE_CHECK_LAUNCH("k_emit_elements2");
     return 0;
 }
 

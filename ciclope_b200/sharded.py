@@ -605,6 +605,17 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     dev = m.vol.device
     Zl, Y, X = m.Zl, m.Y, m.X
     rank = ctx.rank
+    wide = m.field_overflow      # variable-length *NODE lines (some '{:12.6f}' field needs > 12 characters)
+    nodes_buf = None
+    if not wide:
+        # fixed 53-byte *NODE lines need nothing but the mesh: start them before any host work so that the
+        # GPU formats nodes while the host prepares the element / set sections
+        with torch.cuda.device(dev):
+            nodes_buf = torch.empty(max(53 * m.n_nd, 1) + 64, dtype=torch.uint8, device=dev)
+            p_xt0 = m.ftab.data_ptr()
+            p_yt0 = p_xt0 + 16 * (X + 1)
+            _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt0, p_yt0,
+                      p_yt0 + 16 * (Y + 1) + 16 * m.z0, Y, X, m.z0, nodes_buf.data_ptr(), _lib.stream())
     if m.is_bool:
         # a boolean volume has one grey value (True -> SET1): the histogram is the element count,
         # which every rank already knows from vol2ugrid's all-gather
@@ -651,7 +662,6 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     o_first = blob.add(first.tobytes())
     o_hdr = blob.add(bytes(256 * vfe._ELEM_HDR_SLOT))
     o_hlen = blob.add(bytes(256))                      # no headers inside the slab buffers
-    wide = m.field_overflow      # variable-length *NODE lines (some '{:12.6f}' field needs > 12 characters)
     slot = 32 if wide else 16
     if wide:
         with torch.cuda.device(dev):
@@ -702,7 +712,8 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         s = _lib.stream()
         dblob = blob.to_device(dev)
         base = dblob.data_ptr()
-        nodes_buf = torch.empty(max((96 if wide else 53) * m.n_nd, 1) + 64, dtype=torch.uint8, device=dev)
+        if wide:
+            nodes_buf = torch.empty(max(96 * m.n_nd, 1) + 64, dtype=torch.uint8, device=dev)
         elem_buf = torch.empty(max(m.n_el * max_line, 1) + 64, dtype=torch.uint8, device=dev)
         items_buf = torch.empty(n_items * (len(str(max(max_node_id, m.max_eid))) + 1) + 64, dtype=torch.uint8,
                                 device=dev)
@@ -722,9 +733,6 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
                       scan_workspace(max(n_ntiles, 1), dev).data_ptr(), s)
             _lib.call("cfe_emit_nodes_wide", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt, Y, X, m.z0,
                       nlen8.data_ptr(), ntile_off.data_ptr(), nodes_buf.data_ptr(), s)
-        else:
-            _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt,
-                      Y, X, m.z0, nodes_buf.data_ptr(), s)
         perm = None
         single_gv = int(gvs[0])
         if len(gvs) > 1:
