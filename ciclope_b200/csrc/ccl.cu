@@ -346,6 +346,57 @@ k_ccl_write_mask(const u32* __restrict__ bits, const u32* __restrict__ pref, i64
     }
 }
 
+// Flat volumes (X % 32 == 0, 16-byte aligned): one thread per WORD walks the word's runs once (the
+// 16-voxel version above visits a run that crosses the half-word twice), then the warp redistributes
+// the 32 keep-words so that every store instruction writes 512 contiguous bytes.
+__global__ void __launch_bounds__(256)
+k_ccl_write_mask_words(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 n_words, int W,
+                       const u32* __restrict__ parent, const u64* __restrict__ best,
+                       const u32* __restrict__ keep_flag, int drop, const uint8_t* src, u32 fill, uint8_t* out)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 lane = threadIdx.x & 31u;
+    const u64 key = keep_flag ? 1ull : *best;
+    const u32 winner = 0xffffffffu - (u32)(key & 0xffffffffu);
+    u32 keep = 0;
+    if (i < n_words && key) {
+        const u32 word = __ldg(bits + i);
+        if (word) {
+            const u32 carry = (i % W) ? (__ldg(bits + i - 1) >> 31) : 0u;
+            const u32 pf = __ldg(pref + i);
+            u32 rest = word;
+            while (rest) {
+                const int b = __ffs((int)rest) - 1;
+                const u32 shifted = rest >> b;
+                const int len = (~shifted == 0u) ? 32 - b : __ffs((int)~shifted) - 1;
+                const u32 seg = (len >= 32) ? 0xffffffffu : (((1u << len) - 1u) << b);
+                const u32 root = __ldg(parent + run_id(word, carry, pf, b));
+                if ((keep_flag ? (keep_flag[root] == 0xffffffffu) : (root == winner)) != (drop != 0)) keep |= seg;
+                rest &= ~seg;
+            }
+        }
+    }
+    const i64 chunk0 = (i - lane) * 2;            // first 16-byte chunk of the warp's 32 words
+    const u32 f4 = (fill & 0xffu) * 0x01010101u;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const u32 c = (u32)k * 32u + lane;        // chunk of the warp handled by this lane
+        const u32 kw = __shfl_sync(CFE_FULL_MASK, keep, c >> 1);
+        const i64 g = chunk0 + c;
+        if (g >= 2 * n_words) continue;
+        const u32 k16 = (kw >> (16u * (c & 1u))) & 0xffffu;
+        const u32 mx = spread_nibble(k16) * 0xffu, my = spread_nibble(k16 >> 4) * 0xffu,
+                  mz = spread_nibble(k16 >> 8) * 0xffu, mw = spread_nibble(k16 >> 12) * 0xffu;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (src) o = reinterpret_cast<const uint4*>(src)[g];
+        o.x = (o.x & ~mx) | (f4 & mx);
+        o.y = (o.y & ~my) | (f4 & my);
+        o.z = (o.z & ~mz) | (f4 & mz);
+        o.w = (o.w & ~mw) | (f4 & mw);
+        reinterpret_cast<uint4*>(out)[g] = o;
+    }
+}
+
 extern "C" size_t cfe_ccl_max_runs(int64_t rows, int64_t X)
 {
     // n_runs <= rows * ceil(X/2); the tail holds one flag per block-local CCL tile
@@ -428,8 +479,8 @@ extern "C" int cfe_ccl_write_select(const uint32_t* bits, const uint32_t* pref, 
                       ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
     const u64* b = reinterpret_cast<const u64*>(best);
     if (flat)
-        k_ccl_write_mask<true><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, drop, src,
-                                                       (u32)fill, out_mask);
+        k_ccl_write_mask_words<<<(unsigned)((rows * W + 255) / 256), 256, 0, stream>>>(
+            bits, pref, rows * W, W, parent, b, keep, drop, src, (u32)fill, out_mask);
     else
         k_ccl_write_mask<false><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, drop, src,
                                                         (u32)fill, out_mask);

@@ -18,39 +18,61 @@
 // ------------------------------------------------------------------------------------------
 // K0: pack (v > thr) into bit rows
 
-__device__ __forceinline__ u32 cmp_nibble(u32 x, u32 thr4, bool all)
+// 4 bits: byte k of x > thr (unsigned), thr in [0, 254].  y4 = (thr + 1) in every byte; x > thr <=> x >= y:
+// the low 7 bits are compared by a borrow-free subtraction ((x | H) - (y & ~H) keeps bit 7 of a byte
+// set iff x7 >= y7 in the low 7 bits), the top bits by logic; the four bit-7 flags are then gathered
+// with one multiply (7+21, 15+14, 23+7, 31+0 -> bits 28..31, no two partial products collide).
+__device__ __forceinline__ u32 cmp_nibble(u32 x, u32 y4, bool all)
 {
-    u32 m = all ? 0xffffffffu : __vcmpgtu4(x, thr4);
-    return ((m & 0x08040201u) * 0x01010101u) >> 24;
+    const u32 H = 0x80808080u;
+    const u32 d = (x | H) - (y4 & ~H);
+    const u32 ge = ((x & ~y4) | (~(x ^ y4) & d)) & H;
+    return all ? 0xfu : (ge * 0x00204081u) >> 28;
 }
+
+#define PACK_UNROLL 4
 
 // FLAT: X % 32 == 0 and vol 16-byte aligned -> the volume is a flat array of 16-byte chunks.
 template <bool FLAT>
 __global__ void __launch_bounds__(256) k_pack_bits(const uint8_t* __restrict__ vol, i64 rows, int X, int W,
                                                    int thr, int invert, u32* __restrict__ bits)
 {
-    const i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const i64 nchunks = rows * 2 * (i64)W;
     const bool all = thr < 0;
-    const u32 thr4 = (u32)(thr < 0 ? 0 : thr) * 0x01010101u;
-    u32 m16 = 0;
-    if (g < nchunks) {
-        if (FLAT) {
-            uint4 v = __ldg(reinterpret_cast<const uint4*>(vol) + g);
-            m16 = cmp_nibble(v.x, thr4, all) | (cmp_nibble(v.y, thr4, all) << 4) |
-                  (cmp_nibble(v.z, thr4, all) << 8) | (cmp_nibble(v.w, thr4, all) << 12);
-            if (invert) m16 ^= 0xffffu;
-        } else {
-            const i64 row = g / (2 * W);
-            const int c0 = (int)(g - row * 2 * W) * 16;
-            const uint8_t* p = vol + row * (i64)X + c0;
+    const bool none = thr >= 255;                              // no uint8 value exceeds 255
+    const u32 thr4 = (u32)((thr < 0 || none) ? 1 : thr + 1) * 0x01010101u;   // y = thr + 1 per byte
+    // PACK_UNROLL chunks per thread, 256 chunks apart, all loads issued first (bytes in flight)
+    const i64 g0 = (i64)blockIdx.x * (256 * PACK_UNROLL) + threadIdx.x;
+    uint4 v[PACK_UNROLL];
+    if (FLAT) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (c0 + k < X) m16 |= (u32)(((int)p[k] > thr) != (invert != 0)) << k;   // pad bits stay 0
+        for (int u = 0; u < PACK_UNROLL; ++u) {
+            const i64 g = g0 + 256 * u;
+            v[u] = g < nchunks ? __ldg(reinterpret_cast<const uint4*>(vol) + g) : make_uint4(0u, 0u, 0u, 0u);
         }
     }
-    const u32 other = __shfl_xor_sync(CFE_FULL_MASK, m16, 1);
-    if (g < nchunks && !(threadIdx.x & 1)) bits[g >> 1] = m16 | (other << 16);
+#pragma unroll
+    for (int u = 0; u < PACK_UNROLL; ++u) {
+        const i64 g = g0 + 256 * u;
+        u32 m16 = 0;
+        if (g < nchunks) {
+            if (FLAT) {
+                m16 = cmp_nibble(v[u].x, thr4, all) | (cmp_nibble(v[u].y, thr4, all) << 4) |
+                      (cmp_nibble(v[u].z, thr4, all) << 8) | (cmp_nibble(v[u].w, thr4, all) << 12);
+                if (none) m16 = 0;
+                if (invert) m16 ^= 0xffffu;
+            } else {
+                const i64 row = g / (2 * W);
+                const int c0 = (int)(g - row * 2 * W) * 16;
+                const uint8_t* p = vol + row * (i64)X + c0;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (c0 + k < X) m16 |= (u32)(((int)p[k] > thr) != (invert != 0)) << k;   // pad bits stay 0
+            }
+        }
+        const u32 other = __shfl_xor_sync(CFE_FULL_MASK, m16, 1);
+        if (g < nchunks && !(threadIdx.x & 1)) bits[g >> 1] = m16 | (other << 16);
+    }
 }
 
 static int pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, int invert, uint32_t* bits,
@@ -59,7 +81,7 @@ static int pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, int i
     if (rows <= 0 || X <= 0) return 0;
     const int W = (int)((X + 31) / 32);
     const i64 nchunks = rows * 2 * (i64)W;
-    const i64 blocks = (nchunks + 255) / 256;
+    const i64 blocks = (nchunks + 256 * PACK_UNROLL - 1) / (256 * PACK_UNROLL);
     if (blocks > 0x7fffffffLL) { cfe_set_error("cfe_pack_bits: volume too large"); return -1; }
     const bool flat = (X % 32 == 0) && ((reinterpret_cast<uintptr_t>(vol) & 15u) == 0);
     if (flat)

@@ -116,6 +116,19 @@ def test_vol2ugrid_golden(cfe, golden, name):
         assert np.array_equal(v, g[name + "/refnode/" + k]), k
 
 
+@pytest.mark.parametrize("shape", [(5, 6, 64), (4, 7, 45)])
+def test_vol2ugrid_gvmin_sweep(cfe, orc, shape):
+    # every byte-compare corner of the SWAR threshold test (flat 16-byte path and ragged rows)
+    rng = np.random.RandomState(3)
+    vol = rng.randint(0, 256, size=shape).astype(np.uint8)
+    vol[0, 0, :8] = [0, 1, 127, 128, 129, 254, 255, 200]
+    for gvmin in (-1, 0, 1, 126, 127, 128, 199.5, 200, 253, 254, 255, 300):
+        got = cfe.vol2ugrid(vol, GVmin=gvmin)
+        want = orc.vol2ugrid(vol, GVmin=gvmin)
+        assert np.array_equal(got.cells[0].data.reshape(-1, 8), want.cells[0].data.reshape(-1, 8)), gvmin
+        assert np.array_equal(got.cell_data["GV"][0], want.cell_data["GV"][0]), gvmin
+
+
 def test_vol2ugrid_reference_known_answers(cfe):
     # test/test_ciclope.py:75-87
     mesh = cfe.vol2ugrid(cases.trab(), [0.12, 0.12, 0.12], GVmin=100, locking_strategy="exact",
