@@ -133,10 +133,11 @@ def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, ou
         W = (X + 31) // 32
         rows = Z * Y
         bits = empty_u32(rows * W, dev)
+        # the first kernel goes out before anything else is allocated: the GPU is idle until then
+        _lib.call("cfe_pack_bits_le" if invert else "cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
         pref = empty_u32(rows * W, dev)
         stats = torch.empty(2, dtype=torch.int64, device=dev)  # [n_runs, best]: both written by the kernels
         ws = scan_workspace(rows * W, dev)
-        _lib.call("cfe_pack_bits_le" if invert else "cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
         _lib.call("cfe_scan_run_starts", bits.data_ptr(), rows, X, pref.data_ptr(), stats.data_ptr(),
                   ws.data_ptr(), s)
         max_runs = lib.cfe_ccl_max_runs(rows, X)

@@ -77,6 +77,21 @@ def _format_tables_device(xs, ys, zs, dev, overflow_ptr, stream):
     return out, tab
 
 
+_TABLES = collections.OrderedDict()
+
+
+def _tables_key(voxelsize, Z, Y, X, dev, stream):
+    """Cache key of the per-axis coordinate tables: they are a pure function of the voxel size (value
+    AND type: np.float32 / int voxel sizes give float32 / int64 points) and of the grid shape."""
+    if isinstance(voxelsize, np.ndarray):
+        vs = ("nd", str(voxelsize.dtype), voxelsize.shape, voxelsize.tobytes())
+    elif isinstance(voxelsize, list):
+        vs = tuple((type(v).__name__, repr(v)) for v in voxelsize)
+    else:
+        vs = (type(voxelsize).__name__, repr(voxelsize))
+    return (vs, Z, Y, X, dev.index, stream)
+
+
 def _int_lock(v, name):
     if isinstance(v, (bool, np.bool_)) or int(v) != v:
         raise TypeError("%s must be an integer" % name)
@@ -316,19 +331,27 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         s = _lib.stream()
         W, WN = (X + 31) // 32, (X + 32) // 32
         rows, nrows = Z * Y, (Z + 1) * (Y + 1)
+        # the first kernel goes out before anything else is allocated: the GPU is idle until then
         bits = empty_u32(rows * W, dev)
+        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
         epref = empty_u32(rows * W, dev)
         nbits = empty_u32(nrows * WN, dev)
         npref = empty_u32(nrows * WN, dev)
         ws = scan_workspace(max(rows * W, nrows * WN), dev)
-
         # n_el, n_nd, -, field overflow, then first[0..12] (position of every set's first id; [12] = n_ids)
         stats = torch.zeros(17, dtype=torch.int64, device=dev)
-        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
         _lib.call("cfe_scan_elements", bits.data_ptr(), rows * W, epref.data_ptr(), stats.data_ptr(),
                   ws.data_ptr(), s)
         _lib.call("cfe_scan_nodes", bits.data_ptr(), None, Z, Y, X, Z + 1, nbits.data_ptr(), npref.data_ptr(),
                   stats.data_ptr() + 8, ws.data_ptr(), s)
+        # per-axis coordinate values and their text fields (memoised: a pure function of voxel size and shape)
+        tkey = _tables_key(voxelsize, Z, Y, X, dev, s)
+        tables = _TABLES.get(tkey)
+        if tables is None:
+            m.xs, m.ys, m.zs = _coordinate_tables(voxelsize, Z, Y, X)
+            m.ftab, m.coord_vals = _format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
+        else:
+            m.xs, m.ys, m.zs, m.ftab, m.coord_vals, cached_overflow = tables
         # (host work from here to the read-back overlaps the kernels above)
         # boundary-set descriptors: node sets X0..Z1 then cell sets X0..Z1
         boxes = _boundary_boxes(locking_strategy, p, k, Z, Y, X)
@@ -372,13 +395,16 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         # one pass: predicates, look-back positions and the ids themselves (voxelFE.py:163-192, 205-247)
         _lib.call("cfe_sets_onepass", descs_dev.data_ptr(), 12, n_tiles, Z, Y, X, 0, 0, bits.data_ptr(),
                   epref.data_ptr(), None, ws_sets.data_ptr(), set_ids.data_ptr(), stats.data_ptr() + 32, s)
-        # per-axis coordinate values and their text fields
-        m.xs, m.ys, m.zs = _coordinate_tables(voxelsize, Z, Y, X)
-        m.ftab, m.coord_vals = _format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
         # the one device->host read: counts + first id of every set
         host = read_back(stats)
         n_el, n_nd = host[0], host[1]
-        m.field_overflow = bool(host[3])
+        if tables is None:
+            m.field_overflow = bool(host[3])
+            _TABLES[tkey] = (m.xs, m.ys, m.zs, m.ftab, m.coord_vals, m.field_overflow)
+            while len(_TABLES) > 8:
+                _TABLES.popitem(last=False)
+        else:
+            m.field_overflow = cached_overflow
         first = host[4:17]
         n_ids = first[12]
         for q in range(11, -1, -1):
