@@ -88,7 +88,7 @@ def run_reference(args, rank):
             "config": workload_config(args.size, args.gpus, note="CPU port timed on a %d^3 sample per step" % edge),
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -358,10 +358,32 @@ def run_gpu(args, rank, world, local_rank):
             "step_ms": {"min": round(min(step_wall), 3), "median": round(statistics.median(step_wall), 3),
                         "max": round(max(step_wall), 3)},
             "entry_point_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL prints its version
+    banner there) goes to stderr."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

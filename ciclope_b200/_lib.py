@@ -60,6 +60,7 @@ _SIGNATURES = {
     "cfe_sets_count": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cfe_sets_fill": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
                               c_vp]),
+    "cfe_set_counts": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_sets_onepass_tile": (c_i64, []),
     "cfe_sets_onepass": (c_int, [c_vp, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
                                  c_vp, c_vp]),

@@ -629,6 +629,33 @@ extern "C" int cfe_sets_onepass(const CfeSetDesc* descs_dev, int n_sets, int64_t
     return 0;
 }
 
+// Two-pass form, between count and fill: out[0] = stats[0] (n_el), out[1] = stats[1] (n_nd),
+// out[2 + q] = number of ids of set q (difference of the scanned tile offsets at the sets' tile bases,
+// stats[2] = total), out[2 + n_sets] = stats[3] (field overflow flag): the vector a z-slab rank
+// all-gathers, assembled in one launch instead of a chain of tensor ops.
+__global__ void k_set_counts(const CfeSetDesc* __restrict__ descs, int n_sets, i64 n_tiles,
+                             const u64* __restrict__ tile_off, const u64* __restrict__ stats, i64* __restrict__ out)
+{
+    const int q = threadIdx.x;
+    const u64 total = stats[2];
+    if (q < n_sets) {
+        const i64 t0 = descs[q].tile_base, t1 = q + 1 < n_sets ? descs[q + 1].tile_base : n_tiles;
+        const u64 a = t0 < n_tiles ? tile_off[t0] : total, b = t1 < n_tiles ? tile_off[t1] : total;
+        out[2 + q] = (i64)(b - a);
+    }
+    if (q == 0) { out[0] = (i64)stats[0]; out[1] = (i64)stats[1]; out[2 + n_sets] = (i64)stats[3]; }
+}
+
+extern "C" int cfe_set_counts(const CfeSetDesc* descs_dev, int n_sets, int64_t n_tiles, const uint64_t* tile_off,
+                              const uint64_t* stats, int64_t* out, cudaStream_t stream)
+{
+    if (n_sets > 32) { cfe_set_error("cfe_set_counts: at most 32 sets"); return -1; }
+    k_set_counts<<<1, 32, 0, stream>>>(descs_dev, n_sets, n_tiles, reinterpret_cast<const u64*>(tile_off),
+                                       reinterpret_cast<const u64*>(stats), reinterpret_cast<i64*>(out));
+    CFE_CHECK_LAUNCH("k_set_counts");
+    return 0;
+}
+
 // generic exclusive scan u32 -> u64 (small arrays: tile counts, per-bin histograms)
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_u32(const u32* __restrict__ in, i64 n, u64* __restrict__ out, u64* __restrict__ total, u64* __restrict__ ws)

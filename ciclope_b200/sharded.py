@@ -26,7 +26,7 @@ import torch
 from . import _lib
 from . import voxelFE as vfe
 from ._lib import CfeItemSeg, CfeSetDesc
-from ._util import bytes_to_device_async, empty_u32, scan_workspace, to_device_async
+from ._util import bytes_to_device_async, empty_u32, read_back, scan_workspace, to_device_async
 
 
 # --------------------------------------------------------------------------------------------
@@ -363,7 +363,7 @@ def ccl_program(ctx, vol, force_host_merge=False):
                   ckey.data_ptr(), size.data_ptr(), result.data_ptr(), s)
         _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
                   stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), s)
-        res = result.cpu().tolist()                             # the one host read of the stage
+        res = read_back(result)                                 # the one host read of the stage
     if res[2]:
         # some rank has more boundary components / edges than the fixed capacity: every rank sees the
         # same flag (nothing was marked) and redoes the merge host-driven at exact sizes
@@ -497,16 +497,16 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
     m.rank, m.size = ctx.rank, ctx.size
     m.vol, m.is_bool, m.thr = vol, is_bool, thr
     m.Zg, m.Zl, m.Y, m.X, m.z0, m.n_layers = Zg, Zl, Y, X, z0, n_layers
-    m.xs, m.ys, m.zs = vfe._coordinate_tables(voxelsize, Zg, Y, X)
     with torch.cuda.device(dev):
         s = _lib.stream()
         bits = empty_u32(rows * W, dev)
+        # the first kernel goes out before anything else is allocated or computed on the host
+        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
         epref = empty_u32(rows * W, dev)
         nbits = empty_u32(nrows * WN, dev)
         npref = empty_u32(nrows * WN, dev)
         ws = scan_workspace(max(rows * W, nrows * WN), dev)
         stats = torch.zeros(4, dtype=torch.int64, device=dev)
-        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
         top_bits = bits[(Zl - 1) * PW: Zl * PW]
     halo = yield from ctx.shift_up(top_bits)
     with torch.cuda.device(dev):
@@ -550,21 +550,33 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         descs_dev = bytes_to_device_async(bytes(descs), dev)
         tile_count = empty_u32(n_tiles, dev)
         tile_off = torch.empty(max(n_tiles, 1) + 1, dtype=torch.int64, device=dev)
-        bases = to_device_async([descs[q].tile_base for q in range(12)], torch.int64, dev)
         # element ids need the global offset -> counts first, ids after the all-gather
         _lib.call("cfe_sets_count", descs_dev.data_ptr(), 12, n_tiles, Zl, Y, X, z0, 0, bits.data_ptr(),
                   epref.data_ptr(), _lib.ptr(halo), tile_count.data_ptr(), s)
         _lib.call("cfe_scan_u32", tile_count.data_ptr(), n_tiles, tile_off.data_ptr(), stats.data_ptr() + 16,
                   ws.data_ptr(), s)
-        m.ftab, m.coord_vals = vfe._format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
-        tile_off[n_tiles] = stats[2]
-        first_t = tile_off[bases.clamp(max=n_tiles)]
-        count_t = torch.cat([first_t[1:], stats[2:3]]) - first_t
-        mine = torch.cat([stats[:2], count_t, stats[3:4]])   # n_el, n_nd, 12 set counts, field overflow
+        # per-axis coordinate values and their text fields (memoised: a pure function of voxel size and shape)
+        tkey = vfe._tables_key(voxelsize, Zg, Y, X, dev, s)
+        tables = vfe._TABLES.get(tkey)
+        if tables is None:
+            m.xs, m.ys, m.zs = vfe._coordinate_tables(voxelsize, Zg, Y, X)
+            m.ftab, m.coord_vals = vfe._format_tables_device(m.xs, m.ys, m.zs, dev, stats.data_ptr() + 24, s)
+        else:
+            m.xs, m.ys, m.zs, m.ftab, m.coord_vals, cached_overflow = tables
+            if cached_overflow:
+                stats[3] = 1
+        mine = torch.empty(15, dtype=torch.int64, device=dev)   # n_el, n_nd, 12 set counts, field overflow
+        _lib.call("cfe_set_counts", descs_dev.data_ptr(), 12, n_tiles, tile_off.data_ptr(), stats.data_ptr(),
+                  mine.data_ptr(), s)
     gathered = yield from ctx.all_gather(mine)
     with torch.cuda.device(dev):
         s = _lib.stream()
-        table = torch.stack(gathered).cpu().tolist()    # the one host sync: [rank][14]
+        table = read_back(torch.stack(gathered)) if len(gathered) > 1 else read_back(gathered[0])
+        table = [table[15 * k: 15 * k + 15] for k in range(len(gathered))]    # the one host sync: [rank][15]
+        if tables is None:
+            vfe._TABLES[tkey] = (m.xs, m.ys, m.zs, m.ftab, m.coord_vals, bool(table[ctx.rank][14]))
+            while len(vfe._TABLES) > 8:
+                vfe._TABLES.popitem(last=False)
         n_el_r = [t[0] for t in table]
         n_nd_r = [t[1] for t in table]
         m.n_el, m.n_nd = n_el_r[ctx.rank], n_nd_r[ctx.rank]

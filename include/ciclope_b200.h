@@ -167,6 +167,12 @@ int cfe_sets_fill(const CfeSetDesc* descs, int n_sets, int64_t n_tiles, int64_t 
                   int64_t z0, int64_t eid_offset, const uint32_t* bits, const uint32_t* pref,
                   const uint32_t* halo_below, const uint64_t* tile_off, int64_t* ids, cfe_stream_t s);
 
+/* Between cfe_sets_count (+ cfe_scan_u32 of the tile counts, total in stats[2]) and cfe_sets_fill:
+ * out = [stats[0] (n_el), stats[1] (n_nd), ids per set (n_sets values), stats[3] (field overflow)] --
+ * the vector a z-slab rank all-gathers (global ids / positions need every rank's counts). */
+int cfe_set_counts(const CfeSetDesc* descs, int n_sets, int64_t n_tiles, const uint64_t* tile_off,
+                   const uint64_t* stats, int64_t* out, cfe_stream_t s);
+
 /* Single-pass form of the two calls above (one predicate evaluation per candidate; positions by
  * decoupled look-back over the tiles).  Tiles hold cfe_sets_onepass_tile() candidates: tile_base of the
  * descriptors is counted in those units.  ids must hold sum(n_cand) entries, ws = look-back workspace for
