@@ -291,7 +291,7 @@ struct ElemEmitParams {
     const uint2* perm;       // GV-major order: {local voxel index, raster rank} (PERM = true)
     i64 n_el;
     const uint8_t* vol;      // grey values (only read when PERM)
-    const u64* first;        // [256] index (in emission order) of the first element of each GV block
+    const u64* first;        // [256] emission index of the first element with grey value >= g (n_el when none)
     const char* hdr_text;    // [256][ELEM_HDR_SLOT]
     const uint8_t* hdr_len;  // [256]; 0 = no header for this GV (e.g. slabs other than the first)
     int single_gv;           // PERM = false: the one grey value
@@ -513,11 +513,23 @@ __device__ __forceinline__ int id_digits(u64 v)
     return digits_u32((u32)v);
 }
 
+// Grey value of emission index j in GV-major order: first[g] is non-decreasing in g (absent grey values
+// carry the start of the next present one, n_el after the last), so the block of j is the largest g
+// with first[g] <= j -- eight L1-resident probes instead of a random read of the volume.
+__device__ __forceinline__ int gv_of_index(const u64* __restrict__ first, u64 j)
+{
+    int lo = 0;
+#pragma unroll
+    for (int step = 128; step > 0; step >>= 1)
+        if (__ldg(first + lo + step) <= j) lo += step;
+    return lo;
+}
+
 template <bool PERM>
 __device__ __forceinline__ void elem_ids(const ElemEmitParams& P, i64 j, u64& b, u64& eid, int& gv)
 {
     u32 v, rank;
-    if (PERM) { const uint2 e = __ldg(P.perm + j); v = e.x; rank = e.y; gv = (int)__ldg(P.vol + v); }
+    if (PERM) { const uint2 e = __ldg(P.perm + j); v = e.x; rank = e.y; gv = gv_of_index(P.first, (u64)j); }
     else { v = __ldg(P.elem_vox + j); rank = (u32)j; gv = P.single_gv; }
     const u32 s = fd_div(v, P.dYX);
     const u32 rem = v - s * P.YX32;
@@ -781,7 +793,7 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
     auto load_tile = [&](i64 t) {
         const i64 jj = t * 32 + lane;
         if (jj < P.n_el) {
-            if (PERM) { const uint2 e = __ldg(P.perm + jj); nx_v = e.x; nx_rank = e.y; nx_gv = (int)__ldg(P.vol + nx_v); }
+            if (PERM) { const uint2 e = __ldg(P.perm + jj); nx_v = e.x; nx_rank = e.y; nx_gv = gv_of_index(P.first, (u64)jj); }
             else { nx_v = __ldg(P.elem_vox + jj); nx_rank = (u32)jj; }
             nx_flags = __ldg(P.nd8 + jj);
             nx_len = (u32)__ldg(P.len8 + jj);

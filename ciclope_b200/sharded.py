@@ -668,8 +668,7 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
 
     my_hist = hist_r[rank]
     first = np.zeros(256, dtype=np.int64)
-    first[1:] = np.cumsum(my_hist)[:-1]
-    first[my_hist == 0] = -1
+    first[1:] = np.cumsum(my_hist)[:-1]   # emission index of the first element with grey value >= g
     blob = vfe._Blob()
     o_first = blob.add(first.tobytes())
     o_hdr = blob.add(bytes(256 * vfe._ELEM_HDR_SLOT))

@@ -697,8 +697,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         hdr_text[g * _ELEM_HDR_SLOT: g * _ELEM_HDR_SLOT + len(h)] = h
         hdr_len[g] = len(h)
     first = np.zeros(256, dtype=np.int64)
-    first[1:] = np.cumsum(hist)[:-1]
-    first[hist == 0] = -1        # never matches an emission index
+    first[1:] = np.cumsum(hist)[:-1]   # emission index of the first element with grey value >= g
 
     blob = _Blob()
     o_hdr = blob.add(bytes(hdr_text))

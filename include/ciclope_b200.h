@@ -226,8 +226,10 @@ int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab,
                    const char* ztab, int64_t Y, int64_t X, int64_t z0, char* out, cfe_stream_t s);
 
 /* *ELEMENT lines (voxelFE.py:639-647).  perm == NULL: raster order, one grey value
- * (single_gv); otherwise perm holds {voxel, raster rank} pairs in GV-major order and vol is
- * read for the grey value.  first[gv] = emission index of the first element of block gv;
+ * (single_gv); otherwise perm holds {voxel, raster rank} pairs in GV-major order.
+ * first[g] (256 entries, non-decreasing) = emission index of the first element whose grey value is >= g
+ * (n_el when there is none): block gv starts at first[gv] and the grey value of emission index j is the
+ * largest g with first[g] <= j, so the volume is not read again;
  * hdr_text/hdr_len = '*ELEMENT, TYPE=.., ELSET=SET<gv>\n' per gv in 64-byte slots.
  * *total = bytes written; blk_off[gv] = offset where block gv (header included) starts (optional).
  * Two entry points (three launches): cfe_element_lengths (line lengths + exclusive scan of the
