@@ -77,6 +77,8 @@ _SIGNATURES = {
     "cfe_element_lengths": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,
                                     c_i64, c_int, c_vp, c_vp, c_vp]),
     "cfe_fill_elements": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_fill_elements_gv": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                     c_vp]),
     "cfe_emit_elements": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_i64, c_i64,
                                   c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_emit_items": (c_int, [c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -87,8 +89,8 @@ _SIGNATURES = {
     "cfe_gen_emit_elements": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_gv_histogram": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "cfe_partition_tiles": (c_i64, [c_i64]),
-    "cfe_partition_hist": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
-    "cfe_partition_scatter": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_partition_hist": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_partition_scatter": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGNATURES)

@@ -1238,7 +1238,7 @@ extern "C" int64_t cfe_partition_tiles(int64_t n_el) { return (n_el + PART_TILE 
 
 __global__ void __launch_bounds__(PART_THREADS)
 k_part_hist(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox, i64 n_el, i64 n_tiles,
-            u32* __restrict__ mat)
+            u32* __restrict__ mat, const uint8_t* __restrict__ gv8)
 {
     __shared__ u32 h[256];
     h[threadIdx.x] = 0;
@@ -1249,7 +1249,7 @@ k_part_hist(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox, i
 #pragma unroll 4
     for (int t = 0; t < PART_STEPS; ++t) {
         const i64 j = w0 + t * 32 + lane;
-        if (j < n_el) atomicAdd(&h[__ldg(vol + __ldg(elem_vox + j))], 1u);
+        if (j < n_el) atomicAdd(&h[gv8 ? __ldg(gv8 + j) : __ldg(vol + __ldg(elem_vox + j))], 1u);
     }
     __syncthreads();
     mat[(i64)threadIdx.x * n_tiles + tile] = h[threadIdx.x];
@@ -1257,7 +1257,7 @@ k_part_hist(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox, i
 
 __global__ void __launch_bounds__(PART_THREADS)
 k_part_scatter(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox, i64 n_el, i64 n_tiles,
-               const u64* __restrict__ mat_off, uint2* __restrict__ perm)
+               const u64* __restrict__ mat_off, uint2* __restrict__ perm, const uint8_t* __restrict__ gv8)
 {
     __shared__ u32 wh[PART_WARPS][256];
     for (int i = threadIdx.x; i < PART_WARPS * 256; i += PART_THREADS) (&wh[0][0])[i] = 0;
@@ -1274,7 +1274,7 @@ k_part_scatter(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox
         vox[t] = 0;
         if (j < n_el) {
             vox[t] = __ldg(elem_vox + j);
-            gv[t] = (int)__ldg(vol + vox[t]);
+            gv[t] = (int)(gv8 ? __ldg(gv8 + j) : __ldg(vol + vox[t]));
             atomicAdd(&wh[warp][gv[t]], 1u);
         }
     }
@@ -1308,23 +1308,23 @@ k_part_scatter(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox
 }
 
 extern "C" int cfe_partition_hist(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, uint32_t* mat,
-                                  cudaStream_t stream)
+                                  const uint8_t* gv8, cudaStream_t stream)
 {
     const i64 n_tiles = cfe_partition_tiles(n_el);
     if (n_tiles == 0) return 0;
-    k_part_hist<<<(unsigned)n_tiles, PART_THREADS, 0, stream>>>(vol, elem_vox, n_el, n_tiles, mat);
+    k_part_hist<<<(unsigned)n_tiles, PART_THREADS, 0, stream>>>(vol, elem_vox, n_el, n_tiles, mat, gv8);
     CFE_CHECK_LAUNCH("k_part_hist");
     return 0;
 }
 
 extern "C" int cfe_partition_scatter(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el,
-                                     const uint64_t* mat_off, void* perm, cudaStream_t stream)
+                                     const uint64_t* mat_off, void* perm, const uint8_t* gv8, cudaStream_t stream)
 {
     const i64 n_tiles = cfe_partition_tiles(n_el);
     if (n_tiles == 0) return 0;
     k_part_scatter<<<(unsigned)n_tiles, PART_THREADS, 0, stream>>>(vol, elem_vox, n_el, n_tiles,
                                                                    reinterpret_cast<const u64*>(mat_off),
-                                                                   reinterpret_cast<uint2*>(perm));
+                                                                   reinterpret_cast<uint2*>(perm), gv8);
     CFE_CHECK_LAUNCH("k_part_scatter");
     return 0;
 }

@@ -383,7 +383,8 @@ __device__ __forceinline__ int nd64(u64 v) { return (v >> 32) ? digits_u64(v) : 
 __global__ void __launch_bounds__(FILLE_WORDS)
 k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_words, FastDiv d_wpr, u32 wpr,
                 u32 X, FastDiv dY, u32 Y, i64 SN, i64 RN, i64 z0, i64 eid_offset, u32* __restrict__ list,
-                uint8_t* __restrict__ len8, uint8_t* __restrict__ nd8)
+                uint8_t* __restrict__ len8, uint8_t* __restrict__ nd8, const uint8_t* __restrict__ vol,
+                uint8_t* __restrict__ gv8)
 {
     __shared__ u32 sm[FILLE_WORDS * 32];
     __shared__ uint8_t sl[FILLE_WORDS * 32];
@@ -450,9 +451,13 @@ k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 
     const u32 total = s_total;
     u32* dst = list + base0;
     for (u32 q = threadIdx.x; q < total; q += FILLE_WORDS) {
-        dst[q] = sm[q];
+        const u32 v = sm[q];
+        dst[q] = v;
         len8[base0 + q] = sl[q];
         nd8[base0 + q] = sn[q];
+        // compact grey values in element order (cell_GV, voxelFE.py:160): the CTA's voxels are a span
+        // of 128 words = 4 KB of the volume, so these byte loads hit the sectors once
+        if (gv8) gv8[base0 + q] = __ldg(vol + v);
     }
 }
 
@@ -464,6 +469,16 @@ extern "C" int cfe_fill_elements(const uint32_t* bits, const uint32_t* pref, int
                                  int64_t z0, int64_t eid_offset, int64_t n_el, uint32_t* list, void* ws,
                                  cudaStream_t stream)
 {
+    return cfe_fill_elements_gv(bits, pref, n_words, Y, X, z0, eid_offset, n_el, list, ws, nullptr, nullptr, stream);
+}
+
+// Same, and gv8[j] = vol[list[j]]: the grey value of every element in element order (vol = the slab the
+// bits were packed from).  The GV histogram and the GV-major partition then read n_el consecutive bytes
+// instead of gathering from the volume.
+extern "C" int cfe_fill_elements_gv(const uint32_t* bits, const uint32_t* pref, int64_t n_words, int64_t Y,
+                                    int64_t X, int64_t z0, int64_t eid_offset, int64_t n_el, uint32_t* list,
+                                    void* ws, const uint8_t* vol, uint8_t* gv8, cudaStream_t stream)
+{
     if (n_words <= 0 || n_el <= 0) return 0;
     if (n_words >= (1LL << 32)) { cfe_set_error("cfe_fill_elements: too many words"); return -1; }
     const u32 wpr = (u32)((X + 31) / 32);
@@ -472,7 +487,7 @@ extern "C" int cfe_fill_elements(const uint32_t* bits, const uint32_t* pref, int
     const i64 blocks = (n_words + FILLE_WORDS - 1) / FILLE_WORDS;
     k_fill_elements<<<(unsigned)blocks, FILLE_WORDS, 0, stream>>>(
         bits, pref, (u32)n_words, make_fastdiv(wpr), wpr, (u32)X, make_fastdiv((u32)Y), (u32)Y, (X + 1) * (Y + 1),
-        X + 1, z0, eid_offset, list, len8, nd8);
+        X + 1, z0, eid_offset, list, len8, nd8, vol, gv8);
     CFE_CHECK_LAUNCH("k_fill_elements");
     return 0;
 }

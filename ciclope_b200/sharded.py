@@ -751,13 +751,13 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             mat = empty_u32(256 * n_ptiles, dev)
             mat_off = torch.empty(max(256 * n_ptiles, 1), dtype=torch.int64, device=dev)
             perm = torch.empty((max(m.n_el, 1), 2), dtype=torch.int32, device=dev)
-            _lib.call("cfe_partition_hist", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, mat.data_ptr(), s)
+            _lib.call("cfe_partition_hist", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, mat.data_ptr(), None, s)
             ws_p = scan_workspace(256 * n_ptiles, dev)
             scratch = torch.empty(1, dtype=torch.int64, device=dev)
             _lib.call("cfe_scan_u32", mat.data_ptr(), 256 * n_ptiles, mat_off.data_ptr(), scratch.data_ptr(),
                       ws_p.data_ptr(), s)
             _lib.call("cfe_partition_scatter", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el,
-                      mat_off.data_ptr(), perm.data_ptr(), s)
+                      mat_off.data_ptr(), perm.data_ptr(), None, s)
             single_gv = -1
         el_args = (m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(), base + o_first, base + o_hdr,
                    base + o_hlen, single_gv if single_gv >= 0 else 0, Zl, Y, X, m.z0, m.eid_offset)

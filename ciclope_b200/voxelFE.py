@@ -204,9 +204,12 @@ class VoxelMesh:
     def _gv_array(self):
         dev = self.vol.device
         with torch.cuda.device(dev):
-            out = torch.empty(max(self.n_el, 1), dtype=torch.uint8, device=dev)
-            _lib.call("cfe_gather_gv", self.vol.data_ptr(), self.elem_vox.data_ptr(), self.n_el,
-                      out.data_ptr(), _lib.stream())
+            if getattr(self, "gv8", None) is not None:
+                out = self.gv8
+            else:
+                out = torch.empty(max(self.n_el, 1), dtype=torch.uint8, device=dev)
+                _lib.call("cfe_gather_gv", self.vol.data_ptr(), self.elem_vox.data_ptr(), self.n_el,
+                          out.data_ptr(), _lib.stream())
             a = out[: self.n_el].cpu().numpy()
         return a.view(np.bool_) if self.is_bool else a
 
@@ -417,8 +420,10 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         lib = _lib.load()
         elem_vox = empty_u32(n_el, dev)
         ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(n_el) + 16, dtype=torch.uint8, device=dev)
-        _lib.call("cfe_fill_elements", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, 0, 0, n_el,
-                  elem_vox.data_ptr(), ws_el.data_ptr(), s)
+        # grey-scale volumes: the grey value of every element, compact and in element order (cell_GV)
+        m.gv8 = None if is_bool else torch.empty(max(n_el, 1), dtype=torch.uint8, device=dev)
+        _lib.call("cfe_fill_elements_gv", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, 0, 0, n_el,
+                  elem_vox.data_ptr(), ws_el.data_ptr(), vol.data_ptr(), _lib.ptr(m.gv8), s)
         m.ws_el = ws_el
         node_list = empty_u32(n_nd, dev)
         _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
@@ -609,7 +614,8 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             hist[1] = m.n_el
         else:
             hist_dev = torch.empty(256, dtype=torch.int64, device=dev)
-            _lib.call("cfe_gv_histogram", m.vol.data_ptr(), Z * Y * X, m.thr, hist_dev.data_ptr(), s)
+            # over the n_el compact grey values (every one of them is an element: threshold -1 = all)
+            _lib.call("cfe_gv_histogram", m.gv8.data_ptr(), m.n_el, -1, hist_dev.data_ptr(), s)
             hist = np.asarray(read_back(hist_dev), dtype=np.int64)
     gvs = np.flatnonzero(hist)
     existing_GV = gvs.astype(gv_dtype)                        # np.unique(cell_GV), voxelFE.py:570
@@ -761,13 +767,14 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             mat = empty_u32(256 * n_ptiles, dev)
             mat_off = torch.empty(256 * n_ptiles, dtype=torch.int64, device=dev)
             perm = torch.empty((m.n_el, 2), dtype=torch.int32, device=dev)
-            _lib.call("cfe_partition_hist", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, mat.data_ptr(), s)
+            _lib.call("cfe_partition_hist", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, mat.data_ptr(),
+                      m.gv8.data_ptr(), s)
             ws_p = scan_workspace(256 * n_ptiles, dev)
             scratch_total = torch.empty(1, dtype=torch.int64, device=dev)
             _lib.call("cfe_scan_u32", mat.data_ptr(), 256 * n_ptiles, mat_off.data_ptr(), scratch_total.data_ptr(),
                       ws_p.data_ptr(), s)
             _lib.call("cfe_partition_scatter", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el,
-                      mat_off.data_ptr(), perm.data_ptr(), s)
+                      mat_off.data_ptr(), perm.data_ptr(), m.gv8.data_ptr(), s)
             single_gv = -1
         el_args = (m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(), base + o_first, base + o_hdr,
                    base + o_hlen, single_gv, Z, Y, X, 0, 0)

@@ -76,6 +76,11 @@ int cfe_fill_list(const uint32_t* bits, const uint32_t* pref, int64_t n_words, i
  * cfe_element_lengths(have_lengths = 1) only has to sum tile totals (raster order, same z0/eid_offset). */
 int cfe_fill_elements(const uint32_t* bits, const uint32_t* pref, int64_t n_words, int64_t Y, int64_t X,
                       int64_t z0, int64_t eid_offset, int64_t n_el, uint32_t* list, void* ws, cfe_stream_t s);
+/* same, and gv8[j] = vol[list[j]]: `cell_GV.append(GV)` of voxelFE.py:160, the grey value of every element
+ * in element order (vol = the slab the bits were packed from) */
+int cfe_fill_elements_gv(const uint32_t* bits, const uint32_t* pref, int64_t n_words, int64_t Y, int64_t X,
+                         int64_t z0, int64_t eid_offset, int64_t n_el, uint32_t* list, void* ws,
+                         const uint8_t* vol, uint8_t* gv8, cfe_stream_t s);
 
 /* generic exclusive scan of u32 counts into u64 offsets (tile counts, histograms) */
 int cfe_scan_u32(const uint32_t* in, int64_t n, uint64_t* out, uint64_t* total, void* ws, cfe_stream_t s);
@@ -288,12 +293,14 @@ int cfe_gen_emit_elements(const int64_t* cells, const int64_t* order, const int*
 /* hist256[g] = number of elements (v > thr) with grey value g: np.unique(cell_GV), voxelFE.py:570 */
 int cfe_gv_histogram(const uint8_t* vol, int64_t n_vox, int thr, uint64_t* hist256, cfe_stream_t s);
 
-/* stable partition of the element list by grey value: np.where(cell_GV == GV), voxelFE.py:645 */
+/* stable partition of the element list by grey value: np.where(cell_GV == GV), voxelFE.py:645.
+ * gv8 (optional) = grey values in element order (cfe_fill_elements_gv); without it the kernels gather
+ * vol[elem_vox[j]]. */
 int64_t cfe_partition_tiles(int64_t n_el);
 int cfe_partition_hist(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, uint32_t* mat,
-                       cfe_stream_t s); /* mat: u32 [256][tiles] */
+                       const uint8_t* gv8, cfe_stream_t s); /* mat: u32 [256][tiles] */
 int cfe_partition_scatter(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, const uint64_t* mat_off,
-                          void* perm, cfe_stream_t s); /* perm: uint2 [n_el] */
+                          void* perm, const uint8_t* gv8, cfe_stream_t s); /* perm: uint2 [n_el] */
 
 #ifdef __cplusplus
 }
