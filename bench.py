@@ -320,7 +320,7 @@ def run_gpu(args, rank, world, local_rank):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    # dominant kernel: k_emit_elements (entry point cfe_emit_elements = that one launch).  Algorithmic
+    # dominant kernel: k_emit_elements2 (entry point cfe_emit_elements = that one launch).  Algorithmic
     # bytes per launch = element-section bytes written + 6 B/element read (voxel index, line length,
     # digit flags) -- DESIGN.md section 4.
     elem_bytes = deck_bytes - 53 * n_nd   # everything but the *NODE lines is element lines + O(N^2) text
@@ -332,10 +332,10 @@ def run_gpu(args, rank, world, local_rank):
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         if tr.get("size") == S:
-            traffic = tr.get("k_emit_elements")
+            traffic = tr.get("k_emit_elements2")
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "kernel": "k_emit_elements (entry point cfe_emit_elements, one launch per deck)",
+    roofline = {"bound": "hbm", "kernel": "k_emit_elements2 (entry point cfe_emit_elements, one launch per deck)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom_for_roofline],
                 "ms_per_launch": stage_ms[dom_for_roofline], "dominant_entry_point": dom,

@@ -9,7 +9,8 @@ import os
 import torch  # noqa: F401  (loads libcudart before our library; provides device memory)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libciclope_b200.so")
+# CICLOPE_B200_LIB: alternative build of the same library (kernel tuning experiments, profiles/tools)
+LIB_PATH = os.environ.get("CICLOPE_B200_LIB") or os.path.join(_HERE, "libciclope_b200.so")
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

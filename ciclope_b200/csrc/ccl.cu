@@ -64,8 +64,12 @@ k_ccl_init(u32* __restrict__ parent, u32* __restrict__ size, const u64* __restri
 // per maximal run of (cur & neighbour) bits, i.e. once per pair of overlapping runs.
 // With tile_flag != NULL the pairs that lie inside one (CCL_TS slices x CCL_TR rows) tile were
 // already merged in shared memory by k_ccl_local (flag 1); only tile-border pairs remain.
+#ifndef CCL_TR
 #define CCL_TR 32
+#endif
+#ifndef CCL_TS
 #define CCL_TS 8
+#endif
 #define CCL_TILE_ROWS (CCL_TR * CCL_TS)
 #define CCL_LOCAL_CAP 8192
 
