@@ -214,6 +214,32 @@ def make_sharded_steps(runner, Zg, z0):
     return step, step_e2e
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function), so that
+    the pinned host buffers of the end-to-end leg are allocated on that NUMA node: with 8 ranks copying
+    6 GB decks at once, cross-socket pinned memory is what limits the aggregate D2H rate.  Best effort."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dv = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, dv)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%s (%d cpus)" % (path.split("/")[-2], len(cpus))
+    except Exception as e:  # noqa: BLE001 -- affinity is an optimisation, never a failure
+        return "unbound (%s)" % type(e).__name__
+    return "unbound"
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -222,6 +248,9 @@ def run_gpu(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "not bound (1 GPU)"
+    if rank == 0:
+        sys.stderr.write("[bench] host affinity: %s\n" % numa)
     lib = _lib.require_cuda()
     S = args.size
     global gpu_step, gpu_step_e2e
