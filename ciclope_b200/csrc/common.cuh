@@ -36,6 +36,27 @@ void cfe_count_launch();
         }                                                                             \
     } while (0)
 
+// Function attributes (opt-in dynamic shared memory) are per device: true the first time it is
+// evaluated on the current device for this `mask` (one static mask per launch site; devices 0..63).
+static inline bool cfe_first_on_device(unsigned long long* mask, int* sm_count = nullptr)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (sm_count) {
+        static int sms[64];
+        if (!sms[dev & 63]) {
+            int n = 0;
+            if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+            sms[dev & 63] = n;
+        }
+        *sm_count = sms[dev & 63];
+    }
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // Decoupled look-back.  status[tile] packs a 2-bit flag and a 62-bit value in ONE 64-bit word,
 // so a single volatile store publishes both (no fence needed between flag and value).

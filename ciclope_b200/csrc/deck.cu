@@ -1008,11 +1008,9 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
     elem_params(P, elem_vox, perm, n_el, vol, first, hdr_text, hdr_len, single_gv, Y, X, z0, eid_offset, out,
                 blk_off, ws, &scan_ws);
     const bool wide = elem_wide(P, Zl);
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        CFE_CHECK_CUDA(cudaGetDevice(&dev));
-        CFE_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    static unsigned long long attr_done = 0;
+    int sms = 148;
+    if (cfe_first_on_device(&attr_done, &sms)) {
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
@@ -1124,11 +1122,10 @@ extern "C" int cfe_emit_items(const CfeItemSeg* segs_dev, int n_segs, int64_t n_
     CFE_CHECK_CUDA(cudaMemsetAsync(ws, 0, (size_t)(tiles + 2) * sizeof(u64), stream));
     CFE_CHECK_CUDA(cudaMemsetAsync(total, 0, sizeof(u64), stream));
     if (tiles == 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0;
+    if (cfe_first_on_device(&attr_done)) {
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_items, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             ITEM_STAGE_BYTES));
-        attr_set = true;
     }
     k_emit_items<<<(unsigned)tiles, EMIT_THREADS, ITEM_STAGE_BYTES, stream>>>(
         segs_dev, n_segs, n_items, reinterpret_cast<const i64*>(ids), literals, out_base,
@@ -1556,10 +1553,9 @@ extern "C" int cfe_emit_nodes_wide(const uint32_t* node_list, int64_t n_nodes, c
     NodeWideParams P;
     node_wide_params(P, node_list, n_nodes, xtab32, ytab32, ztab32, Y, X, z0, const_cast<uint8_t*>(len8), nullptr,
                      tile_off, out);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0;
+    if (cfe_first_on_device(&attr_done)) {
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_nodes_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, NODEW_STAGE));
-        attr_set = true;
     }
     k_emit_nodes_wide<<<(unsigned)((n_nodes + 255) / 256), 256, NODEW_STAGE, stream>>>(P);
     CFE_CHECK_LAUNCH("k_emit_nodes_wide");
@@ -1645,10 +1641,9 @@ extern "C" int cfe_gen_emit_nodes(const int64_t* ids, int64_t n, const char* slo
     if (n <= 0) return 0;
     GenNodeParams P = {reinterpret_cast<const i64*>(ids), n, slots, const_cast<uint8_t*>(len8), nullptr,
                        reinterpret_cast<const u64*>(tile_off), out};
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0;
+    if (cfe_first_on_device(&attr_done)) {
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_nodes_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, NODEW_STAGE));
-        attr_set = true;
     }
     k_emit_nodes_gen<<<(unsigned)((n + 255) / 256), 256, NODEW_STAGE, stream>>>(P);
     CFE_CHECK_LAUNCH("k_emit_nodes_gen");
@@ -1746,10 +1741,9 @@ extern "C" int cfe_gen_emit_elements(const int64_t* cells, const int64_t* order,
     GenElemParams P = {reinterpret_cast<const i64*>(cells), reinterpret_cast<const i64*>(order), group,
                        reinterpret_cast<const i64*>(gfirst), hdr_off, hdr_len, lit, n,
                        const_cast<unsigned short*>(len16), nullptr, reinterpret_cast<const u64*>(tile_off), out};
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_done = 0;
+    if (cfe_first_on_device(&attr_done)) {
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, GEN_ELEM_STAGE));
-        attr_set = true;
     }
     k_emit_elements_gen<<<(unsigned)((n + 255) / 256), 256, GEN_ELEM_STAGE, stream>>>(P);
     CFE_CHECK_LAUNCH("k_emit_elements_gen");
