@@ -585,11 +585,23 @@ __global__ void __launch_bounds__(256) k_tile_totals(ElemEmitParams P)
         } else {
             for (i64 j = j0; j < P.n_el; ++j) sum += P.len8[j];
         }
-        const u64 f = __ldg(P.first + P.single_gv);
-        if (f >= (u64)j0 && f < (u64)(j0 + 16)) sum += __ldg(P.hdr_len + P.single_gv);
+        if (!P.perm) {
+            const u64 f = __ldg(P.first + P.single_gv);
+            if (f >= (u64)j0 && f < (u64)(j0 + 16)) sum += __ldg(P.hdr_len + P.single_gv);
+        }
     }
     const u32 other = __shfl_xor_sync(CFE_FULL_MASK, sum, 1);
     if (!(threadIdx.x & 1) && (t >> 1) < P.n_warp_tiles) P.warp_total[t >> 1] = sum + other;
+}
+
+// GV-major order: the '*ELEMENT ...' header of every present grey value joins the tile of its first element
+__global__ void __launch_bounds__(256) k_tile_headers(ElemEmitParams P)
+{
+    const int g = threadIdx.x;
+    const u64 f = __ldg(P.first + g);
+    const u64 nxt = (g < 255) ? __ldg(P.first + g + 1) : (u64)P.n_el;
+    const u32 h = __ldg(P.hdr_len + g);
+    if (h && f < nxt && f < (u64)P.n_el) atomicAdd(P.warp_total + (f >> 5), h);
 }
 
 #define ELEM_WARP_STAGE 3584     // bytes of staging per warp: 32 lines of <= 99 bytes + headers + pad
@@ -790,17 +802,31 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
     u32 nx_v = 0, nx_rank = 0, nx_flags = 0, nx_len = 0;
     int nx_gv = P.single_gv;
     u64 nx_base = 0;
+    // GV-major order: grey value block of the warp's current tile start.  A warp visits its tiles in
+    // ascending order, so the block only moves forward: one (warp-uniform) probe per tile instead of a
+    // search per line; lanes look further only in the rare tile that contains a block boundary.
+    int g_tile = 0;
     auto load_tile = [&](i64 t) {
         const i64 jj = t * 32 + lane;
+        if (PERM) {
+            const u64 j0 = (u64)t * 32u;
+            while (g_tile < 255 && __ldg(P.first + g_tile + 1) <= j0) ++g_tile;
+            nx_gv = g_tile;
+            if (g_tile < 255 && __ldg(P.first + g_tile + 1) <= j0 + 31u)
+                while (nx_gv < 255 && __ldg(P.first + nx_gv + 1) <= (u64)jj) ++nx_gv;
+        }
         if (jj < P.n_el) {
-            if (PERM) { const uint2 e = __ldg(P.perm + jj); nx_v = e.x; nx_rank = e.y; nx_gv = gv_of_index(P.first, (u64)jj); }
+            if (PERM) { const uint2 e = __ldg(P.perm + jj); nx_v = e.x; nx_rank = e.y; }
             else { nx_v = __ldg(P.elem_vox + jj); nx_rank = (u32)jj; }
             nx_flags = __ldg(P.nd8 + jj);
             nx_len = (u32)__ldg(P.len8 + jj);
         }
         nx_base = __ldg(P.warp_off + t);
     };
-    if (wt < P.n_warp_tiles) load_tile(wt);
+    if (wt < P.n_warp_tiles) {
+        if (PERM) g_tile = gv_of_index(P.first, (u64)wt * 32u);
+        load_tile(wt);
+    }
     for (; wt < P.n_warp_tiles; wt += stride) {
         const i64 j = wt * 32 + lane;
         const bool active = j < P.n_el;
@@ -978,10 +1004,15 @@ extern "C" int cfe_element_lengths(const uint32_t* elem_vox, const void* perm, i
                 nullptr, ws, &scan_ws);
     const bool wide = elem_wide(P, Zl);
     const unsigned g1 = (unsigned)((n_el + 255) / 256);
-    if (have_lengths && !perm) {
-        // len8 / nd8 were written by cfe_fill_elements (same z0 / eid_offset): only the tile totals
+    if (have_lengths) {
+        // len8 / nd8 were written by cfe_fill_elements (same z0 / eid_offset) and, for GV-major order,
+        // permuted by cfe_gv_partition: only the tile totals
         k_tile_totals<<<(unsigned)(((n_el + 15) / 16 + 255) / 256), 256, 0, stream>>>(P);
         CFE_CHECK_LAUNCH("k_tile_totals");
+        if (perm) {
+            k_tile_headers<<<1, 256, 0, stream>>>(P);
+            CFE_CHECK_LAUNCH("k_tile_headers");
+        }
     } else {
         if (perm) {
             if (wide) k_elem_lengths<true, true><<<g1, 256, 0, stream>>>(P);
@@ -1221,107 +1252,241 @@ extern "C" int cfe_gv_histogram(const uint8_t* vol, int64_t n_vox, int thr, uint
 }
 
 // ------------------------------------------------------------------------------------------
-// Stable partition of the raster-ordered element list by grey value (one 8-bit radix pass):
-//   pass 1: per-tile 256-bin histogram, stored bin-major  mat[gv][tile]
-//   flat exclusive scan of mat (cfe_scan_u32_inplace)  -> destination of (gv, tile)
-//   pass 2: per-tile stable ranking (warp match.any) and scatter of {voxel, raster rank}.
+// Stable partition of the raster-ordered element list by grey value (np.where(cell_GV == GV),
+// voxelFE.py:645): one 8-bit radix pass.
+//   k_part_hist     per-tile 256-bin histogram, TILE-major  mat[tile][gv] (coalesced), and the sums of
+//                   every chunk of 256 tiles by atomics  chunk[c][gv]
+//   k_part_chunks   one CTA: exclusive scan of the chunk sums per grey value, bin totals -> bin starts
+//   k_part_offsets  per chunk: mat[tile][gv] <- destination of the first element of (gv, tile)
+//   k_part_scatter  the tile is ranked stably in shared memory (warp match.any + per-warp cursors) and
+//                   leaves in GV-major order, so consecutive threads write consecutive destinations;
+//                   the raster-order line lengths (cfe_fill_elements) travel with the elements.
 
 #define PART_THREADS 256
 #define PART_WARPS 8
 #define PART_STEPS 16
 #define PART_TILE (PART_THREADS * PART_STEPS)   // 4096 elements per CTA
+#define PART_CHUNK 256                          // tiles per chunk
 
-extern "C" int64_t cfe_partition_tiles(int64_t n_el) { return (n_el + PART_TILE - 1) / PART_TILE; }
+static inline i64 part_tiles(i64 n_el) { return (n_el + PART_TILE - 1) / PART_TILE; }
+static inline i64 part_chunks(i64 n_el) { return (part_tiles(n_el) + PART_CHUNK - 1) / PART_CHUNK; }
 
-__global__ void __launch_bounds__(PART_THREADS)
-k_part_hist(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox, i64 n_el, i64 n_tiles,
-            u32* __restrict__ mat, const uint8_t* __restrict__ gv8)
+extern "C" size_t cfe_gv_partition_workspace_bytes(int64_t n_el)
 {
-    __shared__ u32 h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const i64 tile = blockIdx.x;
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const i64 w0 = tile * PART_TILE + (i64)warp * (PART_STEPS * 32);
-#pragma unroll 4
-    for (int t = 0; t < PART_STEPS; ++t) {
-        const i64 j = w0 + t * 32 + lane;
-        if (j < n_el) atomicAdd(&h[gv8 ? __ldg(gv8 + j) : __ldg(vol + __ldg(elem_vox + j))], 1u);
+    if (n_el <= 0) return 64;
+    return ((size_t)part_tiles(n_el) + (size_t)part_chunks(n_el) + 1) * 256 * sizeof(u32) + 64;
+}
+
+// 16 consecutive bytes per thread into shared memory (one 16-byte load when possible)
+__device__ __forceinline__ void part_stage_bytes(const uint8_t* __restrict__ src, i64 tile0, u32 nval,
+                                                 uint8_t* __restrict__ dst)
+{
+    const u32 o = threadIdx.x * 16u;
+    const uint8_t* p = src + tile0 + o;
+    if (o + 16u <= nval && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+        *reinterpret_cast<uint4*>(dst + o) = __ldg(reinterpret_cast<const uint4*>(p));
+    } else {
+        for (u32 k = 0; k < 16u && o + k < nval; ++k) dst[o + k] = __ldg(p + k);
     }
-    __syncthreads();
-    mat[(i64)threadIdx.x * n_tiles + tile] = h[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(PART_THREADS)
-k_part_scatter(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox, i64 n_el, i64 n_tiles,
-               const u64* __restrict__ mat_off, uint2* __restrict__ perm, const uint8_t* __restrict__ gv8)
+k_part_hist(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox, i64 n_el,
+            u32* __restrict__ mat, u32* __restrict__ chunk, const uint8_t* __restrict__ gv8)
 {
+    __shared__ u32 h[256];
+    __shared__ __align__(16) uint8_t g[PART_TILE];
+    h[threadIdx.x] = 0;
+    const i64 tile = blockIdx.x;
+    const i64 tile0 = tile * PART_TILE;
+    const u32 nval = (u32)((n_el - tile0 < PART_TILE) ? (n_el - tile0) : PART_TILE);
+    const u32 o = threadIdx.x * 16u;
+    if (gv8) {
+        part_stage_bytes(gv8, tile0, nval, g);
+    } else {
+        for (u32 k = 0; k < 16u && o + k < nval; ++k) g[o + k] = __ldg(vol + __ldg(elem_vox + tile0 + o + k));
+    }
+    __syncthreads();
+    // runs of equal grey values (smooth fields) are added once
+    int prev = -1;
+    u32 run = 0;
+    for (u32 k = 0; k < 16u && o + k < nval; ++k) {
+        const int b = g[o + k];
+        if (b == prev) { ++run; continue; }
+        if (run) atomicAdd(&h[prev], run);
+        prev = b;
+        run = 1;
+    }
+    if (run) atomicAdd(&h[prev], run);
+    __syncthreads();
+    const u32 c = h[threadIdx.x];
+    mat[tile * 256 + threadIdx.x] = c;
+    if (c) atomicAdd(chunk + (tile / PART_CHUNK) * 256 + threadIdx.x, c);
+}
+
+// chunk[c][g] <- number of elements with grey value g in the chunks before c; binbase[g] <- number of
+// elements with a smaller grey value
+__global__ void __launch_bounds__(256) k_part_chunks(u32* __restrict__ chunk, i64 n_chunks, u32* __restrict__ binbase)
+{
+    __shared__ u32 sc[33];
+    const u32 g = threadIdx.x;
+    u32 run = 0;
+#pragma unroll 8
+    for (i64 c = 0; c < n_chunks; ++c) {
+        const u32 v = chunk[c * 256 + g];
+        chunk[c * 256 + g] = run;
+        run += v;
+    }
+    u32 total;
+    binbase[g] = block_exclusive_scan<u32>(run, sc, total);
+}
+
+__global__ void __launch_bounds__(256)
+k_part_offsets(u32* __restrict__ mat, const u32* __restrict__ chunk, const u32* __restrict__ binbase, i64 n_tiles)
+{
+    const u32 g = threadIdx.x;
+    const i64 c = blockIdx.x;
+    u32 run = chunk[c * 256 + g] + binbase[g];
+    const i64 t0 = c * PART_CHUNK;
+    const i64 t1 = (t0 + PART_CHUNK < n_tiles) ? t0 + PART_CHUNK : n_tiles;
+#pragma unroll 8
+    for (i64 t = t0; t < t1; ++t) {
+        const u32 v = mat[t * 256 + g];
+        mat[t * 256 + g] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(PART_THREADS, 4)
+k_part_scatter(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox, i64 n_el,
+               const u32* __restrict__ mat_off, uint2* __restrict__ perm, const uint8_t* __restrict__ gv8,
+               const uint8_t* __restrict__ len_src, const uint8_t* __restrict__ nd_src,
+               uint8_t* __restrict__ len_dst, uint8_t* __restrict__ nd_dst)
+{
+    __shared__ __align__(16) u32 voxin[PART_TILE];
     __shared__ u32 wh[PART_WARPS][256];
+    __shared__ u32 gbase[256];
+    __shared__ u32 sc[33];
+    __shared__ unsigned short jl[PART_TILE];
+    __shared__ __align__(16) uint8_t gvin[PART_TILE];
+    __shared__ __align__(16) uint8_t lenin[PART_TILE];
+    __shared__ __align__(16) uint8_t ndin[PART_TILE];
+
+    const i64 tile = blockIdx.x;
+    const i64 tile0 = tile * PART_TILE;
+    const u32 nval = (u32)((n_el - tile0 < PART_TILE) ? (n_el - tile0) : PART_TILE);
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const u32 my_off = __ldg(mat_off + tile * 256 + threadIdx.x);   // destination of (gv = thread, this tile)
+
+    // ---- stage the tile (16 consecutive elements per thread)
+    {
+        const u32 o = threadIdx.x * 16u;
+        const u32* p = elem_vox + tile0 + o;
+        if (o + 16u <= nval && (reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(voxin + o + 4 * q) = __ldg(reinterpret_cast<const uint4*>(p) + q);
+        } else {
+            for (u32 k = 0; k < 16u && o + k < nval; ++k) voxin[o + k] = __ldg(p + k);
+        }
+        if (gv8) {
+            part_stage_bytes(gv8, tile0, nval, gvin);
+        } else {
+            for (u32 k = 0; k < 16u && o + k < nval; ++k) gvin[o + k] = __ldg(vol + voxin[o + k]);
+        }
+        if (len_src) {
+            part_stage_bytes(len_src, tile0, nval, lenin);
+            part_stage_bytes(nd_src, tile0, nval, ndin);
+        }
+    }
     for (int i = threadIdx.x; i < PART_WARPS * 256; i += PART_THREADS) (&wh[0][0])[i] = 0;
     __syncthreads();
-    const i64 tile = blockIdx.x;
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const i64 w0 = tile * PART_TILE + (i64)warp * (PART_STEPS * 32);
-    u32 vox[PART_STEPS];
+
+    // ---- per-warp counts; warp w owns the 512 consecutive elements [512 w, 512 w + 512), step t its
+    // elements 32 t .. 32 t + 31, so (warp, step, lane) order is raster order
     int gv[PART_STEPS];
+    u32 peers[PART_STEPS];
 #pragma unroll
     for (int t = 0; t < PART_STEPS; ++t) {
-        const i64 j = w0 + t * 32 + lane;
-        gv[t] = -1;
-        vox[t] = 0;
-        if (j < n_el) {
-            vox[t] = __ldg(elem_vox + j);
-            gv[t] = (int)(gv8 ? __ldg(gv8 + j) : __ldg(vol + vox[t]));
-            atomicAdd(&wh[warp][gv[t]], 1u);
-        }
+        const u32 idx = warp * (PART_STEPS * 32) + t * 32 + lane;
+        gv[t] = (idx < nval) ? (int)gvin[idx] : 256;
+        peers[t] = __match_any_sync(CFE_FULL_MASK, gv[t]);
+        if (gv[t] < 256 && (peers[t] & ((1u << lane) - 1u)) == 0) atomicAdd(&wh[warp][gv[t]], (u32)__popc(peers[t]));
     }
     __syncthreads();
     {
-        // thread g turns the per-warp counts of bin g into per-warp destination cursors
+        // thread g: bin total -> start of bin g in the sorted tile -> per-warp cursors
         const int g = threadIdx.x;
-        u64 run = mat_off[(i64)g * n_tiles + tile];
+        u32 tot = 0;
+#pragma unroll
+        for (int w = 0; w < PART_WARPS; ++w) tot += wh[w][g];
+        u32 total;
+        const u32 start = block_exclusive_scan<u32>(tot, sc, total);
+        u32 run = start;
 #pragma unroll
         for (int w = 0; w < PART_WARPS; ++w) {
             const u32 c = wh[w][g];
-            wh[w][g] = (u32)run;  // destinations are < n_el < 2^32
+            wh[w][g] = run;
             run += c;
         }
+        gbase[g] = my_off - start;      // destination of sorted position i with grey value g = gbase[g] + i (mod 2^32)
     }
     __syncthreads();
 #pragma unroll
     for (int t = 0; t < PART_STEPS; ++t) {
-        const i64 j = w0 + t * 32 + lane;
-        const u32 peers = __match_any_sync(CFE_FULL_MASK, gv[t]);
+        const u32 idx = warp * (PART_STEPS * 32) + t * 32 + lane;
         u32 base = 0;
-        if (gv[t] >= 0) base = wh[warp][gv[t]];
-        __syncwarp();
-        if (gv[t] >= 0) {
-            const u32 rank = (u32)__popc(peers & ((1u << lane) - 1u));
-            if (rank == 0) wh[warp][gv[t]] = base + (u32)__popc(peers);
-            perm[base + rank] = make_uint2(vox[t], (u32)j);
+        if (gv[t] < 256) base = wh[warp][gv[t]];
+        __syncwarp();                       // every peer has read the cursor before its leader advances it
+        if (gv[t] < 256) {
+            const u32 rank = (u32)__popc(peers[t] & ((1u << lane) - 1u));
+            jl[base + rank] = (unsigned short)idx;
+            if (rank == 0) wh[warp][gv[t]] = base + (u32)__popc(peers[t]);
         }
         __syncwarp();
     }
+    __syncthreads();
+    // ---- the sorted tile leaves: runs of equal grey value go to consecutive destinations
+#pragma unroll 4
+    for (u32 i = threadIdx.x; i < nval; i += PART_THREADS) {
+        const u32 j = jl[i];
+        const u32 d = gbase[gvin[j]] + i;
+        perm[d] = make_uint2(voxin[j], (u32)(tile0 + j));
+        if (len_src) {
+            len_dst[d] = lenin[j];
+            nd_dst[d] = ndin[j];
+        }
+    }
 }
 
-extern "C" int cfe_partition_hist(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, uint32_t* mat,
-                                  const uint8_t* gv8, cudaStream_t stream)
+// perm[k] = {local voxel index, raster rank} of the k-th element in GV-major order.  gv8 (optional): grey
+// values in element order (cfe_fill_elements_gv); without it the kernels gather vol[elem_vox[j]].
+// ws_src / ws_dst (optional, both or neither): element workspaces; the line lengths that cfe_fill_elements
+// left in ws_src (raster order) are written to ws_dst in GV-major order, which is what
+// cfe_element_lengths(perm, have_lengths = 1) and cfe_emit_elements(perm) then read.
+extern "C" int cfe_gv_partition(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, const uint8_t* gv8,
+                                const void* ws_src, void* ws_dst, void* perm, void* ws_part, cudaStream_t stream)
 {
-    const i64 n_tiles = cfe_partition_tiles(n_el);
-    if (n_tiles == 0) return 0;
-    k_part_hist<<<(unsigned)n_tiles, PART_THREADS, 0, stream>>>(vol, elem_vox, n_el, n_tiles, mat, gv8);
+    if (n_el <= 0) return 0;
+    if (n_el >= (1LL << 32)) { cfe_set_error("cfe_gv_partition: too many elements"); return -1; }
+    if ((ws_src == nullptr) != (ws_dst == nullptr)) { cfe_set_error("cfe_gv_partition: ws_src and ws_dst go together"); return -1; }
+    const i64 n_tiles = part_tiles(n_el), n_chunks = part_chunks(n_el);
+    u32* mat = reinterpret_cast<u32*>(ws_part);
+    u32* chunk = mat + n_tiles * 256;
+    u32* binbase = chunk + n_chunks * 256;
+    const size_t a = ((size_t)n_el + 15) & ~(size_t)15;      // layout of the element workspace (elem_params)
+    const uint8_t* len_src = reinterpret_cast<const uint8_t*>(ws_src);
+    uint8_t* len_dst = reinterpret_cast<uint8_t*>(ws_dst);
+    CFE_CHECK_CUDA(cudaMemsetAsync(chunk, 0, (size_t)n_chunks * 256 * sizeof(u32), stream));
+    k_part_hist<<<(unsigned)n_tiles, PART_THREADS, 0, stream>>>(vol, elem_vox, n_el, mat, chunk, gv8);
     CFE_CHECK_LAUNCH("k_part_hist");
-    return 0;
-}
-
-extern "C" int cfe_partition_scatter(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el,
-                                     const uint64_t* mat_off, void* perm, const uint8_t* gv8, cudaStream_t stream)
-{
-    const i64 n_tiles = cfe_partition_tiles(n_el);
-    if (n_tiles == 0) return 0;
-    k_part_scatter<<<(unsigned)n_tiles, PART_THREADS, 0, stream>>>(vol, elem_vox, n_el, n_tiles,
-                                                                   reinterpret_cast<const u64*>(mat_off),
-                                                                   reinterpret_cast<uint2*>(perm), gv8);
+    k_part_chunks<<<1, 256, 0, stream>>>(chunk, n_chunks, binbase);
+    CFE_CHECK_LAUNCH("k_part_chunks");
+    k_part_offsets<<<(unsigned)n_chunks, 256, 0, stream>>>(mat, chunk, binbase, n_tiles);
+    CFE_CHECK_LAUNCH("k_part_offsets");
+    k_part_scatter<<<(unsigned)n_tiles, PART_THREADS, 0, stream>>>(
+        vol, elem_vox, n_el, mat, reinterpret_cast<uint2*>(perm), gv8, len_src, len_src ? len_src + a : nullptr,
+        len_dst, len_dst ? len_dst + a : nullptr);
     CFE_CHECK_LAUNCH("k_part_scatter");
     return 0;
 }

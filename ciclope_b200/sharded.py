@@ -595,8 +595,10 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         m.set_ids = torch.empty(max(n_ids, 1), dtype=torch.int64, device=dev)
         lib = _lib.load()
         m.ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(m.n_el) + 16, dtype=torch.uint8, device=dev)
-        _lib.call("cfe_fill_elements", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, z0, m.eid_offset, m.n_el,
-                  m.elem_vox.data_ptr(), m.ws_el.data_ptr(), s)
+        # grey-scale slabs: cell_GV compacted in element order (the GV histogram and partition read it)
+        m.gv8 = None if is_bool else torch.empty(max(m.n_el, 1), dtype=torch.uint8, device=dev)
+        _lib.call("cfe_fill_elements_gv", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, z0, m.eid_offset,
+                  m.n_el, m.elem_vox.data_ptr(), m.ws_el.data_ptr(), vol.data_ptr(), _lib.ptr(m.gv8), s)
         _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
                   m.node_list.data_ptr(), s)
         _lib.call("cfe_sets_fill", descs_dev.data_ptr(), 12, n_tiles, Zl, Y, X, z0, m.eid_offset, bits.data_ptr(),
@@ -637,7 +639,8 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         with torch.cuda.device(dev):
             s = _lib.stream()
             hist_dev = torch.zeros(256, dtype=torch.int64, device=dev)
-            _lib.call("cfe_gv_histogram", m.vol.data_ptr(), Zl * Y * X, m.thr, hist_dev.data_ptr(), s)
+            # over the compact grey values of the slab's elements (every one counts: threshold -1)
+            _lib.call("cfe_gv_histogram", m.gv8.data_ptr(), m.n_el, -1, hist_dev.data_ptr(), s)
         hists = yield from ctx.all_gather(hist_dev)
         hist_r = torch.stack(hists).cpu().numpy()        # [rank][256]
     hist = hist_r.sum(axis=0)
@@ -747,22 +750,15 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         perm = None
         single_gv = int(gvs[0])
         if len(gvs) > 1:
-            n_ptiles = lib.cfe_partition_tiles(m.n_el)
-            mat = empty_u32(256 * n_ptiles, dev)
-            mat_off = torch.empty(max(256 * n_ptiles, 1), dtype=torch.int64, device=dev)
             perm = torch.empty((max(m.n_el, 1), 2), dtype=torch.int32, device=dev)
-            _lib.call("cfe_partition_hist", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, mat.data_ptr(), None, s)
-            ws_p = scan_workspace(256 * n_ptiles, dev)
-            scratch = torch.empty(1, dtype=torch.int64, device=dev)
-            _lib.call("cfe_scan_u32", mat.data_ptr(), 256 * n_ptiles, mat_off.data_ptr(), scratch.data_ptr(),
-                      ws_p.data_ptr(), s)
-            _lib.call("cfe_partition_scatter", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el,
-                      mat_off.data_ptr(), perm.data_ptr(), None, s)
+            ws_el = torch.empty(m.ws_el.numel(), dtype=torch.uint8, device=dev)
+            ws_p = torch.empty(lib.cfe_gv_partition_workspace_bytes(m.n_el), dtype=torch.uint8, device=dev)
+            _lib.call("cfe_gv_partition", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, _lib.ptr(m.gv8),
+                      m.ws_el.data_ptr(), ws_el.data_ptr(), perm.data_ptr(), ws_p.data_ptr(), s)
             single_gv = -1
         el_args = (m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(), base + o_first, base + o_hdr,
                    base + o_hlen, single_gv if single_gv >= 0 else 0, Zl, Y, X, m.z0, m.eid_offset)
-        _lib.call("cfe_element_lengths", *el_args, 0 if perm is not None else 1, totals.data_ptr(),
-                  ws_el.data_ptr(), s)
+        _lib.call("cfe_element_lengths", *el_args, 1, totals.data_ptr(), ws_el.data_ptr(), s)
         _lib.call("cfe_emit_elements", *el_args, elem_buf.data_ptr(), blk_off.data_ptr(), ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base, items_buf.data_ptr(),
                   None, totals.data_ptr() + 8, seg_off.data_ptr(), ws.data_ptr(), s)

@@ -508,29 +508,62 @@ def _read_lines(path):
     return list(hit)
 
 
+_CARD_CACHE = {}
+
+
+def _file_key(fname):
+    st = os.stat(fname)
+    return (os.path.abspath(fname), st.st_mtime_ns, st.st_size)
+
+
+def _card_for_gv(fname, fkey, GV):  # noqa: N803 -- the cards' expressions name this variable
+    """The property card of one grey value (voxelFE.py:716-746).  The text is a function of the card file
+    and of the NumPy scalar GV (value and dtype) only, so it is kept per (file, dtype, value)."""
+    key = (fkey, type(GV), repr(GV))
+    hit = _CARD_CACHE.get(key)
+    if hit is not None:
+        return hit
+    parts = []
+    setname = 'SET' + str(GV)
+    scope = {"GV": GV, "np": np}
+    for line in _read_lines(fname):
+        line = line.replace('\n', '')
+        if line.startswith('**'):
+            parts.append(line + '\n')
+            continue
+        line = line.replace('SetName', setname).replace('MatName', 'MAT' + setname)
+        if 'GV' in line:
+            fields = ['{}'.format(eval(f, scope)) if 'GV' in f else f for f in line.split(',')]   # voxelFE.py:734
+            parts.append(','.join(fields) + '\n')
+        else:
+            parts.append(line + '\n')
+    hit = ''.join(parts)
+    if len(_CARD_CACHE) > 4096:
+        _CARD_CACHE.clear()
+    _CARD_CACHE[key] = hit
+    return hit
+
+
 def _property_cards(matprop, prop_GV, existing_GV):
-    """PROPERTY section (voxelFE.py:691-746): O(#GV) lines of host string work."""
+    """PROPERTY section (voxelFE.py:691-746): O(#GV) lines of host string work (eval of the card
+    expressions on NumPy scalars, as the reference does), memoised per card and per whole section: a deck
+    with 255 material sets costs one dictionary look-up when the same cards were printed before."""
+    fkeys = [_file_key(f) for f in matprop["file"]]
+    ex = np.asarray(existing_GV)
+    skey = (tuple(fkeys), tuple(sorted(prop_GV.items())), ex.dtype.str, ex.tobytes())
+    hit = _CARD_CACHE.get(skey)
+    if hit is not None:
+        return hit
     parts = ['** User material property definition:\n',
              '** internal variables are: "SetName", "MatName", "GV"\n']
     for n, fname in enumerate(matprop["file"]):
-        card = _read_lines(fname)
-        for GV in existing_GV:  # noqa: N806 -- the cards' expressions name this variable
-            if not (prop_GV[n][0] <= GV <= prop_GV[n][1]):
-                continue
-            setname = 'SET' + str(GV)
-            scope = {"GV": GV, "np": np}
-            for line in card:
-                line = line.replace('\n', '')
-                if line.startswith('**'):
-                    parts.append(line + '\n')
-                    continue
-                line = line.replace('SetName', setname).replace('MatName', 'MAT' + setname)
-                if 'GV' in line:
-                    fields = ['{}'.format(eval(f, scope)) if 'GV' in f else f for f in line.split(',')]   # voxelFE.py:734
-                    parts.append(','.join(fields) + '\n')
-                else:
-                    parts.append(line + '\n')
-    return ''.join(parts)
+        lo, hi = prop_GV[n]
+        for GV in existing_GV:  # noqa: N806
+            if lo <= GV <= hi:
+                parts.append(_card_for_gv(fname, fkeys[n], GV))
+    hit = ''.join(parts)
+    _CARD_CACHE[skey] = hit
+    return hit
 
 
 def _template_text(templatefile, refnode):
@@ -763,23 +796,16 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         perm = None
         single_gv = int(gvs[0])
         if len(gvs) > 1:
-            n_ptiles = lib.cfe_partition_tiles(m.n_el)
-            mat = empty_u32(256 * n_ptiles, dev)
-            mat_off = torch.empty(256 * n_ptiles, dtype=torch.int64, device=dev)
+            # stable partition by grey value; the raster-order line lengths of vol2ugrid travel along
             perm = torch.empty((m.n_el, 2), dtype=torch.int32, device=dev)
-            _lib.call("cfe_partition_hist", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, mat.data_ptr(),
-                      m.gv8.data_ptr(), s)
-            ws_p = scan_workspace(256 * n_ptiles, dev)
-            scratch_total = torch.empty(1, dtype=torch.int64, device=dev)
-            _lib.call("cfe_scan_u32", mat.data_ptr(), 256 * n_ptiles, mat_off.data_ptr(), scratch_total.data_ptr(),
-                      ws_p.data_ptr(), s)
-            _lib.call("cfe_partition_scatter", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el,
-                      mat_off.data_ptr(), perm.data_ptr(), m.gv8.data_ptr(), s)
+            ws_el = torch.empty(m.ws_el.numel(), dtype=torch.uint8, device=dev)
+            ws_p = torch.empty(lib.cfe_gv_partition_workspace_bytes(m.n_el), dtype=torch.uint8, device=dev)
+            _lib.call("cfe_gv_partition", m.vol.data_ptr(), m.elem_vox.data_ptr(), m.n_el, m.gv8.data_ptr(),
+                      m.ws_el.data_ptr(), ws_el.data_ptr(), perm.data_ptr(), ws_p.data_ptr(), s)
             single_gv = -1
         el_args = (m.elem_vox.data_ptr(), _lib.ptr(perm), m.n_el, m.vol.data_ptr(), base + o_first, base + o_hdr,
                    base + o_hlen, single_gv, Z, Y, X, 0, 0)
-        _lib.call("cfe_element_lengths", *el_args, 0 if perm is not None else 1, totals.data_ptr(),
-                  ws_el.data_ptr(), s)
+        _lib.call("cfe_element_lengths", *el_args, 1, totals.data_ptr(), ws_el.data_ptr(), s)
         _lib.call("cfe_emit_elements", *el_args, out.data_ptr() + off_elem, None, ws_el.data_ptr(), s)
         _lib.call("cfe_emit_items", base + o_segs, len(segs), n_items, m.set_ids.data_ptr(), base + o_lits,
                   out.data_ptr() + off_elem, totals.data_ptr(), totals.data_ptr() + 8, None, ws.data_ptr(), s)

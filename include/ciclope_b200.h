@@ -294,13 +294,15 @@ int cfe_gen_emit_elements(const int64_t* cells, const int64_t* order, const int*
 int cfe_gv_histogram(const uint8_t* vol, int64_t n_vox, int thr, uint64_t* hist256, cfe_stream_t s);
 
 /* stable partition of the element list by grey value: np.where(cell_GV == GV), voxelFE.py:645.
+ * perm[k] = {local voxel index, raster rank} (uint2) of the k-th element in GV-major order.
  * gv8 (optional) = grey values in element order (cfe_fill_elements_gv); without it the kernels gather
- * vol[elem_vox[j]]. */
-int64_t cfe_partition_tiles(int64_t n_el);
-int cfe_partition_hist(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, uint32_t* mat,
-                       const uint8_t* gv8, cfe_stream_t s); /* mat: u32 [256][tiles] */
-int cfe_partition_scatter(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, const uint64_t* mat_off,
-                          void* perm, const uint8_t* gv8, cfe_stream_t s); /* perm: uint2 [n_el] */
+ * vol[elem_vox[j]].  ws_src / ws_dst (optional, both or neither) = element workspaces
+ * (cfe_emit_elements_workspace_bytes): the line lengths cfe_fill_elements left in ws_src in raster
+ * order are written to ws_dst in GV-major order, so that cfe_element_lengths(perm, have_lengths = 1)
+ * and cfe_emit_elements(perm) can run on ws_dst.  ws_part: cfe_gv_partition_workspace_bytes(n_el). */
+size_t cfe_gv_partition_workspace_bytes(int64_t n_el);
+int cfe_gv_partition(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, const uint8_t* gv8,
+                     const void* ws_src, void* ws_dst, void* perm, void* ws_part, cfe_stream_t s);
 
 #ifdef __cplusplus
 }
