@@ -89,6 +89,9 @@ _SIGNATURES = {
     "cfe_gen_elem_lengths": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "cfe_gen_emit_elements": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_gv_histogram": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    "cfe_proj_bits": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_scale_crop_f32": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "cfe_threshold_u8": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "cfe_gv_partition_workspace_bytes": (ctypes.c_size_t, [c_i64]),
     "cfe_gv_partition": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }

@@ -873,3 +873,158 @@ extern "C" int cfe_refnode_sums(const int64_t* ids, const int64_t* first, const 
     CFE_CHECK_LAUNCH("k_refnode_sums");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// ParOSol deck (voxelFE.py:285-472).  The O(N^3) pieces of vol2h5ParOSol:
+//   k_proj_bits       the three max-projections of recon_utils.bbox (recon_utils.py:258-272) from packed
+//                     bits: "row has a set bit" per voxel row and the OR of all rows; one warp per row
+//   k_scale_crop_f32  Image dataset  (sub_block * young_modulus).astype(float32)  (voxelFE.py:350-357):
+//                     crop to the bounding box and map every byte through a 256-entry float table that
+//                     the host fills with NumPy's own products, so the values are the reference's bits
+
+#define PROJ_COLS 8      // column words kept in registers per lane (X <= 8192); wider rows use atomics directly
+
+__global__ void __launch_bounds__(256)
+k_proj_bits(const u32* __restrict__ bits, i64 rows, int W, uint8_t* __restrict__ rowany, u32* __restrict__ colbits)
+{
+    const u32 lane = threadIdx.x & 31u;
+    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    u32 acc[PROJ_COLS];
+#pragma unroll
+    for (int k = 0; k < PROJ_COLS; ++k) acc[k] = 0;
+    for (i64 row = warp0; row < rows; row += nwarps) {
+        const u32* p = bits + row * W;
+        u32 any = 0;
+#pragma unroll
+        for (int k = 0; k < PROJ_COLS; ++k) {
+            const int w = (int)lane + 32 * k;
+            if (w < W) {
+                const u32 word = __ldg(p + w);
+                acc[k] |= word;
+                any |= word;
+            }
+        }
+        for (int w = (int)lane + 32 * PROJ_COLS; w < W; w += 32) {
+            const u32 word = __ldg(p + w);
+            if (word) atomicOr(colbits + w, word);
+            any |= word;
+        }
+        const bool row_any = __any_sync(CFE_FULL_MASK, any != 0);
+        if (lane == 0) rowany[row] = row_any ? 1 : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < PROJ_COLS; ++k) {
+        const int w = (int)lane + 32 * k;
+        if (w < W && acc[k]) atomicOr(colbits + w, acc[k]);
+    }
+}
+
+// Projections of the packed bits of a (rows, X) volume: rowany[row] = 1 when the row has a set bit,
+// colbits = OR of all rows (W = ceil(X / 32) words).  bits = cfe_pack_bits of the volume.
+extern "C" int cfe_proj_bits(const uint32_t* bits, int64_t rows, int64_t X, uint8_t* rowany, uint32_t* colbits,
+                             cudaStream_t stream)
+{
+    if (X <= 0) return 0;
+    const int W = (int)((X + 31) / 32);
+    CFE_CHECK_CUDA(cudaMemsetAsync(colbits, 0, (size_t)W * sizeof(u32), stream));
+    if (rows <= 0) return 0;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    i64 blocks = (rows + 7) / 8;
+    if (blocks > (i64)sms * 8) blocks = (i64)sms * 8;
+    k_proj_bits<<<(unsigned)blocks, 256, 0, stream>>>(bits, rows, W, rowany, colbits);
+    CFE_CHECK_LAUNCH("k_proj_bits");
+    return 0;
+}
+
+#define CROP_X_PER_CTA 2048
+
+__global__ void __launch_bounds__(256)
+k_scale_crop_f32(const uint8_t* __restrict__ vol, i64 sY, i64 sX, i64 z0, i64 y0, i64 x0, i64 ny, i64 nx,
+                 i64 xchunks, const float* __restrict__ lut, float* __restrict__ out)
+{
+    __shared__ float t[256];
+    t[threadIdx.x] = __ldg(lut + threadIdx.x);
+    __syncthreads();
+    const i64 row = (i64)blockIdx.x / xchunks;                 // (z, y) of the cropped block
+    const i64 xc = (i64)blockIdx.x - row * xchunks;
+    const i64 z = row / ny, y = row - z * ny;
+    const uint8_t* src = vol + ((z0 + z) * sY + (y0 + y)) * sX + x0;
+    float* dst = out + row * nx;
+    const i64 xb = xc * CROP_X_PER_CTA + threadIdx.x;
+    uint8_t v[CROP_X_PER_CTA / 256];
+#pragma unroll
+    for (int k = 0; k < CROP_X_PER_CTA / 256; ++k) {
+        const i64 x = xb + 256 * k;
+        v[k] = (x < nx) ? __ldg(src + x) : (uint8_t)0;
+    }
+#pragma unroll
+    for (int k = 0; k < CROP_X_PER_CTA / 256; ++k) {
+        const i64 x = xb + 256 * k;
+        if (x < nx) dst[x] = t[v[k]];
+    }
+}
+
+// out[z][y][x] = lut[vol[z0 + z][y0 + y][x0 + x]] for the (nz, ny, nx) block of the (., Y, X) volume
+extern "C" int cfe_scale_crop_f32(const uint8_t* vol, int64_t Y, int64_t X, int64_t z0, int64_t y0, int64_t x0,
+                                  int64_t nz, int64_t ny, int64_t nx, const float* lut256, float* out,
+                                  cudaStream_t stream)
+{
+    if (nz <= 0 || ny <= 0 || nx <= 0) return 0;
+    const i64 xchunks = (nx + CROP_X_PER_CTA - 1) / CROP_X_PER_CTA;
+    const i64 blocks = nz * ny * xchunks;
+    if (blocks >= (1LL << 31)) { cfe_set_error("cfe_scale_crop_f32: block too large"); return -1; }
+    k_scale_crop_f32<<<(unsigned)blocks, 256, 0, stream>>>(vol, Y, X, z0, y0, x0, ny, nx, xchunks, lut256, out);
+    CFE_CHECK_LAUNCH("k_scale_crop_f32");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// segment (preprocess.py:20-46):  image > T  for uint8 images, 16 voxels per thread (borrow-free SWAR
+// compare, one 16-byte load and one 16-byte store), bool bytes 0 / 1 out.
+
+__device__ __forceinline__ u32 swar_gt_u8(u32 x, u32 t4)
+{
+    // per byte: 0x01 where x > t (unsigned); t4 = t replicated.  x > t  <=>  carry out of  x + (255 - t)
+    // computed without inter-byte carries: low 7 bits added separately, top bits combined by logic
+    const u32 H = 0x80808080u;
+    const u32 y = ~t4;                                   // 255 - t per byte
+    const u32 low = (x & ~H) + (y & ~H);                 // bit 7 = carry of the low 7 bits
+    const u32 carry = ((x & y) | ((x | y) & low)) & H;   // carry out of bit 7
+    return carry >> 7;
+}
+
+__global__ void __launch_bounds__(256)
+k_threshold_u8(const uint8_t* __restrict__ img, i64 n, u32 t4, int t, uint8_t* __restrict__ out)
+{
+    const i64 n16 = n >> 4;
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n16; g += (i64)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(img) + g);
+        uint4 r;
+        r.x = swar_gt_u8(v.x, t4); r.y = swar_gt_u8(v.y, t4); r.z = swar_gt_u8(v.z, t4); r.w = swar_gt_u8(v.w, t4);
+        reinterpret_cast<uint4*>(out)[g] = r;
+    }
+    for (i64 i = (n16 << 4) + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        out[i] = (uint8_t)((int)img[i] > t);
+}
+
+// out[i] = img[i] > t (bytes 0 / 1).  t outside 0..254 gives the constant answer.  img and out 16-byte aligned.
+extern "C" int cfe_threshold_u8(const uint8_t* img, int64_t n, int t, uint8_t* out, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    if (t < 0) { CFE_CHECK_CUDA(cudaMemsetAsync(out, 1, (size_t)n, stream)); return 0; }
+    if (t >= 255) { CFE_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)n, stream)); return 0; }
+    if ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(out)) & 15u) {
+        cfe_set_error("cfe_threshold_u8: buffers must be 16-byte aligned");
+        return -1;
+    }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    i64 blocks = (n / 16 + 255) / 256;
+    if (blocks > (i64)sms * 16) blocks = (i64)sms * 16;
+    if (blocks < 1) blocks = 1;
+    k_threshold_u8<<<(unsigned)blocks, 256, 0, stream>>>(img, n, 0x01010101u * (u32)t, t, out);
+    CFE_CHECK_LAUNCH("k_threshold_u8");
+    return 0;
+}

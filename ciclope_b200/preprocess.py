@@ -171,3 +171,89 @@ def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, ou
 def component_stats(best):
     """(size, root run id) of the kept component from the packed `best` word."""
     return best >> 32, 0xFFFFFFFF - (best & 0xFFFFFFFF)
+
+
+# --------------------------------------------------------------------------------------------
+# The two steps right before the hot path in ciclope's pipeline (pipeline.py:163-169)
+
+def threshold_otsu(image):
+    """Otsu threshold of a uint8 image, as ``skimage.filters.threshold_otsu`` computes it for integer images
+    (one bin per integer from min to max, float64 cumulative sums, argmax of the between-class variance).
+    The 256-bin histogram is the GPU's (``cfe_gv_histogram``); the 256-term arithmetic is NumPy's, in the
+    library's order of operations.  scikit-image is neither in the reference checkout nor installed here, so
+    this function is restated from its published algorithm and its parity is not pinned by a golden vector."""
+    vol, is_bool, _ = as_device_volume(image, allow_2d=True)
+    if vol.numel() == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
+    dev = vol.device
+    with torch.cuda.device(dev):
+        hist_dev = torch.empty(256, dtype=torch.int64, device=dev)
+        _lib.call("cfe_gv_histogram", vol.data_ptr(), vol.numel(), -1, hist_dev.data_ptr(), _lib.stream())
+        hist = np.asarray(read_back(hist_dev), dtype=np.int64)
+    present = np.flatnonzero(hist)
+    lo, hi = int(present[0]), int(present[-1])
+    if lo == hi:
+        return np.bool_(lo) if is_bool else np.uint8(lo)
+    counts = hist[lo:hi + 1].astype(np.float64)
+    centers = np.arange(lo, hi + 1)
+    weight1 = np.cumsum(counts)
+    weight2 = np.cumsum(counts[::-1])[::-1]
+    mean1 = np.cumsum(counts * centers) / weight1
+    mean2 = (np.cumsum((counts * centers)[::-1]) / weight2[::-1])[::-1]
+    variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+    return centers[np.argmax(variance12)]
+
+
+def segment(image, threshold_value):
+    """Threshold image (drop-in for preprocess.py:20-46).
+
+    Parameters
+    ----------
+    image
+        Image data (uint8; NumPy array or CUDA tensor).
+    threshold_value (optional)
+        Threshold value. If empty an Otsu threshold is calculated.
+
+    Returns
+    -------
+    BWimage
+        Binary image after thresholding (``image > T``; a CUDA bool tensor for tensor input).
+    T
+        Threshold value.
+    """
+    if threshold_value is None:
+        T = threshold_otsu(image)
+    else:
+        T = int(threshold_value)
+    vol, _is_bool, from_numpy = as_device_volume(image, allow_2d=True)
+    squeeze = (image.ndim == 2)
+    dev = vol.device
+    with torch.cuda.device(dev):
+        out = torch.empty(vol.shape, dtype=torch.uint8, device=dev)
+        _lib.call("cfe_threshold_u8", vol.data_ptr(), vol.numel(), max(-1, min(255, int(T))), out.data_ptr(),
+                  _lib.stream())
+    out = out.view(torch.bool)
+    if squeeze:
+        out = out[0]
+    return (out.cpu().numpy() if from_numpy else out), T
+
+
+def add_cap(I, cap_thickness, cap_val):  # noqa: E741 -- the reference's parameter name
+    """Add caps to 3D image (drop-in for preprocess.py:210-231): ``cap_thickness`` slices of value
+    ``cap_val`` before the first and after the last slice.  Pure data movement (two fills and a copy in
+    device memory).  uint8 images with a cap value that NumPy keeps in uint8."""
+    vol, is_bool, from_numpy = as_device_volume(I)
+    probe = np.ones(1, np.bool_ if is_bool else np.uint8) * cap_val      # dtype / range rules of the reference
+    if probe.dtype != np.uint8:
+        raise TypeError("add_cap on the GPU keeps uint8 images; cap_val %r gives %s" % (cap_val, probe.dtype))
+    c = int(cap_thickness)
+    Z, Y, X = (int(v) for v in vol.shape)
+    if c <= 0 or Z + 2 * c <= 0:
+        # I_cap[c:-c] is empty for c = 0 (and the shapes are negative below that): the reference fails here
+        raise ValueError("could not broadcast input array from shape ({},{},{}) into shape (0,{},{})"
+                         .format(Z, Y, X, Y, X))
+    out = torch.empty((Z + 2 * c, Y, X), dtype=torch.uint8, device=vol.device)
+    out[:c].fill_(int(probe[0]))
+    out[Z + c:].fill_(int(probe[0]))
+    out[c:Z + c].copy_(vol)
+    return out.cpu().numpy() if from_numpy else out

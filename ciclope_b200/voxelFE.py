@@ -882,3 +882,7 @@ def matpropdictionary(proplist):
         matprop['file'].append(proplist[3 * i])
         matprop['range'].append([int(proplist[3 * i + 1]), int(proplist[3 * i + 2])])
     return matprop
+
+
+# vol2h5ParOSol (voxelFE.py:285-472) lives in parosol.py; the reference exposes it from this module
+from .parosol import parosol_datasets, vol2h5ParOSol  # noqa: E402,F401

@@ -304,6 +304,20 @@ size_t cfe_gv_partition_workspace_bytes(int64_t n_el);
 int cfe_gv_partition(const uint8_t* vol, const uint32_t* elem_vox, int64_t n_el, const uint8_t* gv8,
                      const void* ws_src, void* ws_dst, void* perm, void* ws_part, cfe_stream_t s);
 
+/* ------------------------------------------------------------------ ParOSol deck, segmentation */
+
+/* vol2h5ParOSol (voxelFE.py:285-472), the O(N^3) parts.  cfe_proj_bits: the max-projections behind the
+ * bounding box (recon_utils.py:258-272, bbox) from the packed bits of `rows` voxel rows of X voxels:
+ * rowany[row] = 1 when the row has a set bit, colbits (ceil(X/32) words) = OR of all rows.
+ * cfe_scale_crop_f32: Image dataset (voxelFE.py:350-357): out[z][y][x] = lut256[vol[z0+z][y0+y][x0+x]],
+ * lut256 = (arange(256) * young_modulus).astype(float32) computed by the caller with NumPy. */
+int cfe_proj_bits(const uint32_t* bits, int64_t rows, int64_t X, uint8_t* rowany, uint32_t* colbits, cfe_stream_t s);
+int cfe_scale_crop_f32(const uint8_t* vol, int64_t Y, int64_t X, int64_t z0, int64_t y0, int64_t x0,
+                       int64_t nz, int64_t ny, int64_t nx, const float* lut256, float* out, cfe_stream_t s);
+
+/* segment (preprocess.py:20-46): out[i] = img[i] > t, bytes 0 / 1; buffers 16-byte aligned */
+int cfe_threshold_u8(const uint8_t* img, int64_t n, int t, uint8_t* out, cfe_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -377,3 +377,126 @@ def matpropdictionary(proplist):
         matprop['file'].append(proplist[3 * i])
         matprop['range'].append([int(proplist[3 * i + 1]), int(proplist[3 * i + 2])])
     return matprop
+
+
+# --------------------------------------------------------------------------------------------
+# vol2h5ParOSol <- src/ciclope/core/voxelFE.py:285-472 (+ recon_utils.bbox, recon_utils.py:232-318, and
+# preprocess._collect_from_elements, preprocess.py:422-456).  The HDF5 container is h5py's; this restates
+# the five datasets the reference hands to create_dataset, in the reference's order.
+
+def bbox(bw):
+    """recon_utils.py:258-318 with pad = 0: ([row0, col0, slice0], [rowd, cold, sliced])."""
+    maxROW = np.max(np.max(bw, 0), 1)
+    maxCOL = np.max(np.max(bw, 0), 0)
+    maxSLICE = np.max(np.max(bw, 1), 1)
+    row0 = list(maxROW).index(True)
+    row1 = len(maxROW) - list(maxROW[::-1]).index(True) - 1
+    col0 = list(maxCOL).index(True)
+    col1 = len(maxCOL) - list(maxCOL[::-1]).index(True) - 1
+    slice0 = list(maxSLICE).index(True)
+    slice1 = len(maxSLICE) - list(maxSLICE[::-1]).index(True) - 1
+    return [row0, col0, slice0], [row1 - row0, col1 - col0, slice1 - slice0]
+
+
+def vol2h5ParOSol_datasets(voldata, topDisplacement, voxelsize=1, poisson_ratio=0.3, young_modulus=18e3,
+                           topHorizontaFixedlDisplacement=True, locking_strategy="plane", plane_lock_num=1,
+                           node_level_lock_num=1):
+    out = collections.OrderedDict()
+    origin, dims = bbox(voldata)                                       # voxelFE.py:336
+    origin = [origin[2], origin[0], origin[1]]
+    dims = [dims[2], dims[0], dims[1]]
+    end = [origin[i] + dims[i] for i in range(3)]
+    sub_block = voldata[origin[0]:end[0] + 1, origin[1]:end[1] + 1, origin[2]:end[2] + 1]
+    out["Image"] = np.asarray((sub_block * young_modulus).astype(np.float32), dtype='<f4')      # :354-357
+    out["Voxelsize"] = np.asarray(voxelsize, dtype='<f8')
+    out["Poisons_ratio"] = np.asarray(poisson_ratio, dtype='<f8')
+    lb, tb = set(), set()
+
+    def collect(els, nodes, dirs):                                     # preprocess.py:449-456
+        for el in els:
+            z, y, x = el
+            for dz in (0, 1):
+                for dy in (0, 1):
+                    for dx in (0, 1):
+                        for d in dirs:
+                            nodes.add((z + dz, y + dy, x + dx, d))
+
+    if locking_strategy == "plane":                                    # :371-398
+        low, top = [], []
+        for i in range(plane_lock_num):
+            low2d = np.argwhere(sub_block[i] != 0)
+            low.append(np.hstack((np.full((low2d.shape[0], 1), i), low2d)))
+            idx = sub_block.shape[0] - 1 - i
+            top2d = np.argwhere(sub_block[idx] != 0)
+            top.append(np.hstack((np.full((top2d.shape[0], 1), idx), top2d)))
+        low, top = np.vstack(low), np.vstack(top)
+        collect(low, lb, (0, 1, 2))
+        collect(top, tb, (0, 1, 2) if topHorizontaFixedlDisplacement else (2,))
+    elif locking_strategy == "exact":                                  # :400-443
+        Nz, Ny, Nx = sub_block.shape
+        slice_nodes, row_nodes = (Ny + 1) * (Nx + 1), Nx + 1
+        existing = np.zeros((Nz + 1) * slice_nodes, dtype=bool)
+        for z, y, x in np.argwhere(sub_block != 0):
+            base = z * slice_nodes + y * row_nodes + x
+            for off in (0, 1, row_nodes, row_nodes + 1, slice_nodes, slice_nodes + 1,
+                        slice_nodes + row_nodes, slice_nodes + row_nodes + 1):
+                existing[base + off] = True
+        for idx in np.flatnonzero(existing).tolist():
+            z = idx // slice_nodes
+            y = (idx % slice_nodes) // row_nodes
+            x = (idx % slice_nodes) % row_nodes
+            if z < node_level_lock_num:
+                for d in (0, 1, 2):
+                    lb.add((z, y, x, d))
+            if z >= (Nz + 1) - node_level_lock_num:
+                if topHorizontaFixedlDisplacement:
+                    for d in (0, 1, 2):
+                        tb.add((z, y, x, d))
+                else:
+                    tb.add((z, y, x, 2))
+    else:
+        raise ValueError("locking_strategy must be 'plane' or 'exact'")
+    all_nodes = list(lb) + list(tb)                                    # :449 -- CPython set order
+    out["Fixed_Displacement_Coordinates"] = np.array(all_nodes, dtype=np.uint16)
+    values = np.zeros(len(all_nodes), dtype=np.float32)
+    for i, (_, _, _, d) in enumerate(all_nodes[len(lb):], start=len(lb)):
+        if d == 2:
+            values[i] = topDisplacement
+    out["Fixed_Displacement_Values"] = values
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# segment <- src/ciclope/utils/preprocess.py:20-46;  add_cap <- preprocess.py:210-231
+
+def threshold_otsu_u8(image):
+    """skimage.filters.threshold_otsu for an integer image (scikit-image is not in the checkout nor
+    installed: PARITY UNPINNED for this function).  Restated from scikit-image 0.19's published algorithm:
+    histogram with one bin per integer from image.min() to image.max(), class weights / means by cumulative
+    sums in float64, threshold = bin centre maximising weight1 * weight2 * (mean1 - mean2)^2."""
+    image = np.asarray(image)
+    lo, hi = int(image.min()), int(image.max())
+    if lo == hi:
+        return image.dtype.type(lo)
+    counts = np.bincount(image.ravel().astype(np.int64) - lo, minlength=hi - lo + 1).astype(np.float64)
+    centers = np.arange(lo, hi + 1)
+    weight1 = np.cumsum(counts)
+    weight2 = np.cumsum(counts[::-1])[::-1]
+    mean1 = np.cumsum(counts * centers) / weight1
+    mean2 = (np.cumsum((counts * centers)[::-1]) / weight2[::-1])[::-1]
+    variance12 = weight1[:-1] * weight2[1:] * (mean1[:-1] - mean2[1:]) ** 2
+    return centers[np.argmax(variance12)]
+
+
+def segment(image, threshold_value):
+    if threshold_value is None:
+        T = threshold_otsu_u8(image)
+    else:
+        T = int(threshold_value)
+    return image > T, T
+
+
+def add_cap(I, cap_thickness, cap_val):  # noqa: E741
+    I_cap = np.ones([I.shape[0] + 2 * cap_thickness, I.shape[1], I.shape[2]], I.dtype) * cap_val
+    I_cap[cap_thickness:-cap_thickness, :, :] = I
+    return I_cap

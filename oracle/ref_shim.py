@@ -26,6 +26,7 @@ import types
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get("CICLOPE_REFERENCE_ROOT", "/root/reference")
+H5PY_FILES = {}      # datasets "written" through the h5py stand-in, by file path
 
 
 def _install_stubs():
@@ -35,9 +36,32 @@ def _install_stubs():
         sys.modules[name] = m
         return m
 
-    for name in ("h5py", "imageio", "png", "tifffile"):
+    for name in ("imageio", "png", "tifffile"):
         if name not in sys.modules:
             mod(name)
+    if "h5py" not in sys.modules:
+        # recording stand-in for the three h5py calls vol2h5ParOSol makes (voxelFE.py:328-330, 357-471):
+        # H5PY_FILES[path][dataset name] = np.array(data, dtype=dtype), which is what h5py stores
+        class _Group:
+            def __init__(self, store):
+                self._store = store
+
+            def create_dataset(self, name, data=None, dtype=None):
+                self._store[name] = np.array(data, dtype=dtype)
+
+        class File:
+            def __init__(self, path, mode):
+                assert mode == 'w'
+                self._store = H5PY_FILES[path] = collections.OrderedDict()
+
+            def create_group(self, name):
+                assert name == "Image_Data"
+                return _Group(self._store)
+
+            def close(self):
+                pass
+
+        mod("h5py", File=File)
     if "matplotlib" not in sys.modules:
         mpl = mod("matplotlib")
         mpl.pyplot = mod("matplotlib.pyplot")

@@ -429,3 +429,91 @@ def fill_cases():
     m = blobs((20, 24, 70), 0.6, 9)
     C.append(("blobs_dense_grey", grey_from_mask(m, 10), dict(fill_val=255, makecopy=True)))
     return C
+
+
+def parosol_cases():
+    """(name, volume, kwargs of vol2h5ParOSol) -- small volumes whose non-zero voxels do not fill the array
+    (so that the bounding-box crop does something), bool and uint8, both locking strategies."""
+    rng = np.random.default_rng(77)
+    out = []
+    shapes = [(5, 6, 7), (9, 8, 10), (3, 12, 5), (1, 4, 4), (2, 3, 3), (12, 33, 40), (7, 64, 65)]
+    for si, shape in enumerate(shapes):
+        for dens in (0.25, 0.6):
+            for dt in ("bool", "u01", "grey"):
+                if dt == "grey" and (si > 1 or dens > 0.5):
+                    continue
+                v = rng.random(shape) < dens
+                if shape[0] > 2:
+                    v[0] = False
+                v[:, 0] = False
+                v[:, :, -1] = False
+                if not v.any():
+                    v[-1, -1, 0] = True
+                if dt == "u01":
+                    v = v.astype(np.uint8)
+                elif dt == "grey":
+                    # recon_utils.bbox looks for projections EQUAL to 1: grey values above 1 hide a row /
+                    # column / slice from it (often a ValueError, sometimes a smaller box)
+                    g = (v * rng.integers(1, 256, shape)).astype(np.uint8)
+                    if si == 1:
+                        # ones, with one grey voxel in the far corner of their box: its slice, row and column
+                        # have maximum 7, so the reference's box stops one short of it on every axis
+                        g = v.astype(np.uint8)
+                        g[-1, -1, -2] = 7
+                    v = g
+                for strat, kw in (("plane", dict(plane_lock_num=1)), ("plane", dict(plane_lock_num=2)),
+                                  ("exact", dict(node_level_lock_num=1)), ("exact", dict(node_level_lock_num=3))):
+                    for thf in (True, False):
+                        name = "s%d_d%d_%s_%s%d_%d" % (si, int(dens * 100), dt, strat,
+                                                       list(kw.values())[0], int(thf))
+                        k = dict(topDisplacement=-0.04, voxelsize=0.0195, poisson_ratio=0.3, young_modulus=18e3,
+                                 topHorizontaFixedlDisplacement=thf, locking_strategy=strat)
+                        k.update(kw)
+                        out.append((name, v, k))
+    # a blob volume, anisotropic voxel size given as a list, another modulus
+    b = blobs((20, 24, 28), 0.3, 3)
+    out.append(("blobs_plane", b, dict(topDisplacement=0.1, voxelsize=[0.01, 0.02, 0.03], poisson_ratio=0.25,
+                                       young_modulus=1234.5, topHorizontaFixedlDisplacement=True,
+                                       locking_strategy="plane", plane_lock_num=1)))
+    g = grey_from_mask(b, 5)
+    out.append(("grey_exact", g, dict(topDisplacement=-1.0, voxelsize=0.5, poisson_ratio=0.3, young_modulus=70.0,
+                                      topHorizontaFixedlDisplacement=False, locking_strategy="exact",
+                                      node_level_lock_num=2)))
+    return out
+
+
+def segment_cases():
+    """(name, uint8 image, threshold)"""
+    rng = np.random.default_rng(5)
+    out = []
+    for si, shape in enumerate([(4, 5, 6), (3, 17, 33), (8, 16, 64), (5, 7, 11)]):
+        img = rng.integers(0, 256, shape).astype(np.uint8)
+        for t in (0, 1, 63, 127, 128, 200, 254, 255, 300, -5, 63.7):
+            out.append(("s%d_t%s" % (si, t), img, t))
+    return out
+
+
+def check_parosol_against_golden(g, name, run):
+    """run() -> {dataset name: array} (or raises); compared with what the unmodified reference handed to
+    h5py for the same case: same error class, same dataset order, same dtype / shape / bytes."""
+    import hashlib
+    key = "po/" + name
+    if key + "/error" in g.files:
+        try:
+            run()
+        except BaseException as e:  # noqa: BLE001
+            assert type(e).__name__ == str(g[key + "/error"]), (name, type(e).__name__)
+            return
+        raise AssertionError("%s: the reference raises %s" % (name, g[key + "/error"]))
+    ds = run()
+    names = [str(n) for n in g[key + "/names"]]
+    assert list(ds) == names
+    for k in names:
+        want = g[key + "/" + k]
+        got = np.asarray(ds[k])
+        if want.dtype.kind == "U":          # dtype / shape / SHA-256
+            assert got.dtype.str == str(want[0]) and str(got.shape) == str(want[1]), (name, k)
+            assert hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == str(want[2]), (name, k)
+        else:
+            assert got.dtype == want.dtype and got.shape == want.shape, (name, k, got.dtype, got.shape)
+            assert np.array_equal(got, want), (name, k)

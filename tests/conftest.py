@@ -38,3 +38,10 @@ def golden_reuse():
     import numpy as np
     from tests import cases
     return np.load(os.path.join(cases.GOLDEN_DIR, "reuse.npz"), allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_parosol():
+    import numpy as np
+    from tests import cases
+    return np.load(os.path.join(cases.GOLDEN_DIR, "parosol.npz"), allow_pickle=False)

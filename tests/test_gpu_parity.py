@@ -457,3 +457,119 @@ def test_mesh2voxelfe_is_repeatable_on_one_mesh(cfe, golden, tmp_path):
         m = dict(g["m"]); m["matprop"] = m["matprop"]()
         cfe.mesh2voxelfe(mesh, fileout=p, **m)
         assert cases.mask_timestamp(open(p, "rb").read()) == bytes(golden["blobs_grey_property/deck"])
+
+
+# --------------------------------------------------------------------------------------------
+# vol2h5ParOSol (voxelFE.py:285-472), segment (preprocess.py:20-46), add_cap (preprocess.py:210-231)
+
+PAROSOL_CASES = {c[0]: c for c in cases.parosol_cases()}
+
+
+@pytest.mark.parametrize("name", list(PAROSOL_CASES))
+def test_parosol_datasets_vs_reference(cfe, golden_parosol, name):
+    from ciclope_b200.parosol import parosol_datasets
+    _, vol, kw = PAROSOL_CASES[name]
+    cases.check_parosol_against_golden(golden_parosol, name, lambda: parosol_datasets(vol.copy(), **kw))
+
+
+def test_parosol_file_through_h5py_calls(cfe, orc, tmp_path, monkeypatch):
+    """vol2h5ParOSol makes the reference's h5py calls (File / create_group / create_dataset in the same
+    order with the same dtypes); h5py itself is not installed, so a recording stand-in takes its place."""
+    import sys
+    import types
+    rec = []
+
+    class _Group:
+        def create_dataset(self, name, data=None, dtype=None):
+            rec.append((name, np.array(data, dtype=dtype)))
+
+    class File:
+        def __init__(self, path, mode):
+            rec.append(("File", path, mode))
+
+        def create_group(self, name):
+            rec.append(("group", name))
+            return _Group()
+
+        def close(self):
+            rec.append(("close",))
+
+    monkeypatch.setitem(sys.modules, "h5py", types.SimpleNamespace(File=File))
+    vol = cases.blobs((20, 24, 28), 0.3, 3)
+    path = str(tmp_path / "x.h5")
+    cfe.vol2h5ParOSol(vol, path, -0.04, voxelsize=0.0195)
+    want = orc.vol2h5ParOSol_datasets(vol, -0.04, voxelsize=0.0195)
+    assert rec[0] == ("File", path, "w") and rec[1] == ("group", "Image_Data") and rec[-1] == ("close",)
+    got = rec[2:-1]
+    assert [n for n, _ in got] == list(want)
+    for (n, a), b in zip(got, want.values()):
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), n
+
+
+def test_parosol_without_h5py_raises(cfe, tmp_path):
+    try:
+        import h5py  # noqa: F401
+        pytest.skip("h5py is installed")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError):
+        cfe.vol2h5ParOSol(cases.blobs((8, 8, 8), 0.4, 1), str(tmp_path / "x.h5"), 0.1)
+
+
+@pytest.mark.parametrize("shape,seed", [((40, 64, 96), 1), ((33, 50, 70), 2), ((64, 128, 160), 3)])
+def test_parosol_vs_oracle_larger(cfe, orc, shape, seed):
+    """bigger volumes with an empty margin, both strategies, device input; sorted order = same rows"""
+    import torch
+    from ciclope_b200.parosol import parosol_datasets
+    inner = cases.blobs(tuple(s - 6 for s in shape), 0.35, seed)
+    vol = np.zeros(shape, dtype=bool)
+    vol[2:-4, 1:-5, 3:-3] = inner
+    for strat, kw in (("plane", dict(plane_lock_num=2)), ("exact", dict(node_level_lock_num=2))):
+        want = orc.vol2h5ParOSol_datasets(vol, 0.25, voxelsize=[0.1, 0.2, 0.3], young_modulus=17000.5,
+                                          locking_strategy=strat, **kw)
+        got = parosol_datasets(torch.from_numpy(vol).cuda(), 0.25, voxelsize=[0.1, 0.2, 0.3],
+                               young_modulus=17000.5, locking_strategy=strat, **kw)
+        for k in want:
+            a, b = np.asarray(got[k]), want[k]
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), (strat, k)
+        srt = parosol_datasets(vol, 0.25, locking_strategy=strat, node_order="sorted", **kw)
+        a = srt["Fixed_Displacement_Coordinates"]
+        b = want["Fixed_Displacement_Coordinates"]
+        assert a.shape == b.shape
+        assert sorted(map(tuple, a.tolist())) == sorted(map(tuple, b.tolist()))
+
+
+def test_segment_and_caps_vs_reference(cfe, golden_parosol):
+    import torch
+    g = golden_parosol
+    for name, img, t in cases.segment_cases():
+        bw, T = cfe.segment(img, t)
+        assert T == int(g["seg/" + name + "/T"]) and bw.dtype == np.bool_ and bw.shape == img.shape
+        assert np.array_equal(np.packbits(bw.ravel()), g["seg/" + name + "/bw"]), name
+        bw_t, _ = cfe.segment(torch.from_numpy(img).cuda(), t)
+        assert bw_t.dtype == torch.bool and np.array_equal(bw_t.cpu().numpy(), bw)
+    i = 0
+    while "cap/%d/in" % i in g.files:
+        th, val = (int(v) for v in g["cap/%d/args" % i])
+        res = cfe.add_cap(g["cap/%d/in" % i], th, val)
+        want = g["cap/%d/out" % i]
+        assert res.dtype == want.dtype and np.array_equal(res, want)
+        i += 1
+    with pytest.raises(ValueError):
+        cfe.add_cap(g["cap/0/in"], 0, 1)
+    with pytest.raises(TypeError):
+        cfe.add_cap(g["cap/0/in"], 2, 0.5)
+
+
+def test_segment_otsu_vs_oracle(cfe, orc):
+    rng = np.random.default_rng(11)
+    for shape in [(20, 30, 40), (7, 33, 65)]:
+        img = np.concatenate([rng.normal(70, 12, shape[0] * shape[1] * shape[2] // 2),
+                              rng.normal(170, 15, shape[0] * shape[1] * shape[2] - shape[0] * shape[1] * shape[2] // 2)]
+                             ).clip(0, 255).astype(np.uint8).reshape(shape)
+        bw, T = cfe.segment(img, None)
+        bw_o, T_o = orc.segment(img, None)
+        assert T == T_o and np.array_equal(bw, bw_o)
+    flat = np.full((4, 5, 6), 9, dtype=np.uint8)
+    bw, T = cfe.segment(flat, None)
+    assert T == 9 and not bw.any()

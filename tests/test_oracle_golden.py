@@ -168,3 +168,40 @@ def test_oracle_errors():
     assert orc.matpropdictionary(["a.inp", "1", "100", "b.inp", "101", "255"]) == errs["matpropdictionary_triples"]
     with pytest.raises(IOError):
         orc.matpropdictionary(["a.inp", "1"])
+
+
+# --------------------------------------------------------------------------------------------
+# vol2h5ParOSol / segment / add_cap (tests/golden/make_golden_parosol.py)
+
+PAROSOL_CASES = {c[0]: c for c in cases.parosol_cases()}
+
+
+@pytest.mark.parametrize("name", list(PAROSOL_CASES))
+def test_oracle_parosol(golden_parosol, name):
+    _, vol, kw = PAROSOL_CASES[name]
+    cases.check_parosol_against_golden(golden_parosol, name, lambda: orc.vol2h5ParOSol_datasets(vol.copy(), **kw))
+
+
+def test_oracle_segment_and_caps(golden_parosol):
+    g = golden_parosol
+    for name, img, t in cases.segment_cases():
+        bw, T = orc.segment(img, t)
+        assert T == int(g["seg/" + name + "/T"]) and bw.dtype == np.bool_
+        assert np.array_equal(np.packbits(bw.ravel()), g["seg/" + name + "/bw"]), name
+    i = 0
+    while "cap/%d/in" % i in g.files:
+        th, val = (int(v) for v in g["cap/%d/args" % i])
+        res = orc.add_cap(g["cap/%d/in" % i], th, val)
+        want = g["cap/%d/out" % i]
+        assert res.dtype == want.dtype and np.array_equal(res, want)
+        i += 1
+    assert i == 3
+
+
+def test_oracle_otsu_separates_two_populations():
+    # no golden vector exists for Otsu (scikit-image is absent): sanity of the restated algorithm only
+    rng = np.random.default_rng(3)
+    img = np.concatenate([rng.normal(60, 8, 5000), rng.normal(180, 10, 3000)]).clip(0, 255).astype(np.uint8)
+    T = orc.threshold_otsu_u8(img.reshape(20, 20, 20))
+    assert 90 <= T <= 150
+    assert orc.threshold_otsu_u8(np.full((3, 3, 3), 7, dtype=np.uint8)) == 7
