@@ -90,15 +90,66 @@ def _corner_rows(els, dirs):
     return out.reshape(-1, 4)
 
 
+_REPLAY_OK = None
+
+
+def _pyset_replay(rows):
+    """list(set(map(tuple, rows))) through the C replay of CPython's hash table (csrc/pyset.cu)."""
+    import ctypes
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    out = np.empty_like(rows)
+    n = ctypes.c_int64(0)
+    rc = _lib.load().cfe_host_pyset_order(rows.ctypes.data, len(rows), out.ctypes.data, ctypes.addressof(n))
+    if rc != 0:
+        raise _lib.CfeError(_lib.load().cfe_last_error().decode())
+    return out[:n.value]
+
+
+def _replay_matches_interpreter():
+    """The replay is only used when it reproduces THIS interpreter's set order on a sample that crosses
+    every growth rule of the table (checked once per process)."""
+    global _REPLAY_OK
+    if _REPLAY_OK is None:
+        rng = np.random.default_rng(12345)
+        ok = True
+        for n, hi in ((300, 6), (20000, 40), (150000, 70)):
+            rows = np.stack([rng.integers(0, hi, n), rng.integers(0, hi, n), rng.integers(0, hi, n),
+                             rng.integers(0, 3, n)], axis=1)
+            want = np.array(list(set(map(tuple, rows.tolist()))), dtype=np.int64).reshape(-1, 4)
+            try:
+                got = _pyset_replay(rows)
+            except Exception:  # noqa: BLE001
+                ok = False
+                break
+            if got.shape != want.shape or not np.array_equal(got, want):
+                ok = False
+                break
+        _REPLAY_OK = ok
+    return _REPLAY_OK
+
+
 def _ordered_unique(rows, node_order):
-    """The reference's ``list(set)`` of the row tuples (CPython set order), or the sorted unique rows."""
+    """The reference's ``list(set)`` of the row tuples (CPython set order), or the sorted unique rows;
+    an int64 array [n, 4]."""
+    if len(rows) == 0:
+        return np.zeros((0, 4), dtype=np.int64)
     if node_order == "sorted":
-        if len(rows) == 0:
-            return []
-        return [tuple(r) for r in np.unique(rows, axis=0).tolist()]
+        m = int(rows[:, :3].max()) + 1
+        key = ((rows[:, 0] * m + rows[:, 1]) * m + rows[:, 2]) * 4 + rows[:, 3]
+        key = np.unique(key)
+        out = np.empty((len(key), 4), dtype=np.int64)
+        out[:, 3] = key % 4
+        key //= 4
+        out[:, 2] = key % m
+        key //= m
+        out[:, 1] = key % m
+        out[:, 0] = key // m
+        return out
+    if rows.min() >= 0 and _replay_matches_interpreter():
+        return _pyset_replay(rows)
     s = set()
     s.update(map(tuple, rows.tolist()))       # one add per row, in order, like the reference's loop
-    return list(s)
+    return np.array(list(s), dtype=np.int64).reshape(-1, 4)
 
 
 def parosol_datasets(voldata, topDisplacement, voxelsize=1, poisson_ratio=0.3, young_modulus=18e3,
@@ -196,12 +247,16 @@ def parosol_datasets(voldata, topDisplacement, voxelsize=1, poisson_ratio=0.3, y
 
     lb = _ordered_unique(lb_rows, node_order)
     tb = _ordered_unique(tb_rows, node_order)
-    all_nodes = lb + tb                                              # voxelFE.py:449
-    fix_coord = np.array(all_nodes, dtype=np.uint16)                 # (n, 4), or (0,) when empty
-    values = np.zeros(len(all_nodes), dtype=np.float32)
-    if tb:
-        d = np.array(tb, dtype=np.int64)[:, 3]
-        values[len(lb):][d == 2] = topDisplacement                   # voxelFE.py:453-456
+    all_nodes = np.concatenate([lb, tb])                             # voxelFE.py:449
+    n_all = len(all_nodes)
+    # np.array(list_of_tuples, dtype=uint16): (n, 4), or (0,) when there is no node at all
+    if n_all and (all_nodes.min() < 0 or all_nodes.max() > 65535):
+        raise OverflowError("Python integer {} out of bounds for uint16".format(
+            int(all_nodes.max() if all_nodes.max() > 65535 else all_nodes.min())))
+    fix_coord = all_nodes.astype(np.uint16) if n_all else np.array([], dtype=np.uint16)
+    values = np.zeros(n_all, dtype=np.float32)
+    if len(tb):
+        values[len(lb):][tb[:, 3] == 2] = topDisplacement            # voxelFE.py:453-456
     out = {}
     out["Image"] = image if image_on_device else image.cpu().numpy()
     out["Voxelsize"] = np.asarray(voxelsize, dtype=H5T_IEEE_F64LE)

@@ -315,6 +315,11 @@ int cfe_proj_bits(const uint32_t* bits, int64_t rows, int64_t X, uint8_t* rowany
 int cfe_scale_crop_f32(const uint8_t* vol, int64_t Y, int64_t X, int64_t z0, int64_t y0, int64_t x0,
                        int64_t nz, int64_t ny, int64_t nx, const float* lut256, float* out, cfe_stream_t s);
 
+/* HOST function (no device work): the distinct rows of `rows` (n x 4 int64, 0 <= v < 2^61 - 1, insertion
+ * order) in the order CPython's list(set(map(tuple, rows))) returns them -- the order in which the reference
+ * writes Fixed_Displacement_Coordinates (voxelFE.py:449).  out: capacity n x 4. */
+int cfe_host_pyset_order(const int64_t* rows, int64_t n, int64_t* out, int64_t* n_out);
+
 /* segment (preprocess.py:20-46): out[i] = img[i] > t, bytes 0 / 1; buffers 16-byte aligned */
 int cfe_threshold_u8(const uint8_t* img, int64_t n, int t, uint8_t* out, cfe_stream_t s);
 

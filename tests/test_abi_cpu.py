@@ -113,3 +113,24 @@ def test_vol2ugrid_argument_errors_before_any_gpu_work():
         vol2ugrid(np.ones((2, 2, 2), dtype=bool), locking_strategy="both")
     with pytest.raises(TypeError):
         vol2ugrid(np.ones((2, 2, 2), dtype=bool), voxelsize=(1, 1, 1))
+
+
+def test_pyset_replay_matches_this_interpreter():
+    """cfe_host_pyset_order (host C code, csrc/pyset.cu) must give list(set(...)) of the running CPython:
+    that order is what the reference writes into Fixed_Displacement_Coordinates (voxelFE.py:449)."""
+    import numpy as np
+    from ciclope_b200 import parosol
+    rng = np.random.default_rng(2)
+    for n, hi in [(1, 2), (7, 2), (40, 3), (700, 9), (6000, 30), (49000, 60), (52000, 200), (260000, 120)]:
+        rows = np.stack([rng.integers(0, hi, n), rng.integers(0, hi, n), rng.integers(0, hi, n),
+                         rng.integers(0, 3, n)], axis=1)
+        want = np.array(list(set(map(tuple, rows.tolist()))), dtype=np.int64).reshape(-1, 4)
+        got = parosol._pyset_replay(rows)
+        assert got.shape == want.shape and np.array_equal(got, want), n
+    # boundary-plane shaped input: element-major corner expansion with many duplicates
+    els = np.argwhere(rng.random((90, 110)) < 0.4)
+    els = np.hstack((np.zeros((len(els), 1), dtype=np.int64), els))
+    rows = parosol._corner_rows(els, (0, 1, 2))
+    want = np.array(list(set(map(tuple, rows.tolist()))), dtype=np.int64).reshape(-1, 4)
+    assert np.array_equal(parosol._pyset_replay(rows), want)
+    assert parosol._replay_matches_interpreter()
