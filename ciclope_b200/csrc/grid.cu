@@ -938,31 +938,43 @@ extern "C" int cfe_proj_bits(const uint32_t* bits, int64_t rows, int64_t X, uint
     return 0;
 }
 
-#define CROP_X_PER_CTA 2048
-
+// one warp per row of the cropped block; a lane converts 4 consecutive voxels (one 32-bit load when the
+// source address allows, one 16-byte store when the output row is 16-byte aligned)
 __global__ void __launch_bounds__(256)
-k_scale_crop_f32(const uint8_t* __restrict__ vol, i64 sY, i64 sX, i64 z0, i64 y0, i64 x0, i64 ny, i64 nx,
-                 i64 xchunks, const float* __restrict__ lut, float* __restrict__ out)
+k_scale_crop_f32(const uint8_t* __restrict__ vol, i64 sY, i64 sX, i64 z0, i64 y0, i64 x0, i64 rows, FastDiv dny,
+                 u32 ny, i64 nx, const float* __restrict__ lut, float* __restrict__ out)
 {
     __shared__ float t[256];
     t[threadIdx.x] = __ldg(lut + threadIdx.x);
     __syncthreads();
-    const i64 row = (i64)blockIdx.x / xchunks;                 // (z, y) of the cropped block
-    const i64 xc = (i64)blockIdx.x - row * xchunks;
-    const i64 z = row / ny, y = row - z * ny;
-    const uint8_t* src = vol + ((z0 + z) * sY + (y0 + y)) * sX + x0;
-    float* dst = out + row * nx;
-    const i64 xb = xc * CROP_X_PER_CTA + threadIdx.x;
-    uint8_t v[CROP_X_PER_CTA / 256];
-#pragma unroll
-    for (int k = 0; k < CROP_X_PER_CTA / 256; ++k) {
-        const i64 x = xb + 256 * k;
-        v[k] = (x < nx) ? __ldg(src + x) : (uint8_t)0;
-    }
-#pragma unroll
-    for (int k = 0; k < CROP_X_PER_CTA / 256; ++k) {
-        const i64 x = xb + 256 * k;
-        if (x < nx) dst[x] = t[v[k]];
+    const u32 lane = threadIdx.x & 31u;
+    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const bool vec_out = ((nx & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+    for (i64 row = warp0; row < rows; row += nwarps) {
+        const u32 z = fd_div((u32)row, dny);
+        const u32 y = (u32)row - z * ny;
+        const uint8_t* src = vol + ((z0 + z) * sY + (y0 + y)) * sX + x0;
+        float* dst = out + row * nx;
+        const bool vec_in = (reinterpret_cast<uintptr_t>(src) & 3u) == 0;
+        const i64 nx4 = nx & ~(i64)3;
+#pragma unroll 4
+        for (i64 x = (i64)lane * 4; x < nx4; x += 128) {
+            u32 w;
+            if (vec_in) {
+                w = __ldg(reinterpret_cast<const u32*>(src + x));
+            } else {
+                w = (u32)__ldg(src + x) | ((u32)__ldg(src + x + 1) << 8) | ((u32)__ldg(src + x + 2) << 16) |
+                    ((u32)__ldg(src + x + 3) << 24);
+            }
+            const float4 f = make_float4(t[w & 255u], t[(w >> 8) & 255u], t[(w >> 16) & 255u], t[w >> 24]);
+            if (vec_out) {
+                *reinterpret_cast<float4*>(dst + x) = f;
+            } else {
+                dst[x] = f.x; dst[x + 1] = f.y; dst[x + 2] = f.z; dst[x + 3] = f.w;
+            }
+        }
+        for (i64 x = nx4 + lane; x < nx; x += 32) dst[x] = t[__ldg(src + x)];
     }
 }
 
@@ -972,10 +984,14 @@ extern "C" int cfe_scale_crop_f32(const uint8_t* vol, int64_t Y, int64_t X, int6
                                   cudaStream_t stream)
 {
     if (nz <= 0 || ny <= 0 || nx <= 0) return 0;
-    const i64 xchunks = (nx + CROP_X_PER_CTA - 1) / CROP_X_PER_CTA;
-    const i64 blocks = nz * ny * xchunks;
-    if (blocks >= (1LL << 31)) { cfe_set_error("cfe_scale_crop_f32: block too large"); return -1; }
-    k_scale_crop_f32<<<(unsigned)blocks, 256, 0, stream>>>(vol, Y, X, z0, y0, x0, ny, nx, xchunks, lut256, out);
+    const i64 rows = nz * ny;
+    if (rows >= (1LL << 32) || ny >= (1LL << 32)) { cfe_set_error("cfe_scale_crop_f32: block too large"); return -1; }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    i64 blocks = (rows + 7) / 8;
+    if (blocks > (i64)sms * 8) blocks = (i64)sms * 8;
+    k_scale_crop_f32<<<(unsigned)blocks, 256, 0, stream>>>(vol, Y, X, z0, y0, x0, rows, make_fastdiv((u32)ny),
+                                                           (u32)ny, nx, lut256, out);
     CFE_CHECK_LAUNCH("k_scale_crop_f32");
     return 0;
 }
