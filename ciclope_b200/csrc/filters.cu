@@ -1,0 +1,147 @@
+// Gaussian smoothing ahead of the segmentation (pipeline.py:146-148: skimage.filters.gaussian(I, sigma,
+// preserve_range=True) = scipy.ndimage.gaussian_filter(I.astype(float64), sigma, mode='nearest',
+// truncate=4.0)) and the threshold of the resulting float64 image (preprocess.py:46).
+//
+// scipy filters one axis after the other (0, 1, 2), each pass in float64 with the symmetric-kernel loop of
+// NI_Correlate1D:   o = x[0] * w[0];  for j = -r .. -1:  o += (x[j] + x[-j]) * w[j]
+// (farthest pair first, no fused multiply-add, 'nearest' = clamped indices).  The kernels below do exactly
+// that arithmetic with __dmul_rn / __dadd_rn, so the result has scipy's bits.
+#include <cstdint>
+
+#include "common.cuh"
+
+#define GAUSS_MAX_RADIUS 255
+
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+k_gauss1d(const TIN* __restrict__ in, double* __restrict__ out, i64 n_total, i64 n_axis, i64 stride,
+          const double* __restrict__ weights, int r)
+{
+    __shared__ double w[2 * GAUSS_MAX_RADIUS + 1];
+    for (int i = threadIdx.x; i < 2 * r + 1; i += blockDim.x) w[i] = weights[i];
+    __syncthreads();
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (i64)gridDim.x * blockDim.x) {
+        const i64 pos = (stride == 1 && n_total < (1LL << 32)) ? (i64)((u32)i % (u32)n_axis)
+                                                               : (i64)(((u64)i / (u64)stride) % (u64)n_axis);
+        const TIN* line = in + (i - pos * stride);
+        double acc = __dmul_rn((double)line[pos * stride], w[r]);
+        for (int j = -r; j < 0; ++j) {
+            i64 a = pos + j, b = pos - j;
+            if (a < 0) a = 0;
+            if (b > n_axis - 1) b = n_axis - 1;
+            const double s = __dadd_rn((double)line[a * stride], (double)line[b * stride]);
+            acc = __dadd_rn(acc, __dmul_rn(s, w[r + j]));
+        }
+        out[i] = acc;
+    }
+}
+
+// Strided axes (inner > 1): the array is [outer][n_axis][inner] with `inner` contiguous elements.  A CTA
+// owns a compact tile of 32 inner x 64 axis positions (thread = 8 consecutive axis positions of one
+// column), so the 2 r + 1 taps of neighbouring outputs are re-read from L1 instead of L2.
+#define GAUSS_TA 64
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+k_gauss_strided(const TIN* __restrict__ in, double* __restrict__ out, i64 n_axis, i64 inner, u32 tiles_inner,
+                const double* __restrict__ weights, int r)
+{
+    __shared__ double w[2 * GAUSS_MAX_RADIUS + 1];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < 2 * r + 1; i += 256) w[i] = weights[i];
+    __syncthreads();
+    const u32 ba = blockIdx.x / tiles_inner;
+    const u32 bx = blockIdx.x - ba * tiles_inner;
+    const i64 col = (i64)bx * 32 + threadIdx.x;
+    if (col >= inner) return;
+    const i64 a0 = (i64)ba * GAUSS_TA + threadIdx.y * (GAUSS_TA / 8);
+    const i64 base = (i64)blockIdx.y * n_axis * inner + col;
+    const TIN* line = in + base;
+#pragma unroll 1
+    for (int t = 0; t < GAUSS_TA / 8; ++t) {
+        const i64 pos = a0 + t;
+        if (pos >= n_axis) break;
+        double acc = __dmul_rn((double)line[pos * inner], w[r]);
+        for (int j = -r; j < 0; ++j) {
+            i64 a = pos + j, b = pos - j;
+            if (a < 0) a = 0;
+            if (b > n_axis - 1) b = n_axis - 1;
+            const double s = __dadd_rn((double)line[a * inner], (double)line[b * inner]);
+            acc = __dadd_rn(acc, __dmul_rn(s, w[r + j]));
+        }
+        out[base + pos * inner] = acc;
+    }
+}
+
+static int gauss_grid(i64 n_total)
+{
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    i64 blocks = (n_total + 255) / 256;
+    if (blocks > (i64)sms * 16) blocks = (i64)sms * 16;
+    return (int)blocks;
+}
+
+// One pass of scipy.ndimage.correlate1d(input, weights, axis, mode='nearest') for a symmetric kernel of
+// 2 r + 1 weights over an array of n_total elements whose filtered axis has n_axis entries `stride` elements
+// apart (C order: stride = product of the later dimensions).  in_is_u8: the input is uint8 (first pass),
+// else float64.  in and out must not alias.
+extern "C" int cfe_gauss1d(const void* in, int in_is_u8, double* out, int64_t n_total, int64_t n_axis,
+                           int64_t stride, const double* weights, int r, cudaStream_t stream)
+{
+    if (n_total <= 0) return 0;
+    if (r < 0 || r > GAUSS_MAX_RADIUS) { cfe_set_error("cfe_gauss1d: radius must be in 0..%d", GAUSS_MAX_RADIUS); return -1; }
+    if (n_axis <= 0 || stride <= 0 || in == (const void*)out || n_total % (n_axis * stride)) {
+        cfe_set_error("cfe_gauss1d: bad arguments");
+        return -1;
+    }
+    const i64 outer = n_total / (n_axis * stride);
+    const i64 tiles_inner = (stride + 31) / 32, tiles_axis = (n_axis + GAUSS_TA - 1) / GAUSS_TA;
+    if (stride >= 32 && outer <= 65535 && tiles_inner * tiles_axis < (1LL << 31)) {
+        const dim3 grid((unsigned)(tiles_inner * tiles_axis), (unsigned)outer), block(32, 8);
+        if (in_is_u8)
+            k_gauss_strided<uint8_t><<<grid, block, 0, stream>>>(reinterpret_cast<const uint8_t*>(in), out, n_axis,
+                                                                 stride, (u32)tiles_inner, weights, r);
+        else
+            k_gauss_strided<double><<<grid, block, 0, stream>>>(reinterpret_cast<const double*>(in), out, n_axis,
+                                                                stride, (u32)tiles_inner, weights, r);
+        CFE_CHECK_LAUNCH("k_gauss_strided");
+        return 0;
+    }
+    const int blocks = gauss_grid(n_total);
+    if (in_is_u8)
+        k_gauss1d<uint8_t><<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(in), out, n_total, n_axis,
+                                                      stride, weights, r);
+    else
+        k_gauss1d<double><<<blocks, 256, 0, stream>>>(reinterpret_cast<const double*>(in), out, n_total, n_axis,
+                                                     stride, weights, r);
+    CFE_CHECK_LAUNCH("k_gauss1d");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_threshold_f64(const double* __restrict__ img, i64 n, double t, uint8_t* __restrict__ out)
+{
+    // 4 values per thread -> one 32-bit store
+    const i64 n4 = n >> 2;
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (i64)gridDim.x * blockDim.x) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(img) + 2 * g);
+        const double2 b = __ldg(reinterpret_cast<const double2*>(img) + 2 * g + 1);
+        const u32 r = (a.x > t ? 1u : 0u) | (a.y > t ? 0x100u : 0u) | (b.x > t ? 0x10000u : 0u) | (b.y > t ? 0x1000000u : 0u);
+        reinterpret_cast<u32*>(out)[g] = r;
+    }
+    for (i64 i = (n4 << 2) + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        out[i] = img[i] > t ? 1 : 0;
+}
+
+// out[i] = img[i] > t for a float64 image (NaN compares false, as in NumPy); img 16-byte, out 4-byte aligned
+extern "C" int cfe_threshold_f64(const double* img, int64_t n, double t, uint8_t* out, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(img) & 15u) || (reinterpret_cast<uintptr_t>(out) & 3u)) {
+        cfe_set_error("cfe_threshold_f64: misaligned buffers");
+        return -1;
+    }
+    k_threshold_f64<<<gauss_grid(n / 4 + 1), 256, 0, stream>>>(img, n, t, out);
+    CFE_CHECK_LAUNCH("k_threshold_f64");
+    return 0;
+}

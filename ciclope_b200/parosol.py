@@ -128,23 +128,10 @@ def _replay_matches_interpreter():
     return _REPLAY_OK
 
 
-def _ordered_unique(rows, node_order):
-    """The reference's ``list(set)`` of the row tuples (CPython set order), or the sorted unique rows;
-    an int64 array [n, 4]."""
+def _ordered_unique(rows):
+    """The reference's ``list(set)`` of the row tuples (CPython set order); an int64 array [n, 4]."""
     if len(rows) == 0:
         return np.zeros((0, 4), dtype=np.int64)
-    if node_order == "sorted":
-        m = int(rows[:, :3].max()) + 1
-        key = ((rows[:, 0] * m + rows[:, 1]) * m + rows[:, 2]) * 4 + rows[:, 3]
-        key = np.unique(key)
-        out = np.empty((len(key), 4), dtype=np.int64)
-        out[:, 3] = key % 4
-        key //= 4
-        out[:, 2] = key % m
-        key //= m
-        out[:, 1] = key % m
-        out[:, 0] = key // m
-        return out
     if rows.min() >= 0 and _replay_matches_interpreter():
         return _pyset_replay(rows)
     s = set()
@@ -207,11 +194,37 @@ def parosol_datasets(voldata, topDisplacement, voxelsize=1, poisson_ratio=0.3, y
                     parts.append(np.hstack((np.full((yx.shape[0], 1), lab), yx)))
                 return np.vstack(parts) if parts else np.zeros((0, 3), dtype=np.int64)
 
-            # the reference labels the rows with i / idx as computed, before any wrap-around
-            low = elements(low_planes, [i for i in range(p)])
-            top = elements(top_planes, [nz - 1 - i for i in range(p)])
-            lb_rows = _corner_rows(low, (0, 1, 2))
-            tb_rows = _corner_rows(top, (0, 1, 2) if topHorizontaFixedlDisplacement else (2,))
+            top_dirs = (0, 1, 2) if topHorizontaFixedlDisplacement else (2,)
+            if node_order == "sorted":
+                # no insertion sequence needed: the nodes of the selected planes as boolean node layers
+                def plane_nodes(planes, dirs):
+                    layers = {}
+                    for i in planes:
+                        q = plane[i]
+                        for dz in (0, 1):
+                            ex = layers.setdefault(i + dz, np.zeros((ny + 1, nx + 1), dtype=bool))
+                            ex[:-1, :-1] |= q
+                            ex[:-1, 1:] |= q
+                            ex[1:, :-1] |= q
+                            ex[1:, 1:] |= q
+                    rows = []
+                    for z in sorted(layers):
+                        yx = np.argwhere(layers[z])
+                        rows.append(np.hstack((np.full((yx.shape[0], 1), z), yx)))
+                    nodes = np.vstack(rows) if rows else np.zeros((0, 3), dtype=np.int64)
+                    out = np.empty((len(nodes), len(dirs), 4), dtype=np.int64)
+                    out[..., :3] = nodes[:, None, :]
+                    out[..., 3] = np.asarray(dirs, dtype=np.int64)[None, :]
+                    return out.reshape(-1, 4)
+
+                lb_rows = plane_nodes(low_planes, (0, 1, 2))
+                tb_rows = plane_nodes(top_planes, top_dirs)
+            else:
+                # the reference labels the rows with i / idx as computed, before any wrap-around
+                low = elements(low_planes, [i for i in range(p)])
+                top = elements(top_planes, [nz - 1 - i for i in range(p)])
+                lb_rows = _corner_rows(low, (0, 1, 2))
+                tb_rows = _corner_rows(top, top_dirs)
         elif locking_strategy == "exact":
             k = node_level_lock_num
             lo_levels = [z for z in range(nz + 1) if z < k]
@@ -245,8 +258,11 @@ def parosol_datasets(voldata, topDisplacement, voxelsize=1, poisson_ratio=0.3, y
         else:
             raise ValueError("locking_strategy must be 'plane' or 'exact'")
 
-    lb = _ordered_unique(lb_rows, node_order)
-    tb = _ordered_unique(tb_rows, node_order)
+    if node_order == "sorted":
+        lb, tb = lb_rows, tb_rows               # distinct and in (z, y, x, dof) order by construction
+    else:
+        lb = _ordered_unique(lb_rows)
+        tb = _ordered_unique(tb_rows)
     all_nodes = np.concatenate([lb, tb])                             # voxelFE.py:449
     n_all = len(all_nodes)
     # np.array(list_of_tuples, dtype=uint16): (n, 4), or (0,) when there is no node at all

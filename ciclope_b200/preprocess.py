@@ -221,6 +221,22 @@ def segment(image, threshold_value):
     T
         Threshold value.
     """
+    if _is_float64(image):
+        # the smoothed image of pipeline.py:146-148 (gaussian() below)
+        if threshold_value is None:
+            raise NotImplementedError("Otsu threshold of a float image is not available on the GPU path: "
+                                      "pass threshold_value")
+        T = int(threshold_value)
+        from_numpy = isinstance(image, np.ndarray)
+        t = torch.from_numpy(np.ascontiguousarray(image)) if from_numpy else image.contiguous()
+        _lib.require_cuda()
+        if not t.is_cuda:
+            t = t.cuda()
+        with torch.cuda.device(t.device):
+            out = torch.empty(t.shape, dtype=torch.uint8, device=t.device)
+            _lib.call("cfe_threshold_f64", t.data_ptr(), t.numel(), float(T), out.data_ptr(), _lib.stream())
+        out = out.view(torch.bool)
+        return (out.cpu().numpy() if from_numpy else out), T
     if threshold_value is None:
         T = threshold_otsu(image)
     else:
@@ -257,3 +273,72 @@ def add_cap(I, cap_thickness, cap_val):  # noqa: E741 -- the reference's paramet
     out[Z + c:].fill_(int(probe[0]))
     out[c:Z + c].copy_(vol)
     return out.cpu().numpy() if from_numpy else out
+
+
+def _is_float64(image):
+    return (isinstance(image, np.ndarray) and image.dtype == np.float64) or \
+           (isinstance(image, torch.Tensor) and image.dtype == torch.float64)
+
+
+def _gaussian_kernel1d(sigma, radius):
+    """scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius): the same NumPy expressions, so the
+    weights have scipy's bits."""
+    sigma2 = sigma * sigma
+    x = np.arange(-radius, radius + 1)
+    phi_x = np.exp(-0.5 / sigma2 * x ** 2)
+    return phi_x / phi_x.sum()
+
+
+def gaussian(image, sigma=1, mode='nearest', cval=0, preserve_range=False, truncate=4.0):
+    """Gaussian smoothing of a 3D image: the call ciclope's pipeline makes before segmenting
+    (pipeline.py:146-148, ``skimage.filters.gaussian(I, sigma=..., preserve_range=True)``), which is
+    ``scipy.ndimage.gaussian_filter(I.astype(float64), sigma, mode='nearest', truncate=4.0)``: one
+    float64 pass per axis (0, 1, 2) in scipy's order of operations, so the result is bit-identical to
+    scipy's.  ``image``: uint8 or float64, NumPy array or CUDA tensor; returns float64 of the same kind.
+    Only ``preserve_range=True`` and ``mode='nearest'`` (what the pipeline uses) are available."""
+    if not preserve_range:
+        raise NotImplementedError("gaussian: only preserve_range=True (the pipeline's call) is available")
+    if mode != 'nearest':
+        raise NotImplementedError("gaussian: only mode='nearest' (skimage's default) is available")
+    from_numpy = isinstance(image, np.ndarray)
+    if _is_float64(image):
+        t = torch.from_numpy(np.ascontiguousarray(image)) if from_numpy else image.contiguous()
+        is_u8 = False
+    else:
+        t, is_bool, from_numpy = as_device_volume(image)
+        if is_bool:
+            raise TypeError("gaussian: uint8 or float64 images")
+        is_u8 = True
+    if t.dim() != 3:
+        raise ValueError("image must be 3-D [slices, rows, cols]")
+    sig = np.asarray(sigma, dtype=np.float64)
+    if np.any(sig < 0.0):
+        raise ValueError("Sigma values less than zero are not valid")
+    sigmas = [float(sig)] * 3 if sig.ndim == 0 else [float(v) for v in sig]
+    if len(sigmas) != 3:
+        raise RuntimeError("sequence argument must have length equal to input rank")
+    _lib.require_cuda()
+    if not t.is_cuda:
+        t = t.cuda()
+    dev = t.device
+    shape = [int(v) for v in t.shape]
+    n_total = t.numel()
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        cur, cur_u8 = t, is_u8
+        for axis in range(3):
+            sd = sigmas[axis]
+            if not sd > 1e-15:                                  # scipy skips these axes
+                continue
+            r = int(truncate * sd + 0.5)
+            w = _gaussian_kernel1d(sd, r)[::-1]
+            dw = torch.from_numpy(np.ascontiguousarray(w)).pin_memory().to(dev, non_blocking=True)
+            out = torch.empty(shape, dtype=torch.float64, device=dev)
+            stride = int(np.prod(shape[axis + 1:], dtype=np.int64))
+            if n_total:
+                _lib.call("cfe_gauss1d", cur.data_ptr(), 1 if cur_u8 else 0, out.data_ptr(), n_total, shape[axis],
+                          stride, dw.data_ptr(), r, s)
+            cur, cur_u8 = out, False
+        if cur_u8:                                              # every sigma was 0: the float64 copy
+            cur = cur.to(torch.float64)
+    return cur.cpu().numpy() if from_numpy else cur

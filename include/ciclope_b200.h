@@ -323,6 +323,18 @@ int cfe_host_pyset_order(const int64_t* rows, int64_t n, int64_t* out, int64_t* 
 /* segment (preprocess.py:20-46): out[i] = img[i] > t, bytes 0 / 1; buffers 16-byte aligned */
 int cfe_threshold_u8(const uint8_t* img, int64_t n, int t, uint8_t* out, cfe_stream_t s);
 
+/* ------------------------------------------------------------------ Gaussian smoothing (pipeline.py:146-148) */
+
+/* One pass of scipy.ndimage.correlate1d(input, weights, axis, mode='nearest') with a symmetric kernel of
+ * 2 r + 1 float64 weights (device pointer), float64 arithmetic in scipy's order of operations (bit-exact):
+ * skimage.filters.gaussian(I, sigma, preserve_range=True) is three such passes (axes 0, 1, 2).  n_total
+ * elements; the filtered axis has n_axis entries `stride` elements apart.  in: uint8 (in_is_u8) or float64. */
+int cfe_gauss1d(const void* in, int in_is_u8, double* out, int64_t n_total, int64_t n_axis, int64_t stride,
+                const double* weights, int r, cfe_stream_t s);
+
+/* image > t for a float64 image: bytes 0 / 1 (preprocess.py:46 after smoothing) */
+int cfe_threshold_f64(const double* img, int64_t n, double t, uint8_t* out, cfe_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -500,3 +500,30 @@ def add_cap(I, cap_thickness, cap_val):  # noqa: E741
     I_cap = np.ones([I.shape[0] + 2 * cap_thickness, I.shape[1], I.shape[2]], I.dtype) * cap_val
     I_cap[cap_thickness:-cap_thickness, :, :] = I
     return I_cap
+
+
+# --------------------------------------------------------------------------------------------
+# gaussian <- pipeline.py:146-148: skimage.filters.gaussian(I, sigma, preserve_range=True), i.e.
+# scipy.ndimage.gaussian_filter(I.astype(float64), sigma, mode='nearest', truncate=4.0) (scikit-image's
+# defaults).  Restated in NumPy with the order of operations of scipy's NI_Correlate1D symmetric loop;
+# tests pin it bit-for-bit against the installed scipy (the dependency the reference itself imports).
+
+def gaussian(image, sigma, truncate=4.0):
+    a = np.asarray(image).astype(np.float64)
+    sig = [float(sigma)] * a.ndim if np.ndim(sigma) == 0 else [float(v) for v in sigma]
+    for axis in range(a.ndim):
+        sd = sig[axis]
+        if not sd > 1e-15:
+            continue
+        lw = int(truncate * sd + 0.5)
+        x = np.arange(-lw, lw + 1)
+        w = np.exp(-0.5 / (sd * sd) * x ** 2)
+        w = (w / w.sum())[::-1]
+        n = a.shape[axis]
+        idx = np.arange(n)
+        acc = np.take(a, idx, axis=axis) * w[lw]
+        for jj in range(-lw, 0):
+            acc = acc + (np.take(a, np.clip(idx + jj, 0, n - 1), axis=axis) +
+                         np.take(a, np.clip(idx - jj, 0, n - 1), axis=axis)) * w[lw + jj]
+        a = acc
+    return a

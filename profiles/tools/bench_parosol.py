@@ -8,7 +8,7 @@ import numpy as np
 import torch
 from ciclope_b200 import _lib, synth
 from ciclope_b200.parosol import parosol_datasets
-from ciclope_b200.preprocess import remove_unconnected, segment
+from ciclope_b200.preprocess import gaussian, remove_unconnected, segment
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 grey = synth.greyscale((S, S, S), seed=0, bvtv=0.30, device="cuda")
@@ -48,6 +48,10 @@ g = lambda: segment(grey, 80)
 res["segment_ms"] = timeit(g)
 res["segment_entry_point_ms"] = profile(g)
 res["segment_gbs"] = 2 * S ** 3 / (res["segment_entry_point_ms"]["cfe_threshold_u8"] * 1e-3) / 1e9
+if S <= 512:
+    gs = lambda: gaussian(grey, sigma=1.0, preserve_range=True)
+    res["gaussian_sigma1_ms"] = timeit(gs, k=3)
+    res["gaussian_entry_point_ms"] = profile(gs)
 ds = f()
 img = ds["Image"]
 res["image_shape"] = list(img.shape)

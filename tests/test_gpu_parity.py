@@ -573,3 +573,28 @@ def test_segment_otsu_vs_oracle(cfe, orc):
     flat = np.full((4, 5, 6), 9, dtype=np.uint8)
     bw, T = cfe.segment(flat, None)
     assert T == 9 and not bw.any()
+
+
+@pytest.mark.parametrize("shape,sigma", [((20, 30, 40), 1.0), ((7, 9, 5), 2.5), ((33, 17, 64), 0.5),
+                                         ((12, 40, 33), [0.0, 1.3, 2.0]), ((64, 96, 130), 1.5), ((9, 9, 9), 3.7)])
+def test_gaussian_bit_exact_vs_scipy_and_oracle(cfe, orc, shape, sigma):
+    """pipeline.py:146-148; float64 work, compared BIT FOR BIT (tolerance 0) with the oracle and with the
+    installed scipy.ndimage.gaussian_filter that skimage.filters.gaussian wraps"""
+    import torch
+    from scipy import ndimage
+    img = np.random.default_rng(4).integers(0, 256, shape).astype(np.uint8)
+    got = cfe.gaussian(img, sigma=sigma, preserve_range=True)
+    assert isinstance(got, np.ndarray) and got.dtype == np.float64 and got.shape == img.shape
+    assert np.array_equal(got, orc.gaussian(img, sigma))
+    assert np.array_equal(got, ndimage.gaussian_filter(img.astype(float), sigma, mode='nearest', truncate=4.0))
+    # float64 input, tensor in / tensor out, then the threshold of the smoothed image
+    got2 = cfe.gaussian(torch.from_numpy(img.astype(np.float64)).cuda(), sigma=sigma, preserve_range=True)
+    assert got2.dtype == torch.float64 and np.array_equal(got2.cpu().numpy(), got)
+    bw, T = cfe.segment(got2, 100.9)
+    assert T == 100 and bw.dtype == torch.bool and np.array_equal(bw.cpu().numpy(), got > 100)
+    bw_np, _ = cfe.segment(got, 100)
+    assert np.array_equal(bw_np, got > 100)
+    with pytest.raises(NotImplementedError):
+        cfe.segment(got, None)
+    with pytest.raises(NotImplementedError):
+        cfe.gaussian(img, sigma=1.0)

@@ -205,3 +205,13 @@ def test_oracle_otsu_separates_two_populations():
     T = orc.threshold_otsu_u8(img.reshape(20, 20, 20))
     assert 90 <= T <= 150
     assert orc.threshold_otsu_u8(np.full((3, 3, 3), 7, dtype=np.uint8)) == 7
+
+
+@pytest.mark.parametrize("shape,sigma", [((20, 30, 40), 1.0), ((7, 9, 5), 2.5), ((33, 17, 64), 0.5),
+                                         ((12, 40, 33), [0.0, 1.3, 2.0]), ((9, 9, 9), 3.7)])
+def test_oracle_gaussian_is_scipy_bit_for_bit(shape, sigma):
+    from scipy import ndimage
+    img = np.random.default_rng(4).integers(0, 256, shape).astype(np.uint8)
+    want = ndimage.gaussian_filter(img.astype(float), sigma, mode='nearest', truncate=4.0)
+    got = orc.gaussian(img, sigma)
+    assert got.dtype == np.float64 and np.array_equal(got, want)
