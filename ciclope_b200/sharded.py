@@ -136,8 +136,54 @@ class LocalRunner:
         return results
 
 
+class PeerExchange:
+    """The small collectives of the z-slab path (counts, one packed bit plane, boundary vertices) as ONE
+    kernel over NVLink peer memory (``cfe_peer_exchange``, csrc/peer.cu) instead of an NCCL call each.
+    torch.distributed._symmetric_memory allocates the buffer and exchanges the peer pointers once; the
+    data path is the library's kernel: remote stores into every peer's slot, a release / acquire signal per
+    peer, then a local gather.  Payloads above ``CHUNK`` bytes stay with NCCL."""
+
+    SLOTS = 4
+    CHUNK = 1 << 20          # bytes per source rank and slot
+    SIG_OFFSET = 256         # first u32 of the signal pad used here (the front is symmetric memory's own)
+
+    def __init__(self, dist, group, device):
+        import torch.distributed._symmetric_memory as symm
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 32:
+            raise RuntimeError("peer exchange handles up to 32 ranks")
+        pg = group if group is not None else dist.group.WORLD
+        with torch.cuda.device(device):
+            self.buf = symm.empty(self.SLOTS * self.world * self.CHUNK, dtype=torch.uint8, device=device)
+            self.hdl = symm.rendezvous(self.buf, pg)
+            if self.hdl.signal_pad_size < 4 * (self.SIG_OFFSET + self.SLOTS * self.world):
+                raise RuntimeError("signal pad too small")
+            self.counter = torch.zeros(2, dtype=torch.int32, device=device)
+            self.hdl.barrier()                  # every rank's pad and counter are ready before the first kernel
+        self.device = device
+        self.epoch = 0
+
+    def exchange(self, t, send_mask=None):
+        """-> tensor [world, *t.shape]; row p = rank p's ``t`` (only the rows of ranks that sent to me)"""
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        self.epoch += 1
+        slot = self.epoch % self.SLOTS
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        if send_mask is None:
+            send_mask = (1 << self.world) - 1
+        _lib.call("cfe_peer_exchange", t.data_ptr(), nbytes, self.hdl.buffer_ptrs_dev, self.hdl.signal_pad_ptrs_dev,
+                  self.rank, self.world, slot * self.world * self.CHUNK, self.CHUNK, self.epoch, send_mask,
+                  self.SIG_OFFSET + slot * self.world, self.counter.data_ptr(), out.data_ptr(), _lib.stream())
+        return out
+
+
 class DistRunner:
-    """Runs one rank program per process over torch.distributed (NCCL on GPUs, gloo on CPU)."""
+    """Runs one rank program per process over torch.distributed (NCCL on GPUs, gloo on CPU).  On GPUs the
+    small exchanges go through :class:`PeerExchange` (one kernel over NVLink peer memory); NCCL carries the
+    large planes, and everything when symmetric memory cannot be set up (``CICLOPE_B200_PEER=0`` forces
+    that)."""
 
     def __init__(self, group=None, device=None):
         import torch.distributed as dist
@@ -146,6 +192,21 @@ class DistRunner:
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
         self.device = device
+        self.peer = None
+        self.peer_error = None
+        if device is None and dist.get_backend(group) == "nccl" and torch.cuda.is_available():
+            device = torch.device("cuda", torch.cuda.current_device())      # one process per GPU
+        if (device is not None and torch.device(device).type == "cuda" and self.size > 1
+                and dist.get_backend(group) == "nccl" and os.environ.get("CICLOPE_B200_PEER", "1") != "0"):
+            try:
+                self.peer = PeerExchange(dist, group, torch.device(device))
+            except Exception as e:  # noqa: BLE001 -- no P2P / symmetric memory on this box: NCCL does it all
+                self.peer_error = "%s: %s" % (type(e).__name__, e)
+            # all ranks take the same path
+            ok = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.peer = None
 
     def ctx(self):
         return Ctx(self.rank, self.size, self.device)
@@ -153,6 +214,8 @@ class DistRunner:
     def _gather(self, t):
         """all_gather_into_tensor: one flat output, far less Python / launch overhead than the list API"""
         t = t.contiguous()
+        if self.peer is not None and t.is_cuda and 0 < t.numel() * t.element_size() <= PeerExchange.CHUNK:
+            return self.peer.exchange(t)
         flat = t.reshape(-1)
         out = torch.empty(self.size * flat.numel(), dtype=t.dtype, device=t.device)
         self.dist.all_gather_into_tensor(out, flat, group=self.group)
@@ -171,6 +234,11 @@ class DistRunner:
             out = self._gather(pad)
             return [out[k, :c] for k, c in enumerate(ns)]
         if kind == "shift_up":
+            if self.peer is not None and t.is_cuda and 0 < t.numel() * t.element_size() <= PeerExchange.CHUNK:
+                # the plane goes to the rank above only; the signals still synchronise every rank
+                mask = (1 << (self.rank + 1)) if self.rank + 1 < self.size else 0
+                out = self.peer.exchange(t, send_mask=mask)
+                return out[self.rank - 1] if self.rank > 0 else None
             if t.numel() * t.element_size() <= self.SHIFT_VIA_GATHER_BYTES:
                 # small planes: one all-gather is cheaper to issue than a send/recv pair
                 out = self._gather(t)

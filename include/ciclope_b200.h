@@ -335,6 +335,18 @@ int cfe_gauss1d(const void* in, int in_is_u8, double* out, int64_t n_total, int6
 /* image > t for a float64 image: bytes 0 / 1 (preprocess.py:46 after smoothing) */
 int cfe_threshold_f64(const double* img, int64_t n, double t, uint8_t* out, cfe_stream_t s);
 
+/* ------------------------------------------------------------------ z-slab collectives over peer memory */
+
+/* All-gather / neighbour shift of a small payload as one kernel over NVLink peer memory (csrc/peer.cu).
+ * peer_bufs_dev / peer_sigs_dev: device arrays [world] of the ranks' symmetric buffers and signal pads
+ * (torch.distributed._symmetric_memory: buffer_ptrs_dev, signal_pad_ptrs_dev).  Buffer layout
+ * [slot][source rank][chunk_cap]; slot_off = byte offset of the slot used by this epoch; sig_base = first
+ * u32 of the signal pad used by this slot (world words).  Every rank calls with the same epoch; out =
+ * [world][nbytes].  counter: 2 zeroed u32 of local device memory. */
+int cfe_peer_exchange(const void* src, int64_t nbytes, const void* peer_bufs_dev, const void* peer_sigs_dev,
+                      int rank, int world, int64_t slot_off, int64_t chunk_cap, uint32_t epoch, uint32_t send_mask,
+                      uint32_t sig_base, uint32_t* counter, void* out, cfe_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif
