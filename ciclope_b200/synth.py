@@ -64,6 +64,14 @@ def trabecular(shape, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3):
     return f > t
 
 
+def foam(shape, seed=0, bvtv=0.12, device="cuda", radius=4, passes=3):
+    """Fragmented foam (BASELINE.json configs[3]): the same field thresholded BELOW the percolation level,
+    so that the foreground falls apart into many components of similar size (232 at 192^3 with the defaults,
+    i.e. ~3 * 10^5 at 2048^3; the largest holds ~20 % of the foreground) -- the case that stresses the
+    cross-slab merge of the sharded labelling."""
+    return trabecular(shape, seed, bvtv, device, radius, passes)
+
+
 def greyscale(shape, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3):
     """uint8 volume: GV = 1 + blurred field quantised to 0..254 inside the bone mask, 0 outside
     (the `masked[~L] = 0` pattern of ciclope example 01)."""

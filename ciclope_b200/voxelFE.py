@@ -829,6 +829,40 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     return out[:length]
 
 
+_PINNED_CHUNKS = {}
+
+
+def _write_device_bytes(deck, path, chunk=64 << 20):
+    """Device bytes -> file: two pinned staging buffers, the copy of chunk k + 1 runs while chunk k is
+    written (no pageable copies, no intermediate bytes objects)."""
+    n = deck.numel()
+    dev = deck.device
+    bufs = _PINNED_CHUNKS.get(chunk)
+    if bufs is None:
+        bufs = _PINNED_CHUNKS[chunk] = [torch.empty(chunk, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    with torch.cuda.device(dev), open(path, 'wb') as INP:
+        copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream.wait_stream(torch.cuda.current_stream(dev))
+        events = [None, None]
+        spans = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+
+        def start(k):
+            lo, hi = spans[k]
+            with torch.cuda.stream(copy_stream):
+                bufs[k & 1][:hi - lo].copy_(deck[lo:hi], non_blocking=True)
+                events[k & 1] = torch.cuda.Event()
+                events[k & 1].record(copy_stream)
+
+        if spans:
+            start(0)
+        for k, (lo, hi) in enumerate(spans):
+            events[k & 1].synchronize()
+            if k + 1 < len(spans):
+                start(k + 1)
+            INP.write(memoryview(bufs[k & 1].numpy())[:hi - lo])
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+
+
 def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'ELSET'], eltype='C3D8',
                  matpropbits=8, refnode=None, verbose=False):
     """Generate ABAQUS voxel Finite Element (FE) input file from 3D Unstructured Grid mesh data
@@ -850,10 +884,7 @@ def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'E
         fileout[:n].copy_(deck, non_blocking=True)
         torch.cuda.current_stream(deck.device).synchronize()
         return n
-    chunk = 256 << 20
-    with open(fileout, 'wb') as INP:
-        for lo in range(0, n, chunk):
-            INP.write(deck[lo:lo + chunk].cpu().numpy().tobytes())
+    _write_device_bytes(deck, fileout)
     if isinstance(mesh, VoxelMesh):
         n_points, n_cells = mesh.n_points, mesh.n_el
     else:

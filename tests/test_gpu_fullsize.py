@@ -126,3 +126,18 @@ def test_oracle_parity_256(tmp_path):
                 first = False
         hs.append((h.hexdigest(), os.path.getsize(str(tmp_path / name))))
     assert hs[0] == hs[1]
+
+
+def test_fullsize_foam_sharded_equals_single():
+    """configs[3] at 512^3: ~4 * 10^3 components; 8 emulated z-slabs keep the same component as one GPU"""
+    import torch
+    from ciclope_b200 import remove_unconnected, sharded, synth
+    from ciclope_b200.preprocess import component_stats, largest_component_device
+    vol = synth.foam((512, 512, 512), seed=0, device="cuda")
+    L = remove_unconnected(vol)
+    _, best = largest_component_device(vol.view(torch.uint8))
+    size, _root = component_stats(best)
+    assert int(L.sum()) == size and bool((L & ~vol).sum() == 0)
+    assert size < 0.5 * int(vol.sum())                           # fragmented: no dominant component
+    m8, winner = sharded.emulate_remove_unconnected(vol, 8)
+    assert torch.equal(m8, L) and winner[0] == size

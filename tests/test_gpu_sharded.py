@@ -228,3 +228,22 @@ def test_ids_beyond_32_bits(sh):
     z1 = [eid_base + 1 + i for i, (s, r, c) in enumerate(zip(*np.nonzero(bw))) if s == Zl - 1]
     got = mesh.set_ids[mesh.set_first[11]: mesh.set_first[11] + mesh.set_count[11]].cpu().tolist()
     assert got == z1
+
+
+@pytest.mark.parametrize("n", [2, 8])
+def test_foam_many_components_across_slabs(sh, orc, n):
+    """BASELINE.json configs[3] in small: a fragmented foam (hundreds of components, many of them cut by the
+    slab interfaces); single GPU and z-slabs against the CPU oracle."""
+    import torch
+    from ciclope_b200 import remove_unconnected, synth
+    vol = synth.foam((160, 192, 192), seed=3, device="cuda")
+    host = vol.cpu().numpy()
+    assert orc.count_components(host) > 100
+    want = orc.remove_unconnected(host)
+    got = remove_unconnected(vol)
+    assert np.array_equal(got.cpu().numpy(), want)
+    mask, winner = sh.emulate_remove_unconnected(vol, n)
+    assert np.array_equal(mask.cpu().numpy(), want) and winner[0] == int(want.sum())
+    # components that straddle an interface: foreground voxels facing each other across the cut
+    cuts = [a for a, _ in sh.slab_ranges(host.shape[0], n)][1:]
+    assert sum(int((host[c - 1] & host[c]).sum()) for c in cuts) > 0
