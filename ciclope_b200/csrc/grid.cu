@@ -1044,3 +1044,81 @@ extern "C" int cfe_threshold_u8(const uint8_t* img, int64_t n, int t, uint8_t* o
     CFE_CHECK_LAUNCH("k_threshold_u8");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------
+// embed (preprocess.py:233-355): the embedding mask before the emboss,  box & ~(I > 0)  (:327), and the
+// final  I[BW_embedding] = embed_val  (:331-337).  Both are one pass over the volume, 16 voxels per thread.
+
+__global__ void __launch_bounds__(256)
+k_box_andnot_u8(const uint8_t* __restrict__ img, i64 n_rows, FastDiv dY, u32 Y, int X, int z0, int z1, int y0,
+                int y1, int x0, int x1, uint8_t* __restrict__ out)
+{
+    // one warp per row; inside the box a voxel is 1 when the image is 0
+    const u32 lane = threadIdx.x & 31u;
+    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    for (i64 row = warp0; row < n_rows; row += nwarps) {
+        const u32 z = fd_div((u32)row, dY);
+        const u32 y = (u32)row - z * Y;
+        const bool row_in = (int)z >= z0 && (int)z < z1 && (int)y >= y0 && (int)y < y1;
+        const uint8_t* src = img + row * X;
+        uint8_t* dst = out + row * X;
+        for (int x = (int)lane; x < X; x += 32)
+            dst[x] = (row_in && x >= x0 && x < x1 && __ldg(src + x) == 0) ? 1 : 0;
+    }
+}
+
+// out = 1 where (z, y, x) lies in [z0,z1) x [y0,y1) x [x0,x1) and img == 0, else 0
+extern "C" int cfe_box_andnot_u8(const uint8_t* img, int64_t Z, int64_t Y, int64_t X, int64_t z0, int64_t z1,
+                                 int64_t y0, int64_t y1, int64_t x0, int64_t x1, uint8_t* out, cudaStream_t stream)
+{
+    const i64 rows = Z * Y;
+    if (rows <= 0 || X <= 0) return 0;
+    if (rows >= (1LL << 32) || X >= (1LL << 31)) { cfe_set_error("cfe_box_andnot_u8: volume too large"); return -1; }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    i64 blocks = (rows + 7) / 8;
+    if (blocks > (i64)sms * 8) blocks = (i64)sms * 8;
+    k_box_andnot_u8<<<(unsigned)blocks, 256, 0, stream>>>(img, rows, make_fastdiv((u32)Y), (u32)Y, (int)X, (int)z0,
+                                                         (int)z1, (int)y0, (int)y1, (int)x0, (int)x1, out);
+    CFE_CHECK_LAUNCH("k_box_andnot_u8");
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_masked_set_u8(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, i64 n, u32 val4,
+                uint8_t* __restrict__ out)
+{
+    const i64 n16 = n >> 4;
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n16; g += (i64)gridDim.x * blockDim.x) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(img) + g);
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(mask) + g);
+        uint4 r;
+        // mask bytes are 0 / 1: 0xff per selected byte
+        const u32 mx = m.x * 0xffu, my = m.y * 0xffu, mz = m.z * 0xffu, mw = m.w * 0xffu;
+        r.x = (a.x & ~mx) | (val4 & mx); r.y = (a.y & ~my) | (val4 & my);
+        r.z = (a.z & ~mz) | (val4 & mz); r.w = (a.w & ~mw) | (val4 & mw);
+        reinterpret_cast<uint4*>(out)[g] = r;
+    }
+    for (i64 i = (n16 << 4) + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
+        out[i] = mask[i] ? (uint8_t)val4 : img[i];
+}
+
+// out[i] = mask[i] ? val : img[i]  (mask bytes 0 / 1; out may alias img; all 16-byte aligned)
+extern "C" int cfe_masked_set_u8(const uint8_t* img, const uint8_t* mask, int64_t n, int val, uint8_t* out,
+                                 cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(out)) & 15u) {
+        cfe_set_error("cfe_masked_set_u8: buffers must be 16-byte aligned");
+        return -1;
+    }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    i64 blocks = (n / 16 + 255) / 256;
+    if (blocks > (i64)sms * 16) blocks = (i64)sms * 16;
+    if (blocks < 1) blocks = 1;
+    k_masked_set_u8<<<(unsigned)blocks, 256, 0, stream>>>(img, mask, n, 0x01010101u * (u32)(val & 255), out);
+    CFE_CHECK_LAUNCH("k_masked_set_u8");
+    return 0;
+}

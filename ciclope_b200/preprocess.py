@@ -342,3 +342,127 @@ def gaussian(image, sigma=1, mode='nearest', cval=0, preserve_range=False, trunc
         if cur_u8:                                              # every sigma was 0: the float64 copy
             cur = cur.to(torch.float64)
     return cur.cpu().numpy() if from_numpy else cur
+
+
+# --------------------------------------------------------------------------------------------
+# embed (preprocess.py:233-355): another client of the labelling kernels
+
+def _bool_projections(sub):
+    """(maxROW, maxCOL, maxSLICE) of ``sub > 0`` as host bool arrays (recon_utils.py:260-262)."""
+    from .parosol import _projections
+    if sub.numel() == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    return _projections(sub, True, _lib.stream())
+
+
+def _bbox_pad(sub, pad):
+    """recon_utils.bbox(bw, pad) (recon_utils.py:258-298) of the device volume ``sub > 0``."""
+    from .parosol import _first_last_true
+    max_row, max_col, max_slice = _bool_projections(sub)
+    row0, row1 = _first_last_true(max_row)
+    col0, col1 = _first_last_true(max_col)
+    slice0, slice1 = _first_last_true(max_slice)
+    row0 = row0 - pad
+    rowd = row1 - row0 + pad
+    col0 = col0 - pad
+    cold = col1 - col0 + pad
+    slice0 = slice0 - pad
+    sliced = slice1 - slice0 + pad
+    if pad > 0:
+        row0, col0, slice0 = max(row0, 0), max(col0, 0), max(slice0, 0)
+        nz, ny, nx = (int(v) for v in sub.shape)
+        if slice0 + sliced > nz:
+            sliced = nz - slice0
+        if row0 + rowd > ny:
+            rowd = ny - row0
+        if col0 + cold > nx:
+            cold = nx - col0
+    return [row0, col0, slice0], [rowd, cold, sliced]
+
+
+def embed(I, embed_depth, embed_dir, embed_val=None, pad=0, makecopy=False):  # noqa: E741
+    """Add embedding to 3D image (drop-in for preprocess.py:233-355).
+
+    Direction and depth of the embedded region should be given; zeroes in the input image are background.
+    The box of the embedding comes from the reference's projections and bounding box (with its padding
+    rules), the embedding itself is the largest 6-connected part of ``box & ~(I > 0)``
+    (``remove_unconnected``, i.e. the labelling kernels), which gets ``embed_val`` (default ``I.max() + 1``).
+    As in the reference the input is modified in place and returned unless ``makecopy`` is true.
+
+    Returns ``(I, BW_embedding)``; NumPy in, NumPy out; CUDA tensors stay on the device.
+    """
+    vol, is_bool, from_numpy = as_device_volume(I)
+    Z, Y, X = (int(v) for v in vol.shape)
+    dev = vol.device
+    if embed_dir not in ("-z", "+z", "-x", "+x", "-y", "+y"):
+        # the reference binarises the image first and fails on the direction afterwards: same exception
+        raise IOError("EMBED_DIR parameter unknown. Valid entries are -x, +x, -y, +y, -z, and +z.")
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        if embed_val is None:
+            mx = torch.zeros(1, dtype=torch.int32, device=dev)
+            _lib.call("cfe_max_u8", vol.data_ptr(), vol.numel(), mx.data_ptr(), s)
+            top = int(read_back(mx)[0])
+            with np.errstate(over="ignore"):
+                embed_val = (np.bool_(top) if is_bool else np.uint8(top)) + 1      # I.max() + 1, NumPy's rules
+        probe = np.zeros(1, dtype=np.bool_ if is_bool else np.uint8)
+        probe[0] = embed_val                                   # the cast (or OverflowError) of I[mask] = embed_val
+        val = int(probe[0])
+        max_row, max_col, max_slice = _bool_projections(vol)
+
+        def first_last(m, which):
+            idx = np.where(m == True)[-1]  # noqa: E712 -- the reference's expression
+            return idx[which]                                  # IndexError on an all-background image
+
+        d = int(embed_depth)
+        if embed_dir == "-z":
+            start = int(first_last(max_slice, -1))
+            sl = (slice(start - d, None), slice(None), slice(None))
+        elif embed_dir == "+z":
+            start = int(first_last(max_slice, 0))
+            sl = (slice(None, start + d), slice(None), slice(None))
+        elif embed_dir == "-x":
+            start = int(first_last(max_col, -1))
+            sl = (slice(None), slice(None), slice(start - d, None))
+        elif embed_dir == "+x":
+            start = int(first_last(max_col, 0))
+            sl = (slice(None), slice(None), slice(None, start + d))
+        elif embed_dir == "+y":
+            start = int(first_last(max_row, -1))
+            sl = (slice(None), slice(start - d, None), slice(None))
+        else:
+            start = int(first_last(max_row, 0))
+            sl = (slice(None), slice(None, start + d), slice(None))
+        sub = vol[sl].contiguous()
+        o, size = _bbox_pad(sub, pad if embed_dir != "-y" else 0)     # the reference passes no pad for "-y"
+        rows, cols, slices = (slice(o[0], o[0] + size[0]), slice(o[1], o[1] + size[1]),
+                              slice(o[2], o[2] + size[2]))
+        if embed_dir in ("-z", "+z"):
+            box = (sl[0], rows, cols)
+        elif embed_dir in ("-x", "+x"):
+            box = (slices, rows, sl[2])
+        else:
+            box = (slices, sl[1], cols)
+        (z0, z1, _), (y0, y1, _), (x0, x1, _) = (b.indices(n) for b, n in zip(box, (Z, Y, X)))
+        cand = torch.empty((Z, Y, X), dtype=torch.uint8, device=dev)
+        _lib.call("cfe_box_andnot_u8", vol.data_ptr(), Z, Y, X, z0, max(z1, z0), y0, max(y1, y0), x0, max(x1, x0),
+                  cand.data_ptr(), s)
+    mask, best = largest_component_device(cand)                # remove_unconnected(BW_embedding & ~BW_I)
+    if best == 0:
+        raise ValueError("attempt to get argmax of an empty sequence")
+    in_place = isinstance(I, torch.Tensor) and I.is_cuda and I.is_contiguous() and not makecopy
+    with torch.cuda.device(dev):
+        out = vol if in_place else torch.empty_like(vol)
+        _lib.call("cfe_masked_set_u8", vol.data_ptr(), mask.data_ptr(), vol.numel(), val, out.data_ptr(), _lib.stream())
+    bw = mask.view(torch.bool)
+    res = out.view(torch.bool) if is_bool else out
+    if from_numpy:
+        res_h = res.cpu().numpy()
+        if makecopy:
+            return res_h, bw.cpu().numpy()
+        I[...] = res_h
+        return I, bw.cpu().numpy()
+    if makecopy or in_place:
+        return (I if in_place else res), bw
+    I.copy_(res)
+    return I, bw

@@ -323,6 +323,13 @@ int cfe_host_pyset_order(const int64_t* rows, int64_t n, int64_t* out, int64_t* 
 /* segment (preprocess.py:20-46): out[i] = img[i] > t, bytes 0 / 1; buffers 16-byte aligned */
 int cfe_threshold_u8(const uint8_t* img, int64_t n, int t, uint8_t* out, cfe_stream_t s);
 
+/* embed (preprocess.py:233-355).  cfe_box_andnot_u8: out = 1 where (z, y, x) is inside the box
+ * [z0,z1) x [y0,y1) x [x0,x1) and img == 0 (BW_embedding & ~BW_I, :327), else 0.  cfe_masked_set_u8:
+ * out[i] = mask[i] ? val : img[i] (I[BW_embedding] = embed_val, :331-337); out may alias img. */
+int cfe_box_andnot_u8(const uint8_t* img, int64_t Z, int64_t Y, int64_t X, int64_t z0, int64_t z1, int64_t y0,
+                      int64_t y1, int64_t x0, int64_t x1, uint8_t* out, cfe_stream_t s);
+int cfe_masked_set_u8(const uint8_t* img, const uint8_t* mask, int64_t n, int val, uint8_t* out, cfe_stream_t s);
+
 /* ------------------------------------------------------------------ Gaussian smoothing (pipeline.py:146-148) */
 
 /* One pass of scipy.ndimage.correlate1d(input, weights, axis, mode='nearest') with a symmetric kernel of

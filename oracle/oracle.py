@@ -527,3 +527,79 @@ def gaussian(image, sigma, truncate=4.0):
                          np.take(a, np.clip(idx - jj, 0, n - 1), axis=axis)) * w[lw + jj]
         a = acc
     return a
+
+
+# --------------------------------------------------------------------------------------------
+# embed <- src/ciclope/utils/preprocess.py:233-355 (with recon_utils.bbox incl. its padding rules,
+# recon_utils.py:258-298)
+
+def bbox_pad(bw, pad=0):
+    maxROW = np.max(np.max(bw, 0), 1)
+    maxCOL = np.max(np.max(bw, 0), 0)
+    maxSLICE = np.max(np.max(bw, 1), 1)
+    row0 = list(maxROW).index(True)
+    row1 = len(maxROW) - list(maxROW[::-1]).index(True) - 1
+    col0 = list(maxCOL).index(True)
+    col1 = len(maxCOL) - list(maxCOL[::-1]).index(True) - 1
+    slice0 = list(maxSLICE).index(True)
+    slice1 = len(maxSLICE) - list(maxSLICE[::-1]).index(True) - 1
+    row0 = row0 - pad
+    rowd = row1 - row0 + pad
+    col0 = col0 - pad
+    cold = col1 - col0 + pad
+    slice0 = slice0 - pad
+    sliced = slice1 - slice0 + pad
+    if pad > 0:
+        row0, col0, slice0 = max(row0, 0), max(col0, 0), max(slice0, 0)
+        if slice0 + sliced > bw.shape[0]:
+            sliced = bw.shape[0] - slice0
+        if row0 + rowd > bw.shape[1]:
+            rowd = bw.shape[1] - row0
+        if col0 + cold > bw.shape[2]:
+            cold = bw.shape[2] - col0
+    return [row0, col0, slice0], [rowd, cold, sliced]
+
+
+def embed_box(BW_I, embed_depth, embed_dir, pad=0):
+    """The three slices of the embedding box (preprocess.py:268-325), before the emboss."""
+    if embed_dir == "-z":
+        start = np.where(np.max(BW_I.max(1), 1) == True)[-1][-1]  # noqa: E712
+        o, s = bbox_pad(BW_I[start - embed_depth:, :, :], pad)
+        return (slice(start - embed_depth, None), slice(o[0], o[0] + s[0]), slice(o[1], o[1] + s[1]))
+    if embed_dir == "+z":
+        start = np.where(np.max(BW_I.max(1), 1) == True)[0][0]  # noqa: E712
+        o, s = bbox_pad(BW_I[:start + embed_depth, :, :], pad)
+        return (slice(None, start + embed_depth), slice(o[0], o[0] + s[0]), slice(o[1], o[1] + s[1]))
+    if embed_dir == "-x":
+        start = np.where(np.max(BW_I.max(0), 0) == True)[-1][-1]  # noqa: E712
+        o, s = bbox_pad(BW_I[:, :, start - embed_depth:], pad)
+        return (slice(o[2], o[2] + s[2]), slice(o[0], o[0] + s[0]), slice(start - embed_depth, None))
+    if embed_dir == "+x":
+        start = np.where(np.max(BW_I.max(0), 0) == True)[0][0]  # noqa: E712
+        o, s = bbox_pad(BW_I[:, :, :start + embed_depth], pad)
+        return (slice(o[2], o[2] + s[2]), slice(o[0], o[0] + s[0]), slice(None, start + embed_depth))
+    if embed_dir == "+y":
+        start = np.where(np.max(BW_I.max(0), 1) == True)[-1][-1]  # noqa: E712
+        o, s = bbox_pad(BW_I[:, start - embed_depth:, :], pad)
+        return (slice(o[2], o[2] + s[2]), slice(start - embed_depth, None), slice(o[1], o[1] + s[1]))
+    if embed_dir == "-y":
+        start = np.where(np.max(BW_I.max(0), 1) == True)[0][0]  # noqa: E712
+        o, s = bbox_pad(BW_I[:, :start + embed_depth, :])          # the reference passes no pad here
+        return (slice(o[2], o[2] + s[2]), slice(None, start + embed_depth), slice(o[1], o[1] + s[1]))
+    raise IOError("EMBED_DIR parameter unknown. Valid entries are -x, +x, -y, +y, -z, and +z.")
+
+
+def embed(I, embed_depth, embed_dir, embed_val=None, pad=0, makecopy=False):  # noqa: E741
+    if embed_val is None:
+        embed_val = I.max() + 1
+    BW_I = np.zeros(I.shape, dtype='bool')
+    BW_I[I > 0] = True
+    BW_embedding = np.zeros(BW_I.shape, dtype='bool')
+    BW_embedding[embed_box(BW_I, embed_depth, embed_dir, pad)] = True
+    BW_embedding = remove_unconnected(BW_embedding & ~BW_I)
+    if makecopy:
+        I_output = I.copy()
+        I_output[BW_embedding] = embed_val
+        return I_output, BW_embedding
+    I[BW_embedding] = embed_val
+    return I, BW_embedding

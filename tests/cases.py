@@ -517,3 +517,26 @@ def check_parosol_against_golden(g, name, run):
         else:
             assert got.dtype == want.dtype and got.shape == want.shape, (name, k, got.dtype, got.shape)
             assert np.array_equal(got, want), (name, k)
+
+
+def embed_cases():
+    """(name, uint8 image, kwargs of embed) -- small images with an empty margin, all six directions,
+    depths that run past the margin (negative slice starts), padding, explicit / default value."""
+    rng = np.random.default_rng(21)
+    out = []
+    for si, shape in enumerate([(12, 14, 16), (9, 20, 11), (16, 33, 40)]):
+        for dens in (0.15, 0.5):
+            img = np.zeros(shape, np.uint8)
+            inner = rng.random(tuple(s - 6 for s in shape)) < dens
+            img[3:-3, 3:-3, 3:-3] = inner * rng.integers(1, 200, inner.shape)
+            for d in ["-z", "+z", "-x", "+x", "-y", "+y"]:
+                for depth, pad, val, mc in [(1, 0, None, True), (3, 2, 77, False), (6, 0, 250, True),
+                                            (2, 5, None, False)]:
+                    out.append(("s%d_d%d_%s_%d_%d_%s_%d" % (si, int(dens * 100), d, depth, pad, val, int(mc)), img,
+                                dict(embed_depth=depth, embed_dir=d, embed_val=val, pad=pad, makecopy=mc)))
+    full = np.full((6, 6, 6), 255, np.uint8)
+    out.append(("full_255", full, dict(embed_depth=2, embed_dir="-z", embed_val=None, pad=0, makecopy=True)))
+    out.append(("empty", np.zeros((5, 5, 5), np.uint8), dict(embed_depth=2, embed_dir="+x", embed_val=None, pad=0,
+                                                             makecopy=True)))
+    out.append(("bad_dir", img, dict(embed_depth=2, embed_dir="up", embed_val=1, pad=0, makecopy=True)))
+    return out

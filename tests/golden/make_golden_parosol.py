@@ -51,6 +51,23 @@ def main():
         out["cap/%d/in" % i] = img
         out["cap/%d/args" % i] = np.asarray([th, val])
         out["cap/%d/out" % i] = res
+    import warnings
+    n_emb_err = 0
+    for name, img, kw in cases.embed_cases():
+        arg = img.copy()
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res, bw = pre.embed(arg, **kw)
+        except BaseException as e:  # noqa: BLE001
+            out["emb/" + name + "/error"] = np.asarray(type(e).__name__)
+            n_emb_err += 1
+            continue
+        assert bw.dtype == np.bool_ and res.dtype == img.dtype and (kw["makecopy"] or res is arg)
+        out["emb/" + name + "/out"] = res
+        out["emb/" + name + "/bw"] = np.packbits(bw.ravel())
+        out["emb/" + name + "/arg_after"] = np.asarray(hashlib.sha256(arg.tobytes()).hexdigest())
+    print("embed:", len(cases.embed_cases()), "cases,", n_emb_err, "error cases")
     path = os.path.join(cases.GOLDEN_DIR, "parosol.npz")
     np.savez_compressed(path, **out)
     print("parosol golden:", len(out), "arrays,", os.path.getsize(path), "bytes,", n_err, "error cases")

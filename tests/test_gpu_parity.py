@@ -598,3 +598,23 @@ def test_gaussian_bit_exact_vs_scipy_and_oracle(cfe, orc, shape, sigma):
         cfe.segment(got, None)
     with pytest.raises(NotImplementedError):
         cfe.gaussian(img, sigma=1.0)
+
+
+@pytest.mark.parametrize("case", cases.embed_cases(), ids=lambda c: c[0])
+def test_embed_vs_reference(cfe, golden_parosol, case):
+    """preprocess.py:233-355 against the outputs of the unmodified reference (image, mask, in-place rule)"""
+    from tests.test_oracle_golden import _check_embed
+    name, img, kw = case
+    _check_embed(golden_parosol, name, img, kw, cfe.embed)
+
+
+def test_embed_tensor_in_place(cfe, orc):
+    import torch
+    name, img, kw = [c for c in cases.embed_cases() if c[2]["embed_dir"] == "-z" and not c[2]["makecopy"]][0]
+    want, bw_want = orc.embed(img.copy(), **kw)
+    t = torch.from_numpy(img.copy()).cuda()
+    res, bw = cfe.embed(t, **kw)
+    assert res is t and np.array_equal(t.cpu().numpy(), want) and np.array_equal(bw.cpu().numpy(), bw_want)
+    t2 = torch.from_numpy(img.copy()).cuda()
+    res2, _ = cfe.embed(t2, **dict(kw, makecopy=True))
+    assert res2 is not t2 and np.array_equal(t2.cpu().numpy(), img) and np.array_equal(res2.cpu().numpy(), want)

@@ -215,3 +215,28 @@ def test_oracle_gaussian_is_scipy_bit_for_bit(shape, sigma):
     want = ndimage.gaussian_filter(img.astype(float), sigma, mode='nearest', truncate=4.0)
     got = orc.gaussian(img, sigma)
     assert got.dtype == np.float64 and np.array_equal(got, want)
+
+
+def _check_embed(g, name, img, kw, fn):
+    import warnings
+    key = "emb/" + name
+    arg = img.copy()
+    if key + "/error" in g.files:
+        with pytest.raises(BaseException) as ei:
+            fn(arg, **kw)
+        assert type(ei.value).__name__ == str(g[key + "/error"]), name
+        return
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res, bw = fn(arg, **kw)
+    res, bw = np.asarray(res), np.asarray(bw)
+    want = g[key + "/out"]
+    assert res.dtype == want.dtype and np.array_equal(res, want), name
+    assert bw.dtype == np.bool_ and np.array_equal(np.packbits(bw.ravel()), g[key + "/bw"]), name
+    assert hashlib.sha256(arg.tobytes()).hexdigest() == str(g[key + "/arg_after"]), name   # in place or not
+
+
+@pytest.mark.parametrize("case", cases.embed_cases(), ids=lambda c: c[0])
+def test_oracle_embed(golden_parosol, case):
+    name, img, kw = case
+    _check_embed(golden_parosol, name, img, kw, orc.embed)
