@@ -517,18 +517,12 @@ __device__ __forceinline__ bool voxel_bit(const SetGeom& g, int s, int r, int c)
     return (__ldg(plane + (size_t)r * g.W + (c >> 5)) >> (c & 31)) & 1u;
 }
 
-__device__ __forceinline__ bool set_candidate(const CfeSetDesc& d, const SetGeom& g, i64 k, i64& id)
+// candidate at (ks, kr, kc) of the box (box-relative coordinates) -> keep?, id
+__device__ __forceinline__ bool set_eval(const CfeSetDesc& d, const SetGeom& g, u32 ks, u32 kr, u32 kc, i64& id)
 {
-    // candidate k of the box -> (s, r, c) in GLOBAL coordinates
-    // (a box never has 2^32 candidates: it is a subset of one slab's node grid)
-    const u32 nc = (u32)(d.c1 - d.c0), plane = (u32)(d.r1 - d.r0) * nc;
-    const u32 k32 = (u32)k;
-    const u32 ks = k32 / plane;
-    const u32 rem = k32 - ks * plane;
-    const u32 kr = rem / nc;
-    const i64 s = d.s0 + (i64)ks;
+    const i64 s = d.s0 + (i64)ks;                 // GLOBAL coordinates
     const int r = (int)d.r0 + (int)kr;
-    const int c = (int)d.c0 + (int)(rem - kr * nc);
+    const int c = (int)d.c0 + (int)kc;
     const int sl = (int)(s - g.z0);
     if (d.kind == 2) {
         if (!voxel_bit(g, sl, r, c)) return false;
@@ -537,16 +531,54 @@ __device__ __forceinline__ bool set_candidate(const CfeSetDesc& d, const SetGeom
         id = g.eid_offset + (i64)__ldg(g.pref + wi) + __popc(word & mask_lt(c & 31)) + 1;
         return true;
     }
+    // node (s, r, c): does one of its (up to) 8 voxels inside the voxel box exist?  The two x-neighbours
+    // c - 1, c of a row sit in one word unless c is a multiple of 32: four row probes instead of eight
+    // voxel probes.
+    id = ((i64)(g.X + 1) * (g.Y + 1)) * s + (i64)(g.X + 1) * r + c;
+    const int vlo = (int)(d.vc0 > 0 ? d.vc0 : 0), vhi = (int)(d.vc1 < g.X ? d.vc1 : g.X);   // columns [vlo, vhi)
+    const int ca = (c - 1 > vlo) ? c - 1 : vlo;
+    const int cb = (c < vhi - 1) ? c : vhi - 1;
+    if (ca > cb) return false;
     bool hit = false;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const i64 vs = s - (t >> 2);
-        const int vr = r - ((t >> 1) & 1), vc = c - (t & 1);
-        if (vs < d.vs0 || vs >= d.vs1 || vr < d.vr0 || vr >= d.vr1 || vc < d.vc0 || vc >= d.vc1) continue;
-        hit |= voxel_bit(g, (int)(vs - g.z0), vr, vc);
+    for (int t = 0; t < 4; ++t) {
+        const i64 vs = s - (t >> 1);
+        const int vr = r - (t & 1);
+        if (vs < d.vs0 || vs >= d.vs1 || vr < d.vr0 || vr >= d.vr1 || vr < 0 || vr >= g.Y) continue;
+        const int vsl = (int)(vs - g.z0);
+        const u32* plane;
+        if (vsl >= 0 && vsl < g.Zl) plane = g.bits + (size_t)vsl * g.Y * g.W;
+        else if (vsl == -1 && g.halo_below) plane = g.halo_below;
+        else continue;
+        const u32* rowp = plane + (size_t)vr * g.W;
+        const u32 wa = __ldg(rowp + (ca >> 5));
+        u32 m = (wa >> (ca & 31)) & 1u;
+        if (cb != ca) {
+            const u32 wb = ((cb >> 5) == (ca >> 5)) ? wa : __ldg(rowp + (cb >> 5));
+            m |= (wb >> (cb & 31)) & 1u;
+        }
+        hit |= (m != 0);
     }
-    id = ((i64)(g.X + 1) * (g.Y + 1)) * s + (i64)(g.X + 1) * r + c;
     return hit;
+}
+
+// candidate k of the box -> box-relative (ks, kr, kc)
+// (a box never has 2^32 candidates: it is a subset of one slab's node grid)
+__device__ __forceinline__ void set_decode(const CfeSetDesc& d, i64 k, u32& ks, u32& kr, u32& kc)
+{
+    const u32 nc = (u32)(d.c1 - d.c0), plane = (u32)(d.r1 - d.r0) * nc;
+    const u32 k32 = (u32)k;
+    ks = k32 / plane;
+    const u32 rem = k32 - ks * plane;
+    kr = rem / nc;
+    kc = rem - kr * nc;
+}
+
+__device__ __forceinline__ bool set_candidate(const CfeSetDesc& d, const SetGeom& g, i64 k, i64& id)
+{
+    u32 ks, kr, kc;
+    set_decode(d, k, ks, kr, kc);
+    return set_eval(d, g, ks, kr, kc, id);
 }
 
 __device__ __forceinline__ int find_set(const CfeSetDesc* descs, int n_sets, i64 tile)
@@ -588,7 +620,7 @@ k_sets(const CfeSetDesc* __restrict__ descs, int n_sets, SetGeom g, u32* __restr
 
 extern "C" int64_t cfe_sets_onepass_tile(void) { return SETS1_TILE; }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_sets_onepass(const CfeSetDesc* __restrict__ descs, int n_sets, i64 n_tiles, SetGeom g, u64* __restrict__ ws,
                i64* __restrict__ ids, i64* __restrict__ first)
 {
@@ -601,10 +633,17 @@ k_sets_onepass(const CfeSetDesc* __restrict__ descs, int n_sets, i64 n_tiles, Se
     const i64 k0 = (tile - d.tile_base) * SETS1_TILE + (i64)threadIdx.x * SETS1_ITEMS;
     i64 id[SETS1_ITEMS];
     u32 keep = 0;
+    if (k0 < d.n_cand) {
+        // one decode per thread; the following candidates advance (c, r, s) with carries
+        const u32 nc = (u32)(d.c1 - d.c0), nr = (u32)(d.r1 - d.r0);
+        u32 ks, kr, kc;
+        set_decode(d, k0, ks, kr, kc);
 #pragma unroll
-    for (int j = 0; j < SETS1_ITEMS; ++j) {
-        id[j] = 0;
-        if (k0 + j < d.n_cand && set_candidate(d, g, k0 + j, id[j])) keep |= 1u << j;
+        for (int j = 0; j < SETS1_ITEMS; ++j) {
+            id[j] = 0;
+            if (k0 + j < d.n_cand && set_eval(d, g, ks, kr, kc, id[j])) keep |= 1u << j;
+            if (++kc == nc) { kc = 0; if (++kr == nr) { kr = 0; ++ks; } }
+        }
     }
     u32 tot;
     const u32 e = block_exclusive_scan<u32>((u32)__popc(keep), s_scan, tot);
