@@ -10,5 +10,5 @@ mirror ``ciclope.utils.preprocess.{remove_unconnected, remove_largest, fill_void
 __version__ = "0.1.0"
 
 from . import preprocess, voxelFE  # noqa: E402,F401
-from .preprocess import add_cap, embed, fill_voids, gaussian, remove_largest, remove_unconnected, segment  # noqa: E402,F401
+from .preprocess import add_cap, embed, fill_voids, gaussian, periosteummask, remove_largest, remove_unconnected, segment  # noqa: E402,F401
 from .voxelFE import matpropdictionary, mesh2voxelfe, vol2h5ParOSol, vol2ugrid  # noqa: E402,F401

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libciclope_b200.so")
-SOURCES = ["api.cu", "grid.cu", "ccl.cu", "deck.cu", "pyset.cu", "filters.cu", "peer.cu"]
+SOURCES = ["api.cu", "grid.cu", "ccl.cu", "deck.cu", "pyset.cu", "filters.cu", "peer.cu", "morph.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + INCLUDE]
 

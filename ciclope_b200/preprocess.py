@@ -466,3 +466,78 @@ def embed(I, embed_depth, embed_dir, embed_val=None, pad=0, makecopy=False):  # 
         return (I if in_place else res), bw
     I.copy_(res)
     return I, bw
+
+
+# --------------------------------------------------------------------------------------------
+# periosteummask (preprocess.py:357-420)
+
+def periosteummask(bwimage, closepixels=10, closevoxels=0, remove_objects_smaller_than=None, removeunconn=True,
+                   verbose=False):
+    """Binary mask of periosteum (whole bone) -- drop-in for preprocess.py:357-420.
+
+    Every slice is closed with a disk of radius ``closepixels`` (``skimage.morphology.binary_closing``:
+    scipy's binary dilation with border value 0, then erosion with border value 1) and its holes are filled
+    (``scipy.ndimage.binary_fill_holes``: background not 4-connected to the slice border); isolated clusters
+    are then removed in 3D (``remove_unconnected``).  All of it runs on packed bits on the GPU: the disk
+    dilation is word-parallel, the hole filling is one labelling of the background of the whole stack
+    (slices only meet through their border rows, which are outside by definition) plus a border-flag pass.
+
+    ``remove_objects_smaller_than`` and ``closevoxels > 0`` (scikit-image's ``remove_small_objects`` and the
+    even-sized ``cube`` closing) are not available and raise ``NotImplementedError``; ``closepixels <= 31``.
+    """
+    import logging
+    if verbose:
+        logging.basicConfig(level=logging.INFO)
+    if remove_objects_smaller_than:
+        raise NotImplementedError("periosteummask: remove_objects_smaller_than is not available on the GPU path")
+    if closevoxels > 0:
+        raise NotImplementedError("periosteummask: the final 3D closing (closevoxels > 0) is not available on the GPU path")
+    r = int(closepixels)
+    if r != closepixels or not 0 <= r <= 31:
+        raise NotImplementedError("periosteummask: closepixels must be an integer in 0..31")
+    vol, _is_bool, from_numpy = as_device_volume(bwimage, allow_2d=True)
+    squeeze = (bwimage.ndim == 2)
+    Z, Y, X = (int(v) for v in vol.shape)
+    dev = vol.device
+    lib = _lib.require_cuda()
+    if Z * Y * X == 0:
+        out = torch.zeros((Z, Y, X), dtype=torch.bool, device=dev)
+    else:
+        with torch.cuda.device(dev):
+            s = _lib.stream()
+            W = (X + 31) // 32
+            rows = Z * Y
+            bits = empty_u32(rows * W, dev)
+            _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
+            dil = empty_u32(rows * W, dev)
+            _lib.call("cfe_disk_dilate_bits", bits.data_ptr(), Z, Y, X, r, 0, dil.data_ptr(), s)
+            # background of the closed slices = dilation of the complement of the dilation
+            bg = bits
+            _lib.call("cfe_disk_dilate_bits", dil.data_ptr(), Z, Y, X, r, 1, bg.data_ptr(), s)
+            # fill_holes: label the background of the stack as one tall slice (4-connectivity inside the
+            # slices; consecutive slices only touch through their border rows) and flag what meets a border
+            pref = empty_u32(rows * W, dev)
+            stats = torch.empty(2, dtype=torch.int64, device=dev)
+            ws = scan_workspace(rows * W, dev)
+            _lib.call("cfe_scan_run_starts", bg.data_ptr(), rows, X, pref.data_ptr(), stats.data_ptr(), ws.data_ptr(), s)
+            max_runs = lib.cfe_ccl_max_runs(rows, X)
+            parent = empty_u32(max_runs, dev)
+            size = empty_u32(max_runs, dev)
+            _lib.call("cfe_ccl_label", bg.data_ptr(), pref.data_ptr(), stats.data_ptr(), 1, rows, X,
+                      parent.data_ptr(), size.data_ptr(), s)
+            flag = torch.full((max_runs,), -1, dtype=torch.int32, device=dev)        # 0xffffffff = not at a border
+            _lib.call("cfe_border_flags", bg.data_ptr(), pref.data_ptr(), Z, Y, X, parent.data_ptr(), flag.data_ptr(), s)
+            # mask = 1 everywhere except the background runs that reach a border (flag == 0)
+            mask = torch.ones((Z, Y, X), dtype=torch.uint8, device=dev)
+            _lib.call("cfe_ccl_write_select", bg.data_ptr(), pref.data_ptr(), 1, rows, X, parent.data_ptr(), None,
+                      flag.data_ptr(), 1, mask.data_ptr(), 0, mask.data_ptr(), s)
+        if removeunconn:
+            logging.info("Removing isolated clusters of voxels.")
+            kept, best = largest_component_device(mask)
+            if best == 0:
+                raise ValueError("attempt to get argmax of an empty sequence")      # remove_unconnected, :141
+            mask = kept
+        out = mask.view(torch.bool)
+    if squeeze:
+        out = out[0]
+    return out.cpu().numpy() if from_numpy else out

@@ -330,6 +330,17 @@ int cfe_box_andnot_u8(const uint8_t* img, int64_t Z, int64_t Y, int64_t X, int64
                       int64_t y1, int64_t x0, int64_t x1, uint8_t* out, cfe_stream_t s);
 int cfe_masked_set_u8(const uint8_t* img, const uint8_t* mask, int64_t n, int val, uint8_t* out, cfe_stream_t s);
 
+/* periosteummask (preprocess.py:357-420), slice-wise morphology on packed bits ([Z*Y rows][ceil(X/32)]).
+ * cfe_disk_dilate_bits: every (Y, X) slice dilated by skimage's disk(r) (0 outside the slice); invert_in
+ * dilates the complement, so erosion with border value 1 is the complement of the result and the background
+ * of binary_closing(x, disk(r)) is  dilate(invert_in = 1) of dilate(x).  r <= 31; in != out.
+ * cfe_border_flags: for scipy.ndimage.binary_fill_holes -- flag[root] = 0 for every run that touches the
+ * border of its slice (bits / pref / parent of the labelled background, labelled as ONE slice of Z*Y rows). */
+int cfe_disk_dilate_bits(const uint32_t* in, int64_t Z, int64_t Y, int64_t X, int r, int invert_in, uint32_t* out,
+                         cfe_stream_t s);
+int cfe_border_flags(const uint32_t* bits, const uint32_t* pref, int64_t Z, int64_t Y, int64_t X,
+                     const uint32_t* parent, uint32_t* flag, cfe_stream_t s);
+
 /* ------------------------------------------------------------------ Gaussian smoothing (pipeline.py:146-148) */
 
 /* One pass of scipy.ndimage.correlate1d(input, weights, axis, mode='nearest') with a symmetric kernel of

@@ -603,3 +603,37 @@ def embed(I, embed_depth, embed_dir, embed_val=None, pad=0, makecopy=False):  # 
         return I_output, BW_embedding
     I[BW_embedding] = embed_val
     return I, BW_embedding
+
+
+# --------------------------------------------------------------------------------------------
+# periosteummask <- src/ciclope/utils/preprocess.py:357-420.  The scikit-image pieces (not in the checkout, not
+# installed) are restated from their definitions on top of the installed scipy, which is what they wrap:
+#   morphology.disk(r)              = {x^2 + y^2 <= r^2} on a (2r+1)^2 grid
+#   morphology.binary_closing(a, f) = ndi.binary_erosion(ndi.binary_dilation(a, f), f, border_value=True)
+# PARITY of these two wrappers is unpinned; binary_fill_holes and the loop are the reference's own calls.
+
+def disk(radius):
+    L = np.arange(-radius, radius + 1)
+    X, Y = np.meshgrid(L, L)
+    return (X ** 2 + Y ** 2) <= radius ** 2
+
+
+def binary_closing(image, footprint):
+    from scipy import ndimage
+    dilated = ndimage.binary_dilation(image, structure=footprint)
+    return ndimage.binary_erosion(dilated, structure=footprint, border_value=True)
+
+
+def periosteummask(bwimage, closepixels=10, removeunconn=True):
+    from scipy import ndimage
+    if bwimage.ndim == 3:
+        perimask = np.zeros(np.shape(bwimage), dtype=bool)
+        for sl in range(bwimage.shape[0]):
+            perimask[sl, :, :] = ndimage.binary_fill_holes(binary_closing(bwimage[sl, :, :], disk(closepixels)))
+        if removeunconn:
+            perimask = remove_unconnected(perimask)
+        return perimask
+    perimask = ndimage.binary_fill_holes(binary_closing(bwimage, disk(closepixels)))
+    if removeunconn:
+        perimask = remove_unconnected(perimask[None])[0]
+    return perimask

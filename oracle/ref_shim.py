@@ -74,7 +74,18 @@ def _install_stubs():
         return (lab, n) if return_num else lab
 
     measure = mod("skimage.measure", label=label)
-    morphology = mod("skimage.morphology")
+    # periosteummask (preprocess.py:385-400) calls these scikit-image functions; restated from their
+    # definitions on top of scipy (oracle.disk / oracle.binary_closing carry the same statements)
+    def _disk(radius):
+        L = np.arange(-radius, radius + 1)
+        X, Y = np.meshgrid(L, L)
+        return (X ** 2 + Y ** 2) <= radius ** 2
+
+    def _binary_closing(image, footprint=None):
+        dilated = ndi.binary_dilation(image, structure=footprint)
+        return ndi.binary_erosion(dilated, structure=footprint, border_value=True)
+
+    morphology = mod("skimage.morphology", disk=_disk, binary_closing=_binary_closing)
     filters = mod("skimage.filters", threshold_otsu=None, gaussian=None)
     mod("skimage", measure=measure, morphology=morphology, filters=filters)
 

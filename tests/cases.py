@@ -540,3 +540,29 @@ def embed_cases():
                                                              makecopy=True)))
     out.append(("bad_dir", img, dict(embed_depth=2, embed_dir="up", embed_val=1, pad=0, makecopy=True)))
     return out
+
+
+def periosteum_cases():
+    """(name, bool image 2D / 3D, kwargs of periosteummask): hollow shapes (rings that closing seals, rings it
+    does not), specks, shapes touching the border, widths that are not a multiple of 32."""
+    rng = np.random.default_rng(31)
+    out = []
+    for si, shape in enumerate([(6, 40, 50), (3, 33, 65), (40, 50), (5, 64, 96), (2, 70, 31)]):
+        yy, xx = np.ogrid[:shape[-2], :shape[-1]]
+        cy, cx = shape[-2] / 2.0, shape[-1] / 2.0
+        rad = min(shape[-2:]) / 3.0
+        d = np.hypot(yy - cy, xx - cx)
+        ring = (d < rad) & (d > rad - 2)
+        gap = ring & ~((abs(yy - cy) < 2) & (xx > cx))          # ring with a 3-pixel opening
+        for ri, r in enumerate((0, 1, 3, 10)):
+            for dens in (0.02, 0.1):
+                bw = rng.random(shape) < dens
+                bw = bw | (gap if (ri + si) % 2 else ring)
+                if si == 3:
+                    bw[..., :3, :] = True                        # a slab along the border
+                for ru in (True, False):
+                    out.append(("s%d_r%d_d%d_%d" % (si, r, int(dens * 100), int(ru)), bw,
+                                dict(closepixels=r, removeunconn=ru)))
+    out.append(("empty", np.zeros((3, 20, 20), dtype=bool), dict(closepixels=2, removeunconn=True)))
+    out.append(("full", np.ones((2, 20, 20), dtype=bool), dict(closepixels=2, removeunconn=True)))
+    return out

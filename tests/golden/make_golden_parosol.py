@@ -10,6 +10,8 @@ import hashlib
 import os
 import sys
 
+os.environ.setdefault("TQDM_DISABLE", "1")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -68,6 +70,19 @@ def main():
         out["emb/" + name + "/bw"] = np.packbits(bw.ravel())
         out["emb/" + name + "/arg_after"] = np.asarray(hashlib.sha256(arg.tobytes()).hexdigest())
     print("embed:", len(cases.embed_cases()), "cases,", n_emb_err, "error cases")
+    # periosteummask: the reference's own loop / fill_holes / remove_unconnected; its two scikit-image calls
+    # (disk, binary_closing) go through oracle/ref_shim.py's restatement on top of scipy
+    n_per_err = 0
+    for name, bw, kw in cases.periosteum_cases():
+        try:
+            res = pre.periosteummask(bw.copy(), **kw)
+        except BaseException as e:  # noqa: BLE001
+            out["per/" + name + "/error"] = np.asarray(type(e).__name__)
+            n_per_err += 1
+            continue
+        assert res.dtype == np.bool_ and res.shape == bw.shape
+        out["per/" + name + "/out"] = np.packbits(res.ravel())
+    print("periosteummask:", len(cases.periosteum_cases()), "cases,", n_per_err, "error cases")
     path = os.path.join(cases.GOLDEN_DIR, "parosol.npz")
     np.savez_compressed(path, **out)
     print("parosol golden:", len(out), "arrays,", os.path.getsize(path), "bytes,", n_err, "error cases")

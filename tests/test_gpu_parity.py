@@ -618,3 +618,25 @@ def test_embed_tensor_in_place(cfe, orc):
     t2 = torch.from_numpy(img.copy()).cuda()
     res2, _ = cfe.embed(t2, **dict(kw, makecopy=True))
     assert res2 is not t2 and np.array_equal(t2.cpu().numpy(), img) and np.array_equal(res2.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("case", cases.periosteum_cases(), ids=lambda c: c[0])
+def test_periosteummask_vs_reference(cfe, golden_parosol, case):
+    """preprocess.py:357-420: disk closing + hole filling per slice, then remove_unconnected"""
+    from tests.test_oracle_golden import _check_periosteum
+    name, bw, kw = case
+    _check_periosteum(golden_parosol, name, bw, kw, cfe.periosteummask)
+
+
+def test_periosteummask_larger_vs_oracle(cfe, orc):
+    import torch
+    bw = cases.blobs((24, 150, 200), 0.25, 9)
+    bw[:, 60:90, 80:120] = False                          # a cavity that the closing cannot bridge
+    for r in (2, 7, 31):
+        want = orc.periosteummask(bw, closepixels=r)
+        got = cfe.periosteummask(torch.from_numpy(bw).cuda(), closepixels=r)
+        assert got.dtype == torch.bool and np.array_equal(got.cpu().numpy(), want), r
+    with pytest.raises(NotImplementedError):
+        cfe.periosteummask(bw, closevoxels=2)
+    with pytest.raises(NotImplementedError):
+        cfe.periosteummask(bw, remove_objects_smaller_than=5)

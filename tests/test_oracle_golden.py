@@ -240,3 +240,21 @@ def _check_embed(g, name, img, kw, fn):
 def test_oracle_embed(golden_parosol, case):
     name, img, kw = case
     _check_embed(golden_parosol, name, img, kw, orc.embed)
+
+
+def _check_periosteum(g, name, bw, kw, fn):
+    key = "per/" + name
+    if key + "/error" in g.files:
+        with pytest.raises(BaseException) as ei:
+            fn(bw.copy(), **kw)
+        assert type(ei.value).__name__ == str(g[key + "/error"]), name
+        return
+    res = np.asarray(fn(bw.copy(), **kw))
+    assert res.dtype == np.bool_ and res.shape == bw.shape
+    assert np.array_equal(np.packbits(res.ravel()), g[key + "/out"]), name
+
+
+@pytest.mark.parametrize("case", cases.periosteum_cases(), ids=lambda c: c[0])
+def test_oracle_periosteummask(golden_parosol, case):
+    name, bw, kw = case
+    _check_periosteum(golden_parosol, name, bw, kw, orc.periosteummask)
