@@ -15,6 +15,11 @@
 #include "ciclope_b200.h"
 
 #define EMIT_THREADS 256
+// 1: staged text leaves shared memory through the bulk-copy engine (cp.async.bulk.global.shared::cta);
+// 0: LDS.128 + STG.128 loops (kept for A/B measurements, profiles/tools/build_variant.sh -DEE2_BULK_FLUSH=0)
+#ifndef EE2_BULK_FLUSH
+#define EE2_BULK_FLUSH 1
+#endif
 
 extern "C" size_t cfe_scan_workspace_bytes(int64_t n_items);
 
@@ -239,10 +244,23 @@ __global__ void __launch_bounds__(NODE4_THREADS) k_emit_nodes4(NodeEmitParams P)
     char* dst = P.out + k0 * 53;
     if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
         const u32 n16 = nbytes >> 4;
+#if EE2_BULK_FLUSH
+        // the CTA's 27 KB leave through the bulk-copy engine (cp.async.bulk shared -> global)
+        if (threadIdx.x == 0 && n16) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"((u32)__cvta_generic_to_shared(stage)), "r"(16u * n16) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#else
         for (u32 c = threadIdx.x; c < n16; c += blockDim.x)
             reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(stage)[c];
+#endif
         for (u32 c = (n16 << 2) + threadIdx.x; c < (nbytes >> 2); c += blockDim.x)
             reinterpret_cast<u32*>(dst)[c] = stage[c];
+#if EE2_BULK_FLUSH
+        if (threadIdx.x == 0 && n16) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // before the smem goes away
+#endif
     } else {
         for (u32 c = threadIdx.x; c < (nbytes >> 2); c += blockDim.x) reinterpret_cast<u32*>(dst)[c] = stage[c];
     }
@@ -931,12 +949,24 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
             char* gbase = dst - pad;
             const u32 end = pad + total;
             const u32 c0 = pad ? 1u : 0u, c1 = end >> 4;
+#if EE2_BULK_FLUSH
+            // the aligned middle leaves through the bulk-copy engine (cp.async.bulk shared -> global): one
+            // instruction of one lane instead of an LDS.128 + STG.128 loop of the whole warp
+            if (lane == 0 && c1 > c0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(gbase + 16u * c0), "r"((u32)__cvta_generic_to_shared(stage + 16u * c0)),
+                                "r"(16u * (c1 - c0)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+#else
 #pragma unroll
             for (u32 it = 0; it < (ELEM_WARP_STAGE / 512u); ++it) {
                 const u32 c = c0 + lane + 32u * it;
                 if (c < c1)
                     *reinterpret_cast<uint4*>(gbase + 16u * c) = *reinterpret_cast<const uint4*>(stage + 16u * c);
             }
+#endif
             if (pad) {
                 const u32 k = pad + lane;
                 if (k < 16u && k < end) gbase[k] = stage[k];
@@ -946,8 +976,15 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
                 if (k < end) gbase[k] = stage[k];
             }
         }
+#if EE2_BULK_FLUSH
+        // the bulk copy must have READ the staging region before the next tile overwrites it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
         __syncwarp();     // the staging region is reused by the next tile
     }
+#if EE2_BULK_FLUSH
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
 }
 
 extern "C" size_t cfe_emit_elements_workspace_bytes(int64_t n_el)

@@ -314,16 +314,24 @@ extern "C" int cfe_scan_nodes(const uint32_t* bits, const uint32_t* halo_below, 
 // One CTA expands 256 consecutive words (<= 8192 entries) into shared memory at their final
 // relative positions, then streams the contiguous span to HBM with coalesced stores.
 #define FILL_WORDS 256
+// 1: staged lists leave shared memory through the bulk-copy engine (cp.async.bulk.global.shared::cta)
+#ifndef CFE_BULK_STORE
+#define CFE_BULK_STORE 1
+#endif
 
 __global__ void __launch_bounds__(FILL_WORDS)
 k_fill_list(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_words, FastDiv d_wpr, u32 wpr,
             u32 rowlen, u32* __restrict__ list)
 {
-    __shared__ u32 sm[FILL_WORDS * 32];
+    // entries are staged at sm[off + q], off = (destination word index) mod 4, so that 16-byte chunks of the
+    // staging area are 16-byte chunks of the destination: the aligned middle leaves in ONE bulk copy
+    __shared__ __align__(16) u32 sm[FILL_WORDS * 32 + 4];
     __shared__ u32 s_total;
     const u32 i0 = blockIdx.x * FILL_WORDS;
     const u32 i = i0 + threadIdx.x;
     const u32 base0 = __ldg(pref + i0);
+    u32* dst = list + base0;
+    const u32 off = (u32)(((uintptr_t)dst >> 2) & 3u);
     u32 word = 0, p = 0;
     if (i < n_words) {
         word = __ldg(bits + i);
@@ -335,26 +343,34 @@ k_fill_list(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_wo
         const u32 row = fd_div(i, d_wpr);
         const u32 w = i - row * wpr;
         const u32 base = row * rowlen + w * 32u;
+        u32* q = sm + off + p;
         while (word) {
             const int b = __ffs((int)word) - 1;
             word &= word - 1;
-            sm[p++] = base + (u32)b;
+            *q++ = base + (u32)b;
         }
     }
     __syncthreads();
     const u32 total = s_total;
-    u32* dst = list + base0;
-    // align the destination to 16 bytes, then 16-byte stores
-    const u32 head = (u32)((16u - ((uintptr_t)dst & 15u)) & 15u) >> 2;
+    const u32 head = (4u - off) & 3u;
     const u32 h = head < total ? head : total;
-    if (threadIdx.x < h) dst[threadIdx.x] = sm[threadIdx.x];
     const u32 n4 = (total - h) >> 2;
-    for (u32 k = threadIdx.x; k < n4; k += FILL_WORDS) {
-        uint4 v;
-        v.x = sm[h + 4 * k]; v.y = sm[h + 4 * k + 1]; v.z = sm[h + 4 * k + 2]; v.w = sm[h + 4 * k + 3];
-        reinterpret_cast<uint4*>(dst + h)[k] = v;
+    if (threadIdx.x < h) dst[threadIdx.x] = sm[off + threadIdx.x];
+#if CFE_BULK_STORE
+    if (threadIdx.x == 0 && n4) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(dst + h), "r"((u32)__cvta_generic_to_shared(sm + off + h)), "r"(16u * n4) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    for (u32 k = h + 4 * n4 + threadIdx.x; k < total; k += FILL_WORDS) dst[k] = sm[k];
+#else
+    for (u32 k = threadIdx.x; k < n4; k += FILL_WORDS)
+        reinterpret_cast<uint4*>(dst + h)[k] = reinterpret_cast<const uint4*>(sm + off + h)[k];
+#endif
+    for (u32 k = h + 4 * n4 + threadIdx.x; k < total; k += FILL_WORDS) dst[k] = sm[off + k];
+#if CFE_BULK_STORE
+    if (threadIdx.x == 0 && n4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
 }
 
 extern "C" int cfe_fill_list(const uint32_t* bits, const uint32_t* pref, int64_t n_words,
@@ -386,13 +402,20 @@ k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 
                 uint8_t* __restrict__ len8, uint8_t* __restrict__ nd8, const uint8_t* __restrict__ vol,
                 uint8_t* __restrict__ gv8)
 {
-    __shared__ u32 sm[FILLE_WORDS * 32];
-    __shared__ uint8_t sl[FILLE_WORDS * 32];
-    __shared__ uint8_t sn[FILLE_WORDS * 32];
+    // every array is staged at an offset congruent (mod 16 bytes) with its destination, so that the aligned
+    // middle of the CTA's span leaves in one bulk copy per array
+    __shared__ __align__(16) u32 sm_[FILLE_WORDS * 32 + 4];
+    __shared__ __align__(16) uint8_t sl_[FILLE_WORDS * 32 + 16];
+    __shared__ __align__(16) uint8_t sn_[FILLE_WORDS * 32 + 16];
     __shared__ u32 s_total;
     const u32 i0 = blockIdx.x * FILLE_WORDS;
     const u32 i = i0 + threadIdx.x;
     const u32 base0 = __ldg(pref + i0);
+    const u32 off4 = (u32)(((uintptr_t)(list + base0) >> 2) & 3u);
+    const u32 offl = (u32)((uintptr_t)(len8 + base0) & 15u), offn = (u32)((uintptr_t)(nd8 + base0) & 15u);
+    u32* const sm = sm_ + off4;
+    uint8_t* const sl = sl_ + offl;
+    uint8_t* const sn = sn_ + offn;
     u32 word = 0, p = 0;
     if (i < n_words) {
         word = __ldg(bits + i);
@@ -450,15 +473,50 @@ k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 
     __syncthreads();
     const u32 total = s_total;
     u32* dst = list + base0;
+#if CFE_BULK_STORE
+    // heads / tails by threads, aligned middles by the bulk-copy engine
+    const u32 h4 = min((4u - off4) & 3u, total), n4 = (total - h4) >> 2;
+    const u32 hl = min((16u - offl) & 15u, total), nl = (total - hl) >> 4;
+    const u32 hn = min((16u - offn) & 15u, total), nn = (total - hn) >> 4;
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (n4)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst + h4), "r"((u32)__cvta_generic_to_shared(sm + h4)), "r"(16u * n4) : "memory");
+        if (nl)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(len8 + base0 + hl), "r"((u32)__cvta_generic_to_shared(sl + hl)), "r"(16u * nl) : "memory");
+        if (nn)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(nd8 + base0 + hn), "r"((u32)__cvta_generic_to_shared(sn + hn)), "r"(16u * nn) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    auto edges = [&](u32 q) {
+        if (q < h4 || q >= h4 + 4u * n4) dst[q] = sm[q];
+        if (q < hl || q >= hl + 16u * nl) len8[base0 + q] = sl[q];
+        if (q < hn || q >= hn + 16u * nn) nd8[base0 + q] = sn[q];
+    };
+    if (threadIdx.x < 32u) {
+        // heads are shorter than 16 entries, tails too: the first and the last 32 entries cover them
+        const u32 qa = threadIdx.x, qb = total - 1u - threadIdx.x;
+        if (qa < total) edges(qa);
+        if (threadIdx.x < total && qb >= 32u) edges(qb);
+    }
+    if (gv8) {
+        // compact grey values in element order (cell_GV, voxelFE.py:160): the CTA's voxels are a span
+        // of 128 words = 4 KB of the volume, so these byte loads hit the sectors once
+        for (u32 q = threadIdx.x; q < total; q += FILLE_WORDS) gv8[base0 + q] = __ldg(vol + sm[q]);
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#else
     for (u32 q = threadIdx.x; q < total; q += FILLE_WORDS) {
         const u32 v = sm[q];
         dst[q] = v;
         len8[base0 + q] = sl[q];
         nd8[base0 + q] = sn[q];
-        // compact grey values in element order (cell_GV, voxelFE.py:160): the CTA's voxels are a span
-        // of 128 words = 4 KB of the volume, so these byte loads hit the sectors once
         if (gv8) gv8[base0 + q] = __ldg(vol + v);
     }
+#endif
 }
 
 extern "C" size_t cfe_emit_elements_workspace_bytes(int64_t n_el);

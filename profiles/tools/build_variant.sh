@@ -5,4 +5,4 @@ set -e
 OUT=$1; shift
 cd "$(dirname "$0")/../.."
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Iinclude "$@" \
-  -shared -o "$OUT" ciclope_b200/csrc/api.cu ciclope_b200/csrc/grid.cu ciclope_b200/csrc/ccl.cu ciclope_b200/csrc/deck.cu -lcudart
+  -shared -o "$OUT" ciclope_b200/csrc/*.cu -lcudart
