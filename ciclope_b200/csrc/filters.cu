@@ -72,6 +72,37 @@ k_gauss_strided(const TIN* __restrict__ in, double* __restrict__ out, i64 n_axis
     }
 }
 
+// Contiguous axis (stride 1): a CTA stages GAUSS_TX outputs' worth of one line (+ the clamped halo) in shared
+// memory as float64, then every thread reads its 2 r + 1 taps from there.
+#define GAUSS_TX 1024
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+k_gauss_rows(const TIN* __restrict__ in, double* __restrict__ out, i64 n_axis, u32 chunks,
+             const double* __restrict__ weights, int r)
+{
+    __shared__ double w[2 * GAUSS_MAX_RADIUS + 1];
+    __shared__ double sx[GAUSS_TX + 2 * GAUSS_MAX_RADIUS];
+    for (int i = threadIdx.x; i < 2 * r + 1; i += 256) w[i] = weights[i];
+    const i64 line = (i64)(blockIdx.x / chunks);
+    const i64 x0 = (i64)(blockIdx.x - (u32)line * chunks) * GAUSS_TX;
+    const TIN* src = in + line * n_axis;
+    const int span = (int)((n_axis - x0 < GAUSS_TX ? n_axis - x0 : GAUSS_TX)) + 2 * r;
+    for (int i = threadIdx.x; i < span; i += 256) {
+        i64 x = x0 - r + i;
+        if (x < 0) x = 0;
+        if (x > n_axis - 1) x = n_axis - 1;
+        sx[i] = (double)src[x];
+    }
+    __syncthreads();
+    double* dst = out + line * n_axis + x0;
+    for (int o = threadIdx.x; o < span - 2 * r; o += 256) {
+        const double* c = sx + o + r;
+        double acc = __dmul_rn(c[0], w[r]);
+        for (int j = -r; j < 0; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(c[j], c[-j]), w[r + j]));
+        dst[o] = acc;
+    }
+}
+
 static int gauss_grid(i64 n_total)
 {
     int dev = 0, sms = 148;
@@ -105,6 +136,18 @@ extern "C" int cfe_gauss1d(const void* in, int in_is_u8, double* out, int64_t n_
             k_gauss_strided<double><<<grid, block, 0, stream>>>(reinterpret_cast<const double*>(in), out, n_axis,
                                                                 stride, (u32)tiles_inner, weights, r);
         CFE_CHECK_LAUNCH("k_gauss_strided");
+        return 0;
+    }
+    const i64 chunks = (n_axis + GAUSS_TX - 1) / GAUSS_TX;
+    if (stride == 1 && n_axis >= 64 && (n_total / n_axis) * chunks < (1LL << 31)) {
+        const unsigned grid = (unsigned)((n_total / n_axis) * chunks);
+        if (in_is_u8)
+            k_gauss_rows<uint8_t><<<grid, 256, 0, stream>>>(reinterpret_cast<const uint8_t*>(in), out, n_axis,
+                                                           (u32)chunks, weights, r);
+        else
+            k_gauss_rows<double><<<grid, 256, 0, stream>>>(reinterpret_cast<const double*>(in), out, n_axis,
+                                                          (u32)chunks, weights, r);
+        CFE_CHECK_LAUNCH("k_gauss_rows");
         return 0;
     }
     const int blocks = gauss_grid(n_total);

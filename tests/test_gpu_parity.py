@@ -576,7 +576,8 @@ def test_segment_otsu_vs_oracle(cfe, orc):
 
 
 @pytest.mark.parametrize("shape,sigma", [((20, 30, 40), 1.0), ((7, 9, 5), 2.5), ((33, 17, 64), 0.5),
-                                         ((12, 40, 33), [0.0, 1.3, 2.0]), ((64, 96, 130), 1.5), ((9, 9, 9), 3.7)])
+                                         ((12, 40, 33), [0.0, 1.3, 2.0]), ((64, 96, 130), 1.5), ((9, 9, 9), 3.7),
+                                         ((3, 4, 2100), 2.0), ((2, 3, 1024), [0.0, 0.0, 6.0])])
 def test_gaussian_bit_exact_vs_scipy_and_oracle(cfe, orc, shape, sigma):
     """pipeline.py:146-148; float64 work, compared BIT FOR BIT (tolerance 0) with the oracle and with the
     installed scipy.ndimage.gaussian_filter that skimage.filters.gaussian wraps"""
