@@ -56,6 +56,20 @@ k_gauss_strided(const TIN* __restrict__ in, double* __restrict__ out, i64 n_axis
     const i64 a0 = (i64)ba * GAUSS_TA + threadIdx.y * (GAUSS_TA / 8);
     const i64 base = (i64)blockIdx.y * n_axis * inner + col;
     const TIN* line = in + base;
+    if (a0 - r >= 0 && a0 + GAUSS_TA / 8 - 1 + r <= n_axis - 1) {
+        // interior: no clamping, running offsets instead of an index multiply per tap
+        const i64 span = (i64)r * inner;
+#pragma unroll 2
+        for (int t = 0; t < GAUSS_TA / 8; ++t) {
+            const TIN* c = line + (a0 + t) * inner;
+            double acc = __dmul_rn((double)c[0], w[r]);
+            i64 off = span;
+            for (int j = 0; j < r; ++j, off -= inner)
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn((double)c[-off], (double)c[off]), w[j]));
+            out[base + (a0 + t) * inner] = acc;
+        }
+        return;
+    }
 #pragma unroll 1
     for (int t = 0; t < GAUSS_TA / 8; ++t) {
         const i64 pos = a0 + t;
