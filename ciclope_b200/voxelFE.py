@@ -15,7 +15,6 @@ interpreter arithmetic must produce the digits) and the template copy.
 There is no CPU fallback: without the CUDA library or a CUDA device every function raises.
 """
 import collections
-import ctypes
 import logging
 import math
 import os
