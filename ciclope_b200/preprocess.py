@@ -355,10 +355,10 @@ def _bool_projections(sub):
     return _projections(sub, True, _lib.stream())
 
 
-def _bbox_pad(sub, pad):
-    """recon_utils.bbox(bw, pad) (recon_utils.py:258-298) of the device volume ``sub > 0``."""
+def _bbox_from_projections(max_row, max_col, max_slice, shape, pad):
+    """recon_utils.bbox(bw, pad) (recon_utils.py:264-298) from the three max-projections of ``bw`` (pure host
+    arithmetic): ([row0, col0, slice0], [rowd, cold, sliced])."""
     from .parosol import _first_last_true
-    max_row, max_col, max_slice = _bool_projections(sub)
     row0, row1 = _first_last_true(max_row)
     col0, col1 = _first_last_true(max_col)
     slice0, slice1 = _first_last_true(max_slice)
@@ -370,7 +370,7 @@ def _bbox_pad(sub, pad):
     sliced = slice1 - slice0 + pad
     if pad > 0:
         row0, col0, slice0 = max(row0, 0), max(col0, 0), max(slice0, 0)
-        nz, ny, nx = (int(v) for v in sub.shape)
+        nz, ny, nx = (int(v) for v in shape)
         if slice0 + sliced > nz:
             sliced = nz - slice0
         if row0 + rowd > ny:
@@ -378,6 +378,12 @@ def _bbox_pad(sub, pad):
         if col0 + cold > nx:
             cold = nx - col0
     return [row0, col0, slice0], [rowd, cold, sliced]
+
+
+def _bbox_pad(sub, pad):
+    """recon_utils.bbox(bw, pad) (recon_utils.py:258-298) of the device volume ``sub > 0``."""
+    max_row, max_col, max_slice = _bool_projections(sub)
+    return _bbox_from_projections(max_row, max_col, max_slice, sub.shape, pad)
 
 
 def embed(I, embed_depth, embed_dir, embed_val=None, pad=0, makecopy=False):  # noqa: E741

@@ -134,3 +134,43 @@ def test_pyset_replay_matches_this_interpreter():
     want = np.array(list(set(map(tuple, rows.tolist()))), dtype=np.int64).reshape(-1, 4)
     assert np.array_equal(parosol._pyset_replay(rows), want)
     assert parosol._replay_matches_interpreter()
+
+
+def test_host_logic_of_the_preprocessing_facades():
+    """Pure host pieces of parosol.py / preprocess.py against the oracle's restatement of the reference."""
+    import numpy as np
+    from scipy.ndimage import _filters
+    from ciclope_b200 import parosol, preprocess
+    from oracle import oracle as orc
+    rng = np.random.default_rng(8)
+    # bounding box with padding (recon_utils.py:264-298) from the three projections
+    for shape in [(7, 9, 11), (4, 20, 6), (12, 5, 5)]:
+        for pad in (0, 1, 3, 9):
+            bw = np.zeros(shape, dtype=bool)
+            bw[1:-1, 2:-1, 1:-2] = rng.random(tuple(np.subtract(shape, (2, 3, 3)))) < 0.3
+            if not bw.any():
+                bw[1, 2, 1] = True
+            proj = (np.max(np.max(bw, 0), 1), np.max(np.max(bw, 0), 0), np.max(np.max(bw, 1), 1))
+            assert preprocess._bbox_from_projections(*proj, bw.shape, pad) == orc.bbox_pad(bw, pad)
+    # list.index(True) on a grey projection looks for entries EQUAL to 1
+    assert parosol._first_last_true(np.array([0, 2, 1, 1, 2, 0], dtype=np.uint8)) == (2, 3)
+    with pytest.raises(ValueError):
+        parosol._first_last_true(np.array([0, 2, 5], dtype=np.uint8))
+    # insertion sequence of _collect_from_elements (preprocess.py:449-456)
+    els = np.array([[0, 1, 2], [0, 1, 3], [5, 0, 0]])
+    seq = []
+    for z, y, x in els.tolist():
+        for dz in (0, 1):
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    for d in (0, 2):
+                        seq.append((z + dz, y + dy, x + dx, d))
+    assert parosol._corner_rows(els, (0, 2)).tolist() == [list(t) for t in seq]
+    want = set()
+    for t in seq:
+        want.add(t)                                   # the reference's loop; list(set) is the order it writes
+    assert parosol._ordered_unique(parosol._corner_rows(els, (0, 2))).tolist() == [list(t) for t in list(want)]
+    # Gaussian weights = scipy's
+    for sigma in (0.5, 1.0, 2.7):
+        r = int(4.0 * sigma + 0.5)
+        assert np.array_equal(preprocess._gaussian_kernel1d(sigma, r), _filters._gaussian_kernel1d(sigma, 0, r))
