@@ -477,6 +477,41 @@ def embed(I, embed_depth, embed_dir, embed_val=None, pad=0, makecopy=False):  # 
 # --------------------------------------------------------------------------------------------
 # periosteummask (preprocess.py:357-420)
 
+def _remove_small_objects(vol, min_size):
+    """skimage.morphology.remove_small_objects(bool image, min_size) (preprocess.py:385): the components
+    (6-connectivity in 3D, 4 in 2D -- scikit-image's default connectivity=1) with fewer than ``min_size`` voxels
+    are cleared.  The labelling kernels give every root its size; a per-root flag drives the mask writer.
+    vol: uint8 0/1 CUDA tensor [Z,Y,X]; returns a new one."""
+    lib = _lib.require_cuda()
+    Z, Y, X = (int(v) for v in vol.shape)
+    check_slab_size(Z, Y, X)
+    dev = vol.device
+    out = torch.zeros((Z, Y, X), dtype=torch.uint8, device=dev)
+    if Z * Y * X == 0:
+        return out
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        W = (X + 31) // 32
+        rows = Z * Y
+        bits = empty_u32(rows * W, dev)
+        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, 0, bits.data_ptr(), s)
+        pref = empty_u32(rows * W, dev)
+        stats = torch.empty(2, dtype=torch.int64, device=dev)
+        ws = scan_workspace(rows * W, dev)
+        _lib.call("cfe_scan_run_starts", bits.data_ptr(), rows, X, pref.data_ptr(), stats.data_ptr(), ws.data_ptr(), s)
+        max_runs = lib.cfe_ccl_max_runs(rows, X)
+        parent = empty_u32(max_runs, dev)
+        size = empty_u32(max_runs, dev)
+        _lib.call("cfe_ccl_label", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
+                  parent.data_ptr(), size.data_ptr(), s)
+        # keep[root] = 0xffffffff when the component is NOT too small (sizes are u32 in an int32 tensor)
+        big = ~((size.to(torch.int64) & 0xFFFFFFFF) < min_size)
+        keep = torch.where(big, torch.full_like(size, -1), torch.zeros_like(size))
+        _lib.call("cfe_ccl_write_select", bits.data_ptr(), pref.data_ptr(), Z, Y, X, parent.data_ptr(), None,
+                  keep.data_ptr(), 0, None, 1, out.data_ptr(), s)
+    return out
+
+
 def periosteummask(bwimage, closepixels=10, closevoxels=0, remove_objects_smaller_than=None, removeunconn=True,
                    verbose=False):
     """Binary mask of periosteum (whole bone) -- drop-in for preprocess.py:357-420.
@@ -488,24 +523,29 @@ def periosteummask(bwimage, closepixels=10, closevoxels=0, remove_objects_smalle
     dilation is word-parallel, the hole filling is one labelling of the background of the whole stack
     (slices only meet through their border rows, which are outside by definition) plus a border-flag pass.
 
-    ``remove_objects_smaller_than`` and ``closevoxels > 0`` (scikit-image's ``remove_small_objects`` and the
-    even-sized ``cube`` closing) are not available and raise ``NotImplementedError``; ``closepixels <= 31``.
+    ``remove_objects_smaller_than`` (scikit-image's ``remove_small_objects``) clears the small components first:
+    one more labelling, sizes per root, a flag-driven mask writer.  ``closevoxels > 0`` (the even-sized ``cube``
+    closing) is not available and raises ``NotImplementedError``; ``closepixels <= 31``.
     """
     import logging
     if verbose:
         logging.basicConfig(level=logging.INFO)
-    if remove_objects_smaller_than:
-        raise NotImplementedError("periosteummask: remove_objects_smaller_than is not available on the GPU path")
     if closevoxels > 0:
         raise NotImplementedError("periosteummask: the final 3D closing (closevoxels > 0) is not available on the GPU path")
     r = int(closepixels)
     if r != closepixels or not 0 <= r <= 31:
         raise NotImplementedError("periosteummask: closepixels must be an integer in 0..31")
-    vol, _is_bool, from_numpy = as_device_volume(bwimage, allow_2d=True)
+    vol, is_bool, from_numpy = as_device_volume(bwimage, allow_2d=True)
     squeeze = (bwimage.ndim == 2)
     Z, Y, X = (int(v) for v in vol.shape)
     dev = vol.device
     lib = _lib.require_cuda()
+    if remove_objects_smaller_than:
+        if not is_bool:
+            # scikit-image reads an integer image as a label image here: not the binary case this path handles
+            raise TypeError("periosteummask: remove_objects_smaller_than needs a boolean image")
+        logging.info('Preliminary removal of objects smaller than {} pixels.'.format(remove_objects_smaller_than))
+        vol = _remove_small_objects(vol, remove_objects_smaller_than)
     if Z * Y * X == 0:
         out = torch.zeros((Z, Y, X), dtype=torch.bool, device=dev)
     else:

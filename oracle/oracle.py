@@ -624,8 +624,24 @@ def binary_closing(image, footprint):
     return ndimage.binary_erosion(dilated, structure=footprint, border_value=True)
 
 
-def periosteummask(bwimage, closepixels=10, removeunconn=True):
+def remove_small_objects(ar, min_size):
+    """skimage.morphology.remove_small_objects for a boolean image (connectivity=1), restated on scipy."""
     from scipy import ndimage
+    out = ar.copy()
+    if min_size == 0:
+        return out
+    ccs = np.zeros_like(ar, dtype=np.int32)
+    ndimage.label(ar, ndimage.generate_binary_structure(ar.ndim, 1), output=ccs)
+    component_sizes = np.bincount(ccs.ravel())
+    too_small = component_sizes < min_size
+    out[too_small[ccs]] = 0
+    return out
+
+
+def periosteummask(bwimage, closepixels=10, removeunconn=True, remove_objects_smaller_than=None):
+    from scipy import ndimage
+    if remove_objects_smaller_than:
+        bwimage = remove_small_objects(bwimage, remove_objects_smaller_than)
     if bwimage.ndim == 3:
         perimask = np.zeros(np.shape(bwimage), dtype=bool)
         for sl in range(bwimage.shape[0]):

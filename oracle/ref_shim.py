@@ -85,7 +85,18 @@ def _install_stubs():
         dilated = ndi.binary_dilation(image, structure=footprint)
         return ndi.binary_erosion(dilated, structure=footprint, border_value=True)
 
-    morphology = mod("skimage.morphology", disk=_disk, binary_closing=_binary_closing)
+    def _remove_small_objects(ar, min_size=64, connectivity=1):
+        out = ar.copy()
+        if min_size == 0:
+            return out
+        ccs = np.zeros_like(ar, dtype=np.int32)
+        ndi.label(ar, ndi.generate_binary_structure(ar.ndim, connectivity), output=ccs)
+        too_small = np.bincount(ccs.ravel()) < min_size
+        out[too_small[ccs]] = 0
+        return out
+
+    morphology = mod("skimage.morphology", disk=_disk, binary_closing=_binary_closing,
+                     remove_small_objects=_remove_small_objects)
     filters = mod("skimage.filters", threshold_otsu=None, gaussian=None)
     mod("skimage", measure=measure, morphology=morphology, filters=filters)
 

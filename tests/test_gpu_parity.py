@@ -639,5 +639,15 @@ def test_periosteummask_larger_vs_oracle(cfe, orc):
         assert got.dtype == torch.bool and np.array_equal(got.cpu().numpy(), want), r
     with pytest.raises(NotImplementedError):
         cfe.periosteummask(bw, closevoxels=2)
-    with pytest.raises(NotImplementedError):
-        cfe.periosteummask(bw, remove_objects_smaller_than=5)
+    # preliminary removal of small objects (scikit-image's remove_small_objects on the 3D / 2D image)
+    rng = np.random.default_rng(3)
+    specks = bw | (rng.random(bw.shape) < 0.01)
+    for min_size in (2, 30, 5000):
+        want = orc.periosteummask(specks, closepixels=3, remove_objects_smaller_than=min_size)
+        got = cfe.periosteummask(specks, closepixels=3, remove_objects_smaller_than=min_size)
+        assert got.dtype == np.bool_ and np.array_equal(got, want), min_size
+    sl = specks[5]
+    assert np.array_equal(cfe.periosteummask(sl, closepixels=2, remove_objects_smaller_than=9, removeunconn=False),
+                          orc.periosteummask(sl, closepixels=2, remove_objects_smaller_than=9, removeunconn=False))
+    with pytest.raises(TypeError):
+        cfe.periosteummask(specks.astype(np.uint8), remove_objects_smaller_than=5)
