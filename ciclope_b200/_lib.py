@@ -37,6 +37,7 @@ _SIGNATURES = {
     "cfe_pack_bits": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
     "cfe_pack_bits_le": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
     "cfe_max_u8": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "cfe_value_span_u8": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "cfe_scan_workspace_bytes": (c_sz, [c_i64]),
     "cfe_scan_elements": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_scan_run_starts": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),

@@ -130,6 +130,45 @@ extern "C" int cfe_max_u8(const uint8_t* vol, int64_t n, uint32_t* out, cudaStre
     return 0;
 }
 
+// out[0] = max(out[0], max v), out[1] = min(out[1], min of the non-zero v): a uint8 image is "binary" for
+// measure.label(bw, None, True, 1) (preprocess.py:135, regions of EQUAL value) iff both agree
+__global__ void __launch_bounds__(256) k_value_span_u8(const uint8_t* __restrict__ vol, i64 n, u32* __restrict__ out)
+{
+    u32 m = 0, lo = 0xffffffffu;
+    const i64 n16 = (reinterpret_cast<uintptr_t>(vol) & 15u) ? 0 : n / 16;
+    for (i64 g = (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n16; g += (i64)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(vol) + g);
+        m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+        // zero bytes read as 0xff for the minimum
+        lo = __vminu4(lo, __vminu4(__vminu4(v.x | __vcmpeq4(v.x, 0), v.y | __vcmpeq4(v.y, 0)),
+                                   __vminu4(v.z | __vcmpeq4(v.z, 0), v.w | __vcmpeq4(v.w, 0))));
+    }
+    m = max(max(m & 0xffu, (m >> 8) & 0xffu), max((m >> 16) & 0xffu, m >> 24));
+    lo = min(min(lo & 0xffu, (lo >> 8) & 0xffu), min((lo >> 16) & 0xffu, lo >> 24));
+    for (i64 g = n16 * 16 + (i64)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        const u32 v = vol[g];
+        m = max(m, v);
+        if (v) lo = min(lo, v);
+    }
+    m = __reduce_max_sync(CFE_FULL_MASK, m);
+    lo = __reduce_min_sync(CFE_FULL_MASK, lo);
+    if ((threadIdx.x & 31) == 0) {
+        if (m) atomicMax(out, m);
+        if (lo < 0xffu) atomicMin(out + 1, lo);
+    }
+}
+
+extern "C" int cfe_value_span_u8(const uint8_t* vol, int64_t n, uint32_t* out, cudaStream_t stream)
+{
+    CFE_CHECK_CUDA(cudaMemsetAsync(out, 0, 4, stream));
+    CFE_CHECK_CUDA(cudaMemsetAsync(out + 1, 0xff, 4, stream));
+    if (n <= 0) return 0;
+    const i64 want = (n / 16 + 255) / 256 + 1;
+    k_value_span_u8<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, stream>>>(vol, n, out);
+    CFE_CHECK_LAUNCH("k_value_span_u8");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Word functors for the scan kernel.
 

@@ -21,16 +21,21 @@ def remove_unconnected(bwimage):
     Parameters
     ----------
     bwimage
-        Binary image (bool; uint8 is accepted and read as ``!= 0``).
+        Binary image: bool, or uint8 with ONE non-zero value (0/1, 0/255 ...).  ``measure.label``
+        labels regions of *equal value*, so a uint8 image with several non-zero values is not a binary
+        image to the reference; it raises ``ValueError`` here instead of being
+        read as ``!= 0``.
 
     Returns
     -------
     bwcluster
         Binary image of the largest connected cluster of voxels.
     """
-    vol, _is_bool, from_numpy = as_device_volume(bwimage, allow_2d=True)
+    vol, is_bool, from_numpy = as_device_volume(bwimage, allow_2d=True)
     squeeze = (bwimage.ndim == 2)
+    span = None if is_bool else _value_span(vol)
     mask, best = largest_component_device(vol)
+    _check_binary(span, "remove_unconnected")
     if best == 0:
         # reference: occurrences[1:].argmax() on an empty array (preprocess.py:141)
         raise ValueError("attempt to get argmax of an empty sequence")
@@ -55,9 +60,11 @@ def remove_largest(bwimage):
     bwcluster
         Binary image in which the largest cluster of voxels is removed.
     """
-    vol, _is_bool, from_numpy = as_device_volume(bwimage, allow_2d=True)
+    vol, is_bool, from_numpy = as_device_volume(bwimage, allow_2d=True)
     squeeze = (bwimage.ndim == 2)
+    span = None if is_bool else _value_span(vol)
     mask, best = largest_component_device(vol, drop=True)
+    _check_binary(span, "remove_largest")
     if best == 0:
         raise ValueError("attempt to get argmax of an empty sequence")   # preprocess.py:204
     out = mask.view(torch.bool)
@@ -110,6 +117,25 @@ def fill_voids(I, fill_val=None, makecopy=False):  # noqa: E741 -- the reference
         return I if in_place else filled.to(I.device)
     I.copy_(filled)
     return I
+
+
+def _value_span(vol):
+    """Enqueue the (max, min non-zero) reduction of a uint8 volume; read with _check_binary after the
+    labelling's own host read, so that the stream is synchronised once."""
+    span = torch.empty(2, dtype=torch.int32, device=vol.device)
+    with torch.cuda.device(vol.device):
+        _lib.call("cfe_value_span_u8", vol.data_ptr(), vol.numel(), span.data_ptr(), _lib.stream())
+    return span
+
+
+def _check_binary(span, who):
+    if span is None:
+        return
+    hi, lo = (int(v) & 0xFFFFFFFF for v in read_back(span))
+    if hi and lo != hi:
+        raise ValueError("%s: uint8 image holds several non-zero values (%d..%d); the reference labels regions "
+                         "of equal value (measure.label), which this build does not: pass a bool image or one "
+                         "with a single non-zero value" % (who, lo, hi))
 
 
 def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, out=None):

@@ -664,7 +664,7 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         lib = _lib.load()
         m.ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(m.n_el) + 16, dtype=torch.uint8, device=dev)
         # grey-scale slabs: cell_GV compacted in element order (the GV histogram and partition read it)
-        m.gv8 = None if is_bool else torch.empty(max(m.n_el, 1), dtype=torch.uint8, device=dev)
+        m.gv8 = None if (is_bool and thr >= 0) else torch.empty(max(m.n_el, 1), dtype=torch.uint8, device=dev)
         _lib.call("cfe_fill_elements_gv", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, z0, m.eid_offset,
                   m.n_el, m.elem_vox.data_ptr(), m.ws_el.data_ptr(), vol.data_ptr(), _lib.ptr(m.gv8), s)
         _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
@@ -698,7 +698,7 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             p_yt0 = p_xt0 + 16 * (X + 1)
             _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt0, p_yt0,
                       p_yt0 + 16 * (Y + 1) + 16 * m.z0, Y, X, m.z0, nodes_buf.data_ptr(), _lib.stream())
-    if m.is_bool:
+    if m.gv8 is None:
         # a boolean volume has one grey value (True -> SET1): the histogram is the element count,
         # which every rank already knows from vol2ugrid's all-gather
         hist_r = np.zeros((ctx.size, 256), dtype=np.int64)
@@ -724,11 +724,10 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
     prop_GV = {0: (1, 1)} if binary_model else vfe._resolve_matprop(matprop, GVmax)
 
     from datetime import datetime
-    head = ('** ---------------------------------------------------------\n'
-            '** Abaqus .INP file written by Voxel_FEM script on {}\n'
-            '** ---------------------------------------------------------\n'
-            '** Node coordinates from input model\n'
-            '*NODE\n').format(datetime.now()).encode()
+    # every rank derives the file layout from the header's length, and str(datetime.now()) is 26 or 19
+    # characters long (microsecond == 0): rank 0's stamp travels with the byte totals below and is the
+    # one every rank uses
+    stamp = str(datetime.now()).encode()[:32].ljust(32, b"\0")
     elem_comment = b'** Elements and Element sets from input model\n'
     tail = ''
     if 'PROPERTY' in keywords:
@@ -845,11 +844,17 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             set_bytes[ci] = torch.cat([st[1:], totals[1:2]]) - st
         node_b = nstat[0:1] if wide else to_device_async([53 * m.n_nd], torch.int64, dev)
         bad_b = nstat[1:2] if wide else torch.zeros(1, dtype=torch.int64, device=dev)
-        mine = torch.cat([gv_bytes, set_bytes, node_b, bad_b])
+        stamp_t = to_device_async(np.frombuffer(stamp, dtype=np.int64).tolist(), torch.int64, dev)
+        mine = torch.cat([gv_bytes, set_bytes, node_b, bad_b, stamp_t])
     allb = yield from ctx.all_gather(mine)
     host = torch.cat([torch.stack(allb).reshape(-1), totals, blk_off, seg_off]).cpu().numpy()   # the one sync
-    nb = ctx.size * 272
-    allb = host[:nb].reshape(ctx.size, 272)             # [rank][256 grey values + 14 sets + nodes + bad flag]
+    nb = ctx.size * 276
+    allb = host[:nb].reshape(ctx.size, 276)   # [rank][256 grey values + 14 sets + nodes + bad flag + 4 stamp words]
+    head = ('** ---------------------------------------------------------\n'
+            '** Abaqus .INP file written by Voxel_FEM script on {}\n'
+            '** ---------------------------------------------------------\n'
+            '** Node coordinates from input model\n'
+            '*NODE\n').format(allb[0, 272:276].tobytes().rstrip(b"\0").decode()).encode()
     if allb[:, 271].any():
         raise NotImplementedError("node coordinates that are not finite or not below 1e18 cannot be formatted")
     blk = host[nb + 2: nb + 258].tolist()

@@ -143,6 +143,10 @@ class VoxelMesh:
         self._cell_data = None
         self._point_sets = None
         self._cell_sets = None
+        # what the lazy getters handed out (a set-before-read then compares as edited)
+        self._points_made = None
+        self._cells_made = None
+        self._cells_block = None
 
     # -- sizes ------------------------------------------------------------------------------
     @property
@@ -420,7 +424,8 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         elem_vox = empty_u32(n_el, dev)
         ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(n_el) + 16, dtype=torch.uint8, device=dev)
         # grey-scale volumes: the grey value of every element, compact and in element order (cell_GV)
-        m.gv8 = None if is_bool else torch.empty(max(n_el, 1), dtype=torch.uint8, device=dev)
+        # (a bool volume has the one grey value True -- unless GVmin < 0 makes the False voxels elements too)
+        m.gv8 = None if (is_bool and thr >= 0) else torch.empty(max(n_el, 1), dtype=torch.uint8, device=dev)
         _lib.call("cfe_fill_elements_gv", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, 0, 0, n_el,
                   elem_vox.data_ptr(), ws_el.data_ptr(), vol.data_ptr(), _lib.ptr(m.gv8), s)
         m.ws_el = ws_el
@@ -641,7 +646,7 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
         raise ValueError("min() iterable argument is empty")   # voxelFE.py:564
     with torch.cuda.device(dev):
         s = _lib.stream()
-        if m.is_bool:
+        if m.gv8 is None:
             hist = np.zeros(256, dtype=np.int64)
             hist[1] = m.n_el
         else:

@@ -44,6 +44,10 @@ int cfe_pack_bits(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t
 int cfe_pack_bits_le(const uint8_t* vol, int64_t rows, int64_t X, int thr, uint32_t* bits, cfe_stream_t s);
 /* *out = max(*out, max(vol[0..n))): `I.max()`, the default fill value of fill_voids (preprocess.py:163) */
 int cfe_max_u8(const uint8_t* vol, int64_t n, uint32_t* out, cfe_stream_t s);
+/* out[0] = max v, out[1] = min of the non-zero v (0xffffffff if none): `measure.label(bwimage, None, True, 1)`
+ * (src/ciclope/utils/preprocess.py:135) labels regions of EQUAL value, so a uint8 image is only read as a
+ * binary one when both agree; the facade raises otherwise. */
+int cfe_value_span_u8(const uint8_t* vol, int64_t n, uint32_t* out, cfe_stream_t s);
 
 /* bytes of look-back workspace for a scan over n_items items */
 size_t cfe_scan_workspace_bytes(int64_t n_items);

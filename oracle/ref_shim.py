@@ -70,7 +70,28 @@ def _install_stubs():
 
     def label(img, background=None, return_num=False, connectivity=None):
         assert connectivity == 1, "shim only restates connectivity=1 (6-neighbourhood)"
-        lab, n = ndi.label(np.asarray(img))
+        a = np.asarray(img)
+        if a.dtype == np.bool_:
+            lab, n = ndi.label(a)
+            return (lab, n) if return_num else lab
+        # scikit-image labels regions of EQUAL value (background=None: 0 is the background), numbered by
+        # first appearance in raster order
+        bg = 0 if background is None else background
+        lab = np.zeros(a.shape, dtype=np.int64)
+        n = 0
+        for v in np.unique(a):
+            if v == bg:
+                continue
+            part, k = ndi.label(a == v)
+            lab[part > 0] = part[part > 0] + n
+            n += k
+        if n:
+            flat = lab.ravel()
+            idx = np.flatnonzero(flat)
+            uniq, first = np.unique(flat[idx], return_index=True)
+            remap = np.zeros(n + 1, dtype=np.int64)
+            remap[uniq[np.argsort(first, kind="stable")]] = np.arange(1, n + 1)
+            lab = remap[lab]
         return (lab, n) if return_num else lab
 
     measure = mod("skimage.measure", label=label)

@@ -232,6 +232,10 @@ def deck_cases():
     add("blobs_grey_property", grey_from_mask(m3, 13),
         m=dict(keywords=['NSET', 'ELSET', 'PROPERTY'], matprop=lambda: {"file": [MAT_LINEAR], "range": [[1, 255]]}))
     add("blobs_bool", m3)
+    # GVmin < 0 on a BOOL volume: the False voxels are elements too (two blocks, SET0 and SET1)
+    add("bool_gvmin_neg", b[:3, :4, :6], dict(GVmin=-1))
+    add("bool_gvmin_neg_property", b[:3, :4, :6], dict(GVmin=-0.5),
+        m=dict(keywords=['NSET', 'ELSET', 'PROPERTY'], matprop=lambda: {"file": [MAT_CONST], "range": [[0, 1]]}))
     return C
 
 

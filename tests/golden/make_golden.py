@@ -97,6 +97,10 @@ def main():
     b = cases.rand_binary((5, 7, 9), 0.4, 1)
     empty = np.zeros((3, 3, 3), dtype=bool)
     record("remove_unconnected_all_background", lambda: pre.remove_unconnected(empty))
+    # a uint8 image with several non-zero values: the reference labels regions of equal value and returns
+    # the largest one; ciclope_b200 raises ValueError instead (documented deviation)
+    multi = (cases.rand_binary((6, 8, 10), 0.6, 9) * np.arange(1, 11, dtype=np.uint8) % 4).astype(np.uint8)
+    record("remove_unconnected_multivalued_uint8", lambda: pre.remove_unconnected(multi))
     record("vol2ugrid_bad_strategy", lambda: vfe.vol2ugrid(b, locking_strategy="both"))
     record("vol2ugrid_all_background", lambda: vfe.vol2ugrid(empty))
     record("mesh2voxelfe_all_background",

@@ -67,6 +67,44 @@ def test_remove_unconnected_empty_raises(cfe):
         cfe.remove_unconnected(np.zeros((3, 4, 5), dtype=bool))
 
 
+@pytest.mark.parametrize("value", [1, 7, 255])
+def test_remove_unconnected_uint8_single_value(cfe, golden_ccl, value):
+    # uint8 images with ONE non-zero value are binary images to measure.label as well
+    for name in [n for n, _ in cases.ccl_cases()][:6]:
+        bw, want = _unpack(golden_ccl, name)
+        got = cfe.remove_unconnected(bw.astype(np.uint8) * np.uint8(value))
+        assert got.dtype == np.bool_ and np.array_equal(got, want)
+
+
+def test_remove_unconnected_multivalued_uint8_raises(cfe):
+    """measure.label labels regions of EQUAL value (the reference returns the largest such region,
+    tests/golden/errors.json: no error); this build refuses the image instead of reading it as != 0."""
+    errs = json.load(open(os.path.join(cases.GOLDEN_DIR, "errors.json")))
+    assert errs["remove_unconnected_multivalued_uint8"] is None
+    multi = (cases.rand_binary((6, 8, 10), 0.6, 9) * np.arange(1, 11, dtype=np.uint8) % 4).astype(np.uint8)
+    with pytest.raises(ValueError):
+        cfe.remove_unconnected(multi)
+    with pytest.raises(ValueError):
+        cfe.remove_largest(multi)
+    import torch
+    big = torch.zeros((3, 40, 100), dtype=torch.uint8, device="cuda")
+    big[1, 5, 7] = 200
+    big[2, 39, 99] = 3           # in the scalar tail / another 16-byte chunk
+    with pytest.raises(ValueError):
+        cfe.remove_unconnected(big)
+
+
+def test_mesh_set_before_read_routes_to_generic(cfe, golden):
+    """mesh.points = ... before the lazy array was ever read must count as an edit (not AttributeError)."""
+    c = DECK_CASES["bool_5x7x9"]
+    mesh = cfe.vol2ugrid(c["vol"], **c["u"])
+    mesh.points = golden["bool_5x7x9/points"] * 2.0
+    assert mesh._host_edited()
+    mesh2 = cfe.vol2ugrid(c["vol"], **c["u"])
+    mesh2.cells = [("hexahedron", golden["bool_5x7x9/cells"])]
+    assert mesh2._host_edited()
+
+
 @pytest.mark.parametrize("shape,density,seed", [
     ((32, 32, 32), 0.2, 1), ((32, 32, 32), 0.32, 2), ((17, 23, 129), 0.28, 3), ((40, 33, 96), 0.5, 4),
     ((64, 64, 64), 0.31, 5), ((5, 200, 70), 0.3, 6), ((64, 48, 160), 0.26, 7),
