@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(256) k_value_span_u8(const uint8_t* __restrict
     }
     m = __reduce_max_sync(CFE_FULL_MASK, m);
     lo = __reduce_min_sync(CFE_FULL_MASK, lo);
-    if ((threadIdx.x & 31) == 0) {
-        if (m) atomicMax(out, m);
-        if (lo < 0xffu) atomicMin(out + 1, lo);
+    if ((threadIdx.x & 31) == 0 && m) {      // (a warp that saw a non-zero value: lo is its smallest one)
+        atomicMax(out, m);
+        atomicMin(out + 1, lo);
     }
 }
 

@@ -138,14 +138,15 @@ def _check_binary(span, who):
                          "with a single non-zero value" % (who, lo, hi))
 
 
-def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, out=None):
+def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, out=None, info=None):
     """vol: uint8 CUDA tensor [Z,Y,X].  Returns (uint8 tensor, best) where
     best = (size << 32) | (0xffffffff - root run id), 0 when nothing was labelled.
 
     The tensor is the mask of the largest 6-connected component of ``vol != 0`` -- or, with
     ``drop``, of every labelled voxel outside it; ``invert`` labels ``vol == 0`` instead; with
     ``src`` the unselected voxels keep their ``src`` value and the selected ones get ``fill``
-    (None: the maximum of ``src``, computed on the device).  One device->host read (16 bytes)."""
+    (None: the maximum of ``src``, computed on the device).  One device->host read (16 bytes).
+    ``info`` (a dict) receives the union-find arrays of the labelling (diagnostics)."""
     lib = _lib.require_cuda()
     Z, Y, X = (int(v) for v in vol.shape)
     check_slab_size(Z, Y, X)
@@ -191,6 +192,8 @@ def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, ou
                       parent.data_ptr(), size.data_ptr(), stats.data_ptr() + 8, out.data_ptr(), s)
         host = read_back(stats)
     best = int(host[1]) & 0xFFFFFFFFFFFFFFFF
+    if info is not None:      # diagnostics (benchmarks count the components): parent[i] == i <=> run i is a root
+        info.update(parent=parent, size=size, n_runs=int(host[0]))
     return out, best
 
 

@@ -144,7 +144,7 @@ class PeerExchange:
     peer, then a local gather.  Payloads above ``CHUNK`` bytes stay with NCCL."""
 
     SLOTS = 4
-    CHUNK = 1 << 20          # bytes per source rank and slot
+    CHUNK = 16 << 20         # bytes per source rank and slot (a 2048^2 interface: 0.5 MB of bits + 8 MB of run roots)
     SIG_OFFSET = 256         # first u32 of the signal pad used here (the front is symmetric memory's own)
 
     def __init__(self, dist, group, device):
@@ -337,7 +337,7 @@ BOUNDARY_EDGES = 1 << 16      # ... and interface edges; larger cases take the h
 _MARK = -1                    # 0xffffffff in the u32 size array = "keep this root"
 
 
-def ccl_program(ctx, vol, force_host_merge=False):
+def ccl_program(ctx, vol, force_host_merge=False, info=None):
     """remove_unconnected of the global volume; `vol` = this rank's uint8 slab [Zl,Y,X] on the GPU.
     Returns (uint8 mask slab, winner (size, key) or None).
 
@@ -432,6 +432,8 @@ def ccl_program(ctx, vol, force_host_merge=False):
         _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
                   stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), s)
         res = read_back(result)                                 # the one host read of the stage
+    if info is not None:      # diagnostics: the slab's forest and the gathered boundary graph
+        info.update(parent=parent, stats=stats, packs=P, label=label, Cv=Cv, Ce=Ce, host_merge=bool(res[2]))
     if res[2]:
         # some rank has more boundary components / edges than the fixed capacity: every rank sees the
         # same flag (nothing was marked) and redoes the merge host-driven at exact sizes
@@ -918,22 +920,29 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
 
 
 def write_deck_program(ctx, deck, fileout):
-    """All ranks write their pieces into ONE file at the offsets of the global layout."""
-    if ctx.rank == 0:
-        with open(fileout, "wb") as f:
-            f.truncate(deck.total_bytes)
-    yield from ctx.barrier()
-    fd = os.open(fileout, os.O_WRONLY)
+    """All ranks put their pieces of the global deck at the offsets of the global layout: into ONE file
+    (``fileout`` = path; ``os.pwrite``) or into any object with ``pwrite(buffer, offset)``.  The bytes
+    leave the GPU through the two-buffer pinned ring of ``voxelFE.stream_device_bytes`` (the copy of the
+    next chunk overlaps the write of this one)."""
+    to_path = isinstance(fileout, (str, bytes, os.PathLike))
+    if to_path:
+        if ctx.rank == 0:
+            with open(fileout, "wb") as f:
+                f.truncate(deck.total_bytes)
+        yield from ctx.barrier()
+        fd = os.open(fileout, os.O_WRONLY)
+
+        def put(mv, off):
+            os.pwrite(fd, mv, off)
+    else:
+        put = fileout.pwrite
     try:
-        chunk = 256 << 20
-        for off, buf, lo, hi in deck.writes:
-            for a in range(lo, hi, chunk):
-                b = min(a + chunk, hi)
-                os.pwrite(fd, buf[a:b].cpu().numpy().tobytes(), off + (a - lo))
+        vfe.stream_device_bytes([(off, buf[lo:hi]) for off, buf, lo, hi in deck.writes], put)
         for off, data in deck.literals:
-            os.pwrite(fd, data, off)
+            put(data, off)
     finally:
-        os.close(fd)
+        if to_path:
+            os.close(fd)
     yield from ctx.barrier()
     return deck.total_bytes
 

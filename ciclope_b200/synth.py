@@ -82,41 +82,61 @@ def greyscale(shape, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3):
     return torch.where(f > t, g.to(torch.uint8), torch.zeros((), dtype=torch.uint8, device=f.device))
 
 
-def trabecular_slab(global_shape, z0, z1, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3, group=None):
-    """Slab [z0, z1) of the GLOBAL trabecular volume of shape `global_shape`, generated without ever
-    holding the global field: the noise is a pure function of the global voxel index and the z-blur
-    only needs a halo of radius*passes slices (periodic in the global z).  The threshold comes from
-    the all-reduced histogram when a process group is initialised; every rank then holds exactly
-    the slab that `trabecular(global_shape, ...)[z0:z1]` would give."""
+def field_slab(global_shape, z0, z1, seed=0, device="cuda", radius=4, passes=3):
+    """Slab [z0, z1) of the GLOBAL blurred field of shape `global_shape`, generated without ever holding
+    the global field: the noise is a pure function of the global voxel index and the z-blur only needs a
+    halo of radius*passes slices (periodic in the global z)."""
     Zg, Y, X = global_shape
     h = radius * passes
     if Zg < z1 - z0 + 2 * h:
-        f = field(global_shape, seed, device, radius, passes)[z0:z1]
-    else:
-        zs = (torch.arange(z0 - h, z1 + h, device=device, dtype=torch.int64) % Zg).view(-1, 1, 1)
-        y = torch.arange(Y, device=device, dtype=torch.int64).view(1, Y, 1)
-        x = torch.arange(X, device=device, dtype=torch.int64).view(1, 1, X)
-        idx = (zs * Y + y) * X + x
-        v = idx + _i64(seed * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019)
-        v = (v ^ _lsr(v, 30)) * _i64(0xBF58476D1CE4E5B9)
-        v = (v ^ _lsr(v, 27)) * _i64(0x94D049BB133111EB)
-        v = v ^ _lsr(v, 31)
-        f = _lsr(v, 48).to(torch.int32)
-        del v, idx
-        for _ in range(passes):
-            for axis in range(3):
-                f = _box(f, axis, radius)
-        f = f[h: h + (z1 - z0)].contiguous()
-    hist = torch.bincount(f.reshape(-1).to(torch.int64), minlength=65536)
+        return field(global_shape, seed, device, radius, passes)[z0:z1].contiguous()
+    zs = (torch.arange(z0 - h, z1 + h, device=device, dtype=torch.int64) % Zg).view(-1, 1, 1)
+    y = torch.arange(Y, device=device, dtype=torch.int64).view(1, Y, 1)
+    x = torch.arange(X, device=device, dtype=torch.int64).view(1, 1, X)
+    idx = (zs * Y + y) * X + x
+    v = idx + _i64(seed * 0x9E3779B97F4A7C15 + 0x632BE59BD9B4E019)
+    v = (v ^ _lsr(v, 30)) * _i64(0xBF58476D1CE4E5B9)
+    v = (v ^ _lsr(v, 27)) * _i64(0x94D049BB133111EB)
+    v = v ^ _lsr(v, 31)
+    f = _lsr(v, 48).to(torch.int32)
+    del v, idx
+    for _ in range(passes):
+        for axis in range(3):
+            f = _box(f, axis, radius)
+    return f[h: h + (z1 - z0)].contiguous()
+
+
+def _global_level(f, bvtv, global_shape, z0, z1, group):
+    """(threshold level, global maximum of the field) from the all-reduced histogram of the slabs"""
     import torch.distributed as dist
+    Zg, Y, X = global_shape
+    hist = torch.bincount(f.reshape(-1).to(torch.int64), minlength=65536)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(hist, group=group)
-        n = Zg * Y * X
-    else:
-        n = f.numel() if (z0, z1) == (0, Zg) else None
-        if n is None:
-            raise RuntimeError("trabecular_slab needs an initialised process group to threshold a partial volume")
+    elif (z0, z1) != (0, Zg):
+        raise RuntimeError("a partial volume needs an initialised process group to find the global threshold")
+    n = Zg * Y * X
     above = hist.flip(0).cumsum(0).flip(0)
     ok = (above[1:] <= int(bvtv * n)).nonzero()
-    t = int(ok[0].item())
+    return int(ok[0].item()), int(hist.nonzero().max().item())
+
+
+def trabecular_slab(global_shape, z0, z1, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3, group=None):
+    """Slab [z0, z1) of ``trabecular(global_shape, ...)``: every rank holds exactly the slices the global
+    generator would give (the threshold comes from the all-reduced histogram)."""
+    f = field_slab(global_shape, z0, z1, seed, device, radius, passes)
+    t, _ = _global_level(f, bvtv, global_shape, z0, z1, group)
     return f > t
+
+
+def foam_slab(global_shape, z0, z1, seed=0, bvtv=0.12, device="cuda", radius=4, passes=3, group=None):
+    """Slab [z0, z1) of ``foam(global_shape, ...)`` (BASELINE.json configs[3])."""
+    return trabecular_slab(global_shape, z0, z1, seed, bvtv, device, radius, passes, group)
+
+
+def greyscale_slab(global_shape, z0, z1, seed=0, bvtv=0.30, device="cuda", radius=4, passes=3, group=None):
+    """Slab [z0, z1) of ``greyscale(global_shape, ...)`` (BASELINE.json configs[2])."""
+    f = field_slab(global_shape, z0, z1, seed, device, radius, passes)
+    t, fmax = _global_level(f, bvtv, global_shape, z0, z1, group)
+    g = 1 + ((f - t).clamp(min=0).to(torch.int64) * 254 // max(fmax - t, 1)).clamp(max=254)
+    return torch.where(f > t, g.to(torch.uint8), torch.zeros((), dtype=torch.uint8, device=f.device))

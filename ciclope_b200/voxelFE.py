@@ -834,37 +834,56 @@ def deck_to_device(mesh, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
 
 
 _PINNED_CHUNKS = {}
+STREAM_CHUNK = 64 << 20
 
 
-def _write_device_bytes(deck, path, chunk=64 << 20):
-    """Device bytes -> file: two pinned staging buffers, the copy of chunk k + 1 runs while chunk k is
-    written (no pageable copies, no intermediate bytes objects)."""
-    n = deck.numel()
-    dev = deck.device
+def _pinned_ring(chunk):
     bufs = _PINNED_CHUNKS.get(chunk)
     if bufs is None:
         bufs = _PINNED_CHUNKS[chunk] = [torch.empty(chunk, dtype=torch.uint8).pin_memory() for _ in range(2)]
-    with torch.cuda.device(dev), open(path, 'wb') as INP:
+    return bufs
+
+
+def stream_device_bytes(pieces, sink, chunk=None):
+    """Device bytes -> host consumer through two pinned staging buffers: the copy of chunk k + 1 runs while
+    ``sink(memoryview, offset)`` consumes chunk k (no pageable copies, no intermediate bytes objects, host
+    memory bounded by 2 * chunk whatever the deck size).  ``pieces`` = [(offset, uint8 CUDA tensor)];
+    returns the number of bytes handed to the sink."""
+    chunk = chunk or STREAM_CHUNK
+    pieces = [(off, t) for off, t in pieces if t.numel()]
+    if not pieces:
+        return 0
+    dev = pieces[0][1].device
+    bufs = _pinned_ring(chunk)
+    spans = [(off + lo, t, lo, min(lo + chunk, t.numel())) for off, t in pieces for lo in range(0, t.numel(), chunk)]
+    total = 0
+    with torch.cuda.device(dev):
         copy_stream = torch.cuda.Stream(device=dev)
         copy_stream.wait_stream(torch.cuda.current_stream(dev))
         events = [None, None]
-        spans = [(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
 
         def start(k):
-            lo, hi = spans[k]
+            _, t, lo, hi = spans[k]
             with torch.cuda.stream(copy_stream):
-                bufs[k & 1][:hi - lo].copy_(deck[lo:hi], non_blocking=True)
+                bufs[k & 1][:hi - lo].copy_(t[lo:hi], non_blocking=True)
                 events[k & 1] = torch.cuda.Event()
                 events[k & 1].record(copy_stream)
 
-        if spans:
-            start(0)
-        for k, (lo, hi) in enumerate(spans):
+        start(0)
+        for k, (off, _, lo, hi) in enumerate(spans):
             events[k & 1].synchronize()
             if k + 1 < len(spans):
                 start(k + 1)
-            INP.write(memoryview(bufs[k & 1].numpy())[:hi - lo])
+            sink(memoryview(bufs[k & 1].numpy())[:hi - lo], off)
+            total += hi - lo
         torch.cuda.current_stream(dev).wait_stream(copy_stream)
+    return total
+
+
+def _write_device_bytes(deck, path, chunk=None):
+    """Device bytes -> file (sequential writes of the pinned chunks)."""
+    with open(path, 'wb') as INP:
+        stream_device_bytes([(0, deck)], lambda mv, off: INP.write(mv), chunk)
 
 
 def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'ELSET'], eltype='C3D8',
@@ -873,8 +892,9 @@ def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'E
     (drop-in for voxelFE.py:474-772).  Parameters are the reference's.
 
     ``fileout`` is the path of the .INP file.  Additively it may be a pinned/CPU uint8
-    ``torch.Tensor`` that receives the deck bytes (the number of bytes is returned), which is
-    what the end-to-end benchmark uses as its host buffer.
+    ``torch.Tensor`` that receives the deck bytes, or an object with a ``write(buffer)`` method (an open
+    binary file, a socket file, a hasher ...) that is fed the deck in order through a two-buffer pinned
+    ring -- decks larger than the host's memory stream through it.  Both return the number of bytes.
     """
     if verbose:
         logging.basicConfig(level=logging.INFO)
@@ -888,6 +908,9 @@ def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'E
         fileout[:n].copy_(deck, non_blocking=True)
         torch.cuda.current_stream(deck.device).synchronize()
         return n
+    if hasattr(fileout, "write"):
+        write = fileout.write
+        return stream_device_bytes([(0, deck)], lambda mv, off: write(mv))
     _write_device_bytes(deck, fileout)
     if isinstance(mesh, VoxelMesh):
         n_points, n_cells = mesh.n_points, mesh.n_el

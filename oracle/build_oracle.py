@@ -6,11 +6,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "ciclope_oracle.c")
+    srcs = [os.path.join(_HERE, f) for f in ("ciclope_oracle.c", "stream_oracle.c")]
     out = os.path.join(_HERE, "liboracle.so")
-    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
-    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-std=c99", "-Wall", "-o", out, src])
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-std=c99", "-Wall", "-o", out] + srcs)
     return out
 
 

@@ -251,6 +251,60 @@ def midsize_cases():
     return C
 
 
+def real_lhdl():
+    """The LHDL trabecular bone stack of the reference checkout thresholded at 63 (tests/golden/
+    make_golden_real.py): (bw = image > 63, kept = remove_unconnected(bw) of the reference, masked grey
+    volume = image with everything outside `kept` set to 0), all [200,200,200]."""
+    g = np.load(os.path.join(GOLDEN_DIR, "real_lhdl.npz"))
+    shape = tuple(int(v) for v in g["shape"])
+    n = int(np.prod(shape))
+    bw = np.unpackbits(g["bw"])[:n].astype(bool).reshape(shape)
+    kept = np.unpackbits(g["kept"])[:n].astype(bool).reshape(shape)
+    gv = np.zeros(shape, dtype=np.uint8)
+    gv[kept] = g["kept_gv"]
+    return bw, kept, gv
+
+
+class SectionStreamHasher:
+    """write()-able sink for ``mesh2voxelfe(mesh, template, sink)``: cuts the streamed deck into the sections
+    of ciclope_b200.sections.split_deck from their expected byte counts (the header ends with the first
+    ``*NODE`` line; `lengths` = bytes of nodes, elements, nset, elset in file order, absent sections left
+    out; the tail is the rest) and hashes each one, so that a multi-GB GPU deck is compared with the
+    streamed oracle without ever being held on the host."""
+
+    def __init__(self, lengths):
+        import hashlib
+        self.names = [k for k in ("nodes", "elements", "nset", "elset") if k in lengths] + ["tail"]
+        self.left = [int(lengths[k]) for k in self.names[:-1]] + [None]
+        self.h = [hashlib.sha256() for _ in self.names]
+        self.count = [0] * len(self.names)
+        self.cur = -1            # -1: still inside the header
+        self.head = b""
+
+    def write(self, mv):
+        data = bytes(mv)
+        if self.cur < 0:
+            self.head += data
+            i = self.head.find(b"*NODE\n")
+            if i < 0:
+                return
+            data, self.head, self.cur = self.head[i + 6:], self.head[:i + 6], 0
+        pos = 0
+        while pos < len(data):
+            left = self.left[self.cur]
+            take = len(data) - pos if left is None else min(left, len(data) - pos)
+            self.h[self.cur].update(data[pos:pos + take])
+            self.count[self.cur] += take
+            pos += take
+            if left is not None:
+                self.left[self.cur] -= take
+                if self.left[self.cur] == 0:
+                    self.cur += 1
+
+    def result(self):
+        return {k: {"bytes": self.count[i], "sha256": self.h[i].hexdigest()} for i, k in enumerate(self.names)}
+
+
 def mask_timestamp(deck_bytes):
     """Replace the non-deterministic header line 2 (voxelFE.py:619) so decks can be compared."""
     lines = deck_bytes.split(b"\n", 3)

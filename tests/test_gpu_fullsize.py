@@ -6,7 +6,9 @@ properties -- the CPU oracle needs minutes and tens of GB there:
 * CCL: idempotence, mask is a subset of the input, kept voxels == winner size, sharded == single;
 * structure: line count, fixed 53-byte *NODE lines, ascending ids, element lines re-derived from the
   voxel coordinates for a sample of elements;
-* oracle parity at 256^3 (the largest size the C oracle finishes in seconds).
+* oracle parity at 256^3 with the materialising C oracle, and at 512^3 (binary and grey-scale with 255 material
+  sets) with the section-streamed oracle: per-section SHA-256 of the CUDA deck, streamed off the GPU, against
+  oracle.stream_deck -- which tests/test_stream_oracle.py pins on every golden deck of the reference.
 """
 import hashlib
 import os
@@ -141,3 +143,88 @@ def test_fullsize_foam_sharded_equals_single():
     assert size < 0.5 * int(vol.sum())                           # fragmented: no dominant component
     m8, winner = sharded.emulate_remove_unconnected(vol, 8)
     assert torch.equal(m8, L) and winner[0] == size
+
+
+# ------------------------------------------------------------------ oracle parity at the benchmark size
+
+SECTIONS = ("nodes", "elements", "nset", "elset", "tail")
+
+
+@pytest.fixture(scope="module")
+def oracle_512(big):
+    """Streamed oracle of the 512^3 binary and grey-scale decks (two host threads, ~40 s; the C code
+    releases the GIL) + the oracle's remove_unconnected of the binary volume."""
+    import threading
+
+    from ciclope_b200 import synth
+    from oracle import oracle as orc
+    bw = big.cpu().numpy()
+    grey = synth.greyscale((512, 512, 512), seed=0, bvtv=0.30, device="cuda")
+    grey_host = grey.cpu().numpy()
+    out = {"grey": grey}
+
+    def binary():
+        out["L"] = orc.remove_unconnected(bw)
+        out["bin"] = orc.stream_deck(out["L"], cases.TEMPLATE, voxelsize=VS)
+
+    def greyscale():
+        out["gv"] = orc.stream_deck(grey_host, cases.TEMPLATE, voxelsize=VS, keywords=['NSET', 'ELSET', 'PROPERTY'],
+                                    matprop={"file": [cases.MAT_LINEAR], "range": [[1, 255]]})
+
+    th = [threading.Thread(target=binary), threading.Thread(target=greyscale)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert "bin" in out and "gv" in out, "oracle thread failed"
+    return out
+
+
+def test_oracle_parity_512_binary(big, oracle_512):
+    import torch
+    from ciclope_b200 import mesh2voxelfe, remove_unconnected, vol2ugrid
+    L = remove_unconnected(big)
+    assert torch.equal(L.cpu(), torch.from_numpy(oracle_512["L"]))          # labels kept: bit-exact at 512^3
+    mesh = vol2ugrid(L, VS)
+    want = oracle_512["bin"]
+    assert (mesh.n_el, mesh.n_nd) == (want["n_el"], want["n_nd"])
+    sink = cases.SectionStreamHasher(want)
+    n = mesh2voxelfe(mesh, cases.TEMPLATE, sink)
+    got = sink.result()
+    assert n == len(sink.head) + sum(v["bytes"] for v in got.values())
+    for sec in SECTIONS:
+        assert got[sec] == want[sec], sec
+
+
+def test_oracle_parity_512_greyscale(oracle_512):
+    from ciclope_b200 import mesh2voxelfe, vol2ugrid
+    mesh = vol2ugrid(oracle_512["grey"], VS)
+    want = oracle_512["gv"]
+    assert (mesh.n_el, mesh.n_nd) == (want["n_el"], want["n_nd"])
+    sink = cases.SectionStreamHasher(want)
+    mesh2voxelfe(mesh, cases.TEMPLATE, sink, keywords=['NSET', 'ELSET', 'PROPERTY'],
+                 matprop={"file": [cases.MAT_LINEAR], "range": [[1, 255]]})
+    got = sink.result()
+    for sec in SECTIONS:
+        assert got[sec] == want[sec], sec
+
+
+def test_oracle_parity_512_sharded_sections(big, oracle_512, tmp_path):
+    """the z-slab path (8 emulated ranks, pinned-ring writer, one file) against the same oracle record"""
+    import torch
+    from ciclope_b200 import sharded
+    L = torch.from_numpy(oracle_512["L"]).cuda()
+    out = str(tmp_path / "sharded.inp")
+    sharded.emulate_ct2inp(L, 8, VS, cases.TEMPLATE, out)
+    want = oracle_512["bin"]
+    sink = cases.SectionStreamHasher(want)
+    with open(out, "rb") as f:
+        while True:
+            chunk = f.read(64 << 20)
+            if not chunk:
+                break
+            sink.write(chunk)
+    os.remove(out)
+    got = sink.result()
+    for sec in SECTIONS:
+        assert got[sec] == want[sec], sec
