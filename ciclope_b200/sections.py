@@ -1,6 +1,6 @@
 """Split a CalculiX voxel-FE deck (the text ``mesh2voxelfe`` writes, voxelFE.py:612-768 of the reference) into
 its sections and hash them.  Host-side utility: comparing a z-slab deck written by N ranks with the
-single-GPU deck (or with the CPU oracle's) section by section tells *where* two decks differ, and the
+single-GPU deck (or with a CPU reference deck) section by section tells *where* two decks differ, and the
 header's time-stamp line is left out of the hashes."""
 import collections
 import hashlib
