@@ -602,6 +602,77 @@ extern "C" int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* pr
     return 0;
 }
 
+// Same walk over the overlapping run pairs of an interface, for the device-side merge: the runs carry
+// the dense boundary-vertex index of their component (vA: the neighbour's numbering, vB: this slab's).
+// A trabecular interface has ~10^5 overlapping run pairs but only as many DISTINCT component pairs as
+// there are boundary components, so the pairs are united in a scratch forest over the (<= 2 Cv) vertices
+// and only the unions that actually hooked two trees are appended: a spanning forest of the interface
+// graph, at most nvA + nvB - 1 edges whatever the number of run pairs.
+__device__ __forceinline__ bool uf_union_hooked(u32* parent, u32 a, u32 b)
+{
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return false;
+        if (a < b) { const u32 t = a; a = b; b = t; }
+        const u32 old = atomicMin(parent + a, b);
+        if (old == a) return true;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_ccl_interface_forest(const u32* __restrict__ bitsA, const u32* __restrict__ prefA, const u32* __restrict__ vA,
+                       const u32* __restrict__ bitsB, const u32* __restrict__ prefB, const u32* __restrict__ vB,
+                       i64 n_plane_words, int W, u32 Cv, u32* __restrict__ forest, u32* __restrict__ edges,
+                       u32* __restrict__ count, u32 capacity)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_plane_words) return;
+    const u32 a = __ldg(bitsA + i), b = __ldg(bitsB + i);
+    const u32 both = a & b;
+    if (!both) return;
+    const bool inner = (i % W) != 0;
+    const u32 a_prev = inner ? __ldg(bitsA + i - 1) : 0u;
+    const u32 b_prev = inner ? __ldg(bitsB + i - 1) : 0u;
+    const u32 pa = __ldg(prefA + i), pb = __ldg(prefB + i);
+    u32 pair_starts = both & ~((both << 1) | ((a_prev & b_prev) >> 31));
+    while (pair_starts) {
+        const int bit = __ffs((int)pair_starts) - 1;
+        pair_starts &= pair_starts - 1;
+        const u32 va = __ldg(vA + run_id(a, a_prev >> 31, pa, bit));
+        const u32 vb = __ldg(vB + run_id(b, b_prev >> 31, pb, bit));
+        if (va >= Cv || vb >= Cv) {        // vertex capacity exceeded: the solver sees it in the vertex counts
+            atomicMax(count, capacity + 1u);
+            continue;
+        }
+        if (uf_union_hooked(forest, va, Cv + vb)) {
+            const u32 slot = atomicAdd(count, 1u);
+            if (slot < capacity) { edges[2 * slot] = va; edges[2 * slot + 1] = vb; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_uf_iota(u32* __restrict__ label, i64 n);
+
+// forest: u32[2 * Cv] scratch; edges: u32[2 * capacity] (capacity >= 2 * Cv never overflows); *count = edges
+extern "C" int cfe_ccl_interface_forest(const uint32_t* bitsA, const uint32_t* prefA, const uint32_t* vA,
+                                        const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* vB,
+                                        int64_t Y, int64_t X, int64_t Cv, uint32_t* forest, uint32_t* edges,
+                                        uint32_t* count, int64_t capacity, cudaStream_t stream)
+{
+    const int W = (int)((X + 31) / 32);
+    const i64 n = Y * W;
+    CFE_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(u32), stream));
+    if (n <= 0 || Cv <= 0) return 0;
+    k_uf_iota<<<(unsigned)((2 * Cv + 255) / 256), 256, 0, stream>>>(forest, 2 * Cv);
+    CFE_CHECK_LAUNCH("k_uf_iota");
+    k_ccl_interface_forest<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        bitsA, prefA, vA, bitsB, prefB, vB, n, W, (u32)Cv, forest, edges, count, (u32)capacity);
+    CFE_CHECK_LAUNCH("k_ccl_interface_forest");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Boundary graph of the cross-slab merge: vertices = slab-local components that touch an
 // interface plane (dense indices, sorted by global key), edges = overlapping run pairs.
@@ -662,44 +733,58 @@ __global__ void __launch_bounds__(256) k_fill_u32(u32* __restrict__ a, const u64
 
 // Boundary vertices = slab-local roots owning a run in an interface plane.  vfirst[] (SENT-filled
 // over the run ids) receives the smallest plane-run index of every such root; those first
-// occurrences are numbered densely (plane-run order) and every plane run learns its vertex.
-__global__ void __launch_bounds__(1024)
-k_boundary_vertices(const u32* __restrict__ roots_bot, const u32* __restrict__ roots_top,
-                    const u32* __restrict__ cnt, int use_bot, int use_top, u32* __restrict__ vfirst,
-                    u32* __restrict__ didx, const u32* __restrict__ size, u32 Cv, u32* __restrict__ pack,
-                    u32* __restrict__ vbot, u32* __restrict__ vtop)
+// occurrences are numbered densely (any order: the solver only groups by index) and every plane
+// run learns its vertex.  Three grid-wide passes over the (<= 2 * plane runs) entries.
+__device__ __forceinline__ u32 bv_root(const u32* roots_bot, const u32* roots_top, u32 n_bot, u32 k)
 {
-    __shared__ u32 s_scan[33];
-    const u32 n_bot = use_bot ? cnt[0] : 0u, n_top = use_top ? cnt[1] : 0u, n = n_bot + n_top;
-    const u32 t = threadIdx.x;
-    for (u32 k = t; k < n; k += 1024u) {
-        const u32 r = k < n_bot ? roots_bot[k] : roots_top[k - n_bot];
-        atomicMin(vfirst + r, k);
-    }
-    __syncthreads();
-    u32 carry = 0;
-    for (u32 base = 0; base < n; base += 1024u) {
-        const u32 k = base + t;
+    return k < n_bot ? roots_bot[k] : roots_top[k - n_bot];
+}
+
+__global__ void __launch_bounds__(256)
+k_bv_first(const u32* __restrict__ roots_bot, const u32* __restrict__ roots_top, const u32* __restrict__ cnt,
+           int use_bot, int use_top, u32* __restrict__ vfirst)
+{
+    const u32 n_bot = use_bot ? cnt[0] : 0u, n = n_bot + (use_top ? cnt[1] : 0u);
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        atomicMin(vfirst + bv_root(roots_bot, roots_top, n_bot, k), k);
+}
+
+__global__ void __launch_bounds__(256)
+k_bv_number(const u32* __restrict__ roots_bot, const u32* __restrict__ roots_top, const u32* __restrict__ cnt,
+            int use_bot, int use_top, const u32* __restrict__ vfirst, u32* __restrict__ didx,
+            const u32* __restrict__ size, u32 Cv, u32* __restrict__ pack)
+{
+    const u32 n_bot = use_bot ? cnt[0] : 0u, n = n_bot + (use_top ? cnt[1] : 0u);
+    const u32 lane = threadIdx.x & 31u;
+    for (u32 k0 = blockIdx.x * blockDim.x + threadIdx.x - lane; k0 < n; k0 += gridDim.x * blockDim.x) {
+        const u32 k = k0 + lane;
         u32 r = 0;
         bool flag = false;
         if (k < n) {
-            r = k < n_bot ? roots_bot[k] : roots_top[k - n_bot];
+            r = bv_root(roots_bot, roots_top, n_bot, k);
             flag = vfirst[r] == k;
         }
-        u32 tot;
-        const u32 d = carry + block_exclusive_scan<u32>(flag ? 1u : 0u, s_scan, tot);
+        const u32 vote = __ballot_sync(CFE_FULL_MASK, flag);
+        if (!vote) continue;
+        u32 base = 0;
+        if (lane == 0) base = atomicAdd(pack, (u32)__popc(vote));
+        base = __shfl_sync(CFE_FULL_MASK, base, 0);
         if (flag) {
+            const u32 d = base + (u32)__popc(vote & ((1u << lane) - 1u));
             didx[k] = d;
             if (d < Cv) { pack[4 + d] = r; pack[4 + Cv + d] = size[r]; }
         }
-        carry += tot;
-        __syncthreads();
     }
-    if (t == 0) pack[0] = carry;
-    __syncthreads();
-    for (u32 k = t; k < n; k += 1024u) {
-        const u32 r = k < n_bot ? roots_bot[k] : roots_top[k - n_bot];
-        const u32 v = didx[vfirst[r]];
+}
+
+__global__ void __launch_bounds__(256)
+k_bv_assign(const u32* __restrict__ roots_bot, const u32* __restrict__ roots_top, const u32* __restrict__ cnt,
+            int use_bot, int use_top, const u32* __restrict__ vfirst, const u32* __restrict__ didx,
+            u32* __restrict__ vbot, u32* __restrict__ vtop)
+{
+    const u32 n_bot = use_bot ? cnt[0] : 0u, n = n_bot + (use_top ? cnt[1] : 0u);
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const u32 v = didx[vfirst[bv_root(roots_bot, roots_top, n_bot, k)]];
         if (k < n_bot) vbot[k] = v; else vtop[k - n_bot] = v;
     }
 }
@@ -710,15 +795,20 @@ extern "C" int cfe_ccl_boundary_vertices(const uint32_t* roots_bot, const uint32
                                          int64_t Cv, uint32_t* pack, uint32_t* vbot, uint32_t* vtop,
                                          cudaStream_t stream)
 {
-    k_fill_u32<<<grid_stride_blocks(), 256, 0, stream>>>(vfirst, reinterpret_cast<const u64*>(n_runs), 0xffffffffu);
+    const unsigned gs = grid_stride_blocks();
+    k_fill_u32<<<gs, 256, 0, stream>>>(vfirst, reinterpret_cast<const u64*>(n_runs), 0xffffffffu);
     CFE_CHECK_LAUNCH("k_fill_u32");
-    k_boundary_vertices<<<1, 1024, 0, stream>>>(roots_bot, roots_top, cnt, use_bot, use_top, vfirst, didx, size,
-                                                (u32)Cv, pack, vbot, vtop);
-    CFE_CHECK_LAUNCH("k_boundary_vertices");
+    CFE_CHECK_CUDA(cudaMemsetAsync(pack, 0, sizeof(u32), stream));
+    k_bv_first<<<gs, 256, 0, stream>>>(roots_bot, roots_top, cnt, use_bot, use_top, vfirst);
+    CFE_CHECK_LAUNCH("k_bv_first");
+    k_bv_number<<<gs, 256, 0, stream>>>(roots_bot, roots_top, cnt, use_bot, use_top, vfirst, didx, size, (u32)Cv, pack);
+    CFE_CHECK_LAUNCH("k_bv_number");
+    k_bv_assign<<<gs, 256, 0, stream>>>(roots_bot, roots_top, cnt, use_bot, use_top, vfirst, didx, vbot, vtop);
+    CFE_CHECK_LAUNCH("k_bv_assign");
     // best slab-internal component: roots that are boundary vertices are excluded
     CFE_CHECK_CUDA(cudaMemsetAsync(pack + 2, 0, sizeof(u64), stream));
-    k_ccl_select<<<grid_stride_blocks(), 256, 0, stream>>>(parent, size, reinterpret_cast<const u64*>(n_runs),
-                                                           reinterpret_cast<u64*>(pack + 2), vfirst);
+    k_ccl_select<<<gs, 256, 0, stream>>>(parent, size, reinterpret_cast<const u64*>(n_runs),
+                                         reinterpret_cast<u64*>(pack + 2), vfirst);
     CFE_CHECK_LAUNCH("k_ccl_select");
     return 0;
 }

@@ -332,8 +332,9 @@ def _u32_to_i64(t):
     return t.to(torch.int64) & 0xFFFFFFFF
 
 
-BOUNDARY_VERTS = 1 << 15      # per-rank capacity of the device-side cross-slab merge (vertices)
-BOUNDARY_EDGES = 1 << 16      # ... and interface edges; larger cases take the host-driven path
+BOUNDARY_VERTS = 1 << 16      # per-rank capacity of the device-side cross-slab merge (vertices = slab-local
+                              # components touching an interface); larger cases take the host-driven path
+BOUNDARY_EDGES = 2 * BOUNDARY_VERTS   # spanning-forest edges of one interface: never more than 2 Cv - 1
 _MARK = -1                    # 0xffffffff in the u32 size array = "keep this root"
 
 
@@ -393,7 +394,8 @@ def ccl_program(ctx, vol, force_host_merge=False, info=None):
     PS = 4 + 2 * Cv + 2 * Ce
     with torch.cuda.device(dev):
         s = _lib.stream()
-        pack = torch.zeros(PS, dtype=torch.int32, device=dev)
+        pack = torch.empty(PS, dtype=torch.int32, device=dev)
+        pack[:4].zero_()
         vfirst = empty_u32(max_runs, dev)
         didx = empty_u32(2 * cap, dev)
         vbot = empty_u32(cap, dev)
@@ -413,11 +415,12 @@ def ccl_program(ctx, vol, force_host_merge=False, info=None):
             scratch = torch.zeros(1, dtype=torch.int64, device=dev)
             _lib.call("cfe_scan_run_starts", bitsA.data_ptr(), Y, X, prefA.data_ptr(), scratch.data_ptr(),
                       ws.data_ptr(), s)
-            # plane B is this slab's first plane: its run ids are 0..n_bot-1, so `vbot` stands in for
-            # the parent array and the kernel emits (vertex of A's run, vertex of B's run) straight
-            # into the message
-            _lib.call("cfe_ccl_interface_edges", bitsA.data_ptr(), prefA.data_ptr(), vA.data_ptr(),
-                      bits.data_ptr(), pref.data_ptr(), vbot.data_ptr(), Y, X,
+            # plane B is this slab's first plane: its run ids are 0..n_bot-1, so `vbot` maps them to
+            # vertices; the kernel emits a spanning forest of (vertex of A's run, vertex of B's run)
+            # straight into the message
+            forest = empty_u32(2 * Cv, dev)
+            _lib.call("cfe_ccl_interface_forest", bitsA.data_ptr(), prefA.data_ptr(), vA.data_ptr(),
+                      bits.data_ptr(), pref.data_ptr(), vbot.data_ptr(), Y, X, Cv, forest.data_ptr(),
                       pack.data_ptr() + 4 * (4 + 2 * Cv), pack.data_ptr() + 4, Ce, s)
     packs = yield from ctx.all_gather(pack)
     with torch.cuda.device(dev):

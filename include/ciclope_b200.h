@@ -132,11 +132,19 @@ int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* prefA, const 
                             const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* parentB, int64_t Y,
                             int64_t X, uint32_t* edges, uint32_t* count, int64_t capacity, cfe_stream_t s);
 
+/* The same interface walk for the device-side merge: runs carry dense boundary-vertex indices (vA: the
+ * neighbour's numbering, vB: this slab's, both < Cv); the pairs are united in the scratch forest
+ * (u32[2 Cv]) and only the unions that hooked two trees are appended, i.e. a spanning forest of the
+ * interface graph: <= 2 Cv - 1 edges however many run pairs overlap. */
+int cfe_ccl_interface_forest(const uint32_t* bitsA, const uint32_t* prefA, const uint32_t* vA,
+                             const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* vB, int64_t Y,
+                             int64_t X, int64_t Cv, uint32_t* forest, uint32_t* edges, uint32_t* count,
+                             int64_t capacity, cfe_stream_t s);
+
 /* Device-side cross-slab merge.  cfe_ccl_boundary_vertices numbers this slab's boundary components
  * (roots owning a run of voxel plane 0 / Zl-1), fills the per-rank message
  *   pack = [n_vertices, n_edges, best internal (u64), roots[Cv], sizes[Cv], edges[Ce][2]]  (u32)
- * and the per-run vertex indices vbot / vtop; cfe_ccl_interface_edges (with vA / vbot standing in
- * for rootsA / parentB) appends the edges; after the all-gather cfe_ccl_boundary_solve merges the
+ * and the per-run vertex indices vbot / vtop; cfe_ccl_interface_forest appends the edges; after the all-gather cfe_ccl_boundary_solve merges the
  * graph, picks the winner (largest, ties -> first in raster order) and writes the keep markers.
  * result = {size, key = rank << 32 | root, capacity-overflow flag, winner vertex or -1}. */
 int cfe_ccl_boundary_vertices(const uint32_t* roots_bot, const uint32_t* roots_top, const uint32_t* cnt,

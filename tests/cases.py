@@ -275,7 +275,8 @@ class SectionStreamHasher:
     def __init__(self, lengths):
         import hashlib
         self.names = [k for k in ("nodes", "elements", "nset", "elset") if k in lengths] + ["tail"]
-        self.left = [int(lengths[k]) for k in self.names[:-1]] + [None]
+        self.left = [int(lengths[k]["bytes"] if isinstance(lengths[k], dict) else lengths[k])
+                     for k in self.names[:-1]] + [None]
         self.h = [hashlib.sha256() for _ in self.names]
         self.count = [0] * len(self.names)
         self.cur = -1            # -1: still inside the header

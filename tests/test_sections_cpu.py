@@ -54,3 +54,18 @@ def test_hashes_ignore_the_timestamp_only(golden):
 def per_len(deck):
     sec = sections.split_deck(deck)
     return sec["nodes"][1] - sec["nodes"][0]
+
+
+def test_stream_hasher_equals_section_hashes(golden):
+    """tests.cases.SectionStreamHasher (how the GPU tests hash multi-GB decks on the fly) against
+    sections.section_hashes of the same bytes, fed in odd-sized chunks"""
+    for name in ("blobs_grey_property", "kw_nset", "kw_none", "bool_5x7x9"):
+        deck = bytes(golden[name + "/deck"])
+        want = sections.section_hashes(deck)
+        sink = cases.SectionStreamHasher({k: v for k, v in want.items() if k != "header"})
+        for i in range(0, len(deck), 997):
+            sink.write(memoryview(deck)[i:i + 997])
+        got = sink.result()
+        assert set(got) == set(want) - {"header"}
+        assert all(got[k] == want[k] for k in got)
+        assert len(sink.head) == want["header"]["bytes"]
