@@ -50,215 +50,290 @@ __device__ __forceinline__ void uf_union(u32* parent, u32 a, u32 b)
     }
 }
 
-__global__ void __launch_bounds__(256)
-k_ccl_init(u32* __restrict__ parent, u32* __restrict__ size, const u64* __restrict__ n_runs)
+// ------------------------------------------------------------------------------------------
+// Labelling chain (cfe_ccl_label): three passes, every one of them parallel over its items.
+//
+//   k_ccl_tile     one CTA per tile of TS slices x TR rows (full width): the tile's runs get LOCAL indices in
+//                  raster order (so min local = min global), every overlapping run pair inside the tile is
+//                  first written to a shared-memory queue (cheap, divergent bit loops) and then united by
+//                  all threads, one pair each (the expensive part runs dense), in a shared-memory union-find.
+//                  The tile's forest is flattened, the voxels of every tile-local component are counted
+//                  (shared-memory adds aggregated per warp by match.any) and parent[run] = tile root (as a
+//                  global id), size[tile root] = voxels, size[other runs] = 0 are published.  Tiles with more
+//                  runs / pairs than the shared-memory capacity publish identity parents + run lengths and
+//                  leave their pairs to k_ccl_inner (flag 0).
+//   k_ccl_border   the run pairs that cross a tile border (rows r % TR == 0 against r - 1, slices
+//                  s % TS == 0 against s - 1): union-find in HBM / L2, atomicMin hooking under the smaller id.
+//   k_ccl_finish   per run: parent[i] = final root; a tile root that is not the final root adds its voxel
+//                  count to the final root's (warp-aggregated), so size[root] = voxels of the component.
+#ifndef CCL_TILE_LOG2
+#define CCL_TILE_LOG2 16        // voxels per tile = 2^16 (measured: 2^15 .. 2^17 within 12 %, 2^16 best at 2048^2 rows)
+#endif
+#ifndef CCL_MINBLOCKS
+#define CCL_MINBLOCKS 4         // CTAs per SM the tile kernel is compiled for (shared memory: 50 KB each)
+#endif
+#define CCL_CAP (1 << (CCL_TILE_LOG2 - 4))            // runs per tile held in shared memory (1 per 16 voxels)
+#define CCL_WCAP ((1 << (CCL_TILE_LOG2 - 5)) + 256)   // words per tile (+ one pad word per row)
+#define CCL_MAXROWS 256         // TS * TR
+#define CCL_THREADS 512
+#define CCL_SMEM ((2 * CCL_CAP + 2 * CCL_WCAP) * 4)
+
+struct CclGeom {
+    int Z, Y, W;
+    int TS, TR, tiles_s, tiles_r;
+    FastDiv dW;
+};
+
+// global pair kernel body: unions of word i with word j (same column word in the row above / slice below)
+__device__ __forceinline__ void ccl_pairs_global(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 i,
+                                                 i64 j, bool has_prev, u32 cur, u32* parent)
 {
-    const u64 n = *n_runs;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        parent[i] = (u32)i;
-        size[i] = 0;
+    const u32 nb = __ldg(bits + j);
+    const u32 both = cur & nb;
+    if (!both) return;
+    const u32 cur_prev = has_prev ? __ldg(bits + i - 1) : 0u;
+    const u32 nb_prev = has_prev ? __ldg(bits + j - 1) : 0u;
+    const u32 cur_pref = __ldg(pref + i), nb_pref = __ldg(pref + j);
+    u32 pair_starts = both & ~((both << 1) | ((cur_prev & nb_prev) >> 31));
+    while (pair_starts) {
+        const int b = __ffs((int)pair_starts) - 1;
+        pair_starts &= pair_starts - 1;
+        uf_union(parent, run_id(cur, cur_prev >> 31, cur_pref, b), run_id(nb, nb_prev >> 31, nb_pref, b));
     }
 }
 
-// K2: one thread per word; unions with the rows (s, r-1) and (s-1, r).  A union is issued once
-// per maximal run of (cur & neighbour) bits, i.e. once per pair of overlapping runs.
-// With tile_flag != NULL the pairs that lie inside one (CCL_TS slices x CCL_TR rows) tile were
-// already merged in shared memory by k_ccl_local (flag 1); only tile-border pairs remain.
-#ifndef CCL_TR
-#define CCL_TR 32
-#endif
-#ifndef CCL_TS
-#define CCL_TS 8
-#endif
-#define CCL_TILE_ROWS (CCL_TR * CCL_TS)
-#define CCL_LOCAL_CAP 8192
-
-__global__ void __launch_bounds__(256)
-k_ccl_merge(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 n_words, int W, int Y,
-            u32* __restrict__ parent, const u32* __restrict__ tile_flag, int tiles_r)
+__global__ void __launch_bounds__(CCL_THREADS, CCL_MINBLOCKS)
+k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64* __restrict__ n_runs_p, CclGeom G,
+           u32* __restrict__ parent, u32* __restrict__ size, u32* __restrict__ tile_flag)
 {
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_words) return;
-    const u32 cur = __ldg(bits + i);
-    if (!cur) return;
-    const i64 row = i / W;
-    const int w = (int)(i - row * W);
-    const int r = (int)(row % Y);
-    const i64 s = row / Y;
-    const u32 cur_prev = w ? __ldg(bits + i - 1) : 0u;
-    const u32 cur_pref = __ldg(pref + i);
-#pragma unroll
-    for (int dir = 0; dir < 2; ++dir) {
-        i64 j;
-        if (dir == 0) { if (r == 0) continue; j = i - W; }
-        else { if (s == 0) continue; j = i - (i64)W * Y; }
-        if (tile_flag) {
-            const bool inner = dir == 0 ? (r % CCL_TR) != 0 : (s % CCL_TS) != 0;
-            if (inner && tile_flag[(s / CCL_TS) * tiles_r + r / CCL_TR]) continue;
-        }
-        const u32 nb = __ldg(bits + j);
-        u32 both = cur & nb;
-        if (!both) continue;
-        const u32 nb_prev = w ? __ldg(bits + j - 1) : 0u;
-        const u32 nb_pref = __ldg(pref + j);
-        u32 pair_starts = both & ~((both << 1) | ((cur_prev & nb_prev) >> 31));
-        while (pair_starts) {
-            const int b = __ffs((int)pair_starts) - 1;
-            pair_starts &= pair_starts - 1;
-            uf_union(parent, run_id(cur, cur_prev >> 31, cur_pref, b), run_id(nb, nb_prev >> 31, nb_pref, b));
-        }
-    }
-}
-
-// Block-local union-find: one CTA merges the runs of a tile of CCL_TS slices x CCL_TR rows (full
-// width) in SHARED memory (latency ~30 cycles instead of an L2 round trip per pointer hop), flattens
-// the local forest and writes parent[run] = tile-local root.  Local run indices follow the global
-// raster order restricted to the tile, so the smallest local index is also the smallest global id.
-// Tiles holding more than CCL_LOCAL_CAP runs are left to the global kernel (tile_flag = 0).
-#define CCL_LOCAL_THREADS 512
-
-__global__ void __launch_bounds__(CCL_LOCAL_THREADS)
-k_ccl_local(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64* __restrict__ n_runs_p,
-            int Z, int Y, int W, FastDiv dW, u32* __restrict__ parent, u32* __restrict__ tile_flag, int tiles_r)
-{
-    __shared__ u32 sp[CCL_LOCAL_CAP];
-    __shared__ u32 rb_g[CCL_TILE_ROWS + 1];   // global run id at the start of each tile row
-    __shared__ u32 rb_l[CCL_TILE_ROWS + 1];   // local run index at the start of each tile row
-    __shared__ u32 rw[CCL_TILE_ROWS];         // global word index of each tile row (0xffffffff: outside)
+    extern __shared__ __align__(16) u32 dyn[];
+    u32* const sp = dyn;                        // [CCL_CAP] local union-find
+    u32* const cnt_l = dyn + CCL_CAP;           // [CCL_CAP] voxels per run, then per tile-local component
+    u32* const sb = dyn + 2 * CCL_CAP;          // [CCL_WCAP] the tile's bit words (tile row major)
+    u32* const spf = sb + CCL_WCAP;             // [CCL_WCAP] LOCAL run-start prefix of every word
+    __shared__ u32 rb_g[CCL_MAXROWS + 1];       // global run id at the start of each tile row
+    __shared__ u32 rb_l[CCL_MAXROWS + 1];       // local run index at the start of each tile row
     __shared__ u32 s_scan[33];
-    const int tile_s = blockIdx.x / tiles_r, tile_r = blockIdx.x - tile_s * tiles_r;
-    const int t = threadIdx.x;
+    const int W = G.W, TR = G.TR, n_trows = G.TS * G.TR;
+    const int tile_s = blockIdx.x / G.tiles_r, tile_r = blockIdx.x - tile_s * G.tiles_r;
+    const u32 t = threadIdx.x, lane = t & 31u;
     u32 g0 = 0, cnt = 0;
-    if (t < CCL_TILE_ROWS) {
+    if (t < (u32)n_trows) {
         // tile row t  <->  slice s0 + t / TR, row r0 + t % TR
-        const int s = tile_s * CCL_TS + t / CCL_TR, r = tile_r * CCL_TR + (t % CCL_TR);
-        const bool valid = s < Z && r < Y;
-        const i64 row = (i64)s * Y + r;
-        const i64 n_rows = (i64)Z * Y;
-        if (valid) {
+        const int s = tile_s * G.TS + (int)t / TR, r = tile_r * TR + ((int)t % TR);
+        const i64 row = (i64)s * G.Y + r;
+        const i64 n_rows = (i64)G.Z * G.Y;
+        if (s < G.Z && r < G.Y) {
             g0 = __ldg(pref + row * W);
             const u32 g1 = (row + 1 < n_rows) ? __ldg(pref + (row + 1) * W) : (u32)(*n_runs_p);
             cnt = g1 - g0;
         }
-        rw[t] = valid ? (u32)(row * W) : 0xffffffffu;
         rb_g[t] = g0;
     }
     u32 total;
     const u32 l0 = block_exclusive_scan<u32>(cnt, s_scan, total);
-    if (t < CCL_TILE_ROWS) rb_l[t] = l0;
-    if (t == 0) { rb_l[CCL_TILE_ROWS] = total; tile_flag[blockIdx.x] = total <= CCL_LOCAL_CAP ? 1u : 0u; }
-    if (total > CCL_LOCAL_CAP || total == 0) return;   // uniform for the CTA
-    for (u32 l = t; l < total; l += CCL_LOCAL_THREADS) sp[l] = l;
+    if (t < (u32)n_trows) rb_l[t] = l0;
+    if (t == 0) rb_l[n_trows] = total;
     __syncthreads();
-    // unions between rows of the tile
-    const u32 tile_words = (u32)CCL_TILE_ROWS * (u32)W;
-    const u32 slice_words = (u32)W * (u32)Y;
-    for (u32 wt = t; wt < tile_words; wt += CCL_LOCAL_THREADS) {
-        const u32 tr = fd_div(wt, dW), w = wt - tr * (u32)W;
-        const u32 rbase = rw[tr];
-        if (rbase == 0xffffffffu) continue;
-        const u32 i = rbase + w;
-        const u32 cur = __ldg(bits + i);
+    if (total == 0) {                            // uniform for the CTA
+        if (t == 0) tile_flag[blockIdx.x] = 1u;
+        return;
+    }
+    const u32 tile_words = (u32)n_trows * (u32)W;
+    if (total > CCL_CAP || tile_words > CCL_WCAP) {
+        // over capacity: identity parents, run lengths as sizes; k_ccl_inner unites the tile's pairs in HBM
+        if (t == 0) tile_flag[blockIdx.x] = 0u;
+        for (u32 tr = 0; tr < (u32)n_trows; ++tr) {
+            const u32 gb = rb_g[tr], n = rb_l[tr + 1] - rb_l[tr];
+            for (u32 k = t; k < n; k += CCL_THREADS) { parent[gb + k] = gb + k; size[gb + k] = 0u; }
+        }
+        __syncthreads();
+        for (u32 wt = t; wt < tile_words; wt += CCL_THREADS) {
+            const u32 tr = fd_div(wt, G.dW), w = wt - tr * (u32)W;
+            const int s = tile_s * G.TS + (int)tr / TR, r = tile_r * TR + ((int)tr % TR);
+            if (s >= G.Z || r >= G.Y) continue;
+            const i64 i = ((i64)s * G.Y + r) * W + w;
+            u32 word = __ldg(bits + i);
+            if (!word) continue;
+            const u32 orig = word, carry = w ? (__ldg(bits + i - 1) >> 31) : 0u, pf = __ldg(pref + i);
+            while (word) {
+                const int b = __ffs((int)word) - 1;
+                const u32 shifted = word >> b;
+                const int len = (~shifted == 0u) ? 32 - b : __ffs((int)~shifted) - 1;
+                atomicAdd(size + run_id(orig, carry, pf, b), (u32)len);
+                word = (b + len >= 32) ? 0u : (word & ~(((1u << len) - 1u) << b));
+            }
+        }
+        return;
+    }
+    if (t == 0) tile_flag[blockIdx.x] = 1u;
+    // ---- stage the tile: bit words and LOCAL run prefixes (rows outside the slab read as empty)
+    for (u32 l = t; l < total; l += CCL_THREADS) { sp[l] = l; cnt_l[l] = 0u; }
+    for (u32 wt = t; wt < tile_words; wt += CCL_THREADS) {
+        const u32 tr = fd_div(wt, G.dW), w = wt - tr * (u32)W;
+        const int s = tile_s * G.TS + (int)tr / TR, r = tile_r * TR + ((int)tr % TR);
+        u32 word = 0, pf = 0;
+        if (s < G.Z && r < G.Y) {
+            const i64 i = ((i64)s * G.Y + r) * W + w;
+            word = __ldg(bits + i);
+            pf = __ldg(pref + i) - rb_g[tr] + rb_l[tr];
+        }
+        sb[wt] = word;
+        spf[wt] = pf;
+    }
+    __syncthreads();
+    // ---- one pass over the staged words: run lengths, and the union of every overlapping run pair with the
+    // row above (same slice) and the same row of the slice below, in the shared-memory forest
+    const u32 slice_stride = (u32)TR * (u32)W;
+    for (u32 wt = t; wt < tile_words; wt += CCL_THREADS) {
+        const u32 cur = sb[wt];
         if (!cur) continue;
-        const bool up = (tr % CCL_TR) != 0, back = tr >= CCL_TR;
-        // issue every load of this word before the first use
-        const u32 cur_prev = w ? __ldg(bits + i - 1) : 0u;
-        const u32 cur_pref = __ldg(pref + i);
-        const u32 nbw[2] = {up ? __ldg(bits + i - W) : 0u, back ? __ldg(bits + i - slice_words) : 0u};
-        const u32 cur_off = rb_l[tr] - rb_g[tr];           // local = global + off (mod 2^32)
+        const u32 tr = fd_div(wt, G.dW), w = wt - tr * (u32)W;
+        const u32 cur_prev = w ? sb[wt - 1] : 0u;
+        const u32 cur_pref = spf[wt];
+        const u32 carry = cur_prev >> 31;
+        {   // voxels of every run: a run's pieces in different words add up in its own counter
+            u32 rest = cur;
+            while (rest) {
+                const int b = __ffs((int)rest) - 1;
+                const u32 shifted = rest >> b;
+                const int len = (~shifted == 0u) ? 32 - b : __ffs((int)~shifted) - 1;
+                atomicAdd(cnt_l + run_id(cur, carry, cur_pref, b), (u32)len);
+                rest = (b + len >= 32) ? 0u : (rest & ~(((1u << len) - 1u) << b));
+            }
+        }
 #pragma unroll
         for (int dir = 0; dir < 2; ++dir) {
-            const u32 both = cur & nbw[dir];
+            if (dir == 0 ? (tr % (u32)TR) == 0 : tr < (u32)TR) continue;
+            const u32 j = dir == 0 ? wt - (u32)W : wt - slice_stride;
+            const u32 nb = sb[j];
+            const u32 both = cur & nb;
             if (!both) continue;
-            const u32 j = dir == 0 ? i - (u32)W : i - slice_words;
-            const u32 tn = dir == 0 ? tr - 1 : tr - CCL_TR;
-            const u32 nb_prev = w ? __ldg(bits + j - 1) : 0u;
-            const u32 nb_pref = __ldg(pref + j);
-            const u32 nb_off = rb_l[tn] - rb_g[tn];
+            const u32 nb_prev = w ? sb[j - 1] : 0u;
+            const u32 nb_pref = spf[j];
             u32 pair_starts = both & ~((both << 1) | ((cur_prev & nb_prev) >> 31));
             while (pair_starts) {
                 const int b = __ffs((int)pair_starts) - 1;
                 pair_starts &= pair_starts - 1;
-                uf_union(sp, run_id(cur, cur_prev >> 31, cur_pref, b) + cur_off,
-                         run_id(nbw[dir], nb_prev >> 31, nb_pref, b) + nb_off);
+                uf_union(sp, run_id(cur, carry, cur_pref, b), run_id(nb, nb_prev >> 31, nb_pref, b));
             }
         }
     }
     __syncthreads();
-    // flatten and publish: thread t owns tile row t; the root's global id is found by a binary
-    // search over the row starts, memoised because consecutive runs mostly share their root
-    if (t < CCL_TILE_ROWS) {
-        const u32 lbeg = rb_l[t], lend = rb_l[t + 1], gbeg = rb_g[t];
-        u32 last_root = 0xffffffffu, last_gid = 0;
-        for (u32 l = lbeg; l < lend; ++l) {
-            u32 x = l, q;
-            while ((q = sp[x]) != x) x = q;
-            if (x != last_root) {
-                int lo = 0, hi = CCL_TILE_ROWS;      // invariant: rb_l[lo] <= x < rb_l[hi]
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rb_l[mid] <= x) lo = mid; else hi = mid; }
-                last_root = x;
-                last_gid = rb_g[lo] + (x - rb_l[lo]);
-            }
-            parent[gbeg + (l - lbeg)] = last_gid;
+    // ---- flatten (in place: concurrent readers only ever see ancestors)
+    for (u32 l = t; l < total; l += CCL_THREADS) {
+        u32 x = l, p;
+        while ((p = sp[x]) != x) x = p;
+        sp[l] = x;
+    }
+    __syncthreads();
+    // ---- voxels per tile-local component: every non-root run adds its length to its root's counter
+    // (neighbouring runs mostly share the root: one shared-memory add per warp and root via match.any)
+    for (u32 base = 0; base < total; base += CCL_THREADS) {
+        const u32 l = base + t;
+        u32 root = 0xffffffffu, add = 0;
+        if (l < total) {
+            const u32 r = sp[l];
+            if (r != l) { root = r; add = cnt_l[l]; }
         }
+        if (!__any_sync(CFE_FULL_MASK, root != 0xffffffffu)) continue;
+        const u32 peers = __match_any_sync(CFE_FULL_MASK, root);
+        const u32 sum = __reduce_add_sync(peers, add);
+        if (root != 0xffffffffu && ((u32)__ffs((int)peers) - 1u) == lane) atomicAdd(cnt_l + root, sum);
+    }
+    __syncthreads();
+    // ---- publish: the rows of one slice of the tile are consecutive in raster order, so local indices map to
+    // global run ids piecewise linearly with one piece per slice (<= 16 pieces)
+    for (u32 l = t; l < total; l += CCL_THREADS) {
+        const u32 root = sp[l];
+        int ka = 0, kb = 0;
+#pragma unroll 1
+        for (int k = 1; k < G.TS; ++k) {
+            const u32 sl = rb_l[k * TR];
+            ka += (sl <= l);
+            kb += (sl <= root);
+        }
+        const u32 g = rb_g[ka * TR] + (l - rb_l[ka * TR]);
+        parent[g] = rb_g[kb * TR] + (root - rb_l[kb * TR]);
+        size[g] = (root == l) ? cnt_l[l] : 0u;
+    }
+}
+
+// Run pairs across tile borders.  Work items = words of the border rows: first the rows r = k * TR (k >= 1) of
+// every slice (against row r - 1), then every row of the slices s = k * TS (k >= 1) (against slice s - 1).
+__global__ void __launch_bounds__(256)
+k_ccl_border(const u32* __restrict__ bits, const u32* __restrict__ pref, CclGeom G, i64 n0, i64 n_items,
+             u32* __restrict__ parent)
+{
+    const i64 it = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const int W = G.W;
+    i64 row;        // global row index s * Y + r
+    int dir;
+    i64 q = it / W;
+    const int w = (int)(it - q * W);
+    if (it < n0) {
+        const int per_slice = G.tiles_r - 1;
+        const i64 s = q / per_slice;
+        const int r = ((int)(q - s * per_slice) + 1) * G.TR;
+        row = s * G.Y + r;
+        dir = 0;
+    } else {
+        q -= n0 / W;
+        const i64 k = q / G.Y;
+        const int r = (int)(q - k * G.Y);
+        row = (k + 1) * G.TS * (i64)G.Y + r;
+        dir = 1;
+    }
+    const i64 i = row * W + w;
+    const u32 cur = __ldg(bits + i);
+    if (!cur) return;
+    ccl_pairs_global(bits, pref, i, dir == 0 ? i - W : i - (i64)W * G.Y, w != 0, cur, parent);
+}
+
+// The pairs INSIDE the tiles that did not fit shared memory (flag 0): one CTA per tile, returns at once for
+// the others.
+__global__ void __launch_bounds__(256)
+k_ccl_inner(const u32* __restrict__ bits, const u32* __restrict__ pref, CclGeom G, u32* __restrict__ parent,
+            const u32* __restrict__ tile_flag)
+{
+    if (tile_flag[blockIdx.x]) return;
+    const int tile_s = blockIdx.x / G.tiles_r, tile_r = blockIdx.x - tile_s * G.tiles_r;
+    const int W = G.W, n_trows = G.TS * G.TR;
+    const u32 tile_words = (u32)n_trows * (u32)W;
+    for (u32 wt = threadIdx.x; wt < tile_words; wt += blockDim.x) {
+        const u32 tr = fd_div(wt, G.dW), w = wt - tr * (u32)W;
+        const int s = tile_s * G.TS + (int)tr / G.TR, r = tile_r * G.TR + ((int)tr % G.TR);
+        if (s >= G.Z || r >= G.Y) continue;
+        const i64 i = ((i64)s * G.Y + r) * W + w;
+        const u32 cur = __ldg(bits + i);
+        if (!cur) continue;
+        if ((tr % (u32)G.TR) != 0) ccl_pairs_global(bits, pref, i, i - W, w != 0, cur, parent);
+        if (tr >= (u32)G.TR) ccl_pairs_global(bits, pref, i, i - (i64)W * G.Y, w != 0, cur, parent);
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_ccl_flatten(u32* __restrict__ parent, const u64* __restrict__ n_runs)
+k_ccl_finish(u32* __restrict__ parent, u32* __restrict__ size, const u64* __restrict__ n_runs)
 {
     const u64 n = *n_runs;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
-        u32 r = (u32)i, p;
-        while ((p = parent[r]) != r) r = p;
-        parent[i] = r;
-    }
-}
-
-// K3a: component sizes.  One thread per word; every maximal segment of set bits inside the word
-// adds its popcount to size[root(run)].  Additions are aggregated per warp (match.any) and,
-// for the root met first by the block (almost always the dominant component), per block.
-__global__ void __launch_bounds__(256)
-k_ccl_sizes(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 n_words, int W,
-            const u32* __restrict__ parent, u32* __restrict__ size)
-{
-    __shared__ u32 s_root;
-    __shared__ u32 s_sum;
-    if (threadIdx.x == 0) { s_root = 0xffffffffu; s_sum = 0; }
-    __syncthreads();
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    u32 word = 0, carry = 0, pf = 0;
-    if (i < n_words) {
-        word = __ldg(bits + i);
-        if (word) {
-            carry = (i % W) ? (__ldg(bits + i - 1) >> 31) : 0u;
-            pf = __ldg(pref + i);
+    const u32 lane = threadIdx.x & 31u;
+    for (u64 base = (u64)blockIdx.x * blockDim.x + threadIdx.x - lane; base < n; base += (u64)gridDim.x * blockDim.x) {
+        const u64 i = base + lane;
+        u32 r = 0xffffffffu, add = 0;
+        if (i < n) {
+            const u32 p = parent[i];
+            u32 x = p, qn;
+            while ((qn = parent[x]) != x) x = qn;
+            if (x != p) parent[i] = x;
+            const u32 sz = size[i];
+            if (sz && x != (u32)i) { r = x; add = sz; size[i] = 0u; }
         }
+        if (!__any_sync(CFE_FULL_MASK, add != 0)) continue;
+        const u32 peers = __match_any_sync(CFE_FULL_MASK, r);
+        const u32 sum = __reduce_add_sync(peers, add);
+        if (r != 0xffffffffu && ((u32)__ffs((int)peers) - 1u) == lane) atomicAdd(size + r, sum);
     }
-    const u32 orig = word;
-    while (__any_sync(CFE_FULL_MASK, word != 0)) {
-        u32 root = 0xffffffffu, cnt = 0;
-        if (word) {
-            const int b = __ffs((int)word) - 1;
-            // segment = run of ones starting at b
-            const u32 shifted = word >> b;
-            const int len = (~shifted == 0u) ? 32 - b : __ffs((int)~shifted) - 1;
-            root = __ldg(parent + run_id(orig, carry, pf, b));
-            cnt = (u32)len;
-            word = (b + len >= 32) ? 0u : (word & ~(((1u << len) - 1u) << b));
-        }
-        const u32 peers = __match_any_sync(CFE_FULL_MASK, root);
-        // sum cnt over the peer group (every lane of a group holds the same `peers` mask)
-        const u32 sum = __reduce_add_sync(peers, cnt);
-        const bool leader = ((u32)__ffs((int)peers) - 1u) == (threadIdx.x & 31u);
-        if (leader && root != 0xffffffffu) {
-            u32 cached = atomicCAS(&s_root, 0xffffffffu, root);
-            if (cached == 0xffffffffu || cached == root) atomicAdd(&s_sum, sum);
-            else atomicAdd(size + root, sum);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_root != 0xffffffffu) atomicAdd(size + s_root, s_sum);
 }
 
 // K3b: arg-max over roots of (size, then smallest id)  ->  best = (size << 32) | ~id
@@ -415,6 +490,25 @@ static unsigned grid_stride_blocks()
     return (unsigned)(sms * 8);  // 8 CTAs of 256 threads per SM
 }
 
+// Tile shape of k_ccl_tile: about 2^16 voxels per tile (2 * 10^3 runs at the run density of trabecular
+// volumes, half the shared-memory capacity), as square as possible in (slices, rows) because the pairs that
+// cross a tile border (1 / TS + 1 / TR of them) are united in HBM.
+static void ccl_geometry(CclGeom& G, i64 Z, i64 Y, i64 X)
+{
+    G.Z = (int)Z; G.Y = (int)Y; G.W = (int)((X + 31) / 32);
+    G.dW = make_fastdiv((u32)G.W);
+    int rows = 8;
+    while (rows < CCL_MAXROWS && (i64)(rows * 2) * X <= (1 << CCL_TILE_LOG2)) rows *= 2;
+    int ts = 1;
+    while (ts * ts < rows) ts *= 2;          // 8 -> 4 x 2, 16 -> 4 x 4, 32 -> 8 x 4, 64 -> 8 x 8, 128 -> 16 x 8, 256 -> 16 x 16
+    while (ts > 1 && ts / 2 >= Z) ts /= 2;   // thin slabs: spend the rows on y
+    int tr = rows / ts;
+    while (tr > 1 && tr / 2 >= Y) tr /= 2;
+    G.TS = ts; G.TR = tr;
+    G.tiles_s = (int)((Z + ts - 1) / ts);
+    G.tiles_r = (int)((Y + tr - 1) / tr);
+}
+
 // Phase 1: label the slab.  After this call parent[run] = root run id (min run id of the
 // component inside this slab) and size[root] = voxels of the component inside this slab.
 extern "C" int cfe_ccl_label(const uint32_t* bits, const uint32_t* pref, const uint64_t* n_runs, int64_t Z,
@@ -422,25 +516,27 @@ extern "C" int cfe_ccl_label(const uint32_t* bits, const uint32_t* pref, const u
 {
     const i64 rows = Z * Y;
     if (rows <= 0 || X <= 0) return 0;
-    const int W = (int)((X + 31) / 32);
-    const i64 n_words = rows * W;
-    const unsigned gs_blocks = grid_stride_blocks();
+    CclGeom G;
+    ccl_geometry(G, Z, Y, X);
     const u64* nr = reinterpret_cast<const u64*>(n_runs);
-    k_ccl_init<<<gs_blocks, 256, 0, stream>>>(parent, size, nr);
-    CFE_CHECK_LAUNCH("k_ccl_init");
-    const unsigned wb = (unsigned)((n_words + 255) / 256);
     // tile flags live behind the n_runs <= rows*ceil(X/2) entries of `size` (see cfe_ccl_max_runs)
-    const int tiles_s = (int)((Z + CCL_TS - 1) / CCL_TS), tiles_r = (int)((Y + CCL_TR - 1) / CCL_TR);
     u32* tile_flag = size + (size_t)rows * (size_t)((X + 1) / 2);
-    k_ccl_local<<<(unsigned)(tiles_s * tiles_r), CCL_LOCAL_THREADS, 0, stream>>>(
-        bits, pref, nr, (int)Z, (int)Y, W, make_fastdiv((u32)W), parent, tile_flag, tiles_r);
-    CFE_CHECK_LAUNCH("k_ccl_local");
-    k_ccl_merge<<<wb, 256, 0, stream>>>(bits, pref, n_words, W, (int)Y, parent, tile_flag, tiles_r);
-    CFE_CHECK_LAUNCH("k_ccl_merge");
-    k_ccl_flatten<<<gs_blocks, 256, 0, stream>>>(parent, nr);
-    CFE_CHECK_LAUNCH("k_ccl_flatten");
-    k_ccl_sizes<<<wb, 256, 0, stream>>>(bits, pref, n_words, W, parent, size);
-    CFE_CHECK_LAUNCH("k_ccl_sizes");
+    static unsigned long long attr_mask = 0;
+    if (cfe_first_on_device(&attr_mask))
+        CFE_CHECK_CUDA(cudaFuncSetAttribute(k_ccl_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, CCL_SMEM));
+    const unsigned n_tiles = (unsigned)(G.tiles_s * G.tiles_r);
+    k_ccl_tile<<<n_tiles, CCL_THREADS, CCL_SMEM, stream>>>(bits, pref, nr, G, parent, size, tile_flag);
+    CFE_CHECK_LAUNCH("k_ccl_tile");
+    k_ccl_inner<<<n_tiles, 256, 0, stream>>>(bits, pref, G, parent, tile_flag);
+    CFE_CHECK_LAUNCH("k_ccl_inner");
+    const i64 n0 = Z * (i64)(G.tiles_r - 1) * G.W;
+    const i64 n1 = (i64)(G.tiles_s - 1) * Y * G.W;
+    if (n0 + n1 > 0) {
+        k_ccl_border<<<(unsigned)((n0 + n1 + 255) / 256), 256, 0, stream>>>(bits, pref, G, n0, n0 + n1, parent);
+        CFE_CHECK_LAUNCH("k_ccl_border");
+    }
+    k_ccl_finish<<<grid_stride_blocks(), 256, 0, stream>>>(parent, size, nr);
+    CFE_CHECK_LAUNCH("k_ccl_finish");
     return 0;
 }
 
@@ -608,6 +704,10 @@ extern "C" int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* pr
 // there are boundary components, so the pairs are united in a scratch forest over the (<= 2 Cv) vertices
 // and only the unions that actually hooked two trees are appended: a spanning forest of the interface
 // graph, at most nvA + nvB - 1 edges whatever the number of run pairs.
+// (compare-and-swap, not atomicMin: atomicMin also LOWERS the parent of a node that another thread hooked a
+// moment ago, which links two trees without anybody appending an edge for it -- the thread that did it goes
+// on to unite the displaced parent with its target, but a third thread can complete that union with an edge
+// that duplicates an appended one.  With CAS a link is created only by the thread that appends its edge.)
 __device__ __forceinline__ bool uf_union_hooked(u32* parent, u32 a, u32 b)
 {
     while (true) {
@@ -615,7 +715,7 @@ __device__ __forceinline__ bool uf_union_hooked(u32* parent, u32 a, u32 b)
         b = uf_find(parent, b);
         if (a == b) return false;
         if (a < b) { const u32 t = a; a = b; b = t; }
-        const u32 old = atomicMin(parent + a, b);
+        const u32 old = atomicCAS(parent + a, a, b);
         if (old == a) return true;
         a = old;
     }
