@@ -46,6 +46,8 @@ _SIGNATURES = {
     "cfe_scan_u32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_ccl_max_runs": (c_sz, [c_i64, c_i64]),
     "cfe_ccl_largest": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_ccl_largest_bits": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_ccl_write_mask_bits": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cfe_ccl_label": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "cfe_ccl_select": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cfe_ccl_write_mask": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),

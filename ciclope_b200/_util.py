@@ -83,3 +83,23 @@ def read_back(t):
     view.copy_(t.reshape(-1), non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
     return view.tolist()
+
+
+def tag_packed(t, bits):
+    """Remember that `bits` (u32 words, the layout of cfe_pack_bits) holds ``t != 0`` bit-packed: the mask
+    writer of remove_unconnected produces them for free, and vol2ugrid of that mask starts from them.  The
+    tag lives on the tensor OBJECT and carries its version counter, so an in-place edit of the mask (or of
+    any view of it) invalidates it."""
+    t._cfe_bits = (bits, t._version, tuple(t.shape))
+    return t
+
+
+def packed_of(t):
+    """The bit-packed ``t != 0`` left by :func:`tag_packed`, or None when absent / stale."""
+    tag = getattr(t, "_cfe_bits", None) if isinstance(t, torch.Tensor) else None
+    if tag is None:
+        return None
+    bits, version, shape = tag
+    if t._version != version or tuple(t.shape) != shape or not t.is_contiguous() or bits.device != t.device:
+        return None
+    return bits

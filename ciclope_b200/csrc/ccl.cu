@@ -431,7 +431,8 @@ k_ccl_write_mask(const u32* __restrict__ bits, const u32* __restrict__ pref, i64
 __global__ void __launch_bounds__(256)
 k_ccl_write_mask_words(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 n_words, int W,
                        const u32* __restrict__ parent, const u64* __restrict__ best,
-                       const u32* __restrict__ keep_flag, int drop, const uint8_t* src, u32 fill, uint8_t* out)
+                       const u32* __restrict__ keep_flag, int drop, const uint8_t* src, u32 fill, uint8_t* out,
+                       u32* __restrict__ sel_bits)
 {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     const u32 lane = threadIdx.x & 31u;
@@ -455,6 +456,7 @@ k_ccl_write_mask_words(const u32* __restrict__ bits, const u32* __restrict__ pre
             }
         }
     }
+    if (sel_bits && i < n_words) sel_bits[i] = keep;     // the selection, bit-packed like `bits`
     const i64 chunk0 = (i - lane) * 2;            // first 16-byte chunk of the warp's 32 words
     const u32 f4 = (fill & 0xffu) * 0x01010101u;
 #pragma unroll
@@ -565,10 +567,9 @@ extern "C" int cfe_ccl_write_mask(const uint32_t* bits, const uint32_t* pref, in
 // labelled voxel EXCEPT the winner's (drop = 1: remove_largest, preprocess.py:204-206; the voids of
 // fill_voids, :176-177).  out = fill on selected voxels, src[voxel] (0 when src is NULL) elsewhere;
 // out == src is allowed (in-place fill).
-extern "C" int cfe_ccl_write_select(const uint32_t* bits, const uint32_t* pref, int64_t Z, int64_t Y, int64_t X,
-                                    const uint32_t* parent, const uint64_t* best, const uint32_t* keep,
-                                    int drop, const uint8_t* src, int fill, uint8_t* out_mask,
-                                    cudaStream_t stream)
+static int write_select(const uint32_t* bits, const uint32_t* pref, int64_t Z, int64_t Y, int64_t X,
+                        const uint32_t* parent, const uint64_t* best, const uint32_t* keep, int drop,
+                        const uint8_t* src, int fill, uint8_t* out_mask, uint32_t* sel_bits, cudaStream_t stream)
 {
     const i64 rows = Z * Y;
     if (rows <= 0 || X <= 0) return 0;
@@ -578,14 +579,36 @@ extern "C" int cfe_ccl_write_select(const uint32_t* bits, const uint32_t* pref, 
     const bool flat = (X % 32 == 0) && ((reinterpret_cast<uintptr_t>(out_mask) & 15u) == 0) &&
                       ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
     const u64* b = reinterpret_cast<const u64*>(best);
+    if (sel_bits && !flat) {
+        cfe_set_error("cfe_ccl_*_bits: the packed selection needs X %% 32 == 0 and 16-byte aligned buffers");
+        return -1;
+    }
     if (flat)
         k_ccl_write_mask_words<<<(unsigned)((rows * W + 255) / 256), 256, 0, stream>>>(
-            bits, pref, rows * W, W, parent, b, keep, drop, src, (u32)fill, out_mask);
+            bits, pref, rows * W, W, parent, b, keep, drop, src, (u32)fill, out_mask, sel_bits);
     else
         k_ccl_write_mask<false><<<cb, 256, 0, stream>>>(bits, pref, rows, (int)X, W, parent, b, keep, drop, src,
                                                         (u32)fill, out_mask);
     CFE_CHECK_LAUNCH("k_ccl_write_mask");
     return 0;
+}
+
+extern "C" int cfe_ccl_write_select(const uint32_t* bits, const uint32_t* pref, int64_t Z, int64_t Y, int64_t X,
+                                    const uint32_t* parent, const uint64_t* best, const uint32_t* keep,
+                                    int drop, const uint8_t* src, int fill, uint8_t* out_mask,
+                                    cudaStream_t stream)
+{
+    return write_select(bits, pref, Z, Y, X, parent, best, keep, drop, src, fill, out_mask, nullptr, stream);
+}
+
+// cfe_ccl_write_mask that also leaves the kept voxels bit-packed (sel_bits: u32[Z*Y*ceil(X/32)], the layout of
+// cfe_pack_bits): vol2ugrid of the mask then starts from the bits instead of re-reading the byte mask.
+// Requires X % 32 == 0 and a 16-byte aligned out_mask.
+extern "C" int cfe_ccl_write_mask_bits(const uint32_t* bits, const uint32_t* pref, int64_t Z, int64_t Y, int64_t X,
+                                       const uint32_t* parent, const uint64_t* best, const uint32_t* keep,
+                                       uint8_t* out_mask, uint32_t* sel_bits, cudaStream_t stream)
+{
+    return write_select(bits, pref, Z, Y, X, parent, best, keep, 0, nullptr, 1, out_mask, sel_bits, stream);
 }
 
 // Labels the slab and keeps the largest component (single-GPU path = phases 1-3 back to back).
@@ -599,6 +622,19 @@ extern "C" int cfe_ccl_largest(const uint32_t* bits, const uint32_t* pref, const
                                uint64_t* best, uint8_t* out_mask, cudaStream_t stream)
 {
     return cfe_ccl_largest_select(bits, pref, n_runs, Z, Y, X, parent, size, best, 0, nullptr, 1, out_mask, stream);
+}
+
+// cfe_ccl_largest + the packed selection (see cfe_ccl_write_mask_bits)
+extern "C" int cfe_ccl_largest_bits(const uint32_t* bits, const uint32_t* pref, const uint64_t* n_runs,
+                                    int64_t Z, int64_t Y, int64_t X, uint32_t* parent, uint32_t* size,
+                                    uint64_t* best, uint8_t* out_mask, uint32_t* sel_bits, cudaStream_t stream)
+{
+    if (Z * Y <= 0 || X <= 0) return 0;
+    int rc = cfe_ccl_label(bits, pref, n_runs, Z, Y, X, parent, size, stream);
+    if (rc) return rc;
+    rc = cfe_ccl_select(parent, size, n_runs, best, stream);
+    if (rc) return rc;
+    return write_select(bits, pref, Z, Y, X, parent, best, nullptr, 0, nullptr, 1, out_mask, sel_bits, stream);
 }
 
 // Same, with the general phase 3 (cfe_ccl_write_select): drop / src / fill.

@@ -19,7 +19,7 @@ import torch
 
 from . import sharded
 from . import voxelFE as vfe
-from ._util import as_device_volume, read_back, to_device_async
+from ._util import as_device_volume, packed_of, read_back, tag_packed, to_device_async
 from . import _lib
 
 _RUNNERS = {}
@@ -65,7 +65,12 @@ def remove_unconnected(bwimage, group=None):
     if winner is None:
         raise ValueError("attempt to get argmax of an empty sequence")
     out = mask.view(torch.bool)
-    return out.cpu().numpy() if from_numpy else out
+    if from_numpy:
+        return out.cpu().numpy()
+    kept = packed_of(mask)
+    if kept is not None:
+        tag_packed(out, kept)
+    return out
 
 
 def _placement_program(ctx, Zl, dev):
@@ -119,6 +124,7 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
     if isinstance(voxelsize, tuple):
         raise TypeError("voxelsize must be a list, a numpy array or a scalar (the reference mis-handles tuples)")
     vol, is_bool, _ = as_device_volume(voldata)
+    packed = packed_of(voldata)
     r = runner(group)
     if z0 is None or Z_global is None:
         z0, Z_global = r.run(_placement_program(r.ctx(), int(vol.shape[0]), vol.device))
@@ -126,7 +132,7 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
     mesh = r.run(sharded.vol2ugrid_program(r.ctx(), vol, is_bool, int(Z_global), int(z0), voxelsize, GVmin=GVmin,
                                            plane_lock_num=plane_lock_num,
                                            node_level_lock_num=node_level_lock_num,
-                                           locking_strategy=locking_strategy))
+                                           locking_strategy=locking_strategy, packed=packed))
     logging.info('Generated the following mesh with {0} nodes and {1} elements:'.format(
         (mesh.Zg + 1) * (mesh.Y + 1) * (mesh.X + 1), mesh.n_el_global))
     if refnodes:

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._util import as_device_volume, check_slab_size, empty_u32, read_back, scan_workspace
+from ._util import as_device_volume, check_slab_size, empty_u32, packed_of, read_back, scan_workspace, tag_packed
 
 
 def remove_unconnected(bwimage):
@@ -44,6 +44,9 @@ def remove_unconnected(bwimage):
         out = out[0]
     if from_numpy:
         return out.cpu().numpy()
+    kept = packed_of(mask)
+    if kept is not None and not squeeze:
+        tag_packed(out, kept)
     return out
 
 
@@ -187,6 +190,12 @@ def largest_component_device(vol, drop=False, invert=False, src=None, fill=1, ou
                 _lib.call("cfe_ccl_largest_select", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
                           parent.data_ptr(), size.data_ptr(), stats.data_ptr() + 8, int(drop), _lib.ptr(src),
                           int(fill), out.data_ptr(), s)
+        elif X % 32 == 0 and out.data_ptr() % 16 == 0:
+            # the mask writer also leaves the kept voxels bit-packed: vol2ugrid(out) starts from them
+            sel = empty_u32(rows * W, dev)
+            _lib.call("cfe_ccl_largest_bits", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
+                      parent.data_ptr(), size.data_ptr(), stats.data_ptr() + 8, out.data_ptr(), sel.data_ptr(), s)
+            tag_packed(out, sel)
         else:
             _lib.call("cfe_ccl_largest", bits.data_ptr(), pref.data_ptr(), stats.data_ptr(), Z, Y, X,
                       parent.data_ptr(), size.data_ptr(), stats.data_ptr() + 8, out.data_ptr(), s)

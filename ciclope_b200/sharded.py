@@ -26,7 +26,7 @@ import torch
 from . import _lib
 from . import voxelFE as vfe
 from ._lib import CfeItemSeg, CfeSetDesc
-from ._util import bytes_to_device_async, empty_u32, read_back, scan_workspace, to_device_async
+from ._util import bytes_to_device_async, empty_u32, read_back, scan_workspace, tag_packed, to_device_async
 
 
 # --------------------------------------------------------------------------------------------
@@ -432,14 +432,22 @@ def ccl_program(ctx, vol, force_host_merge=False, info=None):
         result = torch.zeros(4, dtype=torch.int64, device=dev)
         _lib.call("cfe_ccl_boundary_solve", P.data_ptr(), N, Cv, Ce, rank, label.data_ptr(), comp.data_ptr(),
                   ckey.data_ptr(), size.data_ptr(), result.data_ptr(), s)
-        _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
-                  stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), s)
+        if X % 32 == 0 and out.data_ptr() % 16 == 0:
+            sel = empty_u32(rows * W, dev)          # the kept voxels bit-packed, for vol2ugrid_program
+            _lib.call("cfe_ccl_write_mask_bits", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
+                      stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), sel.data_ptr(), s)
+            tag_packed(out, sel)
+        else:
+            _lib.call("cfe_ccl_write_mask", bits.data_ptr(), pref.data_ptr(), Zl, Y, X, parent.data_ptr(),
+                      stats.data_ptr() + 8, size.data_ptr(), out.data_ptr(), s)
         res = read_back(result)                                 # the one host read of the stage
     if info is not None:      # diagnostics: the slab's forest and the gathered boundary graph
         info.update(parent=parent, stats=stats, packs=P, label=label, Cv=Cv, Ce=Ce, host_merge=bool(res[2]))
     if res[2]:
         # some rank has more boundary components / edges than the fixed capacity: every rank sees the
         # same flag (nothing was marked) and redoes the merge host-driven at exact sizes
+        if hasattr(out, "_cfe_bits"):
+            del out._cfe_bits
         return (yield from _ccl_host_merge(ctx, state))
     if res[0] <= 0:
         return out, None
@@ -551,8 +559,9 @@ class SlabMesh:
 
 
 def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_num=1, node_level_lock_num=1,
-                      locking_strategy="plane", eid_base=0):
-    """vol2ugrid of the global volume [Zg,Y,X]; `vol` = this rank's uint8 slab starting at slice z0."""
+                      locking_strategy="plane", eid_base=0, packed=None):
+    """vol2ugrid of the global volume [Zg,Y,X]; `vol` = this rank's uint8 slab starting at slice z0.
+    `packed`: the slab's ``vol > 0`` already bit-packed (``_util.packed_of`` of a remove_unconnected mask)."""
     _lib.require_cuda()
     if locking_strategy not in ("plane", "exact"):
         raise ValueError("locking_strategy must be 'plane' or 'exact'")
@@ -572,9 +581,12 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
     m.Zg, m.Zl, m.Y, m.X, m.z0, m.n_layers = Zg, Zl, Y, X, z0, n_layers
     with torch.cuda.device(dev):
         s = _lib.stream()
-        bits = empty_u32(rows * W, dev)
-        # the first kernel goes out before anything else is allocated or computed on the host
-        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
+        if packed is not None and thr == 0 and packed.numel() >= rows * W:
+            bits = packed
+        else:
+            bits = empty_u32(rows * W, dev)
+            # the first kernel goes out before anything else is allocated or computed on the host
+            _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
         epref = empty_u32(rows * W, dev)
         nbits = empty_u32(nrows * WN, dev)
         npref = empty_u32(nrows * WN, dev)

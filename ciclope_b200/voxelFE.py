@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from ._lib import CfeItemSeg, CfeSetDesc
-from ._util import (as_device_volume, bytes_to_device_async, check_slab_size, empty_u32, read_back,
+from ._util import (as_device_volume, bytes_to_device_async, check_slab_size, empty_u32, packed_of, read_back,
                     scan_workspace, to_device_async)
 
 CellBlock = collections.namedtuple("CellBlock", ["type", "data"])  # meshio 5.0.0 CellBlock
@@ -326,6 +326,8 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
     check_slab_size(Z, Y, X)
     thr = _gv_threshold(GVmin)
     dev = vol.device
+    # the mask of remove_unconnected arrives with its voxels already bit-packed (GV > 0  <=>  mask)
+    packed = packed_of(voldata) if thr == 0 and vol.dim() == 3 else None
 
     m = VoxelMesh()
     m.vol, m.is_bool, m.thr = vol, is_bool, thr
@@ -338,8 +340,11 @@ def vol2ugrid(voldata, voxelsize=[1, 1, 1], GVmin=0, plane_lock_num=1, node_leve
         W, WN = (X + 31) // 32, (X + 32) // 32
         rows, nrows = Z * Y, (Z + 1) * (Y + 1)
         # the first kernel goes out before anything else is allocated: the GPU is idle until then
-        bits = empty_u32(rows * W, dev)
-        _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
+        if packed is not None and packed.numel() >= rows * W:
+            bits = packed
+        else:
+            bits = empty_u32(rows * W, dev)
+            _lib.call("cfe_pack_bits", vol.data_ptr(), rows, X, thr, bits.data_ptr(), s)
         epref = empty_u32(rows * W, dev)
         nbits = empty_u32(nrows * WN, dev)
         npref = empty_u32(nrows * WN, dev)

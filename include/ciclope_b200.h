@@ -120,6 +120,16 @@ int cfe_ccl_write_mask(const uint32_t* bits, const uint32_t* run_pref, int64_t Z
 int cfe_ccl_write_select(const uint32_t* bits, const uint32_t* run_pref, int64_t Z, int64_t Y, int64_t X,
                          const uint32_t* parent, const uint64_t* best, const uint32_t* keep, int drop,
                          const uint8_t* src, int fill, uint8_t* out, cfe_stream_t s);
+/* cfe_ccl_largest / cfe_ccl_write_mask that also leave the kept voxels bit-packed in sel_bits (u32
+ * [Z*Y*ceil(X/32)], the layout of cfe_pack_bits), so that `vol2ugrid(remove_unconnected(bw))`
+ * (src/ciclope/pipeline.py:177,222) starts from the bits instead of re-reading the byte mask.  Needs
+ * X % 32 == 0 and a 16-byte aligned out_mask (error otherwise). */
+int cfe_ccl_largest_bits(const uint32_t* bits, const uint32_t* run_pref, const uint64_t* n_runs, int64_t Z,
+                         int64_t Y, int64_t X, uint32_t* parent, uint32_t* size, uint64_t* best,
+                         uint8_t* out_mask, uint32_t* sel_bits, cfe_stream_t s);
+int cfe_ccl_write_mask_bits(const uint32_t* bits, const uint32_t* run_pref, int64_t Z, int64_t Y, int64_t X,
+                            const uint32_t* parent, const uint64_t* best, const uint32_t* keep,
+                            uint8_t* out_mask, uint32_t* sel_bits, cfe_stream_t s);
 int cfe_ccl_largest_select(const uint32_t* bits, const uint32_t* run_pref, const uint64_t* n_runs, int64_t Z,
                            int64_t Y, int64_t X, uint32_t* parent, uint32_t* size, uint64_t* best, int drop,
                            const uint8_t* src, int fill, uint8_t* out, cfe_stream_t s);

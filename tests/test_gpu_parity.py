@@ -94,6 +94,32 @@ def test_remove_unconnected_multivalued_uint8_raises(cfe):
         cfe.remove_unconnected(big)
 
 
+def test_packed_mask_tag_is_used_and_invalidated(cfe, orc, tmp_path):
+    """remove_unconnected of a CUDA tensor leaves the kept voxels bit-packed on the result (vol2ugrid starts
+    from them); an in-place edit of the mask must invalidate that."""
+    import torch
+    from ciclope_b200._util import packed_of
+    bw = cases.blobs((12, 20, 64), 0.3, 31)              # X % 32 == 0: the packed path
+    L = cfe.remove_unconnected(torch.from_numpy(bw).cuda())
+    assert packed_of(L) is not None
+    decks = []
+    for vol in (L, L.clone()):                           # tagged / untagged: same deck
+        out = str(tmp_path / "d.inp")
+        cfe.mesh2voxelfe(cfe.vol2ugrid(vol, [0.0195] * 3), cases.TEMPLATE, out)
+        decks.append(cases.mask_timestamp(open(out, "rb").read()))
+    assert decks[0] == decks[1]
+    L[0, 0, :] = True                                    # in-place edit: the tag is stale now
+    assert packed_of(L) is None
+    host = L.cpu().numpy()
+    out = str(tmp_path / "e.inp")
+    cfe.mesh2voxelfe(cfe.vol2ugrid(L, [0.0195] * 3), cases.TEMPLATE, out)
+    orc.mesh2voxelfe(orc.vol2ugrid(host, [0.0195] * 3), cases.TEMPLATE, str(tmp_path / "o.inp"))
+    assert cases.mask_timestamp(open(out, "rb").read()) == cases.mask_timestamp(open(str(tmp_path / "o.inp"), "rb").read())
+    # GVmin != 0 must not use the tag either (thr = 0 is what the bits mean)
+    L2 = cfe.remove_unconnected(torch.from_numpy(bw).cuda())
+    assert cfe.vol2ugrid(L2, [1, 1, 1], GVmin=1).n_el == 0
+
+
 def test_mesh_set_before_read_routes_to_generic(cfe, golden):
     """mesh.points = ... before the lazy array was ever read must count as an edit (not AttributeError)."""
     c = DECK_CASES["bool_5x7x9"]
