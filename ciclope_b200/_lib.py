@@ -95,7 +95,7 @@ _SIGNATURES = {
     "cfe_gen_emit_elements": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_gv_histogram": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "cfe_peer_exchange": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_i64, c_i64, ctypes.c_uint32,
-                                  ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp, c_vp]),
+                                  ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp, c_vp]),
     "cfe_box_andnot_u8": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_masked_set_u8": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
     "cfe_disk_dilate_bits": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),

@@ -163,18 +163,27 @@ class PeerExchange:
             self.hdl.barrier()                  # every rank's pad and counter are ready before the first kernel
         self.device = device
         self.epoch = 0
+        self.shifts_in_a_row = 0
 
-    def exchange(self, t, send_mask=None):
-        """-> tensor [world, *t.shape]; row p = rank p's ``t`` (only the rows of ranks that sent to me)"""
+    def exchange(self, t, shift=False):
+        """-> tensor [world, *t.shape].  All-gather: row p = rank p's ``t``.  ``shift``: ``t`` goes to the rank
+        above only and only row rank - 1 is defined; neighbours alone synchronise, except that every
+        (SLOTS - 2)-th shift in a row is run as a full synchronisation (see csrc/peer.cu)."""
         t = t.contiguous()
         nbytes = t.numel() * t.element_size()
         self.epoch += 1
         slot = self.epoch % self.SLOTS
         out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        if send_mask is None:
-            send_mask = (1 << self.world) - 1
+        full = (1 << self.world) - 1
+        if shift and self.shifts_in_a_row < self.SLOTS - 2:
+            self.shifts_in_a_row += 1
+            send = (1 << (self.rank + 1)) if self.rank + 1 < self.world else 0
+            wait = (1 << (self.rank - 1)) if self.rank > 0 else 0
+        else:
+            self.shifts_in_a_row = 0
+            send = wait = full
         _lib.call("cfe_peer_exchange", t.data_ptr(), nbytes, self.hdl.buffer_ptrs_dev, self.hdl.signal_pad_ptrs_dev,
-                  self.rank, self.world, slot * self.world * self.CHUNK, self.CHUNK, self.epoch, send_mask,
+                  self.rank, self.world, slot * self.world * self.CHUNK, self.CHUNK, self.epoch, send, wait,
                   self.SIG_OFFSET + slot * self.world, self.counter.data_ptr(), out.data_ptr(), _lib.stream())
         return out
 
@@ -235,9 +244,8 @@ class DistRunner:
             return [out[k, :c] for k, c in enumerate(ns)]
         if kind == "shift_up":
             if self.peer is not None and t.is_cuda and 0 < t.numel() * t.element_size() <= PeerExchange.CHUNK:
-                # the plane goes to the rank above only; the signals still synchronise every rank
-                mask = (1 << (self.rank + 1)) if self.rank + 1 < self.size else 0
-                out = self.peer.exchange(t, send_mask=mask)
+                # the plane goes to the rank above only, and only neighbours wait for each other
+                out = self.peer.exchange(t, shift=True)
                 return out[self.rank - 1] if self.rank > 0 else None
             if t.numel() * t.element_size() <= self.SHIFT_VIA_GATHER_BYTES:
                 # small planes: one all-gather is cheaper to issue than a send/recv pair

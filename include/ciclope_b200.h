@@ -382,10 +382,12 @@ int cfe_threshold_f64(const double* img, int64_t n, double t, uint8_t* out, cfe_
  * (torch.distributed._symmetric_memory: buffer_ptrs_dev, signal_pad_ptrs_dev).  Buffer layout
  * [slot][source rank][chunk_cap]; slot_off = byte offset of the slot used by this epoch; sig_base = first
  * u32 of the signal pad used by this slot (world words).  Every rank calls with the same epoch; out =
- * [world][nbytes].  counter: 2 zeroed u32 of local device memory. */
+ * [world][nbytes].  send_mask: bit p = push my chunk to rank p and signal it; wait_mask: bit p = wait for
+ * rank p and gather its chunk (all-gather: both full; shift up: send to rank + 1, wait for rank - 1 -- only
+ * neighbours synchronise).  counter: 2 zeroed u32 of local device memory. */
 int cfe_peer_exchange(const void* src, int64_t nbytes, const void* peer_bufs_dev, const void* peer_sigs_dev,
                       int rank, int world, int64_t slot_off, int64_t chunk_cap, uint32_t epoch, uint32_t send_mask,
-                      uint32_t sig_base, uint32_t* counter, void* out, cfe_stream_t s);
+                      uint32_t wait_mask, uint32_t sig_base, uint32_t* counter, void* out, cfe_stream_t s);
 
 #ifdef __cplusplus
 }
