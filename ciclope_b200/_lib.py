@@ -101,6 +101,9 @@ _SIGNATURES = {
     "cfe_disk_dilate_bits": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
     "cfe_border_flags": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "cfe_gauss1d": (c_int, [c_vp, c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp]),
+    "cfe_spline_prefilter": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp]),
+    "cfe_spline_zoom": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                c_vp, c_int, c_vp, c_vp]),
     "cfe_threshold_f64": (c_int, [c_vp, c_i64, ctypes.c_double, c_vp, c_vp]),
     "cfe_host_pyset_order": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "cfe_proj_bits": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),

@@ -198,6 +198,7 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
                 const int b = __ffs((int)rest) - 1;
                 const u32 shifted = rest >> b;
                 const int len = (~shifted == 0u) ? 32 - b : __ffs((int)~shifted) - 1;
+                CFE_ASSERT(run_id(cur, carry, cur_pref, b) < total);
                 atomicAdd(cnt_l + run_id(cur, carry, cur_pref, b), (u32)len);
                 rest = (b + len >= 32) ? 0u : (rest & ~(((1u << len) - 1u) << b));
             }
@@ -215,6 +216,7 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
             while (pair_starts) {
                 const int b = __ffs((int)pair_starts) - 1;
                 pair_starts &= pair_starts - 1;
+                CFE_ASSERT(run_id(cur, carry, cur_pref, b) < total && run_id(nb, nb_prev >> 31, nb_pref, b) < total);
                 uf_union(sp, run_id(cur, carry, cur_pref, b), run_id(nb, nb_prev >> 31, nb_pref, b));
             }
         }
@@ -254,6 +256,7 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
             kb += (sl <= root);
         }
         const u32 g = rb_g[ka * TR] + (l - rb_l[ka * TR]);
+        CFE_ASSERT(root <= l && (u64)g < *n_runs_p && rb_g[kb * TR] + (root - rb_l[kb * TR]) <= g);
         parent[g] = rb_g[kb * TR] + (root - rb_l[kb * TR]);
         size[g] = (root == l) ? cnt_l[l] : 0u;
     }
@@ -784,6 +787,7 @@ k_ccl_interface_forest(const u32* __restrict__ bitsA, const u32* __restrict__ pr
         }
         if (uf_union_hooked(forest, va, Cv + vb)) {
             const u32 slot = atomicAdd(count, 1u);
+            CFE_ASSERT(slot < 2u * Cv);
             if (slot < capacity) { edges[2 * slot] = va; edges[2 * slot + 1] = vb; }
         }
     }

@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
@@ -35,6 +36,15 @@ void cfe_count_launch();
             return -2;                                                                \
         }                                                                             \
     } while (0)
+
+// Checked builds (profiles/tools/build_variant.sh <out.so> -DCFE_CHECKED): index assertions that trap the
+// kernel (compute-sanitizer is not available on every pool; the asserts + the oracle comparison of
+// profiles/tools/sanitize_cases.py stand in for memcheck on the kernels that index shared memory by data).
+#ifdef CFE_CHECKED
+#define CFE_ASSERT(cond) do { if (!(cond)) { printf("CFE_ASSERT failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define CFE_ASSERT(cond) do { } while (0)
+#endif
 
 // Function attributes (opt-in dynamic shared memory) are per device: true the first time it is
 // evaluated on the current device for this `mask` (one static mask per launch site; devices 0..63).

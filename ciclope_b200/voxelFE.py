@@ -295,6 +295,32 @@ class VoxelMesh:
                 return True
         return False
 
+    # -- export ------------------------------------------------------------------------------
+    def to_meshio(self):
+        """The mesh as a ``meshio.Mesh`` (points, one hexahedron block, GV cell data, point / cell sets):
+        what the reference's ``vol2ugrid`` returns (voxelFE.py:271-274).  Needs meshio and host memory for the
+        materialised arrays (24 B per grid node + 64 B per element)."""
+        import meshio
+        return meshio.Mesh(self.points, [(blk[0], np.asarray(blk[1])) for blk in self.cells],
+                           cell_data={k: list(v) if isinstance(v, list) else [np.asarray(v)]
+                                      for k, v in self.cell_data.items()},
+                           point_sets=self.point_sets, cell_sets=self.cell_sets)
+
+    def write(self, path, file_format=None, **kwargs):
+        """``mesh.write(path)`` of the reference's notebooks and pipeline (pipeline.py:222-233): through meshio
+        when it is installed (every format meshio knows); otherwise ``.vtk`` files are written by the built-in
+        legacy-VTK writer (points, hexahedra, cell data) and other formats raise ImportError."""
+        try:
+            import meshio  # noqa: F401
+        except ImportError:
+            if file_format not in (None, "vtk") or not str(path).lower().endswith(".vtk"):
+                raise ImportError("meshio is not installed: only legacy .vtk files can be written")
+            from .io import write_vtk
+            cells = np.concatenate([np.asarray(blk[1]).reshape(-1, 8) for blk in self.cells]) if self.cells else \
+                np.empty((0, 8), dtype=np.int64)
+            return write_vtk(path, self.points, cells, self.cell_data)
+        return self.to_meshio().write(path, file_format=file_format, **kwargs)
+
     def __repr__(self):
         return "<ciclope_b200 voxel mesh>\n  Number of points: {}\n  Number of cells:\n    hexahedron: {}\n" \
                "  Point sets: {}\n  Cell sets: {}\n  Cell data: GV".format(

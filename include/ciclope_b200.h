@@ -375,6 +375,19 @@ int cfe_gauss1d(const void* in, int in_is_u8, double* out, int64_t n_total, int6
 /* image > t for a float64 image: bytes 0 / 1 (preprocess.py:46 after smoothing) */
 int cfe_threshold_f64(const double* img, int64_t n, double t, uint8_t* out, cfe_stream_t s);
 
+/* Spline resampling, `ndimage.zoom(image, 1 / resampling_factor, order=2)` of
+ * src/ciclope/utils/preprocess.py:49-75 (pipeline.py:150-153).  cfe_spline_prefilter: in-place quadratic
+ * B-spline pre-filter of the float64 array [outer][n][inner] along the axis of length n (mirror boundary,
+ * what scipy uses for mode='constant').  cfe_spline_zoom: 3 x 3 x 3 taps per output sample from per-axis
+ * tables (input indices idx [n_out][3], weights w [n_out][3], out-of-range flags zero [n_out]) computed by
+ * the host facade; out = float64 [Zo][Yo][Xo], or uint8 with scipy's rounding (out_u8).
+ * Tolerance (not bit-exact): 1e-12 absolute on float64 images of 8-bit range. */
+int cfe_spline_prefilter(double* data, int64_t outer, int64_t n, int64_t inner, cfe_stream_t s);
+int cfe_spline_zoom(const double* coef, int64_t Yi, int64_t Xi, int64_t Zo, int64_t Yo, int64_t Xo, const int* iz,
+                    const int* iy, const int* ix, const double* wz, const double* wy, const double* wx,
+                    const uint8_t* zz, const uint8_t* zy, const uint8_t* zx, int out_u8, void* out,
+                    cfe_stream_t s);
+
 /* ------------------------------------------------------------------ z-slab collectives over peer memory */
 
 /* All-gather / neighbour shift of a small payload as one kernel over NVLink peer memory (csrc/peer.cu).

@@ -16,6 +16,7 @@ Nothing under ``ciclope_b200/`` may import this module: it is the checker, not t
 """
 import collections
 import ctypes
+import math
 import os
 from datetime import datetime
 
@@ -613,6 +614,87 @@ def gaussian(image, sigma, truncate=4.0):
 # --------------------------------------------------------------------------------------------
 # embed <- src/ciclope/utils/preprocess.py:233-355 (with recon_utils.bbox incl. its padding rules,
 # recon_utils.py:258-298)
+
+_SPLINE_POLE2 = math.sqrt(8.0) - 3.0
+
+
+def _spline_filter_axis(a, axis):
+    """scipy ni_splines.c apply_filter for order 2 (one pole), mirror boundary -- what spline_filter uses for
+    mode='constant': gain, causal recursion from the mirror sum, anti-causal recursion."""
+    a = np.moveaxis(a, axis, 0).copy()
+    n = a.shape[0]
+    if n < 2:
+        return np.moveaxis(a, 0, axis)
+    z = _SPLINE_POLE2
+    a *= (1.0 - z) * (1.0 - 1.0 / z)
+    z_n_1 = z ** (n - 1)
+    c0 = a[0] + z_n_1 * a[n - 1]
+    z_i = z
+    for i in range(1, n - 1):
+        c0 = c0 + z_i * (a[i] + z_n_1 * a[n - 1 - i])
+        z_i *= z
+    a[0] = c0 / (1 - z_n_1 * z_n_1)
+    for i in range(1, n):
+        a[i] += z * a[i - 1]
+    a[n - 1] = (z * a[n - 2] + a[n - 1]) * z / (z * z - 1)
+    for i in range(n - 2, -1, -1):
+        a[i] = z * (a[i + 1] - a[i])
+    return np.moveaxis(a, 0, axis)
+
+
+def resample(image, voxelsize, resampling_factor):
+    """preprocess.py:49-75: ndimage.zoom(image, 1 / resampling_factor, output=None, order=2) restated (scipy
+    ni_interpolation.c NI_ZoomShift, mode='constant', cval 0, grid_mode False) + voxelsize * factor.
+    Pinned at tolerance 1e-12 (float64) / exactly (uint8) by tests/golden/resample.npz, made with scipy."""
+    inp = np.asarray(image)
+    zoom = 1 / resampling_factor
+    out_shape = tuple(int(round(s * zoom)) for s in inp.shape)
+    f = inp.astype(np.float64)
+    for ax in range(inp.ndim):
+        f = _spline_filter_axis(f, ax)
+    out = f
+    for ax in range(inp.ndim):
+        n_in, n_out = inp.shape[ax], out_shape[ax]
+        zz = (n_in - 1) / (n_out - 1) if n_out > 1 else 1.0
+        idx = np.zeros((n_out, 3), dtype=np.int64)
+        w = np.zeros((n_out, 3))
+        zero = np.zeros(n_out, dtype=bool)
+        for k in range(n_out):
+            cc = k * zz
+            if cc < 0 or cc > n_in - 1:           # map_coordinate, NI_EXTEND_CONSTANT
+                zero[k] = True
+                continue
+            start = int(math.floor(cc + 0.5)) - 1
+            d = cc - math.floor(cc + 0.5)
+            w[k] = [0.5 * (0.5 - d) ** 2, 0.75 - d * d, 0.5 * (0.5 + d) ** 2]
+            for tap in range(3):
+                i = start + tap
+                if n_in <= 1:
+                    i = 0
+                else:                             # spline mode: mirror
+                    s2 = 2 * n_in - 2
+                    if i < 0:
+                        i = s2 * int(-i / s2) + i
+                        i = i + s2 if i <= 1 - n_in else -i
+                    elif i >= n_in:
+                        i -= s2 * int(i / s2)
+                        if i >= n_in:
+                            i = s2 - i
+                idx[k, tap] = i
+        g = np.take(out, idx.reshape(-1), axis=ax)
+        shp = list(out.shape)
+        shp[ax:ax + 1] = [n_out, 3]
+        wshape = [1] * (out.ndim + 1)
+        wshape[ax], wshape[ax + 1] = n_out, 3
+        g = (g.reshape(shp) * w.reshape(wshape)).sum(axis=ax + 1)
+        zshape = [1] * g.ndim
+        zshape[ax] = n_out
+        out = np.where(zero.reshape(zshape), 0.0, g)
+    if inp.dtype == np.uint8:
+        t = np.where(out > 0, out + 0.5, 0.0)
+        out = np.minimum(t, 255.0).astype(np.uint8)
+    return out, voxelsize * resampling_factor
+
 
 def bbox_pad(bw, pad=0):
     maxROW = np.max(np.max(bw, 0), 1)
