@@ -38,7 +38,7 @@ void cfe_count_launch();
     } while (0)
 
 // Checked builds (profiles/tools/build_variant.sh <out.so> -DCFE_CHECKED): index assertions that trap the
-// kernel (compute-sanitizer is not available on every pool; the asserts + the oracle comparison of
+// kernel (compute-sanitizer is not available on every pool; the asserts + the CPU-reference comparison of
 // profiles/tools/sanitize_cases.py stand in for memcheck on the kernels that index shared memory by data).
 #ifdef CFE_CHECKED
 #define CFE_ASSERT(cond) do { if (!(cond)) { printf("CFE_ASSERT failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
