@@ -99,6 +99,8 @@ _SIGNATURES = {
     "cfe_box_andnot_u8": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_masked_set_u8": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
     "cfe_disk_dilate_bits": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
+    "cfe_line_or_bits": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "cfe_unpack_bits": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),
     "cfe_border_flags": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "cfe_gauss1d": (c_int, [c_vp, c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp]),
     "cfe_spline_prefilter": (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp]),

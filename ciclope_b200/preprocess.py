@@ -650,14 +650,15 @@ def periosteummask(bwimage, closepixels=10, closevoxels=0, remove_objects_smalle
     (slices only meet through their border rows, which are outside by definition) plus a border-flag pass.
 
     ``remove_objects_smaller_than`` (scikit-image's ``remove_small_objects``) clears the small components first:
-    one more labelling, sizes per root, a flag-driven mask writer.  ``closevoxels > 0`` (the even-sized ``cube``
-    closing) is not available and raises ``NotImplementedError``; ``closepixels <= 31``.
+    one more labelling, sizes per root, a flag-driven mask writer.  ``closevoxels > 0``: the final 3D closing with
+    ``cube(closevoxels)`` as six separable line passes on packed bits; ``closepixels <= 31``.
     """
     import logging
     if verbose:
         logging.basicConfig(level=logging.INFO)
-    if closevoxels > 0:
-        raise NotImplementedError("periosteummask: the final 3D closing (closevoxels > 0) is not available on the GPU path")
+    cw = int(closevoxels)
+    if cw != closevoxels or cw > 33:
+        raise NotImplementedError("periosteummask: closevoxels must be an integer <= 33")
     r = int(closepixels)
     if r != closepixels or not 0 <= r <= 31:
         raise NotImplementedError("periosteummask: closepixels must be an integer in 0..31")
@@ -709,7 +710,36 @@ def periosteummask(bwimage, closepixels=10, closevoxels=0, remove_objects_smalle
             if best == 0:
                 raise ValueError("attempt to get argmax of an empty sequence")      # remove_unconnected, :141
             mask = kept
+        if cw > 0 and not squeeze:
+            # final 3D closing with cube(closevoxels) (preprocess.py:405-408; the 2D branch has none)
+            logging.info('Final 3D image closing.\n Structuring element CUBE of radius: {}'.format(closepixels))
+            mask = _cube_closing(mask, cw)
         out = mask.view(torch.bool)
     if squeeze:
         out = out[0]
     return out.cpu().numpy() if from_numpy else out
+
+
+def _cube_closing(mask, w):
+    """``skimage.morphology.binary_closing(mask, cube(w))`` of a uint8 0/1 CUDA volume: scipy's dilation
+    (border 0) then erosion (border 1) by ones((w, w, w)), each as three line passes on packed bits; an
+    even-sized structure is centred at w // 2, so the offsets of the two are mirrored (csrc/morph.cu)."""
+    Z, Y, X = (int(v) for v in mask.shape)
+    dev = mask.device
+    L, R = w // 2, w - 1 - w // 2
+    with torch.cuda.device(dev):
+        s = _lib.stream()
+        W = (X + 31) // 32
+        a = empty_u32(Z * Y * W, dev)
+        b = empty_u32(Z * Y * W, dev)
+        _lib.call("cfe_pack_bits", mask.data_ptr(), Z * Y, X, 0, a.data_ptr(), s)
+        for axis in range(3):                                   # dilation: sources q - R .. q + L
+            _lib.call("cfe_line_or_bits", a.data_ptr(), Z, Y, X, axis, R, L, 0, 0, b.data_ptr(), s)
+            a, b = b, a
+        for axis in range(3):                                   # erosion = ~ dilation'(~x): sources q - L .. q + R
+            _lib.call("cfe_line_or_bits", a.data_ptr(), Z, Y, X, axis, L, R, 1 if axis == 0 else 0,
+                      1 if axis == 2 else 0, b.data_ptr(), s)
+            a, b = b, a
+        out = torch.empty((Z, Y, X), dtype=torch.uint8, device=dev)
+        _lib.call("cfe_unpack_bits", a.data_ptr(), Z * Y, X, out.data_ptr(), s)
+    return out

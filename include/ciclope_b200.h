@@ -375,6 +375,15 @@ int cfe_gauss1d(const void* in, int in_is_u8, double* out, int64_t n_total, int6
 /* image > t for a float64 image: bytes 0 / 1 (preprocess.py:46 after smoothing) */
 int cfe_threshold_f64(const double* img, int64_t n, double t, uint8_t* out, cfe_stream_t s);
 
+/* One pass of a separable binary dilation on packed bits: out[q] = OR of src[q + e], e = -a .. +b along `axis`
+ * (0 slices, 1 rows, 2 columns; 0 outside the image), src = in or (invert_in) its complement; invert_out
+ * complements the result.  Three passes dilate by a cube, three more (on the complement) erode:
+ * `morphology.binary_closing(perimask, morphology.cube(closevoxels))`, src/ciclope/utils/preprocess.py:408. */
+int cfe_line_or_bits(const uint32_t* in, int64_t Z, int64_t Y, int64_t X, int axis, int a, int b, int invert_in,
+                     int invert_out, uint32_t* out, cfe_stream_t s);
+/* out[v] = bit v of a packed volume (the inverse of cfe_pack_bits), 0 / 1 bytes */
+int cfe_unpack_bits(const uint32_t* bits, int64_t rows, int64_t X, uint8_t* out, cfe_stream_t s);
+
 /* Spline resampling, `ndimage.zoom(image, 1 / resampling_factor, order=2)` of
  * src/ciclope/utils/preprocess.py:49-75 (pipeline.py:150-153).  cfe_spline_prefilter: in-place quadratic
  * B-spline pre-filter of the float64 array [outer][n][inner] along the axis of length n (mirror boundary,

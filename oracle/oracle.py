@@ -801,7 +801,7 @@ def remove_small_objects(ar, min_size):
     return out
 
 
-def periosteummask(bwimage, closepixels=10, removeunconn=True, remove_objects_smaller_than=None):
+def periosteummask(bwimage, closepixels=10, removeunconn=True, remove_objects_smaller_than=None, closevoxels=0):
     from scipy import ndimage
     if remove_objects_smaller_than:
         bwimage = remove_small_objects(bwimage, remove_objects_smaller_than)
@@ -811,6 +811,8 @@ def periosteummask(bwimage, closepixels=10, removeunconn=True, remove_objects_sm
             perimask[sl, :, :] = ndimage.binary_fill_holes(binary_closing(bwimage[sl, :, :], disk(closepixels)))
         if removeunconn:
             perimask = remove_unconnected(perimask)
+        if closevoxels > 0:      # preprocess.py:405-408; morphology.cube(w) = ones((w, w, w))
+            perimask = binary_closing(perimask, np.ones((closevoxels,) * 3, dtype=bool))
         return perimask
     perimask = ndimage.binary_fill_holes(binary_closing(bwimage, disk(closepixels)))
     if removeunconn:

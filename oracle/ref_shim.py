@@ -116,7 +116,10 @@ def _install_stubs():
         out[too_small[ccs]] = 0
         return out
 
-    morphology = mod("skimage.morphology", disk=_disk, binary_closing=_binary_closing,
+    def _cube(width):
+        return np.ones((width, width, width), dtype=np.uint8)
+
+    morphology = mod("skimage.morphology", disk=_disk, cube=_cube, binary_closing=_binary_closing,
                      remove_small_objects=_remove_small_objects)
     filters = mod("skimage.filters", threshold_otsu=None, gaussian=None)
     mod("skimage", measure=measure, morphology=morphology, filters=filters)

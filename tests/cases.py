@@ -624,4 +624,13 @@ def periosteum_cases():
                                 dict(closepixels=r, removeunconn=ru)))
     out.append(("empty", np.zeros((3, 20, 20), dtype=bool), dict(closepixels=2, removeunconn=True)))
     out.append(("full", np.ones((2, 20, 20), dtype=bool), dict(closepixels=2, removeunconn=True)))
+    # final 3D closing with cube(closevoxels) (preprocess.py:405-408): even and odd widths, shapes touching
+    # the borders, widths that are not a multiple of 32
+    for ci, (shape, cw) in enumerate([((9, 40, 50), 2), ((9, 40, 50), 3), ((12, 33, 65), 4), ((12, 33, 65), 5),
+                                      ((7, 20, 31), 7), ((10, 24, 96), 6)]):
+        bw = rng.random(shape) < 0.08
+        bw[2:-2, 8:-8, 10:-10] |= rng.random((shape[0] - 4, shape[1] - 16, shape[2] - 20)) < 0.5
+        bw[:, :2, :] |= rng.random((shape[0], 2, shape[2])) < 0.5
+        for ru in (True, False):
+            out.append(("cube%d_w%d_%d" % (ci, cw, int(ru)), bw, dict(closepixels=1, closevoxels=cw, removeunconn=ru)))
     return out

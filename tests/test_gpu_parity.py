@@ -701,8 +701,12 @@ def test_periosteummask_larger_vs_oracle(cfe, orc):
         want = orc.periosteummask(bw, closepixels=r)
         got = cfe.periosteummask(torch.from_numpy(bw).cuda(), closepixels=r)
         assert got.dtype == torch.bool and np.array_equal(got.cpu().numpy(), want), r
+    for cw in (2, 5, 8, 33):                              # final 3D closing with cube(closevoxels)
+        want = orc.periosteummask(bw, closepixels=2, closevoxels=cw)
+        got = cfe.periosteummask(torch.from_numpy(bw).cuda(), closepixels=2, closevoxels=cw)
+        assert np.array_equal(got.cpu().numpy(), want), cw
     with pytest.raises(NotImplementedError):
-        cfe.periosteummask(bw, closevoxels=2)
+        cfe.periosteummask(bw, closevoxels=40)
     # preliminary removal of small objects (scikit-image's remove_small_objects on the 3D / 2D image)
     rng = np.random.default_rng(3)
     specks = bw | (rng.random(bw.shape) < 0.01)
