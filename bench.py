@@ -652,7 +652,10 @@ def run_gpu(args, rank, world, local_rank):
     # digit flags) -- DESIGN.md section 4.
     elem_bytes = deck_bytes - 53 * n_nd   # everything but the *NODE lines is element lines + O(N^2) text
     dom = max(entry_ms, key=entry_ms.get)
-    alg = {"cfe_emit_elements": elem_bytes + 6 * n_el, "cfe_emit_nodes": 57 * n_nd}
+    # *NODE emitter: 53 B per line written + the used-node bitmap and its prefix (8 B per 32 grid nodes) read
+    nodes_key = "cfe_emit_nodes_bits" if "cfe_emit_nodes_bits" in entry_ms else "cfe_emit_nodes"
+    alg = {"cfe_emit_elements": elem_bytes + 6 * n_el,
+           "cfe_emit_nodes": 53 * n_nd + ((Z + 1) * (Y + 1) * (X + 1)) // 4 if nodes_key.endswith("bits") else 57 * n_nd}
     achieved = alg["cfe_emit_elements"] / (entry_ms["cfe_emit_elements"] * 1e-3) / 1e9
     traffic, traffic_src = None, None
     try:
@@ -662,15 +665,15 @@ def run_gpu(args, rank, world, local_rank):
             traffic, traffic_src = ent.get("k_emit_elements2"), ent.get("source")
     except Exception:  # noqa: BLE001
         pass
-    nodes_ach = alg["cfe_emit_nodes"] / (entry_ms["cfe_emit_nodes"] * 1e-3) / 1e9
+    nodes_ach = alg["cfe_emit_nodes"] / (entry_ms[nodes_key] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_emit_elements2 (entry point cfe_emit_elements, one launch per deck)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg["cfe_emit_elements"],
                 "ms_per_launch": entry_ms["cfe_emit_elements"], "dominant_entry_point": dom,
-                "other_kernels": {"k_emit_nodes4": {"achieved": nodes_ach, "frac": nodes_ach / peak,
-                                                    "algorithmic_bytes_per_launch": alg["cfe_emit_nodes"],
-                                                    "ms_per_launch": entry_ms["cfe_emit_nodes"]}}}
+                "other_kernels": {"k_emit_nodes4b" if nodes_key.endswith("bits") else "k_emit_nodes4": {
+                    "achieved": nodes_ach, "frac": nodes_ach / peak,
+                    "algorithmic_bytes_per_launch": alg["cfe_emit_nodes"], "ms_per_launch": entry_ms[nodes_key]}}}
     total_alg = 2 * n_vox + deck_bytes
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "cfe_scan_elements": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_scan_run_starts": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_scan_nodes": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_scan_nodes_index": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "cfe_emit_nodes_bits": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_fill_list": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_scan_u32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_ccl_max_runs": (c_sz, [c_i64, c_i64]),

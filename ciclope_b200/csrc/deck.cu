@@ -266,6 +266,157 @@ __global__ void __launch_bounds__(NODE4_THREADS) k_emit_nodes4(NodeEmitParams P)
     }
 }
 
+// List-free variant: the CTA's 512 nodes are expanded from the used-node bitmap itself.  chunk_word[b] (written
+// by the node scan) is the word of the node grid that holds node 512 b; the CTA walks the words from there, 128
+// at a time, and drops the local grid index of every used node with rank in [512 b, 512 b + 512) into a
+// shared-memory list -- usually ~45 words, more only across empty stretches of the grid.  No 4 B / node list is
+// written by a separate pass and read back here; everything after the expansion is k_emit_nodes4.
+#ifndef NODE4B_CTAS_PER_SM
+#define NODE4B_CTAS_PER_SM 8      // 27 KB of shared memory each
+#endif
+struct NodeBitsParams {
+    const u32* nbits;        // used-node bitmap, [node rows][wpr] words
+    const u32* npref;        // exclusive used-node count per word
+    const u32* chunk_word;   // [ceil(n_nodes / 512)]
+    u32 n_words, wpr, rowlen;
+    FastDiv d_wpr;
+};
+
+// PERSISTENT CTAs, software pipelined: while chunk b is expanded and formatted, the bitmap words of the CTA's
+// next chunk are already in flight (their position, chunk_word, was fetched one iteration earlier still), so
+// the two dependent global loads of a chunk never sit on the critical path.
+__global__ void __launch_bounds__(NODE4_THREADS) k_emit_nodes4b(NodeEmitParams P, NodeBitsParams B, u32 n_chunks)
+{
+    __shared__ __align__(16) u32 stage[NODE4_THREADS * 53];
+    u32* const list = stage;          // the 512-entry node list lives in the first 2 KB of the staging area:
+                                      // every thread takes its four entries into registers before any line is staged
+    const u32 G = gridDim.x;
+    u32 b = blockIdx.x;
+    if (b >= n_chunks) return;
+    u32 cw = __ldg(B.chunk_word + b);
+    u32 cw_next = (b + G < n_chunks) ? __ldg(B.chunk_word + b + G) : 0u;
+    u32 word = 0, pref = 0;
+    if (cw + threadIdx.x < B.n_words) { word = __ldg(B.nbits + cw + threadIdx.x); pref = __ldg(B.npref + cw + threadIdx.x); }
+    bool pending_copy = false;
+    for (; b < n_chunks; b += G) {
+        // ---- prefetch: first 128 words of the next chunk, position of the one after
+        u32 nx_word = 0, nx_pref = 0, cw_next2 = 0;
+        if (b + G < n_chunks) {
+            if (cw_next + threadIdx.x < B.n_words) {
+                nx_word = __ldg(B.nbits + cw_next + threadIdx.x);
+                nx_pref = __ldg(B.npref + cw_next + threadIdx.x);
+            }
+            if (b + 2 * G < n_chunks) cw_next2 = __ldg(B.chunk_word + b + 2 * G);
+        }
+        const i64 k0 = (i64)b * NODE4_PER_CTA;                 // first node of this chunk
+        i64 n_here = P.n_nodes - k0;
+        if (n_here > NODE4_PER_CTA) n_here = NODE4_PER_CTA;
+        const u32 lo = (u32)k0, hi = (u32)(k0 + n_here);        // ranks [lo, hi)
+        // the previous chunk's bulk copy must have read the staging area before it is overwritten
+        if (pending_copy && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // ---- expand: local grid index of the used nodes with rank in [lo, hi) -> list
+        for (u32 wbase = cw;; wbase += NODE4_THREADS) {
+            const u32 i = wbase + threadIdx.x;
+            u32 w = word, p = pref;
+            if (wbase != cw) {                                   // rare: a chunk that spans more than 128 words
+                w = 0; p = 0;
+                if (i < B.n_words) { w = __ldg(B.nbits + i); p = __ldg(B.npref + i); }
+            }
+            const u32 pe = p + (u32)__popc(w);
+            if (w && pe > lo && p < hi) {
+                const u32 row = fd_div(i, B.d_wpr);
+                const u32 base = row * B.rowlen + (i - row * B.wpr) * 32u;
+                while (w) {
+                    const int bit = __ffs((int)w) - 1;
+                    w &= w - 1;
+                    if (p >= lo && p < hi) list[p - lo] = base + (u32)bit;
+                    ++p;
+                }
+            }
+            const bool last = (i < B.n_words && pe >= hi) || wbase + NODE4_THREADS >= B.n_words;
+            if (__syncthreads_or(last ? 1 : 0)) break;
+        }
+        // ---- format four lines per thread (k_emit_nodes4)
+        const u32 n4 = (u32)n_here & ~3u;
+        const u32 q0 = threadIdx.x * 4u;
+        u32* Bw = stage + threadIdx.x * 53;
+        uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+        u32 v_tail = 0;
+        if (q0 + 3u < n4) v4 = *reinterpret_cast<const uint4*>(list + q0);
+        if (threadIdx.x < (u32)n_here - n4) v_tail = list[n4 + threadIdx.x];
+        __syncthreads();                                        // the list has been read: the stage may be written
+        if (q0 + 3u < n4) {
+            const u32 vv[4] = {v4.x, v4.y, v4.z, v4.w};
+            u32 pending = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                u32 L[14];
+                node_line_words(P, vv[q], L);
+                const int sh = 8 * q;                          // (53 q) mod 4 == q
+                Bw[13 * q] = pending | (L[0] << sh);
+#pragma unroll
+                for (int i = 1; i < 13; ++i) Bw[13 * q + i] = sh ? __funnelshift_l(L[i - 1], L[i], sh) : L[i];
+                pending = sh ? __funnelshift_l(L[12], L[13], sh) : L[13];
+            }
+            Bw[52] = pending;
+        }
+        char* dst = P.out + k0 * 53;                            // 16-byte aligned: 53 * 512 = 16 * 1696
+        // the last <= 3 nodes of the section: byte-wise lines
+        if (threadIdx.x < (u32)n_here - n4) {
+            u32 L[14];
+            node_line_words(P, v_tail, L);
+            char* line = dst + (size_t)(n4 + threadIdx.x) * 53;
+#pragma unroll
+            for (int q = 0; q < 53; ++q) line[q] = (char)((L[q >> 2] >> (8 * (q & 3))) & 0xffu);
+        }
+        __syncthreads();
+        const u32 nbytes = n4 * 53u;
+        const u32 n16 = nbytes >> 4;
+        if (threadIdx.x == 0 && n16) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"((u32)__cvta_generic_to_shared(stage)), "r"(16u * n16) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        pending_copy = true;
+        for (u32 c = (n16 << 2) + threadIdx.x; c < (nbytes >> 2); c += blockDim.x) reinterpret_cast<u32*>(dst)[c] = stage[c];
+        cw = cw_next; cw_next = cw_next2; word = nx_word; pref = nx_pref;
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // before the smem goes away
+}
+
+// *NODE lines straight from the used-node bitmap (nbits / npref / chunk_word of cfe_scan_nodes_index; n_words =
+// words of the bitmap, (X + 32) / 32 per node row).  `out` must be 16-byte aligned.
+extern "C" int cfe_emit_nodes_bits(const uint32_t* nbits, const uint32_t* npref, const uint32_t* chunk_word,
+                                   int64_t n_words, int64_t n_nodes, const char* xtab, const char* ytab,
+                                   const char* ztab, int64_t Y, int64_t X, int64_t z0, char* out,
+                                   cudaStream_t stream)
+{
+    if (n_nodes <= 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) || n_words <= 0 || n_words >= (1LL << 32)) {
+        cfe_set_error("cfe_emit_nodes_bits: the *NODE section must start 16-byte aligned");
+        return -1;
+    }
+    NodeEmitParams P;
+    P.node_list = nullptr; P.n_nodes = n_nodes; P.xtab = xtab; P.ytab = ytab; P.ztab = ztab;
+    P.SN32 = (u32)((X + 1) * (Y + 1)); P.RN32 = (u32)(X + 1);
+    P.dSN = make_fastdiv(P.SN32); P.dRN = make_fastdiv(P.RN32);
+    P.z0 = z0; P.out = out;
+    NodeBitsParams B;
+    B.nbits = nbits; B.npref = npref; B.chunk_word = chunk_word;
+    B.n_words = (u32)n_words; B.wpr = (u32)((X + 32) / 32); B.rowlen = (u32)(X + 1);
+    B.d_wpr = make_fastdiv(B.wpr);
+    const i64 n_chunks = (n_nodes + NODE4_PER_CTA - 1) / NODE4_PER_CTA;
+    static unsigned long long once = 0;
+    int sms = 148;
+    cfe_first_on_device(&once, &sms);
+    i64 blocks = (i64)sms * NODE4B_CTAS_PER_SM;                  // persistent: every CTA strides over the chunks
+    if (blocks > n_chunks) blocks = n_chunks;
+    k_emit_nodes4b<<<(unsigned)blocks, NODE4_THREADS, 0, stream>>>(P, B, (u32)n_chunks);
+    CFE_CHECK_LAUNCH("k_emit_nodes4b");
+    return 0;
+}
+
 extern "C" int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab, const char* ytab,
                               const char* ztab, int64_t Y, int64_t X, int64_t z0, char* out,
                               cudaStream_t stream)

@@ -14,6 +14,7 @@
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 8
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+#define SCAN_CHUNK 512u         // items per entry of the coarse rank index (= nodes per CTA of k_emit_nodes4b)
 
 // ------------------------------------------------------------------------------------------
 // K0: pack (v > thr) into bit rows
@@ -209,7 +210,7 @@ __device__ __forceinline__ u32 node_used_word(const NodeGeom& g, int s, int r, i
 template <int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_words(const u32* __restrict__ bits, i64 n_words, int W, NodeGeom geom, u32* __restrict__ nbits,
-             u32* __restrict__ pref, u64* __restrict__ total, u64* __restrict__ ws)
+             u32* __restrict__ pref, u64* __restrict__ total, u64* __restrict__ ws, u32* __restrict__ chunk_word)
 {
     __shared__ u32 s_scan[33];
     __shared__ u64 s_excl;
@@ -274,6 +275,17 @@ k_scan_words(const u32* __restrict__ bits, i64 n_words, int W, NodeGeom geom, u3
     }
     __syncthreads();
     u32 run = (u32)s_excl + excl;
+    if (chunk_word) {
+        // coarse rank index for the list-free emitters: chunk_word[m] = the word that holds the item of rank
+        // m * SCAN_CHUNK (a word holds <= 32 items, so at most one chunk starts in it)
+        u32 o = run;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const u32 m = (o + SCAN_CHUNK - 1u) / SCAN_CHUNK;
+            if (cnt[k] && m * SCAN_CHUNK < o + cnt[k]) chunk_word[m] = (u32)(i0 + k);
+            o += cnt[k];
+        }
+    }
     if (i0 + SCAN_ITEMS <= n_words && (reinterpret_cast<uintptr_t>(pref) & 15u) == 0) {
         u32 o[SCAN_ITEMS];
 #pragma unroll
@@ -298,7 +310,7 @@ extern "C" size_t cfe_scan_workspace_bytes(int64_t n_items)
 }
 
 static int launch_scan(int mode, const u32* bits, i64 n_words, int W, const NodeGeom& geom, u32* nbits,
-                       u32* pref, u64* total, void* ws, cudaStream_t stream)
+                       u32* pref, u64* total, void* ws, cudaStream_t stream, u32* chunk_word = nullptr)
 {
     if (n_words >= (1LL << 32) * 32 / 32) {
         // prefixes are u32: a slab holds < 2^32 voxels / nodes
@@ -312,9 +324,9 @@ static int launch_scan(int mode, const u32* bits, i64 n_words, int W, const Node
     if (tiles > 0x7fffffffLL) { cfe_set_error("scan: too many tiles"); return -1; }
     u64* w = reinterpret_cast<u64*>(ws);
     switch (mode) {
-    case 0: k_scan_words<0><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w); break;
-    case 1: k_scan_words<1><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w); break;
-    default: k_scan_words<2><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w); break;
+    case 0: k_scan_words<0><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w, chunk_word); break;
+    case 1: k_scan_words<1><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w, chunk_word); break;
+    default: k_scan_words<2><<<(unsigned)tiles, SCAN_THREADS, 0, stream>>>(bits, n_words, W, geom, nbits, pref, total, w, chunk_word); break;
     }
     CFE_CHECK_LAUNCH("k_scan_words");
     return 0;
@@ -335,15 +347,24 @@ extern "C" int cfe_scan_run_starts(const uint32_t* bits, int64_t rows, int64_t X
     return launch_scan(1, bits, rows * W, W, g, nullptr, pref, reinterpret_cast<u64*>(total), ws, stream);
 }
 
-extern "C" int cfe_scan_nodes(const uint32_t* bits, const uint32_t* halo_below, int64_t Zl, int64_t Y,
-                              int64_t X, int64_t n_layers, uint32_t* nbits, uint32_t* npref,
-                              uint64_t* total, void* ws, cudaStream_t stream)
+// chunk_word (may be NULL): u32 [n_layers*(Y+1)*(X+1) / 512 + 2], receives for every m the index of the word
+// of the node grid that holds the used node of rank 512 m -- the entry point of the list-free *NODE emitter
+extern "C" int cfe_scan_nodes_index(const uint32_t* bits, const uint32_t* halo_below, int64_t Zl, int64_t Y,
+                                    int64_t X, int64_t n_layers, uint32_t* nbits, uint32_t* npref,
+                                    uint64_t* total, uint32_t* chunk_word, void* ws, cudaStream_t stream)
 {
     NodeGeom g;
     g.Zl = (int)Zl; g.Y = (int)Y; g.W = (int)((X + 31) / 32); g.WN = (int)((X + 1 + 31) / 32);
     g.n_layers = (int)n_layers; g.bits = bits; g.halo_below = halo_below;
     const i64 n_words = n_layers * (Y + 1) * (i64)g.WN;
-    return launch_scan(2, bits, n_words, g.WN, g, nbits, npref, reinterpret_cast<u64*>(total), ws, stream);
+    return launch_scan(2, bits, n_words, g.WN, g, nbits, npref, reinterpret_cast<u64*>(total), ws, stream, chunk_word);
+}
+
+extern "C" int cfe_scan_nodes(const uint32_t* bits, const uint32_t* halo_below, int64_t Zl, int64_t Y,
+                              int64_t X, int64_t n_layers, uint32_t* nbits, uint32_t* npref,
+                              uint64_t* total, void* ws, cudaStream_t stream)
+{
+    return cfe_scan_nodes_index(bits, halo_below, Zl, Y, X, n_layers, nbits, npref, total, nullptr, ws, stream);
 }
 
 // ------------------------------------------------------------------------------------------

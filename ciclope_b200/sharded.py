@@ -565,6 +565,17 @@ def _ccl_host_merge(ctx, st):
 class SlabMesh:
     """One rank's part of the global voxel mesh (device-resident)."""
 
+    @property
+    def node_list(self):
+        """Local grid index of every used node of the slab (only the variable-width *NODE path reads it)."""
+        if getattr(self, "_node_list", None) is None:
+            dev = self.vol.device
+            with torch.cuda.device(dev):
+                self._node_list = empty_u32(self.n_nd, dev)
+                _lib.call("cfe_fill_list", self.nbits.data_ptr(), self.npref.data_ptr(), self.n_node_words,
+                          (self.X + 32) // 32, self.X + 1, self._node_list.data_ptr(), _lib.stream())
+        return self._node_list
+
 
 def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_num=1, node_level_lock_num=1,
                       locking_strategy="plane", eid_base=0, packed=None):
@@ -606,8 +617,9 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         s = _lib.stream()
         _lib.call("cfe_scan_elements", bits.data_ptr(), rows * W, epref.data_ptr(), stats.data_ptr(),
                   ws.data_ptr(), s)
-        _lib.call("cfe_scan_nodes", bits.data_ptr(), _lib.ptr(halo), Zl, Y, X, n_layers, nbits.data_ptr(),
-                  npref.data_ptr(), stats.data_ptr() + 8, ws.data_ptr(), s)
+        chunk_word = empty_u32(n_layers * (Y + 1) * (X + 1) // 512 + 2, dev)   # rank index of the *NODE emitter
+        _lib.call("cfe_scan_nodes_index", bits.data_ptr(), _lib.ptr(halo), Zl, Y, X, n_layers, nbits.data_ptr(),
+                  npref.data_ptr(), stats.data_ptr() + 8, chunk_word.data_ptr(), ws.data_ptr(), s)
         # boundary sets: global boxes clipped to the layers this slab owns
         boxes = vfe._boundary_boxes(locking_strategy, p, kk, Zg, Y, X)
         descs = (CfeSetDesc * 12)()
@@ -684,7 +696,6 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         m.set_rank0 = [sum(t[2 + q] for t in table[: ctx.rank]) for q in range(12)]
         m.set_count_global = [sum(t[2 + q] for t in table) for q in range(12)]
         m.elem_vox = empty_u32(m.n_el, dev)
-        m.node_list = empty_u32(m.n_nd, dev)
         m.set_ids = torch.empty(max(n_ids, 1), dtype=torch.int64, device=dev)
         lib = _lib.load()
         m.ws_el = torch.empty(lib.cfe_emit_elements_workspace_bytes(m.n_el) + 16, dtype=torch.uint8, device=dev)
@@ -692,8 +703,9 @@ def vol2ugrid_program(ctx, vol, is_bool, Zg, z0, voxelsize, GVmin=0, plane_lock_
         m.gv8 = None if (is_bool and thr >= 0) else torch.empty(max(m.n_el, 1), dtype=torch.uint8, device=dev)
         _lib.call("cfe_fill_elements_gv", bits.data_ptr(), epref.data_ptr(), rows * W, Y, X, z0, m.eid_offset,
                   m.n_el, m.elem_vox.data_ptr(), m.ws_el.data_ptr(), vol.data_ptr(), _lib.ptr(m.gv8), s)
-        _lib.call("cfe_fill_list", nbits.data_ptr(), npref.data_ptr(), nrows * WN, WN, X + 1,
-                  m.node_list.data_ptr(), s)
+        m.nbits, m.npref, m.chunk_word, m.n_node_words = nbits, npref, chunk_word, nrows * WN
+        if vfe.NODE_EMITTER != "bits":
+            m.node_list                       # k_fill_list now
         _lib.call("cfe_sets_fill", descs_dev.data_ptr(), 12, n_tiles, Zl, Y, X, z0, m.eid_offset, bits.data_ptr(),
                   epref.data_ptr(), _lib.ptr(halo), tile_off.data_ptr(), m.set_ids.data_ptr(), s)
     m.bits, m.epref = bits, epref
@@ -721,8 +733,8 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
             nodes_buf = torch.empty(max(53 * m.n_nd, 1) + 64, dtype=torch.uint8, device=dev)
             p_xt0 = m.ftab.data_ptr()
             p_yt0 = p_xt0 + 16 * (X + 1)
-            _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt0, p_yt0,
-                      p_yt0 + 16 * (Y + 1) + 16 * m.z0, Y, X, m.z0, nodes_buf.data_ptr(), _lib.stream())
+            vfe._emit_node_lines(m, p_xt0, p_yt0, p_yt0 + 16 * (Y + 1) + 16 * m.z0, Y, X, m.z0,
+                                 nodes_buf.data_ptr(), _lib.stream())
     if m.gv8 is None:
         # a boolean volume has one grey value (True -> SET1): the histogram is the element count,
         # which every rank already knows from vol2ugrid's all-gather

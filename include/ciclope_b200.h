@@ -69,6 +69,11 @@ int cfe_scan_run_starts(const uint32_t* bits, int64_t rows, int64_t X, uint32_t*
 int cfe_scan_nodes(const uint32_t* bits, const uint32_t* halo_below, int64_t Zl, int64_t Y, int64_t X,
                    int64_t n_layers, uint32_t* nbits, uint32_t* npref, uint64_t* total, void* ws,
                    cfe_stream_t s);
+/* Same, and chunk_word[m] = index of the node-grid word holding the used node of rank 512 m (u32
+ * [grid nodes / 512 + 2]): the entry point of the list-free *NODE emitter cfe_emit_nodes_bits. */
+int cfe_scan_nodes_index(const uint32_t* bits, const uint32_t* halo_below, int64_t Zl, int64_t Y, int64_t X,
+                         int64_t n_layers, uint32_t* nbits, uint32_t* npref, uint64_t* total,
+                         uint32_t* chunk_word, void* ws, cfe_stream_t s);
 
 /* list[pref[i] + k] = row*row_len + 32*w + (k-th set bit of word i): ascending index lists of
  * the elements (row_len = X) or used nodes (row_len = X+1). */
@@ -251,6 +256,12 @@ int cfe_emit_nodes_wide(const uint32_t* node_list, int64_t n_nodes, const char* 
  * same interpreter arithmetic as the reference).  Writes 53*n_nodes bytes at out. */
 int cfe_emit_nodes(const uint32_t* node_list, int64_t n_nodes, const char* xtab, const char* ytab,
                    const char* ztab, int64_t Y, int64_t X, int64_t z0, char* out, cfe_stream_t s);
+/* The same lines straight from the used-node bitmap (nbits / npref / chunk_word of cfe_scan_nodes_index,
+ * n_words = words of the bitmap): every CTA expands its 512 nodes itself, no node list is materialised.
+ * `out` must be 16-byte aligned. */
+int cfe_emit_nodes_bits(const uint32_t* nbits, const uint32_t* npref, const uint32_t* chunk_word, int64_t n_words,
+                        int64_t n_nodes, const char* xtab, const char* ytab, const char* ztab, int64_t Y,
+                        int64_t X, int64_t z0, char* out, cfe_stream_t s);
 
 /* *ELEMENT lines (voxelFE.py:639-647).  perm == NULL: raster order, one grey value
  * (single_gv); otherwise perm holds {voxel, raster rank} pairs in GV-major order.

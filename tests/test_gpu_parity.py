@@ -120,6 +120,31 @@ def test_packed_mask_tag_is_used_and_invalidated(cfe, orc, tmp_path):
     assert cfe.vol2ugrid(L2, [1, 1, 1], GVmin=1).n_el == 0
 
 
+@pytest.mark.parametrize("shape", [(9, 33, 70), (40, 48, 96), (3, 700, 1030)])
+def test_node_emitters_agree(cfe, shape):
+    """the list-free *NODE emitter (cfe_emit_nodes_bits: every CTA expands the used-node bitmap itself) writes the
+    bytes of the list-driven one (cfe_fill_list + cfe_emit_nodes), including sections whose length is not a
+    multiple of four lines and chunks that span empty stretches of the grid"""
+    import torch
+    from ciclope_b200 import _lib
+    bw = cases.blobs(shape, 0.25, 17)
+    bw[:, shape[1] // 3: shape[1] // 3 + 6, :] = False        # empty rows: chunks that span many empty words
+    m = cfe.vol2ugrid(bw, [0.0195, 0.02, 0.03])
+    n = 53 * m.n_nd
+    a = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    b = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    assert a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+    p_xt = m.ftab.data_ptr()
+    p_yt = p_xt + 16 * (m.X + 1)
+    p_zt = p_yt + 16 * (m.Y + 1)
+    s = _lib.stream()
+    _lib.call("cfe_emit_nodes", m.node_list.data_ptr(), m.n_nd, p_xt, p_yt, p_zt, m.Y, m.X, 0, a.data_ptr(), s)
+    _lib.call("cfe_emit_nodes_bits", m.nbits.data_ptr(), m.npref.data_ptr(), m.chunk_word.data_ptr(),
+              m.n_node_words, m.n_nd, p_xt, p_yt, p_zt, m.Y, m.X, 0, b.data_ptr(), s)
+    assert torch.equal(a, b) and int(a[n:].sum()) == 0
+    assert bytes(a[:53].cpu().numpy()).endswith(b"\n")
+
+
 def test_mesh_set_before_read_routes_to_generic(cfe, golden):
     """mesh.points = ... before the lazy array was ever read must count as an edit (not AttributeError)."""
     c = DECK_CASES["bool_5x7x9"]
