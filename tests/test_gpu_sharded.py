@@ -185,6 +185,92 @@ def test_real_nccl_two_ranks(orc, tmp_path):
         cases.mask_timestamp(open(str(tmp_path / "cpu.inp"), "rb").read())
 
 
+_FACADE_WORKER = """
+import os, sys, json
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from ciclope_b200 import distributed as cfd, sharded
+from tests import cases
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+bw = cases.blobs((40, 48, 96), 0.3, 77)
+a, b = sharded.slab_ranges(bw.shape[0], world)[rank]
+L = cfd.remove_unconnected(bw[a:b])                                  # NumPy slab in -> NumPy slab out
+assert isinstance(L, np.ndarray) and L.dtype == np.bool_
+Lt = cfd.remove_unconnected(torch.from_numpy(bw[a:b].copy()).cuda())  # tensor in -> tagged tensor out
+mesh, refn = cfd.vol2ugrid(Lt, [0.0195] * 3, refnodes=True)           # placement from the gathered slab heights
+cfd.mesh2voxelfe(mesh, cases.TEMPLATE_REFNODE, {out!r}, refnode=[float(v) for v in refn["Z1"]])
+grey = cases.grey_from_mask(bw, 13)
+gm = cfd.vol2ugrid(grey[a:b], [0.0195] * 3, z0=a, Z_global=bw.shape[0])
+cfd.mesh2voxelfe(gm, cases.TEMPLATE, {out_grey!r}, keywords=['NSET', 'ELSET', 'PROPERTY'],
+                 matprop={{"file": [cases.MAT_LINEAR], "range": [[1, 255]]}})
+try:
+    cfd.remove_unconnected(np.zeros((4, 8, 32), dtype=bool))
+    raised = False
+except ValueError:
+    raised = True
+if rank == 0:
+    json.dump({{"refnodes": {{k: [float(x) for x in v] for k, v in refn.items()}}, "empty_raises": raised,
+               "mask_sum": int(L.sum())}}, open({meta!r}, "w"))
+np.save({mask!r} + str(rank) + ".npy", L)
+cfd.shutdown()
+dist.destroy_process_group()
+"""
+
+
+def test_distributed_facade_two_ranks(orc, tmp_path):
+    """ciclope_b200.distributed (the reference's signatures over real ranks: NCCL + peer-memory exchange) against
+    the oracle: kept voxels, reference nodes (float64 sums chained up the slabs), the refnode deck and a
+    grey-scale deck with PROPERTY cards, each written by both ranks into one file."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out, out_grey = str(tmp_path / "facade.inp"), str(tmp_path / "facade_grey.inp")
+    meta, mask = str(tmp_path / "meta.json"), str(tmp_path / "mask")
+    script = tmp_path / "facade_worker.py"
+    script.write_text(_FACADE_WORKER.format(root=ROOT, out=out, out_grey=out_grey, meta=meta, mask=mask))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       cwd=ROOT, capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-3000:]
+    bw = cases.blobs((40, 48, 96), 0.3, 77)
+    L = orc.remove_unconnected(bw)
+    got = np.concatenate([np.load(mask + "%d.npy" % k) for k in range(2)])
+    assert np.array_equal(got, L)
+    m = json.load(open(meta))
+    assert m["empty_raises"] and m["mask_sum"] > 0
+    mesh, refn = orc.vol2ugrid(L, [0.0195] * 3, refnodes=True)
+    for k, v in refn.items():
+        assert np.array_equal(np.asarray(m["refnodes"][k]), v), k          # bit-exact float64 barycentres
+    orc.mesh2voxelfe(mesh, cases.TEMPLATE_REFNODE, str(tmp_path / "cpu.inp"), refnode=[float(v) for v in refn["Z1"]])
+    assert cases.mask_timestamp(open(out, "rb").read()) == cases.mask_timestamp(open(str(tmp_path / "cpu.inp"), "rb").read())
+    grey = cases.grey_from_mask(bw, 13)
+    orc.mesh2voxelfe(orc.vol2ugrid(grey, [0.0195] * 3), cases.TEMPLATE, str(tmp_path / "cpu_grey.inp"),
+                     keywords=['NSET', 'ELSET', 'PROPERTY'], matprop={"file": [cases.MAT_LINEAR], "range": [[1, 255]]})
+    assert cases.mask_timestamp(open(out_grey, "rb").read()) == \
+        cases.mask_timestamp(open(str(tmp_path / "cpu_grey.inp"), "rb").read())
+
+
+def test_refnodes_program_emulated(sh, orc):
+    """the chained reference-node sums of the sharded path on emulated ranks (1-GPU boxes run this one)"""
+    from ciclope_b200 import distributed as cfd
+    bw = cases.blobs((30, 24, 64), 0.3, 5)
+    L = orc.remove_unconnected(bw)
+    _, want = orc.vol2ugrid(L, [0.0195, 0.02, 0.03], refnodes=True)
+    for n in (2, 3, 5):
+        slabs, is_bool, Zg = sh._slab_inputs(L, n)
+        runner = sh.LocalRunner(n)
+        meshes = runner.run([sh.vol2ugrid_program(c, s, is_bool, Zg, z0, [0.0195, 0.02, 0.03])
+                             for c, (s, z0) in zip(runner.ctxs(), slabs)])
+        refs = runner.run([cfd._refnodes_program(c, m) for c, m in zip(runner.ctxs(), meshes)])
+        for got in refs:
+            for k, v in want.items():
+                assert np.array_equal(got[k], v), (n, k)
+
+
 def test_ids_beyond_32_bits(sh):
     """Node / element ids of the 2048^3-class configs exceed 2^32: a thin slab placed at a huge global
     slice offset exercises the 64-bit formatting paths; the expected text is re-derived here from the
