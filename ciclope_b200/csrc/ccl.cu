@@ -117,6 +117,23 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
     const int W = G.W, TR = G.TR, n_trows = G.TS * G.TR;
     const int tile_s = blockIdx.x / G.tiles_r, tile_r = blockIdx.x - tile_s * G.tiles_r;
     const u32 t = threadIdx.x, lane = t & 31u;
+    const u32 tile_words = (u32)n_trows * (u32)W;
+    // ---- stage the tile's bit words and (still global) run prefixes right away: these loads and the row-start
+    // loads of the numbering below are then in flight together (one round of HBM latency per tile, not two)
+    if (tile_words <= CCL_WCAP) {
+        for (u32 wt = t; wt < tile_words; wt += CCL_THREADS) {
+            const u32 tr = fd_div(wt, G.dW), w = wt - tr * (u32)W;
+            const int s = tile_s * G.TS + (int)tr / TR, r = tile_r * TR + ((int)tr % TR);
+            u32 word = 0, pf = 0;
+            if (s < G.Z && r < G.Y) {
+                const i64 i = ((i64)s * G.Y + r) * W + w;
+                word = __ldg(bits + i);
+                pf = __ldg(pref + i);
+            }
+            sb[wt] = word;
+            spf[wt] = pf;
+        }
+    }
     u32 g0 = 0, cnt = 0;
     if (t < (u32)n_trows) {
         // tile row t  <->  slice s0 + t / TR, row r0 + t % TR
@@ -139,7 +156,6 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
         if (t == 0) tile_flag[blockIdx.x] = 1u;
         return;
     }
-    const u32 tile_words = (u32)n_trows * (u32)W;
     if (total > CCL_CAP || tile_words > CCL_WCAP) {
         // over capacity: identity parents, run lengths as sizes; k_ccl_inner unites the tile's pairs in HBM
         if (t == 0) tile_flag[blockIdx.x] = 0u;
@@ -167,19 +183,11 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
         return;
     }
     if (t == 0) tile_flag[blockIdx.x] = 1u;
-    // ---- stage the tile: bit words and LOCAL run prefixes (rows outside the slab read as empty)
+    // ---- global -> LOCAL run prefixes (local = global - first global id of the row + first local index of the row)
     for (u32 l = t; l < total; l += CCL_THREADS) { sp[l] = l; cnt_l[l] = 0u; }
     for (u32 wt = t; wt < tile_words; wt += CCL_THREADS) {
-        const u32 tr = fd_div(wt, G.dW), w = wt - tr * (u32)W;
-        const int s = tile_s * G.TS + (int)tr / TR, r = tile_r * TR + ((int)tr % TR);
-        u32 word = 0, pf = 0;
-        if (s < G.Z && r < G.Y) {
-            const i64 i = ((i64)s * G.Y + r) * W + w;
-            word = __ldg(bits + i);
-            pf = __ldg(pref + i) - rb_g[tr] + rb_l[tr];
-        }
-        sb[wt] = word;
-        spf[wt] = pf;
+        const u32 tr = fd_div(wt, G.dW);
+        spf[wt] += rb_l[tr] - rb_g[tr];
     }
     __syncthreads();
     // ---- one pass over the staged words: run lengths, and the union of every overlapping run pair with the
@@ -229,8 +237,10 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
         sp[l] = x;
     }
     __syncthreads();
-    // ---- voxels per tile-local component: every non-root run adds its length to its root's counter
-    // (neighbouring runs mostly share the root: one shared-memory add per warp and root via match.any)
+    // ---- voxels per tile-local component: every non-root run adds its length to its root's counter.  Runs that
+    // follow each other mostly share the root, so the warp adds up every maximal stretch of lanes with the same
+    // root (head flags -> one inclusive scan -> difference of two prefix values) and the last lane of a stretch
+    // issues one shared-memory add
     for (u32 base = 0; base < total; base += CCL_THREADS) {
         const u32 l = base + t;
         u32 root = 0xffffffffu, add = 0;
@@ -238,22 +248,29 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
             const u32 r = sp[l];
             if (r != l) { root = r; add = cnt_l[l]; }
         }
-        if (!__any_sync(CFE_FULL_MASK, root != 0xffffffffu)) continue;
-        const u32 peers = __match_any_sync(CFE_FULL_MASK, root);
-        const u32 sum = __reduce_add_sync(peers, add);
-        if (root != 0xffffffffu && ((u32)__ffs((int)peers) - 1u) == lane) atomicAdd(cnt_l + root, sum);
+        const u32 prev_root = __shfl_up_sync(CFE_FULL_MASK, root, 1);
+        const u32 heads = __ballot_sync(CFE_FULL_MASK, lane == 0 || prev_root != root);
+        u32 incl = add;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 v = __shfl_up_sync(CFE_FULL_MASK, incl, o);
+            if (lane >= (u32)o) incl += v;
+        }
+        const u32 start = 31u - (u32)__clz((int)(heads & mask_le((int)lane)));     // head lane of my stretch
+        const u32 before = __shfl_sync(CFE_FULL_MASK, incl, start ? start - 1u : 0u);
+        const bool tail = lane == 31u || ((heads >> (lane + 1u)) & 1u);
+        if (tail && root != 0xffffffffu) atomicAdd(cnt_l + root, incl - (start ? before : 0u));
     }
     __syncthreads();
     // ---- publish: the rows of one slice of the tile are consecutive in raster order, so local indices map to
     // global run ids piecewise linearly with one piece per slice (<= 16 pieces)
     for (u32 l = t; l < total; l += CCL_THREADS) {
         const u32 root = sp[l];
-        int ka = 0, kb = 0;
+        int ka = 0, kb = 0;                               // slice of the tile holding l / root (TS is a power of two)
 #pragma unroll 1
-        for (int k = 1; k < G.TS; ++k) {
-            const u32 sl = rb_l[k * TR];
-            ka += (sl <= l);
-            kb += (sl <= root);
+        for (int step = G.TS >> 1; step > 0; step >>= 1) {
+            if (rb_l[(ka + step) * TR] <= l) ka += step;
+            if (rb_l[(kb + step) * TR] <= root) kb += step;
         }
         const u32 g = rb_g[ka * TR] + (l - rb_l[ka * TR]);
         CFE_ASSERT(root <= l && (u64)g < *n_runs_p && rb_g[kb * TR] + (root - rb_l[kb * TR]) <= g);

@@ -313,7 +313,11 @@ __global__ void __launch_bounds__(NODE4_THREADS) k_emit_nodes4b(NodeEmitParams P
         if (n_here > NODE4_PER_CTA) n_here = NODE4_PER_CTA;
         const u32 lo = (u32)k0, hi = (u32)(k0 + n_here);        // ranks [lo, hi)
         // the previous chunk's bulk copy must have read the staging area before it is overwritten
-        if (pending_copy && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // (the node list below lives inside the staging area, so every thread has to wait for that)
+        if (pending_copy) {
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+        }
         // ---- expand: local grid index of the used nodes with rank in [lo, hi) -> list
         for (u32 wbase = cw;; wbase += NODE4_THREADS) {
             const u32 i = wbase + threadIdx.x;
