@@ -85,8 +85,15 @@ struct CclGeom {
 };
 
 // global pair kernel body: unions of word i with word j (same column word in the row above / slice below)
+// `seen` (may be NULL): a small direct-mapped table in shared memory of the (root, root) pairs this CTA has
+// already united.  After k_ccl_tile a run's parent is its tile root, a tile has a handful of roots, and all the
+// words of a border row join the same two tiles: the ~10^7 border pairs of a slab connect only ~10^4..10^5
+// distinct root pairs, and a pair that was united once does not need its pointer chases again.  (A second,
+// device-wide table shared by all CTAs was tried and lost: 1.12 ms against 0.57 ms for this kernel -- the fence
+// and the extra L2 round trip per new pair cost more than the repeated unions they save.)
+#define CCL_SEEN 256
 __device__ __forceinline__ void ccl_pairs_global(const u32* __restrict__ bits, const u32* __restrict__ pref, i64 i,
-                                                 i64 j, bool has_prev, u32 cur, u32* parent)
+                                                 i64 j, bool has_prev, u32 cur, u32* parent, u64* seen = nullptr)
 {
     const u32 nb = __ldg(bits + j);
     const u32 both = cur & nb;
@@ -98,7 +105,15 @@ __device__ __forceinline__ void ccl_pairs_global(const u32* __restrict__ bits, c
     while (pair_starts) {
         const int b = __ffs((int)pair_starts) - 1;
         pair_starts &= pair_starts - 1;
-        uf_union(parent, run_id(cur, cur_prev >> 31, cur_pref, b), run_id(nb, nb_prev >> 31, nb_pref, b));
+        const u32 ra = run_id(cur, cur_prev >> 31, cur_pref, b), rb = run_id(nb, nb_prev >> 31, nb_pref, b);
+        if (!seen) { uf_union(parent, ra, rb); continue; }
+        const u32 ta = parent[ra], tb = parent[rb];            // one hop each: the tile roots (or closer ancestors)
+        if (ta == tb) continue;
+        const u64 key = ta > tb ? (((u64)ta << 32) | tb) : (((u64)tb << 32) | ta);
+        const u32 slot = ((ta * 0x9E3779B1u) ^ (tb * 0x85EBCA77u) ^ ((ta ^ tb) >> 15)) & (CCL_SEEN - 1);
+        if (seen[slot] == key) continue;
+        uf_union(parent, ta, tb);
+        seen[slot] = key;
     }
 }
 
@@ -285,6 +300,9 @@ __global__ void __launch_bounds__(256)
 k_ccl_border(const u32* __restrict__ bits, const u32* __restrict__ pref, CclGeom G, i64 n0, i64 n_items,
              u32* __restrict__ parent)
 {
+    __shared__ u64 s_seen[CCL_SEEN];
+    for (u32 k = threadIdx.x; k < CCL_SEEN; k += blockDim.x) s_seen[k] = ~0ull;
+    __syncthreads();
     const i64 it = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (it >= n_items) return;
     const int W = G.W;
@@ -308,7 +326,7 @@ k_ccl_border(const u32* __restrict__ bits, const u32* __restrict__ pref, CclGeom
     const i64 i = row * W + w;
     const u32 cur = __ldg(bits + i);
     if (!cur) return;
-    ccl_pairs_global(bits, pref, i, dir == 0 ? i - W : i - (i64)W * G.Y, w != 0, cur, parent);
+    ccl_pairs_global(bits, pref, i, dir == 0 ? i - W : i - (i64)W * G.Y, w != 0, cur, parent, s_seen);
 }
 
 // The pairs INSIDE the tiles that did not fit shared memory (flag 0): one CTA per tile, returns at once for
