@@ -59,8 +59,8 @@ _SIGNATURES = {
                                        c_vp, c_vp]),
     "cfe_ccl_plane_roots": (c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "cfe_ccl_interface_edges": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
-    "cfe_ccl_interface_forest": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp,
-                                         c_i64, c_vp]),
+    "cfe_ccl_interface_forest": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp,
+                                         c_vp, c_i64, c_vp]),
     "cfe_ccl_boundary_vertices": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
                                           c_vp, c_vp, c_vp]),
     "cfe_ccl_boundary_solve": (c_int, [c_vp, c_int, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -797,9 +797,9 @@ __device__ __forceinline__ bool uf_union_hooked(u32* parent, u32 a, u32 b)
 
 __global__ void __launch_bounds__(256)
 k_ccl_interface_forest(const u32* __restrict__ bitsA, const u32* __restrict__ prefA, const u32* __restrict__ vA,
-                       const u32* __restrict__ bitsB, const u32* __restrict__ prefB, const u32* __restrict__ vB,
-                       i64 n_plane_words, int W, u32 Cv, u32* __restrict__ forest, u32* __restrict__ edges,
-                       u32* __restrict__ count, u32 capacity)
+                       u32 vA_len, const u32* __restrict__ bitsB, const u32* __restrict__ prefB,
+                       const u32* __restrict__ vB, i64 n_plane_words, int W, u32 Cv, u32* __restrict__ forest,
+                       u32* __restrict__ edges, u32* __restrict__ count, u32 capacity)
 {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_plane_words) return;
@@ -814,7 +814,10 @@ k_ccl_interface_forest(const u32* __restrict__ bitsA, const u32* __restrict__ pr
     while (pair_starts) {
         const int bit = __ffs((int)pair_starts) - 1;
         pair_starts &= pair_starts - 1;
-        const u32 va = __ldg(vA + run_id(a, a_prev >> 31, pa, bit));
+        const u32 ida = run_id(a, a_prev >> 31, pa, bit);
+        // (the neighbour sends the vertices of its first vA_len plane runs only: a plane with more runs than the
+        // message holds is reported like a capacity overflow and the step takes the host-driven merge)
+        const u32 va = ida < vA_len ? __ldg(vA + ida) : 0xffffffffu;
         const u32 vb = __ldg(vB + run_id(b, b_prev >> 31, pb, bit));
         if (va >= Cv || vb >= Cv) {        // vertex capacity exceeded: the solver sees it in the vertex counts
             atomicMax(count, capacity + 1u);
@@ -832,9 +835,9 @@ __global__ void __launch_bounds__(256) k_uf_iota(u32* __restrict__ label, i64 n)
 
 // forest: u32[2 * Cv] scratch; edges: u32[2 * capacity] (capacity >= 2 * Cv never overflows); *count = edges
 extern "C" int cfe_ccl_interface_forest(const uint32_t* bitsA, const uint32_t* prefA, const uint32_t* vA,
-                                        const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* vB,
-                                        int64_t Y, int64_t X, int64_t Cv, uint32_t* forest, uint32_t* edges,
-                                        uint32_t* count, int64_t capacity, cudaStream_t stream)
+                                        int64_t vA_len, const uint32_t* bitsB, const uint32_t* prefB,
+                                        const uint32_t* vB, int64_t Y, int64_t X, int64_t Cv, uint32_t* forest,
+                                        uint32_t* edges, uint32_t* count, int64_t capacity, cudaStream_t stream)
 {
     const int W = (int)((X + 31) / 32);
     const i64 n = Y * W;
@@ -843,7 +846,7 @@ extern "C" int cfe_ccl_interface_forest(const uint32_t* bitsA, const uint32_t* p
     k_uf_iota<<<(unsigned)((2 * Cv + 255) / 256), 256, 0, stream>>>(forest, 2 * Cv);
     CFE_CHECK_LAUNCH("k_uf_iota");
     k_ccl_interface_forest<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
-        bitsA, prefA, vA, bitsB, prefB, vB, n, W, (u32)Cv, forest, edges, count, (u32)capacity);
+        bitsA, prefA, vA, (u32)vA_len, bitsB, prefB, vB, n, W, (u32)Cv, forest, edges, count, (u32)capacity);
     CFE_CHECK_LAUNCH("k_ccl_interface_forest");
     return 0;
 }

@@ -343,6 +343,8 @@ def _u32_to_i64(t):
 BOUNDARY_VERTS = 1 << 16      # per-rank capacity of the device-side cross-slab merge (vertices = slab-local
                               # components touching an interface); larger cases take the host-driven path
 BOUNDARY_EDGES = 2 * BOUNDARY_VERTS   # spanning-forest edges of one interface: never more than 2 Cv - 1
+MSG_RUNS_DIV = 16             # runs of an interface plane carried by the device-side merge: Y * X / 16 ...
+MSG_RUNS_MIN = 4096           # ... but at least this many
 _MARK = -1                    # 0xffffffff in the u32 size array = "keep this root"
 
 
@@ -414,7 +416,11 @@ def ccl_program(ctx, vol, force_host_merge=False, info=None):
                   1 if rank > 0 else 0, 1 if rank + 1 < N else 0, stats.data_ptr(), vfirst.data_ptr(),
                   didx.data_ptr(), parent.data_ptr(), size.data_ptr(), Cv, pack.data_ptr(), vbot.data_ptr(),
                   vtop.data_ptr(), s)
-    recv = yield from ctx.shift_up(torch.cat([top_bits, vtop]))
+    # the interface message: the top bit plane + the vertex of each of its runs.  A plane can hold Y * X / 2 runs,
+    # a real one holds a few per cent of that: the message carries the first MSG_RUNS of them and a plane
+    # with more runs sends the step through the host-driven merge (flagged by the receiver's edge pass)
+    msg_runs = min(cap, max(MSG_RUNS_MIN, (Y * X) // MSG_RUNS_DIV))
+    recv = yield from ctx.shift_up(torch.cat([top_bits, vtop[:msg_runs]]))
     with torch.cuda.device(dev):
         s = _lib.stream()
         if rank > 0:
@@ -427,7 +433,7 @@ def ccl_program(ctx, vol, force_host_merge=False, info=None):
             # vertices; the kernel emits a spanning forest of (vertex of A's run, vertex of B's run)
             # straight into the message
             forest = empty_u32(2 * Cv, dev)
-            _lib.call("cfe_ccl_interface_forest", bitsA.data_ptr(), prefA.data_ptr(), vA.data_ptr(),
+            _lib.call("cfe_ccl_interface_forest", bitsA.data_ptr(), prefA.data_ptr(), vA.data_ptr(), msg_runs,
                       bits.data_ptr(), pref.data_ptr(), vbot.data_ptr(), Y, X, Cv, forest.data_ptr(),
                       pack.data_ptr() + 4 * (4 + 2 * Cv), pack.data_ptr() + 4, Ce, s)
     packs = yield from ctx.all_gather(pack)

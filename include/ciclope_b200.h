@@ -148,10 +148,10 @@ int cfe_ccl_interface_edges(const uint32_t* bitsA, const uint32_t* prefA, const 
                             int64_t X, uint32_t* edges, uint32_t* count, int64_t capacity, cfe_stream_t s);
 
 /* The same interface walk for the device-side merge: runs carry dense boundary-vertex indices (vA: the
- * neighbour's numbering, vB: this slab's, both < Cv); the pairs are united in the scratch forest
+ * neighbour's numbering, of its first vA_len plane runs; vB: this slab's; both < Cv); the pairs are united in the scratch forest
  * (u32[2 Cv]) and only the unions that hooked two trees are appended, i.e. a spanning forest of the
  * interface graph: <= 2 Cv - 1 edges however many run pairs overlap. */
-int cfe_ccl_interface_forest(const uint32_t* bitsA, const uint32_t* prefA, const uint32_t* vA,
+int cfe_ccl_interface_forest(const uint32_t* bitsA, const uint32_t* prefA, const uint32_t* vA, int64_t vA_len,
                              const uint32_t* bitsB, const uint32_t* prefB, const uint32_t* vB, int64_t Y,
                              int64_t X, int64_t Cv, uint32_t* forest, uint32_t* edges, uint32_t* count,
                              int64_t capacity, cfe_stream_t s);

@@ -76,13 +76,17 @@ def test_sharded_ccl_u_shape_across_slabs(sh, orc):
         assert np.array_equal(mask.cpu().numpy(), orc.remove_unconnected(bw)), n
 
 
-@pytest.mark.parametrize("mode", ["host", "overflow"])
+@pytest.mark.parametrize("mode", ["host", "overflow", "message"])
 @pytest.mark.parametrize("n", [2, 4, 8])
 def test_sharded_ccl_fallback_paths(sh, orc, n, mode, monkeypatch):
-    """the host-driven merge, directly and through the capacity-overflow flag of the device path"""
+    """the host-driven merge, directly, through the capacity-overflow flag of the device path, and through an
+    interface plane with more runs than the interface message carries"""
     if mode == "overflow":
         monkeypatch.setattr(sh, "BOUNDARY_VERTS", 4)
         monkeypatch.setattr(sh, "BOUNDARY_EDGES", 8)
+    if mode == "message":
+        monkeypatch.setattr(sh, "MSG_RUNS_MIN", 8)
+        monkeypatch.setattr(sh, "MSG_RUNS_DIV", 10 ** 9)
     for bw in (cases.rand_binary((16, 24, 64), 0.3, 501), cases.blobs((32, 48, 64), 0.3, 3),
                cases.blobs((64, 64, 64), 0.12, 4)):
         mask, winner = sh.emulate_remove_unconnected(bw, n, force_host_merge=(mode == "host"))
