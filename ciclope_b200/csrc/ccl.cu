@@ -478,10 +478,13 @@ k_ccl_write_mask_words(const u32* __restrict__ bits, const u32* __restrict__ pre
     const u32 winner = 0xffffffffu - (u32)(key & 0xffffffffu);
     u32 keep = 0;
     if (i < n_words && key) {
+        // the three loads go out together (the pass is bound by its chain of dependent loads: word -> prefix ->
+        // parent; fetching prefix and carry only for non-empty words added a round of latency to every word)
         const u32 word = __ldg(bits + i);
+        const u32 prev = (i % W) ? __ldg(bits + i - 1) : 0u;
+        const u32 pf = __ldg(pref + i);
         if (word) {
-            const u32 carry = (i % W) ? (__ldg(bits + i - 1) >> 31) : 0u;
-            const u32 pf = __ldg(pref + i);
+            const u32 carry = prev >> 31;
             u32 rest = word;
             while (rest) {
                 const int b = __ffs((int)rest) - 1;

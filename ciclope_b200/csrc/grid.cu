@@ -464,7 +464,14 @@ extern "C" int cfe_fill_list(const uint32_t* bits, const uint32_t* pref, int64_t
 // and last set bit) and only re-derived per element when the ids straddle a power of ten.
 #define FILLE_WORDS 128
 
-__device__ __forceinline__ int nd64(u64 v) { return (v >> 32) ? digits_u64(v) : digits_u32((u32)v); }
+// decimal digits of a 32-bit value without branches: floor(bits * log10(2)) is the digit count or one less
+__constant__ u32 c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+__device__ __forceinline__ int digits_u32_flat(u32 v)
+{
+    const int t = ((32 - __clz((int)(v | 1u))) * 1233) >> 12;
+    return t + ((v | 1u) >= c_pow10[t] ? 1 : 0);
+}
+__device__ __forceinline__ int nd64(u64 v) { return (v >> 32) ? digits_u64(v) : digits_u32_flat((u32)v); }
 
 __global__ void __launch_bounds__(FILLE_WORDS)
 k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_words, FastDiv d_wpr, u32 wpr,
