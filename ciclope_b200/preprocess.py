@@ -214,12 +214,21 @@ def component_stats(best):
 # --------------------------------------------------------------------------------------------
 # The two steps right before the hot path in ciclope's pipeline (pipeline.py:163-169)
 
+# dtype of the histogram counts in skimage.filters.threshold_otsu: float64 in scikit-image 0.18 (the version of the
+# reference's environment file, envs/thkdebian.yml: 0.18.2, and of its notebooks: 0.18.1), float32 from 0.19 on
+# (`_validate_image_histogram` returns `counts.astype('float32')`).  pyproject.toml leaves the version open; on
+# volumes above 2^24 voxels the float32 cumulative sums round and the argmax can move by a bin.  Set this to
+# numpy.float32 to follow a >= 0.19 installation.
+OTSU_COUNTS_DTYPE = np.float64
+
+
 def threshold_otsu(image):
     """Otsu threshold of a uint8 image, as ``skimage.filters.threshold_otsu`` computes it for integer images
-    (one bin per integer from min to max, float64 cumulative sums, argmax of the between-class variance).
-    The 256-bin histogram is the GPU's (``cfe_gv_histogram``); the 256-term arithmetic is NumPy's, in the
-    library's order of operations.  scikit-image is neither in the reference checkout nor installed here, so
-    this function is restated from its published algorithm and its parity is not pinned by a golden vector."""
+    (one bin per integer from min to max, cumulative sums in ``OTSU_COUNTS_DTYPE``, argmax of the between-class
+    variance).  The 256-bin histogram is the GPU's (``cfe_gv_histogram``); the 256-term arithmetic is NumPy's, in
+    the library's order of operations.  scikit-image is neither in the reference checkout nor installed here, so
+    this function is restated from its published algorithm and its parity is NOT pinned by a golden vector
+    (see ``OTSU_COUNTS_DTYPE`` for the one known version dependence)."""
     vol, is_bool, _ = as_device_volume(image, allow_2d=True)
     if vol.numel() == 0:
         raise ValueError("zero-size array to reduction operation minimum which has no identity")
@@ -232,7 +241,7 @@ def threshold_otsu(image):
     lo, hi = int(present[0]), int(present[-1])
     if lo == hi:
         return np.bool_(lo) if is_bool else np.uint8(lo)
-    counts = hist[lo:hi + 1].astype(np.float64)
+    counts = hist[lo:hi + 1].astype(OTSU_COUNTS_DTYPE)
     centers = np.arange(lo, hi + 1)
     weight1 = np.cumsum(counts)
     weight2 = np.cumsum(counts[::-1])[::-1]
