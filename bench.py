@@ -209,7 +209,7 @@ class ClockSampler(threading.Thread):
 
 class CountingSink:
     """Host consumer of the streamed deck in the end-to-end leg: the bytes arrive in pinned host memory
-    (two-buffer ring, 2 x 64 MiB) and are counted; a real caller writes them to a file or a socket.  The
+    (ring of 3 x 64 MiB) and are counted; a real caller writes them to a file or a socket.  The
     deck of the default workload (~49 GB per GPU) does not fit pinned host memory N times over."""
 
     def __init__(self):
@@ -634,7 +634,7 @@ def run_gpu(args, rank, world, local_rank):
         d2h = sink.n // k_e2e
         e2e = {"value": n_vox * world / dt, "unit": "voxels/s", "h2d_bytes_per_step": int(n_vox),
                "d2h_bytes_per_step": int(d2h) + 16 + 136 + 16, "ms_per_step": dt * 1e3, "steps": k_e2e,
-               "sink": "pinned two-buffer ring (2 x 64 MiB), bytes counted on the host; per rank for N > 1",
+               "sink": "pinned ring (3 x 64 MiB), bytes counted on the host; per rank for N > 1",
                "d2h_gbs_per_gpu": d2h / dt / 1e9}
         del vol_host, vol_dev
 

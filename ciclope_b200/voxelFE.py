@@ -895,17 +895,21 @@ _PINNED_CHUNKS = {}
 STREAM_CHUNK = 64 << 20
 
 
+RING = 3        # staging buffers: two copies are always queued behind the one being consumed
+
+
 def _pinned_ring(chunk):
     bufs = _PINNED_CHUNKS.get(chunk)
     if bufs is None:
-        bufs = _PINNED_CHUNKS[chunk] = [torch.empty(chunk, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        bufs = _PINNED_CHUNKS[chunk] = [torch.empty(chunk, dtype=torch.uint8).pin_memory() for _ in range(RING)]
     return bufs
 
 
 def stream_device_bytes(pieces, sink, chunk=None):
-    """Device bytes -> host consumer through two pinned staging buffers: the copy of chunk k + 1 runs while
-    ``sink(memoryview, offset)`` consumes chunk k (no pageable copies, no intermediate bytes objects, host
-    memory bounded by 2 * chunk whatever the deck size).  ``pieces`` = [(offset, uint8 CUDA tensor)];
+    """Device bytes -> host consumer through a ring of pinned staging buffers: the copies of chunks k + 1 and
+    k + 2 are queued on the copy engine while ``sink(memoryview, offset)`` consumes chunk k, so the engine
+    never waits for the host to wake up between chunks (no pageable copies, no intermediate bytes objects,
+    host memory bounded by RING * chunk whatever the deck size).  ``pieces`` = [(offset, uint8 CUDA tensor)];
     returns the number of bytes handed to the sink."""
     chunk = chunk or STREAM_CHUNK
     pieces = [(off, t) for off, t in pieces if t.numel()]
@@ -918,21 +922,22 @@ def stream_device_bytes(pieces, sink, chunk=None):
     with torch.cuda.device(dev):
         copy_stream = torch.cuda.Stream(device=dev)
         copy_stream.wait_stream(torch.cuda.current_stream(dev))
-        events = [None, None]
+        events = [None] * RING
 
         def start(k):
             _, t, lo, hi = spans[k]
             with torch.cuda.stream(copy_stream):
-                bufs[k & 1][:hi - lo].copy_(t[lo:hi], non_blocking=True)
-                events[k & 1] = torch.cuda.Event()
-                events[k & 1].record(copy_stream)
+                bufs[k % RING][:hi - lo].copy_(t[lo:hi], non_blocking=True)
+                events[k % RING] = torch.cuda.Event()
+                events[k % RING].record(copy_stream)
 
-        start(0)
+        for k in range(min(RING - 1, len(spans))):
+            start(k)
         for k, (off, _, lo, hi) in enumerate(spans):
-            events[k & 1].synchronize()
-            if k + 1 < len(spans):
-                start(k + 1)
-            sink(memoryview(bufs[k & 1].numpy())[:hi - lo], off)
+            events[k % RING].synchronize()
+            if k + RING - 1 < len(spans):
+                start(k + RING - 1)          # its buffer held chunk k - 1, consumed in the previous iteration
+            sink(memoryview(bufs[k % RING].numpy())[:hi - lo], off)
             total += hi - lo
         torch.cuda.current_stream(dev).wait_stream(copy_stream)
     return total
