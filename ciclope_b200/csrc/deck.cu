@@ -478,21 +478,20 @@ struct ElemEmitParams {
     u32* warp_total;         // [n_warp_tiles] bytes of every 32-element tile
     u64* warp_off;           // [n_warp_tiles] exclusive scan of warp_total
     i64 n_warp_tiles;
+    u32* tile_counter;       // next chunk of EE2_CHUNK tiles to hand out (k_emit_elements2, dynamic schedule)
 };
 
-// Line builder: bytes are appended to a 32-bit accumulator and leave as aligned 32-bit
-// shared-memory stores; only the first and last partial words of a line use byte stores.
+// Line builder: bytes are appended to a 32-bit accumulator and leave as aligned 32-bit shared-memory
+// stores.  A line's first word is stored whole with its low `d` bytes zero (they belong to the previous
+// line, which sits in the neighbouring lane); the last partial word of every line is merged into the
+// staging area by lw_finish after the warp has synchronised -- no byte stores anywhere.
 struct LineWriter {
     char* wp;      // 4-byte aligned staging address of the word being assembled
     u32 acc;       // its low `d` bytes are valid
     u32 d;         // 0..3
-    u32 lead;      // > 0 until the first word has been stored: bytes [0, lead) of it belong to the
-                   // previous line and must not be overwritten (only looked at when FIRST)
 };
 
-// append the nd significant digits of a raw12 number followed by `sep`.  FIRST = the line's first
-// word may still be pending (fields 0 and 1); later fields use plain predicated word stores.
-template <bool FIRST>
+// append the nd significant digits of a raw12 number followed by `sep`
 __device__ __forceinline__ void lw_append(LineWriter& w, u32 r0, u32 r1, u32 r2, int nd, u32 sep)
 {
     const u32 W0 = r0 + 0x30303030u, W1 = r1 + 0x30303030u, W2 = r2 + 0x30303030u;
@@ -513,20 +512,7 @@ __device__ __forceinline__ void lw_append(LineWriter& w, u32 r0, u32 r1, u32 r2,
     const u32 O3 = __funnelshift_l(A2, 0u, s8);
     const u32 tot = w.d + (u32)nd + 1u;       // bytes now held by O0..O3 (<= 14)
     u32* p = reinterpret_cast<u32*>(w.wp);
-    if (FIRST) {
-        if (tot >= 4u) {
-            if (w.lead) {
-#pragma unroll
-                for (u32 k = 1; k < 4; ++k)
-                    if (k >= w.lead) w.wp[k] = (char)(O0 >> (8 * k));
-                w.lead = 0;
-            } else {
-                p[0] = O0;
-            }
-        }
-    } else {
-        if (tot >= 4u) p[0] = O0;
-    }
+    if (tot >= 4u) p[0] = O0;
     if (tot >= 8u) p[1] = O1;
     if (tot >= 12u) p[2] = O2;
     w.acc = tot >= 8u ? (tot >= 12u ? O3 : O2) : (tot >= 4u ? O1 : O0);
@@ -572,14 +558,7 @@ __device__ __forceinline__ void lw_append_block(LineWriter& w, const u32 (&F)[4]
             else Bm |= field_chars<LAST>(F, k, 12 - N) << (8 * fs);
         }
         const u32 outw = (m == 0) ? (w.acc | (Bm << s8)) : __funnelshift_l(prev, Bm, s8);
-        if (m == 0 && w.lead) {
-#pragma unroll
-            for (u32 q = 1; q < 4; ++q)
-                if (q >= w.lead) w.wp[q] = (char)(outw >> (8 * q));
-            w.lead = 0;
-        } else {
-            reinterpret_cast<u32*>(w.wp)[m] = outw;
-        }
+        reinterpret_cast<u32*>(w.wp)[m] = outw;
         prev = Bm;
     }
     w.acc = __funnelshift_l(prev, 0u, s8);
@@ -607,17 +586,20 @@ __device__ __forceinline__ void lw_append_half(LineWriter& w, const u32 (&F)[4][
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const u32 a0 = F[k][0] - 0x30303030u, a1 = F[k][1] - 0x30303030u, a2 = F[k][2] - 0x30303030u;
-            lw_append<true>(w, a0, a1, a2, raw12_digits(a0, a1, a2), (LAST && k == 3) ? 0x0Au : 0x2Cu);
+            lw_append(w, a0, a1, a2, raw12_digits(a0, a1, a2), (LAST && k == 3) ? 0x0Au : 0x2Cu);
         }
     }
 }
 
-__device__ __forceinline__ void lw_finish(LineWriter& w)
+// The last partial word of a line shares its upper bytes with the first word of the next line, which the
+// neighbouring lane has stored by now (the caller synchronises the warp first): merge, keep the upper bytes.
+// Behind the last line of a tile the upper bytes are leftovers that the flush never copies.
+__device__ __forceinline__ void lw_finish(const LineWriter& w)
 {
-    // the last partial word shares its upper bytes with the next line: byte stores
-#pragma unroll
-    for (u32 k = 0; k < 3; ++k)
-        if (k < w.d) w.wp[k] = (char)(w.acc >> (8 * k));
+    if (w.d) {
+        u32* p = reinterpret_cast<u32*>(w.wp);
+        *p = (*p & (0xFFFFFFFFu << (8u * w.d))) | w.acc;
+    }
 }
 
 // Copy n staged bytes (stage[0..n), stage 16-byte aligned) to an arbitrarily aligned global dst:
@@ -779,134 +761,25 @@ __global__ void __launch_bounds__(256) k_tile_headers(ElemEmitParams P)
 
 #define ELEM_WARP_STAGE 3584     // bytes of staging per warp: 32 lines of <= 99 bytes + headers + pad
 
-// PERM: elements come from the GV-major permutation; WIDE: ids may exceed 32 bits.
-template <bool PERM, bool WIDE>
-__global__ void __launch_bounds__(256) k_emit_elements(ElemEmitParams P)
-{
-    __shared__ __align__(16) char stage_all[8 * ELEM_WARP_STAGE];
-    const u32 lane = threadIdx.x & 31u;
-    char* stage = stage_all + (threadIdx.x >> 5) * ELEM_WARP_STAGE;
-    const i64 wt = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);       // warp tile
-    if (wt >= P.n_warp_tiles) return;
-    const i64 j = wt * 32 + lane;
-    const bool active = j < P.n_el;
-    u64 b = 0, eid = 0;
-    int gv = P.single_gv;
-    u32 len = 0, hl = 0, flags = 0;
-    bool is_first = false;
-    if (active) {
-        elem_ids<PERM>(P, j, b, eid, gv);
-        flags = __ldg(P.nd8 + j);
-        is_first = (u64)j == __ldg(P.first + gv);
-        if (is_first) hl = __ldg(P.hdr_len + gv);
-        len = (u32)__ldg(P.len8 + j) + hl;          // len8 holds the line; the block header rides along
-    }
-    // warp exclusive scan of the byte counts
-    u32 incl = len;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 t = __shfl_up_sync(CFE_FULL_MASK, incl, o);
-        if (lane >= (u32)o) incl += t;
-    }
-    const u32 excl = incl - len;
-    const u32 total = __shfl_sync(CFE_FULL_MASK, incl, 31);
-    const u64 base = __ldg(P.warp_off + wt);
-    char* dst = P.out + base;
-    const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
-    const bool staged = pad + total <= (u32)ELEM_WARP_STAGE;
-    if (active) {
-        if (is_first && P.blk_off) P.blk_off[gv] = base + excl;
-        if (staged) {
-            // eid, b, b+1, b+RN+1, b+RN | b+SN, b+SN+1, b+SN+RN+1, b+SN+RN   (voxelFE.py:145-154)
-            u32 o = pad + excl;
-            if (hl) {
-                const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
-                for (u32 q = 0; q < hl; ++q) stage[o + q] = __ldg(h + q);
-                o += hl;
-            }
-            LineWriter w;
-            w.lead = o & 3u;
-            w.d = w.lead;
-            w.acc = 0;
-            w.wp = stage + (o - w.lead);
-            u32 r0, r1, r2, low4;
-            raw12<WIDE>(eid, r0, r1, r2, low4);
-            lw_append<true>(w, r0, r1, r2, raw12_digits(r0, r1, r2), 0x2Cu);
-            const bool same = (flags & 0x80u) != 0;
-            const int nlo = (int)(flags & 15u);
-            // the four (v, v+1) pairs share everything but the low four digits (unless those wrap)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                u32 F[4][3];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const u64 v0 = b + (q ? P.RN : 0) + (h ? P.SN : 0);
-                    const int f_lo = q ? 3 : 0;               // slot of v
-                    const int f_hi = q ? 2 : 1;               // slot of v + 1
-                    raw12<WIDE>(v0, r0, r1, r2, low4);
-                    F[f_lo][0] = r0 + 0x30303030u; F[f_lo][1] = r1 + 0x30303030u; F[f_lo][2] = r2 + 0x30303030u;
-                    if (low4 != 9999u) {
-                        F[f_hi][0] = F[f_lo][0]; F[f_hi][1] = F[f_lo][1];
-                        F[f_hi][2] = raw4(low4 + 1u) + 0x30303030u;
-                    } else {
-                        u32 dummy;
-                        raw12<WIDE>(v0 + 1, r0, r1, r2, dummy);
-                        F[f_hi][0] = r0 + 0x30303030u; F[f_hi][1] = r1 + 0x30303030u; F[f_hi][2] = r2 + 0x30303030u;
-                    }
-                }
-                if (h == 0) lw_append_half<false>(w, F, nlo, same);
-                else lw_append_half<true>(w, F, nlo, same);
-            }
-            lw_finish(w);
-        } else {
-            // pathological warp tile (dozens of block headers): direct byte writes
-            char* p = dst + excl;
-            if (hl) {
-                const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
-                for (u32 q = 0; q < hl; ++q) p[q] = __ldg(h + q);
-                p += hl;
-            }
-            const u64 vals[9] = {eid, b, b + 1, b + P.RN + 1, b + P.RN, b + P.SN, b + P.SN + 1,
-                                 b + P.SN + P.RN + 1, b + P.SN + P.RN};
-#pragma unroll 1
-            for (int f = 0; f < 9; ++f) {
-                const int n = digits_u64(vals[f]);
-                p += n;
-                put_u64_back(p, vals[f], n);
-                *p++ = (f == 8) ? '\n' : ',';
-            }
-        }
-    }
-    __syncwarp();
-    if (!staged) return;
-    // stream the warp's span [pad, pad + total) to dst: aligned 16-byte chunks, bytes at the edges
-    char* gbase = dst - pad;
-    const u32 end = pad + total;
-    const u32 c0 = pad ? 1u : 0u, c1 = end >> 4;
-    {
-        const char* sp = stage + 16u * (c0 + lane);
-        char* gp = gbase + 16u * (c0 + lane);
-#pragma unroll 2
-        for (u32 c = c0 + lane; c < c1; c += 32u, sp += 512, gp += 512)
-            *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
-    }
-    // partial head / tail chunks: fewer than 16 bytes each, one byte per lane
-    if (pad) {
-        const u32 k = pad + lane;
-        if (k < 16u && k < end) gbase[k] = stage[k];
-    }
-    if (c1 >= c0) {
-        const u32 k = (c1 << 4) + lane;
-        if (k < end) gbase[k] = stage[k];
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // Version 2 of the element emitter: PERSISTENT CTAs that keep a 10000-entry table "four decimal
 // digits -> four ASCII bytes" in shared memory (40 KB, filled once per CTA), so that a 12-digit id
 // costs two divisions and three table reads instead of three SWAR conversions; the ids v, v+1, v+RN,
 // v+RN+1 of one node layer share their eight leading digits unless the low four wrap.  Everything else
 // (warp-autonomous staging, static-layout half blocks, 16-byte flush) is as in k_emit_elements.
+// EE2_LATE_LOADS: the loads of the next tile are issued behind the bulk copy of the current one (their latency
+// then runs in parallel with the copy engine reading the staging area) instead of at the top of the iteration
+// (where the membar of fence.proxy.async waits for them).  EE2_DYNAMIC: tiles are handed out in chunks of
+// EE2_CHUNK consecutive tiles from a global counter instead of a fixed stride, so that no SM idles at the end.
+#ifndef EE2_LATE_LOADS
+#define EE2_LATE_LOADS 0
+#endif
+#ifndef EE2_DYNAMIC
+#define EE2_DYNAMIC 1
+#endif
+#ifndef EE2_CHUNK
+#define EE2_CHUNK 8u
+#endif
 #define EE2_WARPS 16
 #define EE2_THREADS (32 * EE2_WARPS)
 #define EE2_LUT_BYTES 40000
@@ -959,9 +832,13 @@ __device__ __forceinline__ void lw_append_line8(LineWriter& w, const u32 (&F0)[4
     lw_append_block<N, true>(w, F1);
 }
 
+template <bool WIDE> struct ElemId { typedef u32 type; };
+template <> struct ElemId<true> { typedef u64 type; };
+
 template <bool PERM, bool WIDE>
 __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParams P)
 {
+    typedef typename ElemId<WIDE>::type id_t;      // ids of a slab below 2^32 are computed in 32 bits
     extern __shared__ __align__(16) char ee2_smem[];
     u32* lut = reinterpret_cast<u32*>(ee2_smem);
     for (u32 i = threadIdx.x; i < 10000u; i += EE2_THREADS) lut[i] = raw4(i) + 0x30303030u;
@@ -969,93 +846,130 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
     const u32 lane = threadIdx.x & 31u;
     char* stage = ee2_smem + EE2_LUT_BYTES + (threadIdx.x >> 5) * ELEM_WARP_STAGE;
     const u32 RN32 = (u32)P.RN;
-    const i64 stride = (i64)gridDim.x * EE2_WARPS;
-    i64 wt = (i64)blockIdx.x * EE2_WARPS + (threadIdx.x >> 5);
-    // software pipeline: the global loads of the NEXT tile are issued before the current one is formatted
+    // tile and element indices fit 32 bits (elem_vox holds 32-bit voxel indices, so n_el < 2^32)
+    const u32 n_el = (u32)P.n_el, n_tiles = (u32)P.n_warp_tiles;
+#if EE2_DYNAMIC
+    // chunk c = tiles [c * EE2_CHUNK, (c + 1) * EE2_CHUNK); the first gridDim.x * EE2_WARPS chunks are the warps' own,
+    // the counter (zeroed by the launcher) hands out the rest
+    u32 wt = (blockIdx.x * EE2_WARPS + (threadIdx.x >> 5)) * EE2_CHUNK;
+    u32 grabbed = 0;
+#else
+    const u32 stride = gridDim.x * EE2_WARPS;
+    u32 wt = blockIdx.x * EE2_WARPS + (threadIdx.x >> 5);
+#endif
+    // the low words of first[] are all there is (first[g] <= n_el)
+    const u32* first32 = reinterpret_cast<const u32*>(P.first);
+    const u32 first_single = PERM ? 0u : __ldg(first32 + 2 * P.single_gv);
+    // software pipeline: the global loads of the NEXT tile are in flight while the current one is formatted / flushed
     u32 nx_v = 0, nx_rank = 0, nx_flags = 0, nx_len = 0;
     int nx_gv = P.single_gv;
     u64 nx_base = 0;
-    // GV-major order: grey value block of the warp's current tile start.  A warp visits its tiles in
-    // ascending order, so the block only moves forward: one (warp-uniform) probe per tile instead of a
+    // GV-major order: grey value block of the warp's current tile start.  Within a chunk a warp visits its tiles
+    // in ascending order, so the block only moves forward: one (warp-uniform) probe per tile instead of a
     // search per line; lanes look further only in the rare tile that contains a block boundary.
     int g_tile = 0;
-    auto load_tile = [&](i64 t) {
-        const i64 jj = t * 32 + lane;
+    auto load_tile = [&](u32 t) {
+        const u32 jj = t * 32u + lane;
         if (PERM) {
-            const u64 j0 = (u64)t * 32u;
-            while (g_tile < 255 && __ldg(P.first + g_tile + 1) <= j0) ++g_tile;
+            const u32 j0 = t * 32u;
+            while (g_tile < 255 && __ldg(first32 + 2 * (g_tile + 1)) <= j0) ++g_tile;
             nx_gv = g_tile;
-            if (g_tile < 255 && __ldg(P.first + g_tile + 1) <= j0 + 31u)
-                while (nx_gv < 255 && __ldg(P.first + nx_gv + 1) <= (u64)jj) ++nx_gv;
+            if (g_tile < 255 && __ldg(first32 + 2 * (g_tile + 1)) <= j0 + 31u)
+                while (nx_gv < 255 && __ldg(first32 + 2 * (nx_gv + 1)) <= jj) ++nx_gv;
         }
-        if (jj < P.n_el) {
+        if (jj < n_el) {
             if (PERM) { const uint2 e = __ldg(P.perm + jj); nx_v = e.x; nx_rank = e.y; }
-            else { nx_v = __ldg(P.elem_vox + jj); nx_rank = (u32)jj; }
+            else { nx_v = __ldg(P.elem_vox + jj); nx_rank = jj; }
             nx_flags = __ldg(P.nd8 + jj);
             nx_len = (u32)__ldg(P.len8 + jj);
         }
         nx_base = __ldg(P.warp_off + t);
     };
-    if (wt < P.n_warp_tiles) {
+    if (wt < n_tiles) {
         if (PERM) g_tile = gv_of_index(P.first, (u64)wt * 32u);
         load_tile(wt);
     }
-    for (; wt < P.n_warp_tiles; wt += stride) {
-        const i64 j = wt * 32 + lane;
-        const bool active = j < P.n_el;
+    while (wt < n_tiles) {
+        const u32 j = wt * 32u + lane;
+        const bool active = j < n_el;
         const u32 v = nx_v, rank = nx_rank, flags = nx_flags, line_len = nx_len;
         const int gv = nx_gv;
         const u64 base = nx_base;
-        if (wt + stride < P.n_warp_tiles) load_tile(wt + stride);
-        u64 b = 0, eid = 0;
-        u32 len = 0, hl = 0;
-        bool is_first = false;
+        // the tile after this one
+#if EE2_DYNAMIC
+        u32 nxt = wt + 1u;
+        if ((wt & (EE2_CHUNK - 1u)) == EE2_CHUNK - 2u) {
+            // one tile before the chunk ends: ask for the next chunk (the answer is read an iteration later)
+            if (lane == 0) grabbed = atomicAdd(P.tile_counter, 1u);
+        } else if ((wt & (EE2_CHUNK - 1u)) == EE2_CHUNK - 1u) {
+            nxt = (gridDim.x * EE2_WARPS + __shfl_sync(CFE_FULL_MASK, grabbed, 0)) * EE2_CHUNK;
+        }
+#else
+        const u32 nxt = wt + stride;
+#endif
+#if !EE2_LATE_LOADS
+        if (nxt < n_tiles) load_tile(nxt);
+#endif
+        const bool is_first = active && j == (PERM ? __ldg(first32 + 2 * gv) : first_single);
+        u32 hl = 0;
+        if (is_first) hl = __ldg(P.hdr_len + gv);
+        const u32 len = active ? line_len + hl : 0u;   // the block header rides along with its first line
+        // byte offset of every line in the tile: lane * len when all 32 lengths agree (the rule: one vote
+        // and one add-reduction), else a warp scan
+        const u32 total = __reduce_add_sync(CFE_FULL_MASK, len);
+        u32 excl;
+        if (__all_sync(CFE_FULL_MASK, len * 32u == total)) {
+            excl = lane * len;
+        } else {
+            u32 incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 t = __shfl_up_sync(CFE_FULL_MASK, incl, o);
+                if (lane >= (u32)o) incl += t;
+            }
+            excl = incl - len;
+        }
+        char* dst = P.out + base;
+        const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
+        const bool staged = pad + total <= (u32)ELEM_WARP_STAGE;
+        LineWriter w;
+        w.wp = stage; w.acc = 0; w.d = 0;
         if (active) {
             const u32 s = fd_div(v, P.dYX);
             const u32 rem = v - s * P.YX32;
             const u32 r = fd_div(rem, P.dX);
             const u32 c = rem - r * P.X32;
-            b = (u64)(P.SN * ((i64)s + P.z0) + P.RN * (i64)r + (i64)c);
-            eid = (u64)(P.eid_offset + (i64)rank + 1);
-            is_first = (u64)j == __ldg(P.first + gv);
-            if (is_first) hl = __ldg(P.hdr_len + gv);
-            len = line_len + hl;                       // the block header rides along with its first line
-        }
-        u32 incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 t = __shfl_up_sync(CFE_FULL_MASK, incl, o);
-            if (lane >= (u32)o) incl += t;
-        }
-        const u32 excl = incl - len;
-        const u32 total = __shfl_sync(CFE_FULL_MASK, incl, 31);
-        char* dst = P.out + base;
-        const u32 pad = (u32)(reinterpret_cast<uintptr_t>(dst) & 15u);
-        const bool staged = pad + total <= (u32)ELEM_WARP_STAGE;
-        if (active) {
+            id_t b, eid;
+            if (WIDE) {
+                b = (id_t)(P.SN * ((i64)s + P.z0) + P.RN * (i64)r + (i64)c);
+                eid = (id_t)(P.eid_offset + (i64)rank + 1);
+            } else {
+                b = (id_t)((u32)P.SN * (s + (u32)P.z0) + RN32 * r + c);
+                eid = (id_t)((u32)P.eid_offset + rank + 1u);
+            }
             if (is_first && P.blk_off) P.blk_off[gv] = base + excl;
             if (staged) {
                 // eid, b, b+1, b+RN+1, b+RN | b+SN, b+SN+1, b+SN+RN+1, b+SN+RN   (voxelFE.py:145-154)
                 u32 o = pad + excl;
                 if (hl) {
+                    // block header: byte copy; the bytes it leaves in the line's first word start the accumulator
                     const char* h = P.hdr_text + gv * ELEM_HDR_SLOT;
                     for (u32 q = 0; q < hl; ++q) stage[o + q] = __ldg(h + q);
                     o += hl;
+                    for (u32 q = 0; q < (o & 3u) && q < hl; ++q)
+                        w.acc |= (u32)(unsigned char)__ldg(h + hl - 1u - q) << (8u * ((o & 3u) - 1u - q));
                 }
-                LineWriter w;
-                w.lead = o & 3u;
-                w.d = w.lead;
-                w.acc = 0;
-                w.wp = stage + (o - w.lead);
+                w.d = o & 3u;
+                w.wp = stage + (o - w.d);
                 const bool same = (flags & 0x80u) != 0;
                 const int nlo = (int)(flags & 15u);
                 u32 e0, e1, e2, low4;
                 asc12<WIDE>(lut, eid, e0, e1, e2, low4);
                 const int nde = same ? (int)line_len - 9 - 8 * nlo : id_digits<WIDE>(eid);
-                lw_append<true>(w, e0 - 0x30303030u, e1 - 0x30303030u, e2 - 0x30303030u, nde, 0x2Cu);
+                lw_append(w, e0 - 0x30303030u, e1 - 0x30303030u, e2 - 0x30303030u, nde, 0x2Cu);
                 u32 F0[4][3], F1[4][3];
                 layer_fields<WIDE>(lut, b, RN32, F0);
-                layer_fields<WIDE>(lut, b + (u64)P.SN, RN32, F1);
+                layer_fields<WIDE>(lut, b + (id_t)P.SN, RN32, F1);
                 if (same) {
                     switch (nlo) {
                     case 1: lw_append_line8<1>(w, F0, F1); break;
@@ -1073,7 +987,6 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
                     lw_append_half<false>(w, F0, nlo, false);
                     lw_append_half<true>(w, F1, nlo, false);
                 }
-                lw_finish(w);
             } else {
                 // pathological warp tile (dozens of block headers): direct byte writes
                 char* p = dst + excl;
@@ -1085,10 +998,10 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
 #pragma unroll 1
                 for (int f = 0; f < 9; ++f) {
                     // eid, b, b+1, b+RN+1, b+RN, b+SN, b+SN+1, b+SN+RN+1, b+SN+RN
-                    u64 val = eid;
+                    u64 val = (u64)eid;
                     if (f) {
                         const int q = f - 1;
-                        val = b + ((q & 4) ? (u64)P.SN : 0ull) + (((q & 3) == 1 || (q & 3) == 2) ? 1ull : 0ull) +
+                        val = (u64)b + ((q & 4) ? (u64)P.SN : 0ull) + (((q & 3) == 1 || (q & 3) == 2) ? 1ull : 0ull) +
                               (((q & 3) >= 2) ? (u64)P.RN : 0ull);
                     }
                     const int n = digits_u64(val);
@@ -1098,8 +1011,10 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
                 }
             }
         }
-        __syncwarp();
+        __syncwarp();     // every line's whole words are in the staging area
         if (staged) {
+            if (active) lw_finish(w);
+            __syncwarp();
             // stream the warp's span [pad, pad + total) to dst: aligned 16-byte chunks, bytes at the edges
             char* gbase = dst - pad;
             const u32 end = pad + total;
@@ -1122,20 +1037,23 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
                     *reinterpret_cast<uint4*>(gbase + 16u * c) = *reinterpret_cast<const uint4*>(stage + 16u * c);
             }
 #endif
-            if (pad) {
-                const u32 k = pad + lane;
-                if (k < 16u && k < end) gbase[k] = stage[k];
-            }
-            if (c1 >= c0) {
-                const u32 k = (c1 << 4) + lane;
-                if (k < end) gbase[k] = stage[k];
+            // the two partial chunks: lanes 0-15 take the head [pad, 16), lanes 16-31 the tail [16 c1, end)
+            {
+                const bool head = lane < 16u;
+                const u32 k = head ? lane : (c1 << 4) + lane - 16u;
+                const bool ok = k < end && (head ? (pad != 0u && k >= pad) : c1 >= c0);
+                if (ok) gbase[k] = stage[k];
             }
         }
+#if EE2_LATE_LOADS
+        if (nxt < n_tiles) load_tile(nxt);
+#endif
 #if EE2_BULK_FLUSH
         // the bulk copy must have READ the staging region before the next tile overwrites it
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #endif
         __syncwarp();     // the staging region is reused by the next tile
+        wt = nxt;
     }
 #if EE2_BULK_FLUSH
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1169,7 +1087,8 @@ static void elem_params(ElemEmitParams& P, const uint32_t* elem_vox, const void*
     P.len8 = reinterpret_cast<uint8_t*>(w); w += a;
     P.nd8 = reinterpret_cast<uint8_t*>(w); w += a;
     P.warp_total = reinterpret_cast<u32*>(w); w += ((size_t)nw * 4 + 15) & ~(size_t)15;
-    P.warp_off = reinterpret_cast<u64*>(w); w += (size_t)nw * 8 + 16;
+    P.warp_off = reinterpret_cast<u64*>(w); w += (size_t)nw * 8;
+    P.tile_counter = reinterpret_cast<u32*>(w); w += 16;
     *scan_ws = w;
     P.n_warp_tiles = nw;
 }
@@ -1239,8 +1158,14 @@ extern "C" int cfe_emit_elements(const uint32_t* elem_vox, const void* perm, int
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
         CFE_CHECK_CUDA(cudaFuncSetAttribute(k_emit_elements2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EE2_SMEM));
     }
-    // persistent CTAs: two per SM (97 KB of shared memory each), every warp strides over the warp tiles
-    i64 g2 = (P.n_warp_tiles + EE2_WARPS - 1) / EE2_WARPS;
+    // persistent CTAs: two per SM (97 KB of shared memory each)
+#if EE2_DYNAMIC
+    // every warp starts with its own chunk of EE2_CHUNK tiles and takes the following ones from the counter
+    CFE_CHECK_CUDA(cudaMemsetAsync(P.tile_counter, 0, sizeof(u32), stream));
+    i64 g2 = ((P.n_warp_tiles + EE2_CHUNK - 1) / EE2_CHUNK + EE2_WARPS - 1) / EE2_WARPS;
+#else
+    i64 g2 = (P.n_warp_tiles + EE2_WARPS - 1) / EE2_WARPS;     // every warp strides over the warp tiles
+#endif
     if (g2 > 2 * (i64)sms) g2 = 2 * (i64)sms;
     if (perm) {
         if (wide) k_emit_elements2<true, true><<<(unsigned)g2, EE2_THREADS, EE2_SMEM, stream>>>(P);
