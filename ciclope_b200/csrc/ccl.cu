@@ -296,7 +296,11 @@ k_ccl_tile(const u32* __restrict__ bits, const u32* __restrict__ pref, const u64
 
 // Run pairs across tile borders.  Work items = words of the border rows: first the rows r = k * TR (k >= 1) of
 // every slice (against row r - 1), then every row of the slices s = k * TS (k >= 1) (against slice s - 1).
-__global__ void __launch_bounds__(256)
+// The items are ordered so that the TS rows of ONE tile border follow each other (a CTA of 512 threads = one border
+// of 8 slices x 64 words at 2048^2): the rows of a border mostly join the same two tile roots, and the CTA's table
+// of pairs already united then catches the repeats (in slice-major order every CTA re-united them: 0.57 ms).
+#define CCL_BORDER_THREADS 512
+__global__ void __launch_bounds__(CCL_BORDER_THREADS)
 k_ccl_border(const u32* __restrict__ bits, const u32* __restrict__ pref, CclGeom G, i64 n0, i64 n_items,
              u32* __restrict__ parent)
 {
@@ -311,9 +315,14 @@ k_ccl_border(const u32* __restrict__ bits, const u32* __restrict__ pref, CclGeom
     i64 q = it / W;
     const int w = (int)(it - q * W);
     if (it < n0) {
+        // q = ((tile_s * (tiles_r - 1)) + (k - 1)) * TS + slice of the tile
         const int per_slice = G.tiles_r - 1;
-        const i64 s = q / per_slice;
-        const int r = ((int)(q - s * per_slice) + 1) * G.TR;
+        const i64 b = q / G.TS;
+        const int ds = (int)(q - b * G.TS);
+        const i64 ts = b / per_slice;
+        const int r = ((int)(b - ts * per_slice) + 1) * G.TR;
+        const i64 s = ts * G.TS + ds;
+        if (s >= G.Z) return;
         row = s * G.Y + r;
         dir = 0;
     } else {
@@ -572,10 +581,11 @@ extern "C" int cfe_ccl_label(const uint32_t* bits, const uint32_t* pref, const u
     CFE_CHECK_LAUNCH("k_ccl_tile");
     k_ccl_inner<<<n_tiles, 256, 0, stream>>>(bits, pref, G, parent, tile_flag);
     CFE_CHECK_LAUNCH("k_ccl_inner");
-    const i64 n0 = Z * (i64)(G.tiles_r - 1) * G.W;
+    const i64 n0 = (i64)G.tiles_s * G.TS * (i64)(G.tiles_r - 1) * G.W;     // rows of the last tile layer beyond Z: skipped
     const i64 n1 = (i64)(G.tiles_s - 1) * Y * G.W;
     if (n0 + n1 > 0) {
-        k_ccl_border<<<(unsigned)((n0 + n1 + 255) / 256), 256, 0, stream>>>(bits, pref, G, n0, n0 + n1, parent);
+        k_ccl_border<<<(unsigned)((n0 + n1 + CCL_BORDER_THREADS - 1) / CCL_BORDER_THREADS), CCL_BORDER_THREADS, 0, stream>>>(
+            bits, pref, G, n0, n0 + n1, parent);
         CFE_CHECK_LAUNCH("k_ccl_border");
     }
     k_ccl_finish<<<grid_stride_blocks(), 256, 0, stream>>>(parent, size, nr);
