@@ -963,7 +963,7 @@ def deck_program(ctx, m, templatefile, matprop=None, keywords=['NSET', 'ELSET'],
 def write_deck_program(ctx, deck, fileout):
     """All ranks put their pieces of the global deck at the offsets of the global layout: into ONE file
     (``fileout`` = path; ``os.pwrite``) or into any object with ``pwrite(buffer, offset)``.  The bytes
-    leave the GPU through the two-buffer pinned ring of ``voxelFE.stream_device_bytes`` (the copy of the
+    leave the GPU through the pinned staging ring of ``voxelFE.stream_device_bytes`` (the copy of the
     next chunk overlaps the write of this one)."""
     to_path = isinstance(fileout, (str, bytes, os.PathLike))
     if to_path:

@@ -956,7 +956,7 @@ def mesh2voxelfe(mesh, templatefile, fileout, matprop=None, keywords=['NSET', 'E
 
     ``fileout`` is the path of the .INP file.  Additively it may be a pinned/CPU uint8
     ``torch.Tensor`` that receives the deck bytes, or an object with a ``write(buffer)`` method (an open
-    binary file, a socket file, a hasher ...) that is fed the deck in order through a two-buffer pinned
+    binary file, a socket file, a hasher ...) that is fed the deck in order through a three-buffer pinned
     ring -- decks larger than the host's memory stream through it.  Both return the number of bytes.
     """
     if verbose:
