@@ -234,6 +234,8 @@ class HotPath:
         self.world, self.rank, self.Zg, self.z0 = world, rank, Zg, z0
         import torch
         self.torch = torch
+        from ciclope_b200.preprocess import mask_image
+        self.mask_image = mask_image
         if world == 1:
             from ciclope_b200 import preprocess, voxelFE
             self.pre, self.vfe = preprocess, voxelFE
@@ -275,7 +277,7 @@ class HotPath:
         mark()
         L = self.ccl(bw)
         mark()
-        vol = L if grey is None else torch.where(L, grey, torch.zeros((), dtype=torch.uint8, device=grey.device))
+        vol = L if grey is None else self.mask_image(grey, L, makecopy=True)     # masked = I; masked[~L] = 0
         mesh = self.grid(vol)
         mark()
         deck, local_b, total_b = self.deck(mesh, **kw)

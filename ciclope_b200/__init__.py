@@ -10,6 +10,6 @@ mirror ``ciclope.utils.preprocess.{remove_unconnected, remove_largest, fill_void
 __version__ = "0.1.0"
 
 from . import preprocess, voxelFE  # noqa: E402,F401
-from .preprocess import (add_cap, embed, fill_voids, gaussian, periosteummask, remove_largest,  # noqa: E402,F401
-                         remove_unconnected, resample, segment)
+from .preprocess import (add_cap, embed, fill_voids, gaussian, mask_image, periosteummask,  # noqa: E402,F401
+                         remove_largest, remove_unconnected, resample, segment)
 from .voxelFE import matpropdictionary, mesh2voxelfe, vol2h5ParOSol, vol2ugrid  # noqa: E402,F401

@@ -100,6 +100,7 @@ _SIGNATURES = {
                                   ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, c_vp, c_vp, c_vp]),
     "cfe_box_andnot_u8": (c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "cfe_masked_set_u8": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp, c_vp]),
+    "cfe_masked_keep_u8": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "cfe_disk_dilate_bits": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
     "cfe_line_or_bits": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "cfe_unpack_bits": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp]),

@@ -1259,6 +1259,8 @@ extern "C" int cfe_box_andnot_u8(const uint8_t* img, int64_t Z, int64_t Y, int64
     return 0;
 }
 
+// KEEP = false: out = mask ? val : img   (I[mask] = val);   KEEP = true: out = mask ? img : 0   (I[~mask] = 0)
+template <bool KEEP>
 __global__ void __launch_bounds__(256)
 k_masked_set_u8(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, i64 n, u32 val4,
                 uint8_t* __restrict__ out)
@@ -1270,21 +1272,24 @@ k_masked_set_u8(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mas
         uint4 r;
         // mask bytes are 0 / 1: 0xff per selected byte
         const u32 mx = m.x * 0xffu, my = m.y * 0xffu, mz = m.z * 0xffu, mw = m.w * 0xffu;
-        r.x = (a.x & ~mx) | (val4 & mx); r.y = (a.y & ~my) | (val4 & my);
-        r.z = (a.z & ~mz) | (val4 & mz); r.w = (a.w & ~mw) | (val4 & mw);
+        if (KEEP) {
+            r.x = a.x & mx; r.y = a.y & my; r.z = a.z & mz; r.w = a.w & mw;
+        } else {
+            r.x = (a.x & ~mx) | (val4 & mx); r.y = (a.y & ~my) | (val4 & my);
+            r.z = (a.z & ~mz) | (val4 & mz); r.w = (a.w & ~mw) | (val4 & mw);
+        }
         reinterpret_cast<uint4*>(out)[g] = r;
     }
     for (i64 i = (n16 << 4) + (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x)
-        out[i] = mask[i] ? (uint8_t)val4 : img[i];
+        out[i] = KEEP ? (mask[i] ? img[i] : (uint8_t)0) : (mask[i] ? (uint8_t)val4 : img[i]);
 }
 
-// out[i] = mask[i] ? val : img[i]  (mask bytes 0 / 1; out may alias img; all 16-byte aligned)
-extern "C" int cfe_masked_set_u8(const uint8_t* img, const uint8_t* mask, int64_t n, int val, uint8_t* out,
-                                 cudaStream_t stream)
+static int masked_launch(bool keep, const uint8_t* img, const uint8_t* mask, int64_t n, int val, uint8_t* out,
+                         cudaStream_t stream, const char* who)
 {
     if (n <= 0) return 0;
     if ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(out)) & 15u) {
-        cfe_set_error("cfe_masked_set_u8: buffers must be 16-byte aligned");
+        cfe_set_error("%s: buffers must be 16-byte aligned", who);
         return -1;
     }
     int dev = 0, sms = 148;
@@ -1292,7 +1297,21 @@ extern "C" int cfe_masked_set_u8(const uint8_t* img, const uint8_t* mask, int64_
     i64 blocks = (n / 16 + 255) / 256;
     if (blocks > (i64)sms * 16) blocks = (i64)sms * 16;
     if (blocks < 1) blocks = 1;
-    k_masked_set_u8<<<(unsigned)blocks, 256, 0, stream>>>(img, mask, n, 0x01010101u * (u32)(val & 255), out);
+    if (keep) k_masked_set_u8<true><<<(unsigned)blocks, 256, 0, stream>>>(img, mask, n, 0u, out);
+    else k_masked_set_u8<false><<<(unsigned)blocks, 256, 0, stream>>>(img, mask, n, 0x01010101u * (u32)(val & 255), out);
     CFE_CHECK_LAUNCH("k_masked_set_u8");
     return 0;
+}
+
+// out[i] = mask[i] ? val : img[i]  (mask bytes 0 / 1; out may alias img; all 16-byte aligned)
+extern "C" int cfe_masked_set_u8(const uint8_t* img, const uint8_t* mask, int64_t n, int val, uint8_t* out,
+                                 cudaStream_t stream)
+{
+    return masked_launch(false, img, mask, n, val, out, stream, "cfe_masked_set_u8");
+}
+
+// out[i] = mask[i] ? img[i] : 0  -- `masked = I; masked[~L] = 0` of the grey-scale branch (pipeline.py:240-242)
+extern "C" int cfe_masked_keep_u8(const uint8_t* img, const uint8_t* mask, int64_t n, uint8_t* out, cudaStream_t stream)
+{
+    return masked_launch(true, img, mask, n, 0, out, stream, "cfe_masked_keep_u8");
 }

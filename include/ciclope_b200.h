@@ -363,6 +363,10 @@ int cfe_box_andnot_u8(const uint8_t* img, int64_t Z, int64_t Y, int64_t X, int64
                       int64_t y1, int64_t x0, int64_t x1, uint8_t* out, cfe_stream_t s);
 int cfe_masked_set_u8(const uint8_t* img, const uint8_t* mask, int64_t n, int val, uint8_t* out, cfe_stream_t s);
 
+/* grey-scale branch of the pipeline (pipeline.py:240-242: `masked = I; masked[~L] = 0`; example 01 meshes `masked`):
+ * out[i] = mask[i] ? img[i] : 0, mask bytes 0 / 1; buffers 16-byte aligned; out may alias img. */
+int cfe_masked_keep_u8(const uint8_t* img, const uint8_t* mask, int64_t n, uint8_t* out, cfe_stream_t s);
+
 /* periosteummask (preprocess.py:357-420), slice-wise morphology on packed bits ([Z*Y rows][ceil(X/32)]).
  * cfe_disk_dilate_bits: every (Y, X) slice dilated by skimage's disk(r) (0 outside the slice); invert_in
  * dilates the complement, so erosion with border value 1 is the complement of the result and the background

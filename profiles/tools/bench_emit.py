@@ -21,4 +21,4 @@ torch.cuda.synchronize()
 ms = {}
 for name, a, b in _lib.PROFILE:
     ms[name] = ms.get(name, 0.0) + a.elapsed_time(b) / 5
-print(os.environ.get("CICLOPE_B200_LIB", "default"), "grey" if grey else "binary", {k: round(v, 3) for k, v in sorted(ms.items(), key=lambda kv: -kv[1])[:7]})
+print(os.environ.get("CICLOPE_B200_LIB", "default"), "grey" if grey else "binary", {k: round(v, 3) for k, v in sorted(ms.items(), key=lambda kv: -kv[1])[:14]})

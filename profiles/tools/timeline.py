@@ -2,31 +2,44 @@
 idle gap before every kernel, to see where the GPU waits on the host.  Diagnostic only -- numbers
 under a profiler are never bench values.
 
-    python profiles/tools/timeline.py [size] > gpurun_out/timeline.txt
+    python profiles/tools/timeline.py [Z,Y,X] [grey] > gpurun_out/timeline.txt
 """
+import os
 import sys
 
-sys.path.insert(0, '/root/repo')
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 import torch
 from torch.profiler import ProfilerActivity, profile
 
 import bench
 from ciclope_b200 import synth
 
-S = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-vol = synth.trabecular((S, S, S), 0, 0.30, 'cuda')
-for _ in range(5):
-    m, d = bench.gpu_step(vol)
-    del m, d
+shape = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256,2048,2048").split(","))
+grey = len(sys.argv) > 2 and sys.argv[2] == "grey"
+hp = bench.HotPath(1, 0, shape[0], 0)
+if grey:
+    g = synth.greyscale(shape, 0, 0.30, 'cuda')
+    bw = g > 0
+    kw = dict(keywords=['NSET', 'ELSET', 'PROPERTY'], matprop={"file": [bench.MAT_LINEAR], "range": [[1, 255]]})
+else:
+    g, bw, kw = None, synth.trabecular(shape, 0, 0.30, 'cuda'), {}
+
+
+def step():
+    r = hp.step(bw, g, None, **kw)
+    del r
+
+
+for _ in range(4):
+    step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
-        m, d = bench.gpu_step(vol)
-        del m, d
+        step()
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ev.sort(key=lambda e: e.time_range.start)
-# keep the last step: split at the largest gaps
 t_prev = None
 rows = []
 for e in ev:

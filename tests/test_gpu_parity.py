@@ -650,6 +650,34 @@ def test_segment_and_caps_vs_reference(cfe, golden_parosol):
         cfe.add_cap(g["cap/0/in"], 2, 0.5)
 
 
+@pytest.mark.parametrize("shape", [(5, 7, 9), (16, 32, 64), (3, 5, 2050), (1, 1, 15), (2, 3, 16)])
+def test_mask_image_is_the_reference_lines(cfe, shape):
+    """pipeline.py:240-242: `masked = I; masked[~L] = 0` -- in place, like the boolean-index assignment"""
+    import torch
+    rng = np.random.default_rng(sum(shape))
+    img = rng.integers(0, 256, shape).astype(np.uint8)
+    L = rng.random(shape) < 0.4
+    want = img.copy()
+    want[~L] = 0
+    a = img.copy()
+    r = cfe.preprocess.mask_image(a, L)
+    assert r is a and a.dtype == np.uint8 and np.array_equal(a, want)
+    b = img.copy()
+    r = cfe.preprocess.mask_image(b, L.astype(np.uint8), makecopy=True)
+    assert r is not b and np.array_equal(b, img) and np.array_equal(r, want)
+    t = torch.from_numpy(img).cuda()
+    r = cfe.preprocess.mask_image(t, torch.from_numpy(L).cuda())
+    assert r.data_ptr() == t.data_ptr() and np.array_equal(t.cpu().numpy(), want)
+    t = torch.from_numpy(img).cuda()
+    r = cfe.preprocess.mask_image(t, torch.from_numpy(L).cuda(), makecopy=True)
+    assert r.data_ptr() != t.data_ptr() and np.array_equal(t.cpu().numpy(), img) and np.array_equal(r.cpu().numpy(), want)
+    bw = img > 100
+    r = cfe.preprocess.mask_image(bw.copy(), L)
+    assert r.dtype == np.bool_ and np.array_equal(r, bw & L)
+    with pytest.raises(IndexError):
+        cfe.preprocess.mask_image(img.copy(), L[:, :, :-1] if shape[2] > 1 else np.zeros((1, 1, 2), bool))
+
+
 def test_segment_otsu_vs_oracle(cfe, orc):
     rng = np.random.default_rng(11)
     for shape in [(20, 30, 40), (7, 33, 65)]:
