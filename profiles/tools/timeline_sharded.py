@@ -4,7 +4,7 @@ Diagnostic only."""
 import os
 import sys
 
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import torch.distributed as dist
 from torch.profiler import ProfilerActivity, profile
@@ -15,10 +15,17 @@ from ciclope_b200 import sharded, synth
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-S = 512
-Zg, z0 = S * world, S * rank
-vol = synth.trabecular_slab((Zg, S, S), z0, z0 + S, seed=0, bvtv=0.30, device=torch.device("cuda", lr))
-step, _ = bench.make_sharded_steps(sharded.DistRunner(), Zg, z0)
+Zl, Y, X = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256,2048,2048").split(","))
+Zg, z0 = Zl * world, Zl * rank
+vol = synth.trabecular_slab((Zg, Y, X), z0, z0 + Zl, seed=0, bvtv=0.30, device=torch.device("cuda", lr))
+hp = bench.HotPath(world, rank, Zg, z0)
+
+
+def step(v):
+    r = hp.step(v)
+    return r[0], r[1]
+
+
 for _ in range(6):
     m, d = step(vol)
     del m, d
