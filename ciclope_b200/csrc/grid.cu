@@ -697,6 +697,74 @@ __device__ __forceinline__ bool set_eval(const CfeSetDesc& d, const SetGeom& g, 
     return hit;
 }
 
+// Eight candidates (ks, kr, kc .. kc + 7) of one box row at once: the same predicates as set_eval, evaluated on a
+// window of the voxel rows' words instead of voxel by voxel (a thread of k_sets_onepass owns eight consecutive
+// candidates; one by one they probe the same words 30-60 times).  Returns false when the case is left to set_eval.
+__device__ __forceinline__ bool set_eval8(const CfeSetDesc& d, const SetGeom& g, u32 ks, u32 kr, u32 kc,
+                                          i64 (&id)[8], u32& keep)
+{
+    const i64 s = d.s0 + (i64)ks;                 // GLOBAL coordinates
+    const int r = (int)d.r0 + (int)kr;
+    const int c0 = (int)d.c0 + (int)kc;
+    keep = 0;
+    if (d.kind == 2) {
+        const i64 sl = s - g.z0;
+        if (sl < 0 || sl >= g.Zl || c0 < 0) return false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) id[j] = 0;
+        if (r < 0 || r >= g.Y || c0 >= g.X) return true;            // no voxel there: nothing kept
+        const int w = c0 >> 5, sh = c0 & 31;
+        const size_t wi = ((size_t)sl * g.Y + r) * g.W + w;
+        const u32 w0 = __ldg(g.bits + wi);
+        const u32 w1 = (sh > 24 && w + 1 < g.W) ? __ldg(g.bits + wi + 1) : 0u;
+        u32 win = __funnelshift_r(w0, w1, sh) & 0xffu;              // voxels c0 .. c0 + 7
+        if (c0 + 8 > g.X) win &= (1u << (g.X - c0)) - 1u;           // (pad bits are 0 anyway)
+        if (win) {
+            const i64 base = g.eid_offset + (i64)__ldg(g.pref + wi) + __popc(w0 & mask_lt(sh)) + 1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) id[j] = base + __popc(win & ((1u << j) - 1u));
+        }
+        keep = win;
+        return true;
+    }
+    // nodes c0 .. c0 + 7 of node row (s, r): node c exists when one of the voxels {c - 1, c} x {r - 1, r} x {s - 1, s}
+    // inside the voxel box is set
+    const i64 id0 = ((i64)(g.X + 1) * (g.Y + 1)) * s + (i64)(g.X + 1) * r + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) id[j] = id0 + j;
+    const int vlo = (int)(d.vc0 > 0 ? d.vc0 : 0), vhi = (int)(d.vc1 < g.X ? d.vc1 : g.X);   // columns [vlo, vhi)
+    const int cl = c0 - 1;                                          // column of window bit 0
+    const int a = vlo - cl > 0 ? vlo - cl : 0, b = vhi - cl < 9 ? vhi - cl : 9;
+    if (a >= b) return true;
+    const u32 colmask = ((1u << b) - 1u) & ~((1u << a) - 1u);
+    u32 win = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const i64 vs = s - (t >> 1);
+        const int vr = r - (t & 1);
+        if (vs < d.vs0 || vs >= d.vs1 || vr < d.vr0 || vr >= d.vr1 || vr < 0 || vr >= g.Y) continue;
+        const i64 vsl = vs - g.z0;
+        const u32* plane;
+        if (vsl >= 0 && vsl < g.Zl) plane = g.bits + (size_t)vsl * g.Y * g.W;
+        else if (vsl == -1 && g.halo_below) plane = g.halo_below;
+        else continue;
+        const u32* rowp = plane + (size_t)vr * g.W;
+        u32 x;
+        if (cl < 0) {
+            x = __ldg(rowp) << 1;                                   // window bit 0 = column -1
+        } else {
+            const int w = cl >> 5, sh = cl & 31;
+            const u32 w0 = w < g.W ? __ldg(rowp + w) : 0u;
+            const u32 w1 = (sh > 23 && w + 1 < g.W) ? __ldg(rowp + w + 1) : 0u;
+            x = __funnelshift_r(w0, w1, sh);
+        }
+        win |= x;
+    }
+    win &= colmask;
+    keep = (win | (win >> 1)) & 0xffu;
+    return true;
+}
+
 // candidate k of the box -> box-relative (ks, kr, kc)
 // (a box never has 2^32 candidates: it is a subset of one slab's node grid)
 __device__ __forceinline__ void set_decode(const CfeSetDesc& d, i64 k, u32& ks, u32& kr, u32& kc)
@@ -773,11 +841,16 @@ k_sets_onepass(const CfeSetDesc* __restrict__ descs, int n_sets, i64 n_tiles, Se
         const u32 nc = (u32)(d.c1 - d.c0), nr = (u32)(d.r1 - d.r0);
         u32 ks, kr, kc;
         set_decode(d, k0, ks, kr, kc);
+        if (kc + SETS1_ITEMS <= nc && k0 + SETS1_ITEMS <= d.n_cand && set_eval8(d, g, ks, kr, kc, id, keep)) {
+            // the eight candidates sit in one row of the box: evaluated together from the rows' words
+        } else {
+            keep = 0;
 #pragma unroll
-        for (int j = 0; j < SETS1_ITEMS; ++j) {
-            id[j] = 0;
-            if (k0 + j < d.n_cand && set_eval(d, g, ks, kr, kc, id[j])) keep |= 1u << j;
-            if (++kc == nc) { kc = 0; if (++kr == nr) { kr = 0; ++ks; } }
+            for (int j = 0; j < SETS1_ITEMS; ++j) {
+                id[j] = 0;
+                if (k0 + j < d.n_cand && set_eval(d, g, ks, kr, kc, id[j])) keep |= 1u << j;
+                if (++kc == nc) { kc = 0; if (++kr == nr) { kr = 0; ++ks; } }
+            }
         }
     }
     u32 tot;
