@@ -275,16 +275,29 @@ def test_refnodes_program_emulated(sh, orc):
                 assert np.array_equal(got[k], v), (n, k)
 
 
-def test_ids_beyond_32_bits(sh):
+@pytest.mark.parametrize("case", ["wide", "digits_8_9", "digits_9_10", "digits_7_8"])
+def test_ids_beyond_32_bits(sh, case):
     """Node / element ids of the 2048^3-class configs exceed 2^32: a thin slab placed at a huge global
     slice offset exercises the 64-bit formatting paths; the expected text is re-derived here from the
-    voxel coordinates with plain Python integers."""
+    voxel coordinates with plain Python integers.  The other cases keep the ids below 2^32 (the 32-bit
+    variant of the element emitter) and put the powers of ten where digit counts change inside the slab:
+    that is where the benchmark slab (ids up to 1.1e9, element ids up to 3.2e8) lives."""
     import torch
     Zl, Y, X = 6, 48, 64
     RN, SN = X + 1, (X + 1) * (Y + 1)
-    z0 = (1 << 32) // SN + 700_000            # node ids around 6.4e9
+    if case == "wide":
+        z0 = (1 << 32) // SN + 700_000        # node ids around 6.4e9
+        eid_base = 5_000_000_000 - 300        # element ids cross 5e9 inside the slab
+    elif case == "digits_8_9":
+        z0 = 10 ** 9 // SN - 3                # node ids cross 1e9 inside the slab
+        eid_base = 10 ** 8 - 300              # element ids cross 1e8
+    elif case == "digits_9_10":
+        z0 = 4 * 10 ** 9 // SN                # ten-digit node ids below 2^32
+        eid_base = 10 ** 9 - 200              # element ids cross 1e9
+    else:
+        z0 = 10 ** 8 // SN - 2                # node ids cross 1e8
+        eid_base = 10 ** 7 - 150              # element ids cross 1e7
     Zg = z0 + Zl                               # this slab is the last one of the (virtual) global volume
-    eid_base = 5_000_000_000 - 300            # element ids cross 5e9 inside the slab
     vs = [0.01, 0.02, 0.00003]
     bw = cases.rand_binary((Zl, Y, X), 0.35, 77)
     runner = sh.LocalRunner(1)
@@ -306,7 +319,7 @@ def test_ids_beyond_32_bits(sh):
         used.update(n)
         eid += 1
         elines.append(",".join(str(v) for v in [eid] + n))
-    assert max(used) > (1 << 32) and eid > 5_000_000_000
+    assert (max(used) > (1 << 32) and eid > 5_000_000_000) if case == "wide" else max(used) < (1 << 32)
     nlines = []
     for nid in sorted(used):
         s, rem = divmod(nid, SN)
