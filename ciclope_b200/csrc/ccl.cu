@@ -332,6 +332,7 @@ k_ccl_border(const u32* __restrict__ bits, const u32* __restrict__ pref, CclGeom
         row = (k + 1) * G.TS * (i64)G.Y + r;
         dir = 1;
     }
+    CFE_ASSERT(row >= (dir == 0 ? 1 : G.Y) && row < (i64)G.Z * G.Y);
     const i64 i = row * W + w;
     const u32 cur = __ldg(bits + i);
     if (!cur) return;
@@ -838,7 +839,7 @@ k_ccl_interface_forest(const u32* __restrict__ bitsA, const u32* __restrict__ pr
         }
         if (uf_union_hooked(forest, va, Cv + vb)) {
             const u32 slot = atomicAdd(count, 1u);
-            CFE_ASSERT(slot < 2u * Cv);
+            CFE_ASSERT(slot < 2u * Cv || slot >= capacity);   // (the overflow flag above lifts the count past capacity)
             if (slot < capacity) { edges[2 * slot] = va; edges[2 * slot + 1] = vb; }
         }
     }

@@ -959,6 +959,7 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
                     for (u32 q = 0; q < (o & 3u) && q < hl; ++q)
                         w.acc |= (u32)(unsigned char)__ldg(h + hl - 1u - q) << (8u * ((o & 3u) - 1u - q));
                 }
+                CFE_ASSERT(o + line_len <= (u32)ELEM_WARP_STAGE && o + line_len <= pad + total);
                 w.d = o & 3u;
                 w.wp = stage + (o - w.d);
                 const bool same = (flags & 0x80u) != 0;
@@ -1013,6 +1014,8 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
         }
         __syncwarp();     // every line's whole words are in the staging area
         if (staged) {
+            // the formatted line ends where the length pass said it would
+            CFE_ASSERT(!active || (u32)(w.wp - stage) + w.d == pad + excl + len);
             if (active) lw_finish(w);
             __syncwarp();
             // stream the warp's span [pad, pad + total) to dst: aligned 16-byte chunks, bytes at the edges
