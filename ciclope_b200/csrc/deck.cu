@@ -1560,6 +1560,7 @@ k_part_scatter(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox
         __syncwarp();                       // every peer has read the cursor before its leader advances it
         if (gv[t] < 256) {
             const u32 rank = (u32)__popc(peers[t] & ((1u << lane) - 1u));
+            CFE_ASSERT(base + rank < nval);
             jl[base + rank] = (unsigned short)idx;
             if (rank == 0) wh[warp][gv[t]] = base + (u32)__popc(peers[t]);
         }
@@ -1570,7 +1571,9 @@ k_part_scatter(const uint8_t* __restrict__ vol, const u32* __restrict__ elem_vox
 #pragma unroll 4
     for (u32 i = threadIdx.x; i < nval; i += PART_THREADS) {
         const u32 j = jl[i];
+        CFE_ASSERT(j < nval);
         const u32 d = gbase[gvin[j]] + i;
+        CFE_ASSERT((i64)d < n_el);
         perm[d] = make_uint2(voxin[j], (u32)(tile0 + j));
         if (len_src) {
             len_dst[d] = lenin[j];

@@ -409,6 +409,7 @@ k_fill_list(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_wo
     }
     const u32 last = (n_words - i0 < FILL_WORDS ? n_words - i0 : FILL_WORDS) - 1u;
     if (threadIdx.x == last) s_total = p + (u32)__popc(word);
+    CFE_ASSERT(p + (u32)__popc(word) <= FILL_WORDS * 32u);      // the scan's prefixes are consistent with the bits
     if (word) {
         const u32 row = fd_div(i, d_wpr);
         const u32 w = i - row * wpr;
@@ -500,6 +501,7 @@ k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 
     }
     const u32 last = (n_words - i0 < FILLE_WORDS ? n_words - i0 : FILLE_WORDS) - 1u;
     if (threadIdx.x == last) s_total = p + (u32)__popc(word);
+    CFE_ASSERT(p + (u32)__popc(word) <= FILLE_WORDS * 32u);
     if (word) {
         const u32 row = fd_div(i, d_wpr);
         const u32 w = i - row * wpr;
