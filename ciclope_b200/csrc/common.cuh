@@ -46,6 +46,14 @@ void cfe_count_launch();
 #define CFE_ASSERT(cond) do { } while (0)
 #endif
 
+// Bulk copies (cp.async.bulk, the "async proxy") read shared memory that ordinary stores (the generic proxy) wrote:
+// EVERY writer fences its own stores before the barrier that precedes the copy, then one thread issues the copy
+// (the order of the CUDA programming guide's bulk-copy examples: fence, barrier, elected thread).
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // Function attributes (opt-in dynamic shared memory) are per device: true the first time it is
 // evaluated on the current device for this `mask` (one static mask per launch site; devices 0..63).
 static inline bool cfe_first_on_device(unsigned long long* mask, int* sm_count = nullptr)

@@ -237,6 +237,9 @@ __global__ void __launch_bounds__(NODE4_THREADS) k_emit_nodes4(NodeEmitParams P)
         }
         B[52] = pending;
     }
+#if EE2_BULK_FLUSH
+    fence_proxy_async_smem();
+#endif
     __syncthreads();
     i64 n_here = P.n_nodes - k0;
     if (n_here > NODE4_PER_CTA) n_here = NODE4_PER_CTA;
@@ -247,7 +250,6 @@ __global__ void __launch_bounds__(NODE4_THREADS) k_emit_nodes4(NodeEmitParams P)
 #if EE2_BULK_FLUSH
         // the CTA's 27 KB leave through the bulk-copy engine (cp.async.bulk shared -> global)
         if (threadIdx.x == 0 && n16) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                          :: "l"(dst), "r"((u32)__cvta_generic_to_shared(stage)), "r"(16u * n16) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -373,11 +375,11 @@ __global__ void __launch_bounds__(NODE4_THREADS) k_emit_nodes4b(NodeEmitParams P
 #pragma unroll
             for (int q = 0; q < 53; ++q) line[q] = (char)((L[q >> 2] >> (8 * (q & 3))) & 0xffu);
         }
+        fence_proxy_async_smem();
         __syncthreads();
         const u32 nbytes = n4 * 53u;
         const u32 n16 = nbytes >> 4;
         if (threadIdx.x == 0 && n16) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                          :: "l"(dst), "r"((u32)__cvta_generic_to_shared(stage)), "r"(16u * n16) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1017,6 +1019,9 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
             // the formatted line ends where the length pass said it would
             CFE_ASSERT(!active || (u32)(w.wp - stage) + w.d == pad + excl + len);
             if (active) lw_finish(w);
+#if EE2_BULK_FLUSH
+            fence_proxy_async_smem();     // every lane: its staged bytes, for the bulk copy lane 0 issues below
+#endif
             __syncwarp();
             // stream the warp's span [pad, pad + total) to dst: aligned 16-byte chunks, bytes at the edges
             char* gbase = dst - pad;
@@ -1026,7 +1031,6 @@ __global__ void __launch_bounds__(EE2_THREADS, 2) k_emit_elements2(ElemEmitParam
             // the aligned middle leaves through the bulk-copy engine (cp.async.bulk shared -> global): one
             // instruction of one lane instead of an LDS.128 + STG.128 loop of the whole warp
             if (lane == 0 && c1 > c0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(gbase + 16u * c0), "r"((u32)__cvta_generic_to_shared(stage + 16u * c0)),
                                 "r"(16u * (c1 - c0)) : "memory");

@@ -421,6 +421,9 @@ k_fill_list(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_wo
             *q++ = base + (u32)b;
         }
     }
+#if CFE_BULK_STORE
+    fence_proxy_async_smem();
+#endif
     __syncthreads();
     const u32 total = s_total;
     const u32 head = (4u - off) & 3u;
@@ -429,7 +432,6 @@ k_fill_list(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 n_wo
     if (threadIdx.x < h) dst[threadIdx.x] = sm[off + threadIdx.x];
 #if CFE_BULK_STORE
     if (threadIdx.x == 0 && n4) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                      :: "l"(dst + h), "r"((u32)__cvta_generic_to_shared(sm + off + h)), "r"(16u * n4) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -549,6 +551,9 @@ k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 
             }
         }
     }
+#if CFE_BULK_STORE
+    fence_proxy_async_smem();
+#endif
     __syncthreads();
     const u32 total = s_total;
     u32* dst = list + base0;
@@ -558,7 +563,6 @@ k_fill_elements(const u32* __restrict__ bits, const u32* __restrict__ pref, u32 
     const u32 hl = min((16u - offl) & 15u, total), nl = (total - hl) >> 4;
     const u32 hn = min((16u - offn) & 15u, total), nn = (total - hn) >> 4;
     if (threadIdx.x == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (n4)
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                          :: "l"(dst + h4), "r"((u32)__cvta_generic_to_shared(sm + h4)), "r"(16u * n4) : "memory");
