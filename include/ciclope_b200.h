@@ -272,7 +272,9 @@ int cfe_emit_nodes_bits(const uint32_t* nbits, const uint32_t* npref, const uint
  * *total = bytes written; blk_off[gv] = offset where block gv (header included) starts (optional).
  * Two entry points (three launches): cfe_element_lengths (line lengths + exclusive scan of the
  * 32-line tile totals) then cfe_emit_elements (formatting); ws = cfe_emit_elements_workspace_bytes(n_el)
- * bytes of scratch shared by both. */
+ * bytes of scratch shared by both (it also holds the counter from which the emitter's warps take their
+ * chunks of tiles: one workspace per deck in flight, not to be shared by concurrent calls).
+ * n_el < 2^32 (elem_vox holds 32-bit voxel indices of one slab). */
 size_t cfe_emit_elements_workspace_bytes(int64_t n_el);
 /* pass 1: line lengths + tile offsets; *total = bytes of the section */
 int cfe_element_lengths(const uint32_t* elem_vox, const void* perm, int64_t n_el, const uint8_t* vol,
